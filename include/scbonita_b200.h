@@ -1,0 +1,189 @@
+/*
+ * scbonita_b200.h -- C-ABI of the B200-native replacement for scBONITA's rule-inference
+ * fitness hot path (the compiled C simulator the reference loads with
+ * ctypes.cdll.LoadLibrary("./simulator.so"), singleCell.py:453, ruleMaker.py:979).
+ *
+ * Two groups of entry points:
+ *
+ *  1. the reference's own exported symbols, same names and argument lists, so the unchanged
+ *     Python (ruleMaker.__evaluateByNode, ruleMaker.py:1077-1221) keeps working when this
+ *     library is installed as ./simulator.so:
+ *         scSyncBool        replaces simulator.c:350-485
+ *         importanceScore   replaces simulator.c:555-755
+ *         cluster           replaces simulator.c:487-552
+ *  2. a context / batch API with runtime sizes (no compile-time NODE/CELL, simulator.c:6-8)
+ *     that packs the binarized matrix once and scores a whole GA population, or all local-search
+ *     variants, in one launch.  This is what the reference-side binding in INTEGRATION.md
+ *     calls from the two list comprehensions at ruleMaker.py:982-985 / 1030-1033 and from
+ *     __checkNodePossibilities (ruleMaker.py:1235-1266).
+ *
+ * Everything is plain C: pointers, sizes, int status codes.  All int32 tables are in the
+ * reference's layouts (what __evaluateByNode marshals, ruleMaker.py:1089-1129):
+ *     individual        int32[indLen]            rule bit-string
+ *     andLenList        int32[N]                 number of AND-terms per node
+ *     individualParse   int32[N] (or N+1)        start of each node's bits in `individual`
+ *     andNodes          int32[N][7][3]           inputs per AND-term, padded with -1 / [0,0,0]
+ *     andNodeInvertList int32[N][7][3]           inversion flag per input (int comparison, Q3)
+ *     knockouts/knockins int32[N]                ==1 knocks the node out / in
+ *     binMat            int32[rows][rowStride]   binarized expression, gene-major
+ *     nodePositions     int32[N]                 gene row of node i
+ *
+ * The library needs a CUDA device (sm_100a build); there is no CPU fallback: every entry
+ * point fails with SCB_ERR_CUDA when no device is usable.
+ */
+#ifndef SCBONITA_B200_H
+#define SCBONITA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCB_VERSION 100
+
+/* status codes (0 = success); scb_last_error() has the text for the calling thread */
+#define SCB_OK               0
+#define SCB_ERR_INVALID     -1   /* bad argument / contract violation (sizes, simSteps != 100, ...)  */
+#define SCB_ERR_CUDA        -2   /* CUDA runtime error or no device                                   */
+#define SCB_ERR_UNSUPPORTED -3   /* a rule needs > 3 distinct inputs, or N exceeds on-chip capacity   */
+#define SCB_ERR_NOMEM       -4
+
+/* output shapes of a population evaluation */
+#define SCB_MODE_SUM       0   /* int64[P]      sum over cells of the cellwise error = Python's sum(errors),
+                                  ruleMaker.py:1220-1221 (GA fitness)                                 */
+#define SCB_MODE_NODEWISE  1   /* int32[P][N]   errors[i] per node (localSearch != 0, simulator.c:477-479) */
+#define SCB_MODE_CELLWISE  2   /* int32[P][C]   errors[c] per cell (localSearch == 0, simulator.c:481)     */
+
+/* scb_ctx_set_option keys */
+#define SCB_OPT_EARLY_EXIT   1  /* 1 (default): stop a cell tile once its future is proven periodic  */
+#define SCB_OPT_SNAPSHOTS    2  /* 1 (default): resolve cycles with in-flight snapshot compares       */
+#define SCB_OPT_WARPS        3  /* warps per CTA of the simulator kernel (0 = auto)                   */
+#define SCB_OPT_MAX_CTAS     4  /* cap on persistent CTAs (0 = SM count x occupancy)                  */
+#define SCB_OPT_WORDS        5  /* 32-bit words per lane (0 = auto: 4, 2 or 1 by node count)          */
+#define SCB_OPT_CHECK_EVERY  6  /* period-<=2 check cadence in steps (default 4)                      */
+#define SCB_OPT_PERIOD_SEARCH 7 /* extra snapshot-compare steps spent looking for a tile-wide period  */
+
+typedef struct scb_ctx scb_ctx;
+
+/* counters of one evaluation (all optional diagnostics; results do not depend on them) */
+typedef struct scb_stats {
+    int64_t not_found_cells;      /* cells whose state 99 repeats no earlier state        */
+    int64_t undefined_leading;    /* not-found cells before the first found one: the reference reads  */
+                                  /* uninitialised memory there; defined as 0 here, as in the oracle  */
+    int64_t empty_rule_nodes;     /* (individual,node) pairs with no selected AND-term (Q9): value 0  */
+    int64_t unsupported_nodes;    /* rules with > 3 distinct inputs -> SCB_ERR_UNSUPPORTED            */
+    int64_t bad_index_nodes;      /* input index outside [0,N) -> SCB_ERR_INVALID                     */
+    int64_t term_overflow_nodes;  /* more than 7 AND-terms for a node (Q10) -> SCB_ERR_INVALID        */
+    int64_t resolver_chunks;      /* 1024-cell chunks that needed the exact second-pass resolver      */
+    int64_t steps_executed;       /* simulated (tile, step) pairs, for executed-work accounting       */
+    int64_t tiles;                /* tiles simulated (individuals x cell tiles)                       */
+    float   kernel_ms;            /* device time of the last evaluation (CUDA events on the stream)   */
+    float   reserved;
+} scb_stats;
+
+const char *scb_last_error(void);
+int scb_version(void);
+int scb_device_count(void);
+
+/* ---- context: the packed cell matrix of one (dataset, network) pair on one GPU -------------
+ * Packs rows nodePositions[i] of binMat (elemBytes 4: int32 as the reference passes it,
+ * ruleMaker.py:1109-1111; elemBytes 1: uint8) into node-major 32-bit words on the device
+ * (kernel K1).  binMat values must be 0/1.  rowStride is in elements (reference: CELL,
+ * simulator.c:8).  The caller's buffers are not retained. */
+int scb_ctx_create(scb_ctx **ctx, int device, int nodeNum, int lenSamples,
+                   const void *binMat, int elemBytes, int64_t rowStride,
+                   const int32_t *nodePositions);
+int scb_ctx_destroy(scb_ctx *ctx);
+int scb_ctx_set_option(scb_ctx *ctx, int key, int64_t value);
+int scb_ctx_info(scb_ctx *ctx, int *nodeNum, int *lenSamples, int *wordsPerLane, int *warps,
+                 int *ctas, int *smemBytes);
+
+/* ---- whole-population evaluation, host buffers in and out (replaces P calls of scSyncBool,
+ * ruleMaker.py:982-985).  individuals: int32[P][indLen]; andNodes / andNodeInvertList are
+ * [P][N][7][3] when tablesPerIndividual != 0 (each individual owns a model copy,
+ * ruleMaker.py:650) else one shared [N][7][3].  simSteps is fixed at 100.
+ * out: see SCB_MODE_*.  stats may be NULL.  Synchronous. */
+int scb_eval_population(scb_ctx *ctx, int P, const int32_t *individuals, int indLen,
+                        const int32_t *andLenList, const int32_t *individualParse,
+                        const int32_t *andNodes, const int32_t *andNodeInvertList,
+                        int tablesPerIndividual, const int32_t *knockouts,
+                        const int32_t *knockins, int mode, void *out, scb_stats *stats);
+
+/* ---- the same, split so that inputs can stay resident in HBM between launches ------------
+ * scb_pop_upload copies the reference-format tables to the device (async on the context's
+ * stream); scb_pop_run launches rule compilation + simulation + resolver (async);
+ * scb_pop_fetch waits and copies the result of `mode` to the host.  scb_pop_result_dev
+ * exposes the device buffer (int64[P] / int32[P][N] / int32[P][C]) for a collective. */
+int scb_pop_upload(scb_ctx *ctx, int P, const int32_t *individuals, int indLen,
+                   const int32_t *andLenList, const int32_t *individualParse,
+                   const int32_t *andNodes, const int32_t *andNodeInvertList,
+                   int tablesPerIndividual, const int32_t *knockouts, const int32_t *knockins);
+int scb_pop_run(scb_ctx *ctx, int mode);
+int scb_pop_fetch(scb_ctx *ctx, int mode, void *out, scb_stats *stats);
+int scb_pop_result_dev(scb_ctx *ctx, int mode, void **devPtr, int64_t *bytes);
+
+/* stream / timing plumbing for callers that time or chain work on the context's stream */
+int scb_ctx_stream(scb_ctx *ctx, void **cudaStream);
+int scb_ctx_sync(scb_ctx *ctx);
+int scb_ctx_event_record(scb_ctx *ctx, int slot);            /* slot 0..7                     */
+int scb_ctx_event_elapsed_ms(scb_ctx *ctx, int slot0, int slot1, float *ms);
+
+/* ---- local search (ruleMaker.__checkNodePossibilities, ruleMaker.py:1235-1266): all
+ * 2^k - 1 rule bit-strings of `node` on top of the base individual, one launch;
+ * nodeErrors[v-1] = errors[node] of variant v, whose bits (least significant first, as
+ * __bitList produces them, ruleMaker.py:796-802) replace the node's k bits exactly like
+ * ruleMaker.py:1247-1253. */
+int scb_eval_local_search(scb_ctx *ctx, const int32_t *individual, int indLen,
+                          const int32_t *andLenList, const int32_t *individualParse,
+                          const int32_t *andNodes, const int32_t *andNodeInvertList,
+                          const int32_t *knockouts, const int32_t *knockins, int node,
+                          int32_t *nodeErrors, int maxVariants, int *nVariants);
+
+/* ---- attractor companion (singleCell.assignAttractors, singleCell.py:1211-1238):
+ * dist[c][a] = sum_i |attractors[a][i] - cell c's observed state|, decider = first minimum
+ * (pandas idxmin), deciderDistance = the minimum.  dist may be NULL. */
+int scb_hamming_argmin(scb_ctx *ctx, const int32_t *attractors, int nAttr, int32_t *dist,
+                       int32_t *decider, int32_t *deciderDistance);
+
+/* ---- trajectories for attractor extraction.
+ * semantics 0: C `cluster` (simulator.c:487-552), simSteps 100; 1: Python `__cluster`
+ * (singleCell.py:990-1059), simSteps 10.  For every cell: res[c][2] = attractor window as the
+ * respective reference returns it, and the window's states bit-packed node-major:
+ * states[c][s][ceil(N/32)] for s < maxStates (rows res[0]..res[1] inclusive for Python
+ * semantics, [res[0], res[1]) for C).  nStates[c] = number of rows written. */
+int scb_attractors(scb_ctx *ctx, const int32_t *individual, int indLen,
+                   const int32_t *andLenList, const int32_t *individualParse,
+                   const int32_t *andNodes, const int32_t *andNodeInvertList,
+                   const int32_t *knockouts, const int32_t *knockins, int semantics,
+                   int maxStates, int32_t *res, int32_t *nStates, uint32_t *states);
+
+/* ---- the reference's exported symbols (drop-in ./simulator.so) --------------------------
+ * Argument lists are exactly simulator.c:350, :555 and :487.  ctypes passes every argument as
+ * c_void_p (ruleMaker.py:1117-1138), so integers arrive in 64-bit registers: they are
+ * declared intptr_t here and truncated to int.  binMat's row stride and simData's row stride
+ * are the compile-time CELL / NODE of the reference (15000 / 20000) unless changed with
+ * scb_set_legacy_geometry or the environment variables SCB_LEGACY_CELL / SCB_LEGACY_NODE.
+ * These never throw or abort: on error they print to stderr and leave `errors` untouched. */
+void scb_set_legacy_geometry(int nodeStride, int cellStride);
+void scSyncBool(void *simData, const int32_t *individual, intptr_t indLen, intptr_t nodeNum,
+                const int32_t *andLenList, const int32_t *individualParse,
+                const int32_t *andNodes, const int32_t *andNodeInvertList, intptr_t simSteps,
+                const int32_t *knockouts, const int32_t *knockins, intptr_t lenSamples,
+                const int32_t *binMat, const int32_t *nodePositions, int32_t *errors,
+                intptr_t localSearch, intptr_t importanceScores);
+void importanceScore(void *simData, const int32_t *individual, intptr_t indLen, intptr_t nodeNum,
+                     const int32_t *andLenList, const int32_t *individualParse,
+                     const int32_t *andNodes, const int32_t *andNodeInvertList,
+                     intptr_t simSteps, const int32_t *knockouts, const int32_t *knockins,
+                     intptr_t lenSamples, const int32_t *binMat, const int32_t *nodePositions,
+                     double *importanceScores);
+void cluster(void *simData, int32_t *resSubmit, intptr_t sampleIndex, const int32_t *individual,
+             intptr_t indLen, intptr_t nodeNum, const int32_t *andLenList,
+             const int32_t *individualParse, const int32_t *andNodes,
+             const int32_t *andNodeInvertList, intptr_t simSteps, const int32_t *knockouts,
+             const int32_t *knockins, const int32_t *binMat, const int32_t *nodePositions);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,98 @@
+"""ctypes binding of the C-ABI in include/scbonita_b200.h.
+
+The product library is the in-tree ``scbonita_b200/libscbonita_b200.so`` (built by
+``__graft_entry__.build()`` / ``make -C scbonita_b200/csrc``).  There is no CPU fallback: if
+the library is missing, or no CUDA device is usable, calls raise.  ``load(path)`` accepts an
+explicit path only so that the CPU test-suite can point the *same* binding at the host-thread
+emulator build of the kernels under tests/emu/ (test infrastructure, never used by default).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_PATH = os.path.join(_HERE, "libscbonita_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4
+MODE_SUM, MODE_NODEWISE, MODE_CELLWISE = 0, 1, 2
+OPT_EARLY_EXIT, OPT_SNAPSHOTS, OPT_WARPS, OPT_MAX_CTAS, OPT_WORDS, OPT_CHECK_EVERY, OPT_PERIOD_SEARCH = 1, 2, 3, 4, 5, 6, 7
+
+# every symbol include/scbonita_b200.h declares (tests check that the library exports them all)
+SYMBOLS = (
+    "scb_last_error", "scb_version", "scb_device_count",
+    "scb_ctx_create", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info",
+    "scb_eval_population", "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
+    "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
+    "scb_eval_local_search", "scb_hamming_argmin", "scb_attractors",
+    "scb_set_legacy_geometry", "scSyncBool", "importanceScore", "cluster",
+)
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("not_found_cells", ctypes.c_int64), ("undefined_leading", ctypes.c_int64),
+                ("empty_rule_nodes", ctypes.c_int64), ("unsupported_nodes", ctypes.c_int64),
+                ("bad_index_nodes", ctypes.c_int64), ("term_overflow_nodes", ctypes.c_int64),
+                ("resolver_chunks", ctypes.c_int64), ("steps_executed", ctypes.c_int64),
+                ("tiles", ctypes.c_int64), ("kernel_ms", ctypes.c_float), ("reserved", ctypes.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class ScbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("scbonita_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_libs = {}
+
+
+def load(path=None):
+    """Load (once per path) and type the library.  Raises if it is not there."""
+    path = os.path.abspath(path or DEFAULT_PATH)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            "%s not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C scbonita_b200/csrc); scbonita_b200 has no CPU fallback" % path)
+    lib = ctypes.CDLL(path)
+    vp, i32p = ctypes.c_void_p, ctypes.c_void_p
+    lib.scb_last_error.restype = ctypes.c_char_p
+    lib.scb_last_error.argtypes = []
+    lib.scb_version.restype = ctypes.c_int
+    lib.scb_device_count.restype = ctypes.c_int
+    lib.scb_ctx_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                                   ctypes.c_int64, i32p]
+    lib.scb_ctx_destroy.argtypes = [vp]
+    lib.scb_ctx_set_option.argtypes = [vp, ctypes.c_int, ctypes.c_int64]
+    lib.scb_ctx_info.argtypes = [vp] + [ctypes.POINTER(ctypes.c_int)] * 6
+    tables = [i32p, ctypes.c_int, i32p, i32p, i32p, i32p, ctypes.c_int, i32p, i32p]
+    lib.scb_eval_population.argtypes = [vp, ctypes.c_int] + tables + [ctypes.c_int, vp, ctypes.POINTER(Stats)]
+    lib.scb_pop_upload.argtypes = [vp, ctypes.c_int] + tables
+    lib.scb_pop_run.argtypes = [vp, ctypes.c_int]
+    lib.scb_pop_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Stats)]
+    lib.scb_pop_result_dev.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
+    lib.scb_ctx_stream.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.scb_ctx_sync.argtypes = [vp]
+    lib.scb_ctx_event_record.argtypes = [vp, ctypes.c_int]
+    lib.scb_ctx_event_elapsed_ms.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.scb_eval_local_search.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, ctypes.c_int,
+                                          i32p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.scb_hamming_argmin.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p]
+    lib.scb_attractors.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, ctypes.c_int,
+                                   ctypes.c_int, i32p, i32p, vp]
+    lib.scb_set_legacy_geometry.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.scb_set_legacy_geometry.restype = None
+    for name in ("scb_ctx_create", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info", "scb_eval_population",
+                 "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev", "scb_ctx_stream",
+                 "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms", "scb_eval_local_search",
+                 "scb_hamming_argmin", "scb_attractors"):
+        getattr(lib, name).restype = ctypes.c_int
+    _libs[path] = lib
+    return lib
+
+
+def check(lib, rc):
+    if rc != OK:
+        raise ScbError(rc, (lib.scb_last_error() or b"").decode("utf-8", "replace"))

@@ -1,0 +1,572 @@
+/*
+ * scb_api.cu -- host side of the C-ABI declared in include/scbonita_b200.h.
+ *
+ * Owns device memory, the stream and the launch geometry; all arithmetic of the hot path
+ * happens in the kernels (scb_kernels.cuh).  There is deliberately no CPU implementation
+ * behind any entry point: without a usable device every call returns SCB_ERR_CUDA.
+ *
+ * Reference interface replaced: the ctypes boundary of ruleMaker.__evaluateByNode
+ * (ruleMaker.py:1077-1221) onto simulator.c's scSyncBool / importanceScore / cluster.
+ */
+#include "../../include/scbonita_b200.h"
+#include "scb_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#ifdef SCB_EMU
+#define SCB_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch(kernel, grid, block, smem, __VA_ARGS__)
+#else
+#define SCB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(SCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;            /* elements */
+    int ensure(size_t n)
+    {
+        if (n <= cap && p) return SCB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = std::max<size_t>(n, 1);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T));
+        if (e != cudaSuccess) return fail(SCB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+        cap = want;
+        return SCB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct scb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t evRun0 = nullptr, evRun1 = nullptr;
+    int numSM = 0;
+    size_t smemLimit = 0;
+    int N = 0, C = 0, W = 0, Wpad = 0;
+    /* options */
+    int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 4, optSearch = 0;
+    unsigned long long snapLo = (1ull << 16) | (1ull << 32), snapHi = 1ull;   /* steps 16, 32, 64 */
+    /* geometry (derived) */
+    int K = 0, warps = 0, ctas = 0, occ = 1;
+    size_t smemSim = 0, smemRes = 0;
+    int resWarps = 8, resCtas = 0;
+    bool geomValid = false;
+    /* device data */
+    DevBuf<uint32_t> dX;
+    DevBuf<int32_t> dInd, dAndLen, dParse, dAn, dAi, dKo, dKi;
+    DevBuf<uint4> dDescs;
+    DevBuf<int4> dCounts;
+    DevBuf<unsigned long long> dFitness;
+    DevBuf<int32_t> dNodewise, dCellwise;
+    DevBuf<unsigned int> dCounters;      /* [0] K2 work head, [1] resolve count, [2] K3 work head */
+    DevBuf<uint2> dItems;
+    DevBuf<uint32_t> dZ;
+    DevBuf<ScbDiag> dDiag;
+    DevBuf<uint32_t> dAttr;
+    DevBuf<int32_t> dDist, dDecider, dDeciderDist;
+    /* current population */
+    int P = 0, indLen = 0, tpi = 0;
+    int lastMode = -1;
+    bool ran = false;
+    ScbDiag hDiag = {};
+    std::mutex mu;
+};
+
+namespace {
+
+int pick_geometry(scb_ctx *c)
+{
+    const int N = c->N;
+    int K = c->optWords;
+    if (K != 0 && K != 1 && K != 2 && K != 4) return fail(SCB_ERR_INVALID, "SCB_OPT_WORDS must be 0, 1, 2 or 4");
+    if (K == 0) {
+        K = 4;
+        while (K >= 1 && scb_smem_bytes(N, K, 2) > c->smemLimit) K >>= 1;
+        /* small matrices: prefer narrower tiles so that there are enough tiles to fill the GPU */
+        if (K < 1)
+            return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the %zu-byte shared-memory state buffers", N, c->smemLimit);
+    } else if (scb_smem_bytes(N, K, 2) > c->smemLimit) {
+        return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d with %d words per lane exceeds shared memory", N, K);
+    }
+    if (scb_smem_bytes(N, 1, 3) > c->smemLimit)
+        return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the resolver's three state buffers", N);
+    c->K = K;
+    c->smemSim = scb_smem_bytes(N, K, 2);
+    c->smemRes = scb_smem_bytes(N, 1, 3);
+    int occGuess = (int)std::max<size_t>(1, (c->smemLimit + 1024) / (c->smemSim + 1024));
+    int S = c->optWarps;
+    if (S == 0) {
+        S = 32 / occGuess;
+        S = std::min(16, std::max(2, S));
+        S = std::min(S, std::max(1, (N + 3) / 4));
+    }
+    S = std::max(S, K);                 /* the mask arrays need 32*K threads */
+    S = std::min(S, 32);
+    c->warps = S;
+#ifndef SCB_EMU
+    CK(cudaFuncSetAttribute(scb_k_sim<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_sim<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_sim<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
+#endif
+    int occ = 1;
+    if (K == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<4>, S * 32, c->smemSim));
+    else if (K == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<2>, S * 32, c->smemSim));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<1>, S * 32, c->smemSim));
+    if (occ < 1) return fail(SCB_ERR_UNSUPPORTED, "simulator kernel does not fit on an SM (N=%d, K=%d, warps=%d)", N, K, S);
+    c->occ = occ;
+    int ctas = c->numSM * occ;
+    if (c->optMaxCtas > 0) ctas = std::min(ctas, c->optMaxCtas);
+    c->ctas = ctas;
+    int occR = 1;
+    c->resWarps = std::min(8, std::max(1, (N + 3) / 4));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve, c->resWarps * 32, c->smemRes));
+    c->resCtas = c->numSM * std::max(1, occR);
+    if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
+    int rc = c->dZ.ensure((size_t)c->ctas * N * 32 * K);
+    if (rc) return rc;
+    c->geomValid = true;
+    return SCB_OK;
+}
+
+int check_ctx(scb_ctx *c)
+{
+    if (!c) return fail(SCB_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    return SCB_OK;
+}
+
+size_t result_bytes(const scb_ctx *c, int mode)
+{
+    if (mode == SCB_MODE_SUM) return (size_t)c->P * sizeof(long long);
+    if (mode == SCB_MODE_NODEWISE) return (size_t)c->P * c->N * sizeof(int32_t);
+    return (size_t)c->P * c->C * sizeof(int32_t);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *scb_last_error(void) { return g_err; }
+int scb_version(void) { return SCB_VERSION; }
+
+int scb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int scb_ctx_create(scb_ctx **out, int device, int nodeNum, int lenSamples, const void *binMat,
+                   int elemBytes, int64_t rowStride, const int32_t *nodePositions)
+{
+    if (!out) return fail(SCB_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    if (nodeNum <= 0 || lenSamples <= 0) return fail(SCB_ERR_INVALID, "nodeNum and lenSamples must be positive");
+    if (nodeNum > 65535) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > 65535", nodeNum);
+    if (!binMat || !nodePositions) return fail(SCB_ERR_INVALID, "null binMat / nodePositions");
+    if (elemBytes != 4 && elemBytes != 1) return fail(SCB_ERR_INVALID, "elemBytes must be 4 (int32) or 1 (uint8)");
+    if (rowStride < lenSamples) return fail(SCB_ERR_INVALID, "rowStride %lld < lenSamples %d", (long long)rowStride, lenSamples);
+    for (int i = 0; i < nodeNum; ++i)
+        if (nodePositions[i] < 0) return fail(SCB_ERR_INVALID, "nodePositions[%d] is negative", i);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(SCB_ERR_CUDA, "no CUDA device available");
+    if (device < 0 || device >= ndev) return fail(SCB_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    scb_ctx *c = new (std::nothrow) scb_ctx();
+    if (!c) return fail(SCB_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return fail(SCB_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    c->numSM = prop.multiProcessorCount;
+    c->smemLimit = prop.sharedMemPerBlockOptin;
+    c->N = nodeNum; c->C = lenSamples;
+    c->W = (lenSamples + 31) / 32;
+    c->Wpad = ((c->W + 127) / 128) * 128;
+    auto bail = [&](int rc) { scb_ctx_destroy(c); return rc; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaStreamCreate failed"));
+    for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreate(&c->evRun0) != cudaSuccess || cudaEventCreate(&c->evRun1) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
+    int rc;
+    if ((rc = c->dX.ensure((size_t)c->N * c->Wpad))) return bail(rc);
+    if ((rc = c->dDiag.ensure(1))) return bail(rc);
+    if ((rc = c->dCounters.ensure(4))) return bail(rc);
+
+    /* stage the N gene rows the network uses (row i = gene nodePositions[i]) and pack them */
+    const size_t rowBytes = (size_t)lenSamples * elemBytes;
+    DevBuf<unsigned char> stage;
+    if ((rc = stage.ensure((size_t)c->N * rowBytes))) return bail(rc);
+    bool contiguous = true;
+    for (int i = 1; i < nodeNum; ++i) contiguous = contiguous && nodePositions[i] == nodePositions[0] + i;
+    const unsigned char *src = static_cast<const unsigned char *>(binMat);
+    cudaError_t ce = cudaSuccess;
+    if (contiguous) {
+        ce = cudaMemcpy2DAsync(stage.p, rowBytes, src + (size_t)nodePositions[0] * rowStride * elemBytes,
+                               (size_t)rowStride * elemBytes, rowBytes, (size_t)nodeNum, cudaMemcpyHostToDevice, c->stream);
+    } else {
+        for (int i = 0; i < nodeNum && ce == cudaSuccess; ++i)
+            ce = cudaMemcpyAsync(stage.p + (size_t)i * rowBytes, src + (size_t)nodePositions[i] * rowStride * elemBytes,
+                                 rowBytes, cudaMemcpyHostToDevice, c->stream);
+    }
+    if (ce != cudaSuccess) { stage.release(); return bail(fail(SCB_ERR_CUDA, "H2D copy of binMat rows failed: %s", cudaGetErrorString(ce))); }
+    cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), c->stream);
+    ScbPackArgs pa;
+    pa.src = stage.p; pa.elemBytes = elemBytes; pa.rowStride = lenSamples;
+    pa.N = c->N; pa.C = c->C; pa.Wpad = c->Wpad; pa.X = c->dX.p; pa.diag = c->dDiag.p;
+    const int wpb = 4;
+    dim3 grid((unsigned)((c->Wpad / 32 + wpb - 1) / wpb), (unsigned)c->N);
+    SCB_LAUNCH(scb_k_pack, grid, dim3(wpb * 32), 0, c->stream, pa);
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&c->hDiag, c->dDiag.p, sizeof(ScbDiag), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    stage.release();
+    if (ce != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "pack kernel failed: %s", cudaGetErrorString(ce)));
+    if (c->hDiag.nonbinary_cells)
+        return bail(fail(SCB_ERR_INVALID, "binMat holds %llu values other than 0/1 in the network's rows", c->hDiag.nonbinary_cells));
+    if ((rc = pick_geometry(c))) return bail(rc);
+    *out = c;
+    return SCB_OK;
+}
+
+int scb_ctx_destroy(scb_ctx *c)
+{
+    if (!c) return SCB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
+    c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release();
+    c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
+    c->dItems.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
+    c->dDecider.release(); c->dDeciderDist.release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->evRun0) cudaEventDestroy(c->evRun0);
+    if (c->evRun1) cudaEventDestroy(c->evRun1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SCB_OK;
+}
+
+int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    switch (key) {
+        case SCB_OPT_EARLY_EXIT: c->optEarly = value != 0; return SCB_OK;
+        case SCB_OPT_SNAPSHOTS: c->optSnap = value != 0; return SCB_OK;
+        case SCB_OPT_CHECK_EVERY:
+            if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "check cadence must be in [1,99]");
+            c->optChk = (int)value; return SCB_OK;
+        case SCB_OPT_PERIOD_SEARCH:
+            if (value < 0 || value > 99) return fail(SCB_ERR_INVALID, "period search must be in [0,99]");
+            c->optSearch = (int)value; return SCB_OK;
+        case SCB_OPT_WARPS:
+            if (value < 0 || value > 32) return fail(SCB_ERR_INVALID, "warps must be in [0,32]");
+            c->optWarps = (int)value; break;
+        case SCB_OPT_MAX_CTAS:
+            if (value < 0) return fail(SCB_ERR_INVALID, "max CTAs must be >= 0");
+            c->optMaxCtas = (int)value; break;
+        case SCB_OPT_WORDS: {
+            const int old = c->optWords;
+            c->optWords = (int)value;
+            rc = pick_geometry(c);
+            if (rc) { c->optWords = old; pick_geometry(c); }
+            return rc;
+        }
+        default: return fail(SCB_ERR_INVALID, "unknown option %d", key);
+    }
+    return pick_geometry(c);
+}
+
+int scb_ctx_info(scb_ctx *c, int *nodeNum, int *lenSamples, int *wordsPerLane, int *warps, int *ctas, int *smemBytes)
+{
+    if (!c) return fail(SCB_ERR_INVALID, "null context");
+    if (nodeNum) *nodeNum = c->N;
+    if (lenSamples) *lenSamples = c->C;
+    if (wordsPerLane) *wordsPerLane = c->K;
+    if (warps) *warps = c->warps;
+    if (ctas) *ctas = c->ctas;
+    if (smemBytes) *smemBytes = (int)c->smemSim;
+    return SCB_OK;
+}
+
+int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, const int32_t *andLenList,
+                   const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                   int tablesPerIndividual, const int32_t *knockouts, const int32_t *knockins)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (P <= 0 || P > 65535 * 32) return fail(SCB_ERR_INVALID, "population size %d out of range", P);
+    if (indLen < 0) return fail(SCB_ERR_INVALID, "indLen must be >= 0");
+    if (!andLenList || !individualParse || !andNodes || !andNodeInvertList || !knockouts || !knockins || (!individuals && indLen > 0))
+        return fail(SCB_ERR_INVALID, "null table pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const int N = c->N;
+    const size_t tbl = (size_t)N * SCB_MAX_TERMS * SCB_MAX_IN;
+    const size_t ntab = tablesPerIndividual ? (size_t)P : 1;
+    if ((rc = c->dInd.ensure((size_t)P * std::max(indLen, 1)))) return rc;
+    if ((rc = c->dAndLen.ensure(N)) || (rc = c->dParse.ensure(N)) || (rc = c->dKo.ensure(N)) || (rc = c->dKi.ensure(N))) return rc;
+    if ((rc = c->dAn.ensure(ntab * tbl)) || (rc = c->dAi.ensure(ntab * tbl))) return rc;
+    if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
+    if ((rc = c->dFitness.ensure(P))) return rc;
+    const size_t chunks = (size_t)c->Wpad / 32;
+    if ((rc = c->dItems.ensure((size_t)P * chunks))) return rc;
+    cudaStream_t st = c->stream;
+    if (indLen > 0) CK(cudaMemcpyAsync(c->dInd.p, individuals, (size_t)P * indLen * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dAndLen.p, andLenList, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dParse.p, individualParse, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dKo.p, knockouts, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dKi.p, knockins, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dAn.p, andNodes, ntab * tbl * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dAi.p, andNodeInvertList, ntab * tbl * 4, cudaMemcpyHostToDevice, st));
+    c->P = P; c->indLen = indLen; c->tpi = tablesPerIndividual ? 1 : 0;
+    c->ran = false;
+    return SCB_OK;
+}
+
+int scb_pop_run(scb_ctx *c, int mode)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (mode < 0 || mode > 2) return fail(SCB_ERR_INVALID, "unknown mode %d", mode);
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->P <= 0) return fail(SCB_ERR_INVALID, "no population uploaded");
+    if (!c->geomValid && (rc = pick_geometry(c))) return rc;
+    const int N = c->N, P = c->P;
+    cudaStream_t st = c->stream;
+    if (mode == SCB_MODE_NODEWISE && (rc = c->dNodewise.ensure((size_t)P * N))) return rc;
+    if (mode == SCB_MODE_CELLWISE && (rc = c->dCellwise.ensure((size_t)P * c->C))) return rc;
+    CK(cudaEventRecord(c->evRun0, st));
+    CK(cudaMemsetAsync(c->dFitness.p, 0, (size_t)P * 8, st));
+    if (mode == SCB_MODE_NODEWISE) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
+    CK(cudaMemsetAsync(c->dCounters.p, 0, 4 * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
+
+    ScbCompileArgs ca;
+    ca.P = P; ca.N = N; ca.indLen = c->indLen; ca.tablesPerIndividual = c->tpi; ca.Npad = N;
+    ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
+    ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = c->dKo.p; ca.ki = c->dKi.p;
+    ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
+    SCB_LAUNCH(scb_k_compile, dim3((unsigned)((P + 3) / 4)), dim3(128), 0, st, ca);
+    CK(cudaGetLastError());
+
+    ScbSimArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    const int WT = 32 * c->K;
+    sa.X = c->dX.p; sa.N = N; sa.C = c->C; sa.Wpad = c->Wpad;
+    sa.tiles = (c->W + WT - 1) / WT; sa.P = P; sa.Npad = N; sa.mode = mode;
+    sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
+    sa.fitness = c->dFitness.p; sa.nodewise = c->dNodewise.p; sa.cellwise = c->dCellwise.p;
+    sa.workCounter = c->dCounters.p; sa.resolveCount = c->dCounters.p + 1;
+    sa.resolveItems = c->dItems.p; sa.resolveCap = (unsigned)std::min<size_t>(c->dItems.cap, 0xffffffffu);
+    sa.zscratch = c->dZ.p; sa.zstride = (unsigned long long)N * WT;
+    sa.flags = (c->optEarly ? SCB_KF_EARLY : 0u) | (c->optSnap ? SCB_KF_SNAP : 0u);
+    sa.chkEvery = c->optChk; sa.snapLo = c->snapLo; sa.snapHi = c->snapHi; sa.periodSearch = c->optSearch;
+    sa.diag = c->dDiag.p;
+    const long long items = (long long)P * sa.tiles;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, c->ctas));
+    const dim3 block((unsigned)c->warps * 32);
+    if (c->K == 4) SCB_LAUNCH(scb_k_sim<4>, dim3(grid), block, c->smemSim, st, sa);
+    else if (c->K == 2) SCB_LAUNCH(scb_k_sim<2>, dim3(grid), block, c->smemSim, st, sa);
+    else SCB_LAUNCH(scb_k_sim<1>, dim3(grid), block, c->smemSim, st, sa);
+    CK(cudaGetLastError());
+
+    ScbResolveArgs ra;
+    ra.s = sa; ra.itemCursor = c->dCounters.p + 2;
+    SCB_LAUNCH(scb_k_resolve, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->evRun1, st));
+    c->lastMode = mode; c->ran = true;
+    return SCB_OK;
+}
+
+int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->ran) return fail(SCB_ERR_INVALID, "scb_pop_run has not been called for this population");
+    if (mode != c->lastMode && mode != SCB_MODE_SUM) return fail(SCB_ERR_INVALID, "mode %d was not computed by the last run (mode %d)", mode, c->lastMode);
+    cudaStream_t st = c->stream;
+    if (out) {
+        const void *src = mode == SCB_MODE_SUM ? (const void *)c->dFitness.p
+                          : mode == SCB_MODE_NODEWISE ? (const void *)c->dNodewise.p : (const void *)c->dCellwise.p;
+        CK(cudaMemcpyAsync(out, src, result_bytes(c, mode), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(&c->hDiag, c->dDiag.p, sizeof(ScbDiag), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const ScbDiag &d = c->hDiag;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->not_found_cells = (int64_t)d.not_found_cells;
+        stats->undefined_leading = (int64_t)d.undefined_leading;
+        stats->empty_rule_nodes = (int64_t)d.empty_rule_nodes;
+        stats->unsupported_nodes = (int64_t)d.unsupported_nodes;
+        stats->bad_index_nodes = (int64_t)d.bad_index_nodes;
+        stats->term_overflow_nodes = (int64_t)d.term_overflow_nodes;
+        stats->resolver_chunks = (int64_t)d.resolver_chunks;
+        stats->steps_executed = (int64_t)d.steps_executed;
+        stats->tiles = (int64_t)d.tiles;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->evRun0, c->evRun1) == cudaSuccess) stats->kernel_ms = ms;
+    }
+    if (d.bad_index_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules reference an input outside [0,%d)", d.bad_index_nodes, c->N);
+    if (d.term_overflow_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules span more than 7 AND-terms or leave the bit-string", d.term_overflow_nodes);
+    if (d.unsupported_nodes) return fail(SCB_ERR_UNSUPPORTED, "%llu (individual,node) rules use more than 3 distinct inputs", d.unsupported_nodes);
+    return SCB_OK;
+}
+
+int scb_pop_result_dev(scb_ctx *c, int mode, void **devPtr, int64_t *bytes)
+{
+    if (!c || !devPtr) return fail(SCB_ERR_INVALID, "null argument");
+    if (mode < 0 || mode > 2) return fail(SCB_ERR_INVALID, "unknown mode %d", mode);
+    *devPtr = mode == SCB_MODE_SUM ? (void *)c->dFitness.p : mode == SCB_MODE_NODEWISE ? (void *)c->dNodewise.p : (void *)c->dCellwise.p;
+    if (bytes) *bytes = (int64_t)result_bytes(c, mode);
+    return SCB_OK;
+}
+
+int scb_eval_population(scb_ctx *c, int P, const int32_t *individuals, int indLen, const int32_t *andLenList,
+                        const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                        int tablesPerIndividual, const int32_t *knockouts, const int32_t *knockins, int mode,
+                        void *out, scb_stats *stats)
+{
+    int rc = scb_pop_upload(c, P, individuals, indLen, andLenList, individualParse, andNodes, andNodeInvertList,
+                            tablesPerIndividual, knockouts, knockins);
+    if (rc) return rc;
+    if ((rc = scb_pop_run(c, mode))) return rc;
+    return scb_pop_fetch(c, mode, out, stats);
+}
+
+int scb_ctx_stream(scb_ctx *c, void **s)
+{
+    if (!c || !s) return fail(SCB_ERR_INVALID, "null argument");
+    *s = (void *)c->stream;
+    return SCB_OK;
+}
+
+int scb_ctx_sync(scb_ctx *c)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return SCB_OK;
+}
+
+int scb_ctx_event_record(scb_ctx *c, int slot)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (slot < 0 || slot >= 8) return fail(SCB_ERR_INVALID, "event slot out of range");
+    CK(cudaEventRecord(c->ev[slot], c->stream));
+    return SCB_OK;
+}
+
+int scb_ctx_event_elapsed_ms(scb_ctx *c, int s0, int s1, float *ms)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (s0 < 0 || s0 >= 8 || s1 < 0 || s1 >= 8 || !ms) return fail(SCB_ERR_INVALID, "bad event slot");
+    CK(cudaEventSynchronize(c->ev[s1]));
+    CK(cudaEventElapsedTime(ms, c->ev[s0], c->ev[s1]));
+    return SCB_OK;
+}
+
+int scb_eval_local_search(scb_ctx *c, const int32_t *individual, int indLen, const int32_t *andLenList,
+                          const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                          const int32_t *knockouts, const int32_t *knockins, int node, int32_t *nodeErrors,
+                          int maxVariants, int *nVariants)
+{
+    if (!c) return fail(SCB_ERR_INVALID, "null context");
+    if (!individual || !individualParse || !nodeErrors) return fail(SCB_ERR_INVALID, "null argument");
+    const int N = c->N;
+    if (node < 0 || node >= N) return fail(SCB_ERR_INVALID, "node %d out of range", node);
+    /* ruleMaker.py:1237-1242: the node's bits are [parse[node], parse[node+1]) (indLen for the last) */
+    const int start = individualParse[node];
+    const int end = (node == N - 1) ? indLen : individualParse[node + 1];
+    const int k = end - start;
+    if (k < 1 || k > SCB_MAX_TERMS || start < 0 || end > indLen) return fail(SCB_ERR_INVALID, "node %d has %d rule bits", node, k);
+    const int nv = (1 << k) - 1;
+    if (nVariants) *nVariants = nv;
+    if (maxVariants < nv) return fail(SCB_ERR_INVALID, "nodeErrors holds %d entries, %d needed", maxVariants, nv);
+    std::vector<int32_t> pop((size_t)nv * indLen);
+    for (int v = 1; v <= nv; ++v) {
+        int32_t *row = pop.data() + (size_t)(v - 1) * indLen;
+        memcpy(row, individual, (size_t)indLen * 4);
+        /* ruleMaker.py:796-802 (__bitList reverses bin(v)): bit j of the node = (v >> j) & 1 */
+        for (int j = 0; j < k; ++j) row[start + j] = (v >> j) & 1;
+    }
+    std::vector<int32_t> nodewise((size_t)nv * N);
+    int rc = scb_eval_population(c, nv, pop.data(), indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0,
+                                 knockouts, knockins, SCB_MODE_NODEWISE, nodewise.data(), nullptr);
+    if (rc) return rc;
+    for (int v = 0; v < nv; ++v) nodeErrors[v] = nodewise[(size_t)v * N + node];
+    return SCB_OK;
+}
+
+int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t *dist, int32_t *decider,
+                       int32_t *deciderDistance)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!attractors || nAttr <= 0 || !decider || !deciderDistance) return fail(SCB_ERR_INVALID, "bad argument");
+    const int N = c->N, C = c->C, NW = (N + 31) / 32;
+    if (NW > SCB_HAM_MAXW) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > %d for the Hamming kernel", N, SCB_HAM_MAXW * 32);
+    std::lock_guard<std::mutex> lk(c->mu);
+    std::vector<uint32_t> packed((size_t)nAttr * NW, 0u);
+    for (int a = 0; a < nAttr; ++a)
+        for (int i = 0; i < N; ++i) {
+            const int32_t v = attractors[(size_t)a * N + i];
+            if (v != 0 && v != 1) return fail(SCB_ERR_INVALID, "attractor %d node %d is %d, not 0/1", a, i, v);
+            if (v) packed[(size_t)a * NW + (i >> 5)] |= 1u << (i & 31);
+        }
+    if ((rc = c->dAttr.ensure(packed.size())) || (rc = c->dDecider.ensure(C)) || (rc = c->dDeciderDist.ensure(C))) return rc;
+    if (dist && (rc = c->dDist.ensure((size_t)C * nAttr))) return rc;
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(c->dAttr.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, st));
+    ScbHammingArgs ha;
+    ha.X = c->dX.p; ha.N = N; ha.C = C; ha.Wpad = c->Wpad; ha.A = nAttr; ha.attr = c->dAttr.p;
+    ha.dist = dist ? c->dDist.p : nullptr; ha.decider = c->dDecider.p; ha.deciderDistance = c->dDeciderDist.p;
+    const int nthr = 128;
+    SCB_LAUNCH(scb_k_hamming, dim3((unsigned)((C + nthr - 1) / nthr)), dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha);
+    CK(cudaGetLastError());
+    if (dist) CK(cudaMemcpyAsync(dist, c->dDist.p, (size_t)C * nAttr * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(decider, c->dDecider.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(deciderDistance, c->dDeciderDist.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SCB_OK;
+}
+
+}  /* extern "C" */
+
+#include "scb_legacy.inl"

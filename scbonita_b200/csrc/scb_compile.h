@@ -1,0 +1,135 @@
+/*
+ * scb_compile.h -- turn one node's reference-format rule into (<= 3 inputs, 8-bit truth table).
+ *
+ * Semantics restated from the reference (file:line under /root/reference/src/scBONITA/):
+ *   simulator.c:383-394  knockouts[i]==1 -> 0, else knockins[i]==1 -> 1
+ *   simulator.c:395-399  andLenList[i]==1 -> old[andNodes[i][0][0]] != andNodeInvertList[i][0][0]
+ *   simulator.c:400-404  andLenList[i]==0 -> old[andNodes[i][0][0]]
+ *   simulator.c:405-411  otherwise updateBool over bits [parse[i], parse[i+1]) (indLen for the
+ *                        last node), simulator.c:10-50: OR over selected terms of the AND of
+ *                        `old[in] != flag`, input 0 always, inputs 1,2 only when index > -1.
+ * `old != flag` is an int comparison on 0/1 values: flag 0 = identity, 1 = NOT, anything else
+ * = constant TRUE.  Because every literal is a function of one state bit, a node
+ * whose selected terms touch at most three distinct state bits is exactly a 3-input truth
+ * table, which the simulator evaluates with one LOP3 per 32 cells.
+ */
+#ifndef SCB_COMPILE_H
+#define SCB_COMPILE_H
+#include "scb_types.h"
+
+struct ScbNodeFn {
+    int arity;          /* number of inputs the function really depends on (0..3) */
+    int in[3];
+    unsigned lut;       /* 8-bit table, index (x0<<2)|(x1<<1)|x2; don't-care inputs duplicated */
+    unsigned flags;     /* SCB_NF_* */
+};
+
+SCB_HD inline ScbNodeFn scb_const_fn(int v, unsigned flags)
+{
+    ScbNodeFn f;
+    f.arity = 0; f.in[0] = f.in[1] = f.in[2] = 0;
+    f.lut = v ? 0xFFu : 0x00u; f.flags = flags;
+    return f;
+}
+
+SCB_HD inline ScbNodeFn scb_compile_node(int i, int N, int indLen, const int32_t *ind,
+                                         const int32_t *andLen, const int32_t *parse,
+                                         const int32_t *an, const int32_t *ai,
+                                         const int32_t *ko, const int32_t *ki)
+{
+    if (ko[i] == 1) return scb_const_fn(0, 0);
+    if (ki[i] == 1) return scb_const_fn(1, 0);
+    const int32_t *an_i = an + (long long)i * (SCB_MAX_TERMS * SCB_MAX_IN);
+    const int32_t *ai_i = ai + (long long)i * (SCB_MAX_TERMS * SCB_MAX_IN);
+    const int al = andLen[i];
+    if (al == 1 || al == 0) {
+        const int src = an_i[0];
+        if (src < 0 || src >= N) return scb_const_fn(0, SCB_NF_BADIDX);
+        const int fl = (al == 1) ? ai_i[0] : 0;
+        if (fl != 0 && fl != 1) return scb_const_fn(1, 0);
+        ScbNodeFn f;
+        f.arity = 1; f.in[0] = src; f.in[1] = src; f.in[2] = src;
+        f.lut = fl ? 0x0Fu : 0xF0u; f.flags = 0;
+        return f;
+    }
+    unsigned flags = 0;
+    const int start = parse[i];
+    const int end = (i == N - 1) ? indLen : parse[i + 1];
+    int nt = end - start;
+    if (nt > SCB_MAX_TERMS) { flags |= SCB_NF_TERMS; nt = SCB_MAX_TERMS; }
+    if (nt < 0 || start < 0 || end > indLen) { flags |= SCB_NF_TERMS; nt = 0; }
+
+    /* distinct state bits referenced by the selected terms */
+    int vars[3] = {0, 0, 0};
+    int nv = 0;
+    bool any = false, overflow = false;
+    for (int a = 0; a < nt; ++a) {
+        if (!ind[start + a]) continue;
+        any = true;
+        for (int b = 0; b < SCB_MAX_IN; ++b) {
+            const int src = an_i[a * 3 + b];
+            if (b > 0 && src <= -1) continue;
+            if (src < 0 || src >= N) { flags |= SCB_NF_BADIDX; continue; }
+            const int fl = ai_i[a * 3 + b];
+            if (fl != 0 && fl != 1) continue;            /* constant TRUE literal */
+            bool seen = false;
+            for (int k = 0; k < nv; ++k) seen = seen || (vars[k] == src);
+            if (!seen) {
+                if (nv < 3) vars[nv++] = src; else overflow = true;
+            }
+        }
+    }
+    if (overflow) return scb_const_fn(0, flags | SCB_NF_UNSUPPORTED);
+    if (!any) return scb_const_fn(0, flags | SCB_NF_EMPTY);   /* Q9: reference reads orset[0] uninitialised */
+
+    unsigned lut = 0;
+    for (int m = 0; m < 8; ++m) {
+        int v = 0;
+        for (int a = 0; a < nt; ++a) {
+            if (!ind[start + a]) continue;
+            int t = 1;
+            for (int b = 0; b < SCB_MAX_IN; ++b) {
+                const int src = an_i[a * 3 + b];
+                if (b > 0 && src <= -1) continue;
+                if (src < 0 || src >= N) continue;
+                const int fl = ai_i[a * 3 + b];
+                if (fl != 0 && fl != 1) continue;
+                int x = 0;
+                for (int k = 0; k < nv; ++k) if (vars[k] == src) x = (m >> (2 - k)) & 1;
+                t &= (x != fl);
+            }
+            v |= t;
+        }
+        lut |= (unsigned)v << m;
+    }
+    /* drop inputs the table does not depend on */
+    const bool dep[3] = { (((lut >> 4) ^ lut) & 0x0Fu) != 0,
+                          (((lut >> 2) ^ lut) & 0x33u) != 0,
+                          (((lut >> 1) ^ lut) & 0x55u) != 0 };
+    int keep[3] = {0, 0, 0}, nk = 0;
+    for (int k = 0; k < 3; ++k) if (k < nv && dep[k]) keep[nk++] = k;
+    unsigned nl = 0;
+    for (int idx = 0; idx < 8; ++idx) {
+        int m = 0;
+        for (int j = 0; j < nk; ++j) if ((idx >> (2 - j)) & 1) m |= 1 << (2 - keep[j]);
+        nl |= ((lut >> m) & 1u) << idx;
+    }
+    ScbNodeFn f;
+    f.arity = nk; f.flags = flags; f.lut = nl;
+    const int fill = nk ? vars[keep[0]] : 0;
+    for (int j = 0; j < 3; ++j) f.in[j] = j < nk ? vars[keep[j]] : fill;
+    return f;
+}
+
+/* generic table lookup on 32 cells at once (host tests and the emulator; the device path uses
+ * lop3 with an immediate table) */
+SCB_HD inline uint32_t scb_lut_apply(unsigned lut, uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r = 0;
+    for (int idx = 0; idx < 8; ++idx)
+        if ((lut >> idx) & 1u)
+            r |= ((idx & 4) ? a : ~a) & ((idx & 2) ? b : ~b) & ((idx & 1) ? c : ~c);
+    return r;
+}
+
+#endif

@@ -1,0 +1,796 @@
+/*
+ * scb_kernels.cuh -- sm_100a kernels of the rule-inference fitness hot path.
+ *
+ *   K0  scb_k_compile   reference-format rule tables -> per-individual programs of 3-input
+ *                       truth tables (scb_compile.h), sorted by arity
+ *   K1  scb_k_pack      int32 / uint8 binarized matrix -> node-major 32-cells-per-word S_0
+ *   K2  scb_k_sim<K>    the simulator: persistent CTAs, one (individual, cell tile) per work
+ *                       item, state ping-pong in shared memory, one LOP3 per node per 32 cells
+ *   K3  scb_k_resolve   exact second pass for the rare 1024-cell chunks K2 could not prove
+ *                       "attractor found" for, incl. the reference's fill-forward
+ *   K5  scb_k_hamming   cell x attractor Hamming distance + first-minimum argmin
+ *
+ * What is computed (reference simulator.c:350-485): per cell the
+ * synchronous trajectory S_0..S_99; found <=> S_99 equals some earlier S_j; error bits
+ * e = S_98 xor S_0 when found, else the previous cell's e.  The kernels never store the
+ * trajectory: "found" is proven in flight by any observed repeat S_t == S_j (j < t <= 99),
+ * which implies transient + period <= 99; cells without such a proof go to K3.
+ *
+ * Data layout in shared memory (per CTA): two state buffers [N][32*K] uint32 (row = node,
+ * lane l owns words l*K .. l*K+K-1, so every access is a conflict-free LDS/STS.(32*K)),
+ * followed by the CTA's program (uint4 per node) and a few 32*K-word masks.
+ */
+#ifndef SCB_KERNELS_CUH
+#define SCB_KERNELS_CUH
+#include "scb_types.h"
+#include "scb_compile.h"
+
+#ifdef SCB_EMU
+#define SCB_DYN_SMEM(name) unsigned char *name = emu_dyn_smem()
+#else
+#define SCB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * small device helpers
+ * ---------------------------------------------------------------------------------------- */
+template <int K> struct ScbVec { uint32_t v[K]; };
+
+template <int K> SCB_DEV ScbVec<K> scb_ld(const unsigned char *p)
+{
+    ScbVec<K> r;
+    if (K == 4) { uint4 t = *reinterpret_cast<const uint4 *>(p); r.v[0] = t.x; r.v[1 % K] = t.y; r.v[2 % K] = t.z; r.v[3 % K] = t.w; }
+    else if (K == 2) { uint2 t = *reinterpret_cast<const uint2 *>(p); r.v[0] = t.x; r.v[1 % K] = t.y; }
+    else { r.v[0] = *reinterpret_cast<const uint32_t *>(p); }
+    return r;
+}
+template <int K> SCB_DEV void scb_st(unsigned char *p, const ScbVec<K> &r)
+{
+    if (K == 4) *reinterpret_cast<uint4 *>(p) = make_uint4(r.v[0], r.v[1 % K], r.v[2 % K], r.v[3 % K]);
+    else if (K == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(r.v[0], r.v[1 % K]);
+    else *reinterpret_cast<uint32_t *>(p) = r.v[0];
+}
+/* global memory, L2 only (the snapshot scratch is written and re-read by the same thread) */
+template <int K> SCB_DEV ScbVec<K> scb_ldcg(const unsigned char *p)
+{
+#if defined(__CUDA_ARCH__)
+    ScbVec<K> r;
+    if (K == 4) { uint4 t = __ldcg(reinterpret_cast<const uint4 *>(p)); r.v[0] = t.x; r.v[1 % K] = t.y; r.v[2 % K] = t.z; r.v[3 % K] = t.w; }
+    else if (K == 2) { uint2 t = __ldcg(reinterpret_cast<const uint2 *>(p)); r.v[0] = t.x; r.v[1 % K] = t.y; }
+    else { r.v[0] = __ldcg(reinterpret_cast<const uint32_t *>(p)); }
+    return r;
+#else
+    return scb_ld<K>(p);
+#endif
+}
+template <int K> SCB_DEV void scb_stcg(unsigned char *p, const ScbVec<K> &r)
+{
+#if defined(__CUDA_ARCH__)
+    if (K == 4) __stcg(reinterpret_cast<uint4 *>(p), make_uint4(r.v[0], r.v[1 % K], r.v[2 % K], r.v[3 % K]));
+    else if (K == 2) __stcg(reinterpret_cast<uint2 *>(p), make_uint2(r.v[0], r.v[1 % K]));
+    else __stcg(reinterpret_cast<uint32_t *>(p), r.v[0]);
+#else
+    scb_st<K>(p, r);
+#endif
+}
+/* read-only global (S_0 rows) */
+template <int K> SCB_DEV ScbVec<K> scb_ldg(const uint32_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    ScbVec<K> r;
+    if (K == 4) { uint4 t = __ldg(reinterpret_cast<const uint4 *>(p)); r.v[0] = t.x; r.v[1 % K] = t.y; r.v[2 % K] = t.z; r.v[3 % K] = t.w; }
+    else if (K == 2) { uint2 t = __ldg(reinterpret_cast<const uint2 *>(p)); r.v[0] = t.x; r.v[1 % K] = t.y; }
+    else { r.v[0] = __ldg(p); }
+    return r;
+#else
+    return scb_ld<K>(reinterpret_cast<const unsigned char *>(p));
+#endif
+}
+
+SCB_DEV unsigned scb_warp_sum(unsigned v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/* ---- truth-table application: one LOP3 per word with the table as an immediate ---------- */
+#if defined(__CUDA_ARCH__)
+template <int LUT> SCB_DEV uint32_t scb_lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+template <int K, int LUT> SCB_DEV void scb_lop3v(ScbVec<K> &r, const ScbVec<K> &a, const ScbVec<K> &b, const ScbVec<K> &c)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.v[k] = scb_lop3<LUT>(a.v[k], b.v[k], c.v[k]);
+}
+#define SCB_C1(L) case (L): scb_lop3v<K, (L)>(r, a, b, c); break;
+#define SCB_C4(L) SCB_C1(L) SCB_C1((L) + 1) SCB_C1((L) + 2) SCB_C1((L) + 3)
+#define SCB_C16(L) SCB_C4(L) SCB_C4((L) + 4) SCB_C4((L) + 8) SCB_C4((L) + 12)
+#define SCB_C64(L) SCB_C16(L) SCB_C16((L) + 16) SCB_C16((L) + 32) SCB_C16((L) + 48)
+#endif
+
+/* three-input node: any of the 256 tables */
+template <int K> SCB_DEV ScbVec<K> scb_apply3(unsigned lut, const ScbVec<K> &a, const ScbVec<K> &b, const ScbVec<K> &c)
+{
+    ScbVec<K> r;
+#if defined(__CUDA_ARCH__)
+    switch (lut) {
+        SCB_C64(0) SCB_C64(64) SCB_C64(128) SCB_C64(192)
+        default:
+#pragma unroll
+            for (int k = 0; k < K; ++k) r.v[k] = 0;
+    }
+#else
+    for (int k = 0; k < K; ++k) r.v[k] = scb_lut_apply(lut, a.v[k], b.v[k], c.v[k]);
+#endif
+    return r;
+}
+/* two-input node: lut4 bit (x0<<1)|x1 */
+SCB_HD inline unsigned scb_expand2(unsigned l4)
+{
+    return ((l4 & 1u) ? 0x03u : 0u) | ((l4 & 2u) ? 0x0Cu : 0u) | ((l4 & 4u) ? 0x30u : 0u) | ((l4 & 8u) ? 0xC0u : 0u);
+}
+SCB_HD inline unsigned scb_compress2(unsigned l8)
+{
+    return ((l8 >> 0) & 1u) | (((l8 >> 2) & 1u) << 1) | (((l8 >> 4) & 1u) << 2) | (((l8 >> 6) & 1u) << 3);
+}
+template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, const ScbVec<K> &b)
+{
+    ScbVec<K> r;
+#if defined(__CUDA_ARCH__)
+    const ScbVec<K> &c = b;
+    switch (l4) {
+        SCB_C1(0x00) case 1: scb_lop3v<K, 0x03>(r, a, b, c); break;
+        case 2: scb_lop3v<K, 0x0C>(r, a, b, c); break;  case 3: scb_lop3v<K, 0x0F>(r, a, b, c); break;
+        case 4: scb_lop3v<K, 0x30>(r, a, b, c); break;  case 5: scb_lop3v<K, 0x33>(r, a, b, c); break;
+        case 6: scb_lop3v<K, 0x3C>(r, a, b, c); break;  case 7: scb_lop3v<K, 0x3F>(r, a, b, c); break;
+        case 8: scb_lop3v<K, 0xC0>(r, a, b, c); break;  case 9: scb_lop3v<K, 0xC3>(r, a, b, c); break;
+        case 10: scb_lop3v<K, 0xCC>(r, a, b, c); break; case 11: scb_lop3v<K, 0xCF>(r, a, b, c); break;
+        case 12: scb_lop3v<K, 0xF0>(r, a, b, c); break; case 13: scb_lop3v<K, 0xF3>(r, a, b, c); break;
+        case 14: scb_lop3v<K, 0xFC>(r, a, b, c); break;
+        default: scb_lop3v<K, 0xFF>(r, a, b, c); break;
+    }
+#else
+    for (int k = 0; k < K; ++k) r.v[k] = scb_lut_apply(scb_expand2(l4), a.v[k], b.v[k], b.v[k]);
+#endif
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K0: rule compiler.  One warp per individual; two passes (count, then stable scatter by
+ * arity) so that the program order is deterministic.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void scb_k_compile(ScbCompileArgs A)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (p >= A.P) return;
+    const int N = A.N;
+    const int32_t *ind = A.individuals + (long long)p * A.indLen;
+    const long long toff = A.tablesPerIndividual ? (long long)p * N * (SCB_MAX_TERMS * SCB_MAX_IN) : 0;
+    const int32_t *an = A.an + toff, *ai = A.ai + toff;
+    const unsigned lt = (1u << lane) - 1u;
+
+    int c3 = 0, c2 = 0, c1 = 0, c0 = 0;
+    unsigned nUns = 0, nEmp = 0, nBad = 0, nTerm = 0;
+    for (int base = 0; base < N; base += 32) {
+        const int i = base + lane;
+        int ar = -1; unsigned fl = 0;
+        if (i < N) {
+            ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki);
+            ar = f.arity; fl = f.flags;
+        }
+        c3 += __popc(__ballot_sync(0xffffffffu, ar == 3));
+        c2 += __popc(__ballot_sync(0xffffffffu, ar == 2));
+        c1 += __popc(__ballot_sync(0xffffffffu, ar == 1));
+        c0 += __popc(__ballot_sync(0xffffffffu, ar == 0));
+        nUns += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_UNSUPPORTED) != 0));
+        nEmp += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_EMPTY) != 0));
+        nBad += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_BADIDX) != 0));
+        nTerm += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_TERMS) != 0));
+    }
+    int o3 = 0, o2 = c3, o1 = c3 + c2, o0 = c3 + c2 + c1;
+    uint4 *out = A.descs + (long long)p * A.Npad;
+    for (int base = 0; base < N; base += 32) {
+        const int i = base + lane;
+        int ar = -1;
+        ScbNodeFn f = scb_const_fn(0, 0);
+        if (i < N) {
+            f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki);
+            ar = f.arity;
+        }
+        const unsigned b3 = __ballot_sync(0xffffffffu, ar == 3);
+        const unsigned b2 = __ballot_sync(0xffffffffu, ar == 2);
+        const unsigned b1 = __ballot_sync(0xffffffffu, ar == 1);
+        const unsigned b0 = __ballot_sync(0xffffffffu, ar == 0);
+        int pos = -1;
+        if (ar == 3) pos = o3 + __popc(b3 & lt);
+        else if (ar == 2) pos = o2 + __popc(b2 & lt);
+        else if (ar == 1) pos = o1 + __popc(b1 & lt);
+        else if (ar == 0) pos = o0 + __popc(b0 & lt);
+        if (pos >= 0)
+            out[pos] = make_uint4((unsigned)f.in[0], (unsigned)f.in[1], (unsigned)f.in[2], (unsigned)i | (f.lut << 24));
+        o3 += __popc(b3); o2 += __popc(b2); o1 += __popc(b1); o0 += __popc(b0);
+    }
+    if (lane == 0) {
+        A.counts[p] = make_int4(c3, c2, c1, c0);
+        if (nUns) atomicAdd(&A.diag->unsupported_nodes, (unsigned long long)nUns);
+        if (nEmp) atomicAdd(&A.diag->empty_rule_nodes, (unsigned long long)nEmp);
+        if (nBad) atomicAdd(&A.diag->bad_index_nodes, (unsigned long long)nBad);
+        if (nTerm) atomicAdd(&A.diag->term_overflow_nodes, (unsigned long long)nTerm);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K1: bit-pack.  grid = (ceil(Wpad/32/warpsPerBlock), N); a warp produces 32 consecutive
+ * words of one row: 32 coalesced 32-element reads, one ballot each.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void scb_k_pack(ScbPackArgs A)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.y;
+    const int w0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    if (w0 >= A.Wpad) return;
+    const int32_t *s4 = reinterpret_cast<const int32_t *>(A.src) + (long long)row * A.rowStride;
+    const unsigned char *s1 = reinterpret_cast<const unsigned char *>(A.src) + (long long)row * A.rowStride;
+    uint32_t mine = 0;
+    unsigned bad = 0;
+    for (int k = 0; k < 32; ++k) {
+        const long long c = (long long)(w0 + k) * 32 + lane;
+        int v = 0;
+        if (c < A.C) v = (A.elemBytes == 4) ? s4[c] : (int)s1[c];
+        bad += (v != 0 && v != 1);
+        const unsigned b = __ballot_sync(0xffffffffu, v != 0);
+        if (k == lane) mine = b;
+    }
+    if (w0 + lane < A.Wpad) A.X[(long long)row * A.Wpad + w0 + lane] = mine;
+    bad = scb_warp_sum(bad);
+    if (lane == 0 && bad) atomicAdd(&A.diag->nonbinary_cells, (unsigned long long)bad);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * shared pieces of K2 / K3
+ * ---------------------------------------------------------------------------------------- */
+/* shared-memory carve-up, identical formula on host and device */
+SCB_HD inline size_t scb_smem_bytes(int N, int K, int nbuf)
+{
+    return (size_t)nbuf * N * 128 * K + (size_t)N * 16 + (size_t)6 * 32 * K * 4 + 4096 + 256;
+}
+
+/* load individual p's program into shared memory, scaling node indices to row byte offsets */
+template <int K>
+SCB_DEV void scb_load_program(uint4 *desc, const uint4 *g, int4 cnt, int N, int tid, int nthr)
+{
+    const uint32_t ROWB = 128u * K;
+    for (int j = tid; j < N; j += nthr) {
+        uint4 d = g[j];
+        unsigned lut = d.w >> 24;
+        if (j >= cnt.x && j < cnt.x + cnt.y) lut = scb_compress2(lut);
+        else if (j >= cnt.x + cnt.y && j < cnt.x + cnt.y + cnt.z) lut = (lut == 0x0Fu) ? 1u : 0u;   /* NOT : copy */
+        else if (j >= cnt.x + cnt.y + cnt.z) lut = lut ? 1u : 0u;
+        d.x *= ROWB; d.y *= ROWB; d.z *= ROWB;
+        d.w = ((d.w & 0xFFFFFFu) * ROWB) | (lut << 24);
+        desc[j] = d;
+    }
+}
+
+/* one synchronous update S_t -> S_{t+1} for the warp's share of the nodes.
+ *   src, dst : lane-adjusted pointers into the two state buffers
+ *   zg       : lane-adjusted pointer into the global snapshot (ZCMP / ZSNAP)
+ *   tsm      : lane-adjusted pointer into the shared-memory target state (TCMP)
+ * d2 / dz accumulate, per word, the cells whose new state differs from S_{t-1} ... */
+template <int K>
+SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 *desc, int4 cnt,
+                      int warp, int S, unsigned flags, unsigned char *zg, const unsigned char *tsm,
+                      ScbVec<K> &d2, ScbVec<K> &dz)
+{
+#define SCB_POST(r, dsto)                                                                         \
+    do {                                                                                          \
+        if (flags & SCB_SF_CMP2) { ScbVec<K> o = scb_ld<K>(dst + (dsto));                         \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) d2.v[k] |= (r).v[k] ^ o.v[k]; }         \
+        if (flags & SCB_SF_ZCMP) { ScbVec<K> z = scb_ldcg<K>(zg + (dsto));                        \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ z.v[k]; }         \
+        if (flags & SCB_SF_TCMP) { ScbVec<K> z = scb_ld<K>(tsm + (dsto));                         \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ z.v[k]; }         \
+        scb_st<K>(dst + (dsto), (r));                                                             \
+        if (flags & SCB_SF_ZSNAP) scb_stcg<K>(zg + (dsto), (r));                                  \
+    } while (0)
+
+    int j = warp;
+    const int e3 = cnt.x, e2 = cnt.x + cnt.y, e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
+    for (; j < e3; j += S) {
+        const uint4 d = desc[j];
+        const ScbVec<K> a = scb_ld<K>(src + d.x), b = scb_ld<K>(src + d.y), c = scb_ld<K>(src + d.z);
+        ScbVec<K> r = scb_apply3<K>(d.w >> 24, a, b, c);
+        SCB_POST(r, d.w & 0xFFFFFFu);
+    }
+    for (; j < e2; j += S) {
+        const uint4 d = desc[j];
+        const ScbVec<K> a = scb_ld<K>(src + d.x), b = scb_ld<K>(src + d.y);
+        ScbVec<K> r = scb_apply2<K>(d.w >> 24, a, b);
+        SCB_POST(r, d.w & 0xFFFFFFu);
+    }
+    for (; j < e1; j += S) {
+        const uint4 d = desc[j];
+        ScbVec<K> r = scb_ld<K>(src + d.x);
+        const uint32_t inv = (d.w >> 24) ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.v[k] ^= inv;
+        SCB_POST(r, d.w & 0xFFFFFFu);
+    }
+    if (flags & SCB_SF_CONST) {
+        for (; j < e0; j += S) {
+            const uint4 d = desc[j];
+            ScbVec<K> r;
+            const uint32_t val = (d.w >> 24) ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int k = 0; k < K; ++k) r.v[k] = val;
+            scb_st<K>(dst + (d.w & 0xFFFFFFu), r);
+        }
+    }
+#undef SCB_POST
+}
+
+/* valid-cell mask of word w (cells w*32 .. w*32+31 below C) */
+SCB_DEV uint32_t scb_valid_mask(long long w, int C)
+{
+    const long long lo = w * 32;
+    if (lo >= C) return 0u;
+    if (lo + 32 <= C) return 0xffffffffu;
+    return (1u << (unsigned)(C - lo)) - 1u;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K2: the simulator.  Persistent CTAs pull (individual, tile) items from an atomic counter.
+ * A tile is 32*K words (= 1024*K cells) of every node.  Control flow is uniform per CTA.
+ *
+ * Early exit, all bit-exact:
+ *   E2  S_t == S_{t-2} for every valid cell of the tile (period <= 2 from t-2 on):
+ *       S_98 = S_t if 98-t is even, else S_{t-1}; all cells found.
+ *   E3  S_t == snapshot S_s for every valid cell (tile period L | t-s from s on):
+ *       S_98 is (98-t) mod L steps ahead; all cells found.
+ *   R   otherwise cells are individually proven "found" by any repeat seen in a compare; once all
+ *       are, the tile runs plain steps to S_98.  Cells still unproven after the last compare
+ *       at t = 99 are queued, as 1024-cell chunks, for K3, and K2 leaves them out of its sums.
+ * ---------------------------------------------------------------------------------------- */
+template <int K>
+__global__ void scb_k_sim(ScbSimArgs A)
+{
+    SCB_DYN_SMEM(smraw);
+    const int N = A.N;
+    const uint32_t ROWB = 128u * K, BUFB = (uint32_t)N * ROWB;
+    const int WT = 32 * K;                              /* words per tile */
+    unsigned char *sm = smraw;
+    uint4 *desc = reinterpret_cast<uint4 *>(smraw + 2u * BUFB);
+    uint32_t *dm2 = reinterpret_cast<uint32_t *>(desc + N);
+    uint32_t *dmz = dm2 + WT;
+    uint32_t *Rm = dmz + WT;
+    uint32_t *vm = Rm + WT;
+    int *sh = reinterpret_cast<int *>(vm + WT);          /* [0] item, [1],[2] flag words, [4..4+K) chunk flags */
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    const uint32_t laneOff = (uint32_t)lane * 4u * K;
+    const bool early = (A.flags & SCB_KF_EARLY) != 0, useZ = (A.flags & SCB_KF_SNAP) != 0;
+    unsigned char *zg = reinterpret_cast<unsigned char *>(A.zscratch + (unsigned long long)blockIdx.x * A.zstride) + laneOff;
+    const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
+    unsigned long long stepsDone = 0, tilesDone = 0;
+
+    for (;;) {
+        if (tid == 0) sh[0] = (int)atomicAdd(A.workCounter, 1u);
+        __syncthreads();
+        const unsigned item = (unsigned)sh[0];
+        if (item >= total) break;
+        const int p = (int)(item / (unsigned)A.tiles), tile = (int)(item % (unsigned)A.tiles);
+        const int w0 = tile * WT;
+        const int4 cnt = A.counts[p];
+        scb_load_program<K>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+        for (int row = warp; row < N; row += S) {
+            const ScbVec<K> v = scb_ldg<K>(A.X + (long long)row * A.Wpad + w0 + lane * K);
+            scb_st<K>(sm + (uint32_t)row * ROWB + laneOff, v);
+        }
+        if (tid < WT) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); Rm[tid] = 0u; dm2[tid] = 0u; dmz[tid] = 0u; }
+        if (tid == 0) { sh[1] = 0; sh[2] = 0; }
+        __syncthreads();
+
+        uint32_t srcOff = 0u, dstOff = BUFB, finOff = 0u;
+        int t = 0, target = SCB_LAST, zs = -1, ncmp = 0, searchLeft = 0;
+        bool allres = false, allfound = false, plainOnly = false, haveFin = false;
+        while (t < target) {
+            const int tn = t + 1;                       /* this iteration computes S_tn */
+            unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
+            if (!plainOnly) {
+                if (!allres) {
+                    if (tn == SCB_LAST || (early && tn >= 3 && (tn % A.chkEvery) == 0)) f |= SCB_SF_CMP2;
+                    if (useZ && zs >= 0) f |= SCB_SF_ZCMP;
+                    const bool snapNow = tn < 64 ? ((A.snapLo >> tn) & 1ull) != 0ull
+                                                 : ((A.snapHi >> (tn - 64)) & 1ull) != 0ull;
+                    if (useZ && snapNow && tn < SCB_LAST) f |= SCB_SF_ZSNAP;
+                } else if (useZ && zs >= 0 && searchLeft > 0) {
+                    f |= SCB_SF_ZCMP; --searchLeft;   /* all cells proven: look for a tile-wide period */
+                }
+            }
+            ScbVec<K> d2, dz;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
+            scb_step<K>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, zg, nullptr, d2, dz);
+            if (f & SCB_SF_CMP2) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
+            }
+            if (f & SCB_SF_ZCMP) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) if (dz.v[k]) atomicOr(&dmz[lane * K + k], dz.v[k]);
+            }
+            __syncthreads();
+            t = tn;
+            { const uint32_t x = srcOff; srcOff = dstOff; dstOff = x; }   /* src = S_t, dst = S_{t-1} */
+            if (f & (SCB_SF_CMP2 | SCB_SF_ZCMP)) {
+                unsigned int *flagw = reinterpret_cast<unsigned int *>(&sh[1 + (ncmp & 1)]);
+                if (tid < WT) {
+                    const uint32_t v = vm[tid];
+                    const uint32_t m2 = (f & SCB_SF_CMP2) ? dm2[tid] : 0xffffffffu;
+                    const uint32_t mz = (f & SCB_SF_ZCMP) ? dmz[tid] : 0xffffffffu;
+                    const uint32_t r = Rm[tid] | ~m2 | ~mz;   /* a repeat was seen for these cells */
+                    Rm[tid] = r; dm2[tid] = 0u; dmz[tid] = 0u;
+                    const unsigned bits = ((m2 & v) ? 1u : 0u) | ((mz & v) ? 2u : 0u) | ((~r & v) ? 4u : 0u);
+                    if (bits) atomicOr(flagw, bits);
+                }
+                __syncthreads();
+                const unsigned fl = *flagw;
+                if (tid == 0) sh[1 + ((ncmp + 1) & 1)] = 0;    /* the other word serves the next compare */
+                ++ncmp;
+                allres = (fl & 4u) == 0u;
+                if ((f & SCB_SF_CMP2) && !(fl & 1u)) {
+                    /* E2: S_t == S_{t-2} on every valid cell */
+                    allfound = true; haveFin = true;
+                    finOff = ((SCB_LAST - 1 - t) & 1) ? dstOff : srcOff;
+                    break;
+                }
+                if ((f & SCB_SF_ZCMP) && !(fl & 2u) && t <= SCB_LAST - 1 && !plainOnly) {
+                    /* E3: the whole tile is back at snapshot S_zs; period L divides t - zs */
+                    const int L = t - zs;
+                    target = t + (SCB_LAST - 1 - t) % L;
+                    allfound = true; plainOnly = true;
+                } else if (allres && target == SCB_LAST) {
+                    target = SCB_LAST - 1;               /* S_99 is no longer needed */
+                    searchLeft = A.periodSearch;
+                }
+            }
+            if (f & SCB_SF_ZSNAP) zs = tn;
+        }
+        /* loop ran out at t == target (98: src = S_98; 99: dst = S_98; E3: src = S_target == S_98),
+         * or stopped early at t > target when the last cell resolved at t == 99 */
+        if (!haveFin) finOff = (t == SCB_LAST) ? dstOff : srcOff;
+        if (allres) allfound = true;
+        stepsDone += (unsigned long long)t; ++tilesDone;
+
+        /* ---- chunk flags: a 32-word chunk with an unproven valid cell goes to K3 ---------- */
+        if (warp == 0) {
+            bool bad = false;
+            if (!allfound) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) bad = bad || ((~Rm[lane * K + k] & vm[lane * K + k]) != 0u);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, bad);
+            const int LPC = 32 / K;                          /* lanes per chunk */
+            if (lane < K) {
+                const unsigned msk = (LPC == 32) ? 0xffffffffu : (((1u << LPC) - 1u) << (lane * LPC));
+                const int cb = (bal & msk) != 0u;
+                sh[4 + lane] = cb;
+                if (cb) {
+                    const unsigned idx = atomicAdd(A.resolveCount, 1u);
+                    if (idx < A.resolveCap) A.resolveItems[idx] = make_uint2((unsigned)p, (unsigned)(tile * K + lane));
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- errors: e = S_98 xor S_0 on valid cells of proven chunks ---------------------- */
+        ScbVec<K> ok;
+#pragma unroll
+        for (int k = 0; k < K; ++k) ok.v[k] = sh[4 + (lane * K + k) / 32] ? 0u : vm[lane * K + k];
+        const unsigned char *fin = sm + finOff + laneOff;
+        unsigned char *oth = sm + (finOff ? 0u : BUFB) + laneOff;
+        unsigned total32 = 0;
+        for (int j = warp; j < N; j += S) {
+            const uint32_t dsto = desc[j].w & 0xFFFFFFu;
+            const int node = (int)(dsto / ROWB);
+            const ScbVec<K> s98 = scb_ld<K>(fin + dsto);
+            const ScbVec<K> s0 = scb_ldg<K>(A.X + (long long)node * A.Wpad + w0 + lane * K);
+            ScbVec<K> e;
+            unsigned c = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { e.v[k] = (s98.v[k] ^ s0.v[k]) & ok.v[k]; c += (unsigned)__popc(e.v[k]); }
+            total32 += c;
+            if (A.mode == 1) {
+                c = scb_warp_sum(c);
+                if (lane == 0 && c) atomicAdd(&A.nodewise[(long long)p * N + node], (int)c);
+            } else if (A.mode == 2) {
+                scb_st<K>(oth + dsto, e);
+            }
+        }
+        total32 = scb_warp_sum(total32);
+        if (lane == 0 && total32) atomicAdd(&A.fitness[p], (unsigned long long)total32);
+        if (A.mode == 2) {
+            __syncthreads();
+            const unsigned char *eb = sm + (finOff ? 0u : BUFB);
+            for (int idx = tid; idx < WT * 32; idx += nthr) {
+                const int w = idx >> 5, b = idx & 31;
+                const long long c = ((long long)w0 + w) * 32 + b;
+                if (c >= A.C || sh[4 + w / 32]) continue;
+                int n1 = 0;
+                for (int row = 0; row < N; ++row)
+                    n1 += (int)((*reinterpret_cast<const uint32_t *>(eb + (uint32_t)row * ROWB + (uint32_t)w * 4u) >> b) & 1u);
+                A.cellwise[(long long)p * A.C + c] = n1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && tilesDone) {
+        atomicAdd(&A.diag->steps_executed, stepsDone);
+        atomicAdd(&A.diag->tiles, tilesDone);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K3: exact resolver for one 1024-cell chunk (32 words, K = 1), three shared-memory buffers
+ * (A, B, T).  Restates the reference literally on packed words:
+ *   pass a: 99 plain steps -> T = S_99
+ *   pass b: found = OR_j (S_j == T), j = 0..98  (getAttractCycle2, simulator.c:306-331)
+ *   e = S_98 xor S_0; found cells contribute e; a not-found cell repeats the previous found
+ *   cell's e (the reference leaves error[]/totalError untouched, simulator.c:431-482, Q7),
+ *   looking back into earlier chunks when the chunk starts with not-found cells.
+ * ---------------------------------------------------------------------------------------- */
+struct ScbResolveArgs {
+    ScbSimArgs s;
+    unsigned int *itemCursor;     /* persistent work counter for K3 */
+};
+
+/* simulate chunk q of individual p exactly.  On return: buffer A rows hold S_98, buffer B rows
+ * hold e = S_98 xor S_0 (all nodes), Fm[32] = found & valid per word.  All threads call it. */
+SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uint4 *desc, int4 cnt,
+                               uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q,
+                               int tid, int nthr)
+{
+    const int N = A.N;
+    const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
+    const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    const uint32_t laneOff = (uint32_t)lane * 4u;
+    const int w0 = q * 32;
+    unsigned char *bufA = sm, *bufB = sm + BUFB, *bufT = sm + 2u * BUFB;
+    ScbVec<1> d2, dz;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int row = warp; row < N; row += S) {
+            const ScbVec<1> v = scb_ldg<1>(A.X + (long long)row * A.Wpad + w0 + lane);
+            scb_st<1>(bufA + (uint32_t)row * ROWB + laneOff, v);
+        }
+        if (tid < 32) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; if (pass == 0) Fm[tid] = 0u; }
+        __syncthreads();
+        if (pass == 1) {
+            /* j = 0: compare S_0 with T on every row */
+            uint32_t d = 0u;
+            for (int row = warp; row < N; row += S)
+                d |= scb_ld<1>(bufA + (uint32_t)row * ROWB + laneOff).v[0] ^ scb_ld<1>(bufT + (uint32_t)row * ROWB + laneOff).v[0];
+            if (d) atomicOr(&dmz[lane], d);
+            __syncthreads();
+            if (tid < 32) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
+            __syncthreads();
+        }
+        const int last = pass == 0 ? SCB_LAST : SCB_LAST - 1;
+        uint32_t srcOff = 0u, dstOff = BUFB;
+        for (int tn = 1; tn <= last; ++tn) {
+            unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
+            if (pass == 1) f |= SCB_SF_TCMP;
+            d2.v[0] = 0u; dz.v[0] = 0u;
+            scb_step<1>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, nullptr, bufT + laneOff, d2, dz);
+            if (pass == 1 && dz.v[0]) atomicOr(&dmz[lane], dz.v[0]);
+            __syncthreads();
+            if (pass == 1) {
+                if (tid < 32) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
+                __syncthreads();
+            }
+            const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
+        }
+        if (pass == 0) {
+            /* S_99 sits in buffer B (99 is odd): T = B */
+            for (int row = warp; row < N; row += S)
+                scb_st<1>(bufT + (uint32_t)row * ROWB + laneOff, scb_ld<1>(bufB + (uint32_t)row * ROWB + laneOff));
+            __syncthreads();
+        }
+    }
+    /* S_98 in buffer A (98 is even).  e rows -> buffer B */
+    for (int row = warp; row < N; row += S) {
+        ScbVec<1> e;
+        e.v[0] = (scb_ld<1>(bufA + (uint32_t)row * ROWB + laneOff).v[0]
+                  ^ __ldg(A.X + (long long)row * A.Wpad + w0 + lane)) & vm[lane];
+        scb_st<1>(bufB + (uint32_t)row * ROWB + laneOff, e);
+    }
+    if (tid < 32) Fm[tid] &= vm[tid];
+    __syncthreads();
+}
+
+__global__ void scb_k_resolve(ScbResolveArgs R)
+{
+    SCB_DYN_SMEM(smraw);
+    const ScbSimArgs &A = R.s;
+    const int N = A.N;
+    const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
+    unsigned char *sm = smraw;
+    uint4 *desc = reinterpret_cast<uint4 *>(smraw + 3u * BUFB);
+    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
+    uint32_t *Fm = dmz + 32;
+    uint32_t *vm = Fm + 32;
+    uint32_t *F0 = vm + 32;                                /* found & valid of the item's own chunk */
+    uint32_t *V0 = F0 + 32;                                /* valid mask of the item's own chunk    */
+    int *sh = reinterpret_cast<int *>(V0 + 32);            /* [0] item, [2] pending cells, [3] look-back value */
+    int *srcc = sh + 8;                                    /* [1024] source cell of each cell       */
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    const unsigned char *bufB = sm + BUFB;
+    unsigned nItems = *A.resolveCount;
+    if (nItems > A.resolveCap) nItems = A.resolveCap;
+
+    for (;;) {
+        if (tid == 0) sh[0] = (int)atomicAdd(R.itemCursor, 1u);
+        __syncthreads();
+        const unsigned it = (unsigned)sh[0];
+        if (it >= nItems) break;
+        const int p = (int)A.resolveItems[it].x, q = (int)A.resolveItems[it].y;
+        const int4 cnt = A.counts[p];
+        scb_load_program<1>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+        __syncthreads();
+        scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, q, tid, nthr);
+        if (tid < 32) { F0[tid] = Fm[tid]; V0[tid] = vm[tid]; }
+        if (tid == 0) sh[2] = 0;
+        __syncthreads();
+
+        /* source cell of every cell: itself when found, else the nearest earlier found cell of
+         * the chunk (fill-forward), -1 when that lies in an earlier chunk, -2 for padding */
+        unsigned nfHere = 0;
+        for (int i = tid; i < 1024; i += nthr) {
+            const int w = i >> 5, b = i & 31;
+            int s = -2;
+            if ((V0[w] >> b) & 1u) {
+                if ((F0[w] >> b) & 1u) s = i;
+                else {
+                    ++nfHere;
+                    s = -1;
+                    const uint32_t m = F0[w] & ((1u << b) - 1u);
+                    if (m) s = w * 32 + (31 - __clz((int)m));
+                    else for (int ww = w - 1; ww >= 0; --ww)
+                        if (F0[ww]) { s = ww * 32 + (31 - __clz((int)F0[ww])); break; }
+                    if (s == -1) atomicAdd(reinterpret_cast<unsigned int *>(&sh[2]), 1u);
+                }
+            }
+            srcc[i] = s;
+        }
+        if (nfHere) atomicAdd(&A.diag->not_found_cells, (unsigned long long)nfHere);
+        __syncthreads();
+
+        /* per-node sums: found cells plus the copies made by not-found cells */
+        unsigned tot = 0;
+        for (int j = warp; j < N; j += S) {
+            const uint32_t dsto = desc[j].w & 0xFFFFFFu;
+            const int node = (int)(dsto / ROWB);
+            const uint32_t e = *reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)lane * 4u);
+            unsigned c = (unsigned)__popc(e & F0[lane]);
+            uint32_t nfb = ~F0[lane] & V0[lane];
+            while (nfb) {
+                const int b = __ffs((int)nfb) - 1;
+                nfb &= nfb - 1u;
+                const int s = srcc[lane * 32 + b];
+                if (s >= 0) c += (*reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)(s >> 5) * 4u) >> (s & 31)) & 1u;
+            }
+            tot += c;
+            if (A.mode == 1) {
+                c = scb_warp_sum(c);
+                if (lane == 0 && c) atomicAdd(&A.nodewise[(long long)p * N + node], (int)c);
+            }
+        }
+        tot = scb_warp_sum(tot);
+        if (lane == 0 && tot) atomicAdd(&A.fitness[p], (unsigned long long)tot);
+        if (A.mode == 2) {
+            for (int i = tid; i < 1024; i += nthr) {
+                const int s = srcc[i];
+                if (s < 0) continue;
+                int n1 = 0;
+                for (int row = 0; row < N; ++row)
+                    n1 += (int)((*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + (uint32_t)(s >> 5) * 4u) >> (s & 31)) & 1u);
+                A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
+            }
+        }
+        __syncthreads();
+
+        /* leading not-found cells: copy the last found cell of an earlier chunk */
+        const int pend = sh[2];
+        if (pend > 0) {
+            int qq = q - 1, sw = -1, sb = -1;
+            for (; qq >= 0; --qq) {
+                scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, qq, tid, nthr);
+                for (int w = 31; w >= 0; --w) if (Fm[w]) { sw = w; sb = 31 - __clz((int)Fm[w]); break; }
+                if (sw >= 0) break;
+                __syncthreads();
+            }
+            int n1 = 0;
+            if (sw >= 0) {
+                unsigned add = 0;
+                for (int j = warp; j < N; j += S) {
+                    const uint32_t dsto = desc[j].w & 0xFFFFFFu;
+                    const int node = (int)(dsto / ROWB);
+                    const unsigned bit = (*reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)sw * 4u) >> sb) & 1u;
+                    if (lane == 0 && bit) {
+                        add += (unsigned)pend;
+                        if (A.mode == 1) atomicAdd(&A.nodewise[(long long)p * N + node], pend);
+                    }
+                }
+                if (lane == 0 && add) atomicAdd(&A.fitness[p], (unsigned long long)add);
+                if (A.mode == 2)
+                    for (int row = 0; row < N; ++row)
+                        n1 += (int)((*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + (uint32_t)sw * 4u) >> sb) & 1u);
+            } else if (tid == 0) {
+                atomicAdd(&A.diag->undefined_leading, (unsigned long long)pend);
+            }
+            if (A.mode == 2)
+                for (int i = tid; i < 1024; i += nthr)
+                    if (srcc[i] == -1) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
+        }
+        if (tid == 0) atomicAdd(&A.diag->resolver_chunks, 1ull);
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K5: Hamming distance of every cell's observed state to every attractor + first-minimum
+ * argmin (singleCell.py:1211-1238).  One thread per cell.  The cell's state is gathered from
+ * the node-major packed matrix into cell-major words (bit i%32 of word i/32 = node i; a warp's
+ * 32 cells share each source word, so the gather is a broadcast load), attractors are staged
+ * through shared memory as packed node words [A][ceil(N/32)].  POPC-bound.
+ * ---------------------------------------------------------------------------------------- */
+#define SCB_HAM_MAXW 32            /* N <= 1024 */
+#define SCB_HAM_SMEM_WORDS 8192    /* 32 KB of attractor words per pass */
+__global__ void scb_k_hamming(ScbHammingArgs A)
+{
+    SCB_DYN_SMEM(smraw);
+    const int NW = (A.N + 31) / 32;
+    uint32_t *sAttr = reinterpret_cast<uint32_t *>(smraw);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const long long c = (long long)blockIdx.x * nthr + tid;
+    uint32_t cs[SCB_HAM_MAXW];
+#pragma unroll
+    for (int w = 0; w < SCB_HAM_MAXW; ++w) cs[w] = 0u;
+    if (c < A.C) {
+        for (int w = 0; w < NW; ++w) {
+            uint32_t acc = 0u;
+            const int lim = (A.N - w * 32) < 32 ? (A.N - w * 32) : 32;
+            for (int b = 0; b < lim; ++b)
+                acc |= ((A.X[(long long)(w * 32 + b) * A.Wpad + (c >> 5)] >> (c & 31)) & 1u) << b;
+            cs[w] = acc;
+        }
+    }
+    int best = -1, bestD = 0;
+    const int ACH = SCB_HAM_SMEM_WORDS / NW;               /* attractors per shared-memory pass */
+    for (int a0 = 0; a0 < A.A; a0 += ACH) {
+        const int na = (A.A - a0) < ACH ? (A.A - a0) : ACH;
+        __syncthreads();
+        for (int i = tid; i < na * NW; i += nthr) sAttr[i] = A.attr[(long long)a0 * NW + i];
+        __syncthreads();
+        if (c < A.C) {
+            for (int a = 0; a < na; ++a) {
+                int d = 0;
+                for (int w = 0; w < NW; ++w) d += __popc(cs[w] ^ sAttr[a * NW + w]);
+                if (A.dist) A.dist[c * A.A + a0 + a] = d;
+                if (best < 0 || d < bestD) { best = a0 + a; bestD = d; }     /* first minimum */
+            }
+        }
+    }
+    if (c < A.C) {
+        A.decider[c] = best;
+        A.deciderDistance[c] = bestD;
+    }
+}
+
+#endif

@@ -1,0 +1,117 @@
+/*
+ * scb_types.h -- structures shared by the host API and the kernels.
+ *
+ * Compiled two ways: by nvcc for sm_100a (the product), and by g++ with -DSCB_EMU against the
+ * host-thread CUDA emulator in tests/emu/ (test infrastructure only: it lets the CPU test
+ * suite run the *same kernel source* when no GPU is present; it is never built into or
+ * loaded by the product library).
+ */
+#ifndef SCB_TYPES_H
+#define SCB_TYPES_H
+#include <stdint.h>
+
+#ifdef SCB_EMU
+#include "emu_cuda.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#if defined(__CUDACC__) || defined(SCB_EMU)
+#define SCB_HD __host__ __device__
+#define SCB_DEV __device__ __forceinline__
+#else
+#define SCB_HD
+#define SCB_DEV inline
+#endif
+
+#define SCB_MAX_TERMS 7   /* andNodes[NODE][7][3], simulator.c:350 */
+#define SCB_MAX_IN 3
+#define SCB_STEPS 100     /* simulator.c:6 (#define STEP); states S_0 .. S_99 */
+#define SCB_LAST (SCB_STEPS - 1)
+
+/* per-node compile flags */
+#define SCB_NF_UNSUPPORTED 1u
+#define SCB_NF_EMPTY       2u
+#define SCB_NF_BADIDX      4u
+#define SCB_NF_TERMS       8u
+
+/* step flags */
+#define SCB_SF_CMP2   1u   /* compare S_t with S_{t-2} (the row being overwritten)        */
+#define SCB_SF_ZCMP   2u   /* compare S_t with the snapshot in global scratch             */
+#define SCB_SF_ZSNAP  4u   /* write S_t to the snapshot                                    */
+#define SCB_SF_TCMP   8u   /* compare S_t with the target state held in shared memory     */
+#define SCB_SF_CONST 16u   /* also write the constant rows (steps 1 and 2 only)            */
+
+/* kernel behaviour flags (ScbSimArgs.flags) */
+#define SCB_KF_EARLY  1u
+#define SCB_KF_SNAP   2u
+
+struct ScbDiag {                      /* device-side counters, zeroed per evaluation */
+    unsigned long long unsupported_nodes;
+    unsigned long long empty_rule_nodes;
+    unsigned long long bad_index_nodes;
+    unsigned long long term_overflow_nodes;
+    unsigned long long nonbinary_cells;
+    unsigned long long not_found_cells;
+    unsigned long long undefined_leading;
+    unsigned long long resolver_chunks;
+    unsigned long long steps_executed;
+    unsigned long long tiles;
+};
+
+/* One compiled node: d.x, d.y, d.z = input node indices, d.w = node index | lut8 << 24.
+ * Sorted per individual by arity: [arity 3 | arity 2 | arity 1 | constants], counts in an int4
+ * (x = n3, y = n2, z = n1, w = n0).  lut8 follows lop3's convention: bit ((a<<2)|(b<<1)|c). */
+
+struct ScbCompileArgs {
+    int P, N, indLen, tablesPerIndividual, Npad;
+    const int32_t *individuals;   /* [P][indLen] */
+    const int32_t *andLen;        /* [N] */
+    const int32_t *parse;         /* [N] */
+    const int32_t *an, *ai;       /* [P or 1][N][7][3] */
+    const int32_t *ko, *ki;       /* [N] */
+    uint4 *descs;                 /* [P][Npad] */
+    int4 *counts;                 /* [P] */
+    ScbDiag *diag;
+};
+
+struct ScbPackArgs {
+    const void *src;              /* [N][rowStride] elements, row i = node i */
+    int elemBytes;                /* 4 or 1 */
+    long long rowStride;          /* elements */
+    int N, C, Wpad;
+    uint32_t *X;                  /* [N][Wpad] */
+    ScbDiag *diag;
+};
+
+struct ScbSimArgs {
+    const uint32_t *X;            /* packed S_0: [N][Wpad] node-major, 32 cells per word */
+    int N, C, Wpad, tiles, P, Npad, mode;
+    const uint4 *descs;
+    const int4 *counts;
+    unsigned long long *fitness;  /* [P] */
+    int32_t *nodewise;            /* [P][N] or null */
+    int32_t *cellwise;            /* [P][C] or null */
+    unsigned int *workCounter;    /* persistent-CTA work queue head */
+    unsigned int *resolveCount;   /* number of chunks queued for the exact resolver */
+    uint2 *resolveItems;          /* (individual, chunk) */
+    unsigned int resolveCap;
+    uint32_t *zscratch;           /* snapshot scratch, zstride words per CTA */
+    unsigned long long zstride;
+    unsigned int flags;           /* SCB_KF_* */
+    int chkEvery;                 /* cadence of the period<=2 check */
+    unsigned long long snapLo, snapHi;  /* bit t set: take a snapshot when computing S_t */
+    int periodSearch;             /* snapshot-compare steps kept after all cells resolved */
+    ScbDiag *diag;
+};
+
+struct ScbHammingArgs {
+    const uint32_t *X;            /* [N][Wpad] */
+    int N, C, Wpad, A;
+    const uint32_t *attr;         /* [A][N] as 0/1 words?  no: packed [A][ceil(N/32)] node bits */
+    int32_t *dist;                /* [C][A] or null */
+    int32_t *decider;             /* [C] */
+    int32_t *deciderDistance;     /* [C] */
+};
+
+#endif

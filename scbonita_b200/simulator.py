@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference's simulator boundary, on top of the C-ABI.
+
+What it mirrors (file:line under /root/reference/src/scBONITA/):
+
+* ``ruleMaker.__evaluateByNode(individual, KOlist, KIlist, cFunction, localSearch, importanceScores)``
+  (ruleMaker.py:1077-1221) -> :meth:`Simulator.evaluate_by_node` -- same argument meaning and
+  return shapes (``[sum(errors)]`` for the GA, ``errors[:nodeNum]`` for local search).
+* the two list comprehensions that score a GA population one C call at a time
+  (ruleMaker.py:982-985, 1030-1033) -> :meth:`Simulator.evaluate_population` (one launch).
+* ``ruleMaker.__checkNodePossibilities`` (ruleMaker.py:1235-1266) ->
+  :meth:`Simulator.check_node_possibilities` -- same 4-tuple.
+* the distance / decider stage of ``singleCell.assignAttractors`` (singleCell.py:1211-1238) ->
+  :meth:`Simulator.hamming_argmin`.
+
+All arithmetic happens in the CUDA library; this module only marshals numpy arrays.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODE_CELLWISE, MODE_NODEWISE, MODE_SUM, ScbError, Stats  # noqa: F401
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class ModelTables:
+    """The int32 tables of one network model exactly as ``__evaluateByNode`` builds them
+    (ruleMaker.py:1089-1129): andLenList, individualParse, andNodes[N][7][3],
+    andNodeInvertList[N][7][3], nodePositions; ``ind_len`` = len(individual) (``model.size``)."""
+
+    def __init__(self, and_len_list, individual_parse, and_nodes, and_node_invert_list, node_positions, ind_len):
+        self.and_len_list = _i32(and_len_list)
+        self.n = int(self.and_len_list.shape[0])
+        self.individual_parse = _i32(individual_parse)
+        if self.individual_parse.shape[0] < self.n:
+            raise ValueError("individualParse needs at least nodeNum entries")
+        self.and_nodes = _i32(and_nodes).reshape(self.n, 7, 3)
+        self.and_node_invert_list = _i32(and_node_invert_list).reshape(self.n, 7, 3)
+        self.node_positions = _i32(node_positions)
+        self.ind_len = int(ind_len)
+
+
+class Simulator:
+    """One (binarized dataset, network) pair on one GPU: packs the matrix once (K1) and scores
+    rule sets against it.  ``bin_mat`` is the dense gene-major 0/1 matrix (int32 as the
+    reference passes it, or uint8); only rows ``node_positions`` are used."""
+
+    def __init__(self, bin_mat, model, n_cells=None, device=0, lib_path=None):
+        self.lib = _lib.load(lib_path)
+        self.model = model
+        bm = np.asarray(bin_mat)
+        if bm.dtype == np.uint8 or bm.dtype == np.bool_:
+            bm = np.ascontiguousarray(bm, dtype=np.uint8)
+            elem = 1
+        else:
+            bm = _i32(bm)
+            elem = 4
+        if bm.ndim != 2:
+            raise ValueError("bin_mat must be 2-D (genes x cells)")
+        self.n_cells = int(bm.shape[1] if n_cells is None else n_cells)
+        if int(model.node_positions.max(initial=0)) >= bm.shape[0]:
+            raise ValueError("nodePositions exceed the rows of bin_mat")
+        self._ctx = ctypes.c_void_p()
+        rc = self.lib.scb_ctx_create(ctypes.byref(self._ctx), int(device), model.n, self.n_cells, _ptr(bm), elem,
+                                     int(bm.shape[1]), _ptr(model.node_positions))
+        _lib.check(self.lib, rc)
+        self.last_stats = None
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.scb_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key, value):
+        _lib.check(self.lib, self.lib.scb_ctx_set_option(self._ctx, int(key), int(value)))
+
+    def info(self):
+        v = [ctypes.c_int() for _ in range(6)]
+        _lib.check(self.lib, self.lib.scb_ctx_info(self._ctx, *[ctypes.byref(x) for x in v]))
+        keys = ("nodes", "cells", "words_per_lane", "warps", "ctas", "smem_bytes")
+        return dict(zip(keys, (x.value for x in v)))
+
+    # -- population scoring -------------------------------------------------------------------
+    def _knock(self, ko_list, ki_list):
+        """ruleMaker.py:1089-1095: both arrays are filled from *KOlist*, used as indices."""
+        n = self.model.n
+        knockouts = np.zeros(n, dtype=np.int32)
+        knockins = np.zeros(n, dtype=np.int32)
+        for k in ko_list:
+            knockouts[k] = 1
+        for k in ko_list:
+            knockins[k] = 1
+        return knockouts, knockins
+
+    def _tables(self, individuals, and_nodes, and_inv):
+        m = self.model
+        inds = _i32(individuals)
+        if inds.ndim == 1:
+            inds = inds.reshape(1, -1)
+        if inds.shape[1] != m.ind_len:
+            raise ValueError("individuals must have %d bits" % m.ind_len)
+        an = m.and_nodes if and_nodes is None else _i32(and_nodes)
+        ai = m.and_node_invert_list if and_inv is None else _i32(and_inv)
+        per_ind = int(an.ndim == 4)
+        if per_ind and (an.shape[0] != inds.shape[0] or ai.shape != an.shape):
+            raise ValueError("per-individual tables must be [P][N][7][3]")
+        return inds, an, ai, per_ind
+
+    def upload(self, individuals, knockouts=None, knockins=None, and_nodes=None, and_inv=None):
+        """H2D of one population (async on the context's stream)."""
+        m = self.model
+        inds, an, ai, per_ind = self._tables(individuals, and_nodes, and_inv)
+        ko = _i32(knockouts if knockouts is not None else np.zeros(m.n))
+        ki = _i32(knockins if knockins is not None else np.zeros(m.n))
+        self._keep = (inds, an, ai, ko, ki)          # keep the host arrays alive until the copy is done
+        self._P = inds.shape[0]
+        rc = self.lib.scb_pop_upload(self._ctx, inds.shape[0], _ptr(inds), m.ind_len, _ptr(m.and_len_list),
+                                     _ptr(m.individual_parse), _ptr(an), _ptr(ai), per_ind, _ptr(ko), _ptr(ki))
+        _lib.check(self.lib, rc)
+
+    def run(self, mode=MODE_SUM):
+        _lib.check(self.lib, self.lib.scb_pop_run(self._ctx, int(mode)))
+
+    def _out_array(self, mode, P):
+        if mode == MODE_SUM:
+            return np.zeros(P, dtype=np.int64)
+        if mode == MODE_NODEWISE:
+            return np.zeros((P, self.model.n), dtype=np.int32)
+        return np.zeros((P, self.n_cells), dtype=np.int32)
+
+    def fetch(self, mode=MODE_SUM, out=None):
+        out = self._out_array(mode, self._P) if out is None else out
+        st = Stats()
+        rc = self.lib.scb_pop_fetch(self._ctx, int(mode), _ptr(out), ctypes.byref(st))
+        self.last_stats = st.as_dict()
+        _lib.check(self.lib, rc)
+        return out
+
+    def sync(self):
+        _lib.check(self.lib, self.lib.scb_ctx_sync(self._ctx))
+
+    def event_record(self, slot):
+        _lib.check(self.lib, self.lib.scb_ctx_event_record(self._ctx, int(slot)))
+
+    def event_elapsed_ms(self, slot0, slot1):
+        ms = ctypes.c_float()
+        _lib.check(self.lib, self.lib.scb_ctx_event_elapsed_ms(self._ctx, int(slot0), int(slot1), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def result_device_pointer(self, mode=MODE_SUM):
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(self.lib, self.lib.scb_pop_result_dev(self._ctx, int(mode), ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def stream_pointer(self):
+        p = ctypes.c_void_p()
+        _lib.check(self.lib, self.lib.scb_ctx_stream(self._ctx, ctypes.byref(p)))
+        return p.value or 0
+
+    def evaluate_population(self, individuals, knockouts=None, knockins=None, and_nodes=None, and_inv=None,
+                            mode=MODE_SUM):
+        """Score P individuals in one launch.  Returns int64[P] (SUM), int32[P][N] (NODEWISE) or
+        int32[P][C] (CELLWISE).  ``and_nodes`` / ``and_inv`` may be [P][N][7][3] (every GA individual owns
+        a model copy, ruleMaker.py:650) or None for the context's shared model."""
+        self.upload(individuals, knockouts, knockins, and_nodes, and_inv)
+        self.run(mode)
+        return self.fetch(mode)
+
+    # -- the reference's per-individual entry point ------------------------------------------
+    def evaluate_by_node(self, individual, KOlist, KIlist, cFunction=None, localSearch=False,
+                         importanceScores=False, and_nodes=None, and_inv=None):
+        """ruleMaker.__evaluateByNode (ruleMaker.py:1077-1221).  ``cFunction`` is accepted and
+        ignored (the reference passes the ctypes symbol).  Returns ``errors[:nodeNum]`` as a
+        list when ``localSearch`` else ``[sum(errors)]``."""
+        if importanceScores:
+            raise NotImplementedError("importanceScore is served by the legacy symbol (see INTEGRATION.md)")
+        knockouts, knockins = self._knock(KOlist, KIlist)
+        if localSearch:
+            out = self.evaluate_population(individual, knockouts, knockins, and_nodes, and_inv, MODE_NODEWISE)
+            return out[0].tolist()
+        out = self.evaluate_population(individual, knockouts, knockins, and_nodes, and_inv, MODE_SUM)
+        return [int(out[0])]
+
+    def check_node_possibilities(self, node, indy, KOlist, KIlist, scSyncBoolC=None):
+        """ruleMaker.__checkNodePossibilities (ruleMaker.py:1235-1266): all 2^k - 1 rule bit-strings of
+        ``node`` in one launch.  Returns ``(truth, equivs, minny, indErrors)``."""
+        m = self.model
+        start = int(m.individual_parse[node])
+        end = m.ind_len if node == m.n - 1 else int(m.individual_parse[node + 1])
+        truth = list(indy[start:end])
+        equivs = [truth]
+        if end - start == 0:
+            return truth, equivs, equivs, 0.0
+        knockouts, knockins = self._knock(KOlist, KIlist)
+        ind = _i32(indy)
+        nv = 2 ** (end - start) - 1
+        errs = np.zeros(nv, dtype=np.int32)
+        got = ctypes.c_int()
+        rc = self.lib.scb_eval_local_search(self._ctx, _ptr(ind), m.ind_len, _ptr(m.and_len_list),
+                                            _ptr(m.individual_parse), _ptr(m.and_nodes),
+                                            _ptr(m.and_node_invert_list), _ptr(knockouts), _ptr(knockins),
+                                            int(node), _ptr(errs), nv, ctypes.byref(got))
+        _lib.check(self.lib, rc)
+        ind_errors = errs.tolist()
+        ind_options = [[(i >> j) & 1 for j in range(end - start)] for i in range(1, nv + 1)]   # __bitList
+        minny = min(ind_errors)
+        equivs = [ind_options[i] for i in range(nv) if ind_errors[i] <= minny]
+        return equivs[0], equivs, minny, ind_errors
+
+    # -- attractor companion ------------------------------------------------------------------
+    def hamming_argmin(self, attractors, want_dist=True):
+        """singleCell.py:1211-1238: returns (dist[C][A] or None, decider[C], deciderDistance[C])."""
+        at = _i32(attractors)
+        if at.ndim != 2 or at.shape[1] != self.model.n:
+            raise ValueError("attractors must be [A][nodeNum]")
+        A = at.shape[0]
+        dist = np.zeros((self.n_cells, A), dtype=np.int32) if want_dist else None
+        dec = np.zeros(self.n_cells, dtype=np.int32)
+        dd = np.zeros(self.n_cells, dtype=np.int32)
+        rc = self.lib.scb_hamming_argmin(self._ctx, _ptr(at), A, _ptr(dist), _ptr(dec), _ptr(dd))
+        _lib.check(self.lib, rc)
+        return dist, dec, dd

@@ -1,0 +1,133 @@
+/*
+ * emu_cuda.cpp -- host-thread CUDA emulator (see emu_cuda.h).  TEST INFRASTRUCTURE ONLY.
+ *
+ * One std::thread per CUDA thread, all blocks of a launch alive at once (so atomics between
+ * blocks behave), block barrier = std::barrier, warp collectives = per-warp barrier plus an
+ * exchange array.  Launches are synchronous.
+ */
+#include "emu_cuda.h"
+#include <barrier>
+#include <chrono>
+#include <cstdlib>
+#include <memory>
+#include <thread>
+#include <vector>
+
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+namespace {
+struct WarpCtx {
+    std::barrier<> bar;
+    uint32_t slot[32];
+    explicit WarpCtx(int n) : bar(n) {}
+};
+struct BlockCtx {
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<WarpCtx>> warps;
+    unsigned char *smem;
+    explicit BlockCtx(int n) : bar(n), smem(nullptr) {}
+};
+thread_local BlockCtx *tl_block = nullptr;
+thread_local WarpCtx *tl_warp = nullptr;
+}  // namespace
+
+unsigned char *emu_dyn_smem() { return tl_block->smem; }
+void __syncthreads() { tl_block->bar.arrive_and_wait(); }
+void __syncwarp(unsigned) { tl_warp->bar.arrive_and_wait(); }
+
+unsigned __ballot_sync(unsigned, int pred)
+{
+    WarpCtx *w = tl_warp;
+    const int lane = threadIdx.x & 31;
+    w->slot[lane] = pred ? 1u : 0u;
+    w->bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= (w->slot[i] & 1u) << i;
+    w->bar.arrive_and_wait();
+    return r;
+}
+
+uint32_t emu_shfl(uint32_t v, int srcLane)
+{
+    WarpCtx *w = tl_warp;
+    const int lane = threadIdx.x & 31;
+    w->slot[lane] = v;
+    w->bar.arrive_and_wait();
+    const uint32_t r = w->slot[srcLane & 31];
+    w->bar.arrive_and_wait();
+    return r;
+}
+
+void emu_launch_impl(const std::function<void()> &body, dim3 grid, dim3 block, size_t smem)
+{
+    const int nthr = (int)block.x;
+    const int nblk = (int)(grid.x * grid.y);
+    if (nthr % 32 != 0) abort();
+    std::vector<std::unique_ptr<BlockCtx>> blocks;
+    std::vector<std::thread> threads;
+    for (int b = 0; b < nblk; ++b) {
+        auto bc = std::make_unique<BlockCtx>(nthr);
+        for (int w = 0; w < nthr / 32; ++w) {
+            bc->warps.push_back(std::make_unique<WarpCtx>(32));
+            memset(bc->warps.back()->slot, 0, sizeof(bc->warps.back()->slot));
+        }
+        bc->smem = (unsigned char *)aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
+        memset(bc->smem, 0xCD, smem);          /* shared memory starts undefined */
+        blocks.push_back(std::move(bc));
+    }
+    for (int b = 0; b < nblk; ++b)
+        for (int t = 0; t < nthr; ++t) {
+            BlockCtx *bc = blocks[b].get();
+            threads.emplace_back([=, &body]() {
+                threadIdx = dim3(t); blockIdx = dim3(b % grid.x, b / grid.x); blockDim = block; gridDim = grid;
+                tl_block = bc; tl_warp = bc->warps[t / 32].get();
+                body();
+                /* a thread that returns early must not leave the others stuck at a barrier */
+                bc->warps[t / 32]->bar.arrive_and_drop();
+                bc->bar.arrive_and_drop();
+            });
+        }
+    for (auto &th : threads) th.join();
+    for (auto &bc : blocks) free(bc->smem);
+}
+
+/* ---- runtime API ------------------------------------------------------------------------ */
+struct emu_event { std::chrono::steady_clock::time_point t; };
+cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
+{
+    memset(p, 0, sizeof(*p));
+    strcpy(p->name, "host-thread emulator");
+    p->multiProcessorCount = 2; p->sharedMemPerBlockOptin = 232448; p->major = 10; p->minor = 0;
+    p->totalGlobalMem = (size_t)1 << 34;
+    return cudaSuccess;
+}
+cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, ((n + 255) / 256 + 1) * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t)
+{
+    for (size_t r = 0; r < h; ++r) memcpy((char *)d + r * dp, (const char *)s + r * sp, w);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event(); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
+{
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t) { return "emulator"; }
