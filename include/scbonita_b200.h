@@ -78,7 +78,7 @@ typedef struct scb_stats {
     int64_t steps_executed;       /* simulated (tile, step) pairs, for executed-work accounting       */
     int64_t tiles;                /* tiles simulated (individuals x cell tiles)                       */
     float   kernel_ms;            /* device time of the last evaluation (CUDA events on the stream)   */
-    float   reserved;
+    float   sim_ms;               /* of which the simulator kernel K2 alone                           */
 } scb_stats;
 
 const char *scb_last_error(void);
@@ -122,7 +122,12 @@ int scb_pop_run(scb_ctx *ctx, int mode);
 int scb_pop_fetch(scb_ctx *ctx, int mode, void *out, scb_stats *stats);
 int scb_pop_result_dev(scb_ctx *ctx, int mode, void **devPtr, int64_t *bytes);
 
-/* stream / timing plumbing for callers that time or chain work on the context's stream */
+/* stream / timing plumbing for callers that time or chain work on the context's stream.
+ * scb_ctx_flush_l2 overwrites a buffer larger than L2 on the stream (benchmark hygiene);
+ * scb_host_alloc / scb_host_free hand out pinned host memory for asynchronous uploads. */
+int scb_ctx_flush_l2(scb_ctx *ctx);
+int scb_host_alloc(void **ptr, int64_t bytes);
+int scb_host_free(void *ptr);
 int scb_ctx_stream(scb_ctx *ctx, void **cudaStream);
 int scb_ctx_sync(scb_ctx *ctx);
 int scb_ctx_event_record(scb_ctx *ctx, int slot);            /* slot 0..7                     */

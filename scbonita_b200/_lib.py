@@ -22,6 +22,7 @@ SYMBOLS = (
     "scb_ctx_create", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info",
     "scb_eval_population", "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
+    "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
     "scb_eval_local_search", "scb_hamming_argmin", "scb_attractors",
     "scb_set_legacy_geometry", "scSyncBool", "importanceScore", "cluster",
 )
@@ -32,10 +33,10 @@ class Stats(ctypes.Structure):
                 ("empty_rule_nodes", ctypes.c_int64), ("unsupported_nodes", ctypes.c_int64),
                 ("bad_index_nodes", ctypes.c_int64), ("term_overflow_nodes", ctypes.c_int64),
                 ("resolver_chunks", ctypes.c_int64), ("steps_executed", ctypes.c_int64),
-                ("tiles", ctypes.c_int64), ("kernel_ms", ctypes.c_float), ("reserved", ctypes.c_float)]
+                ("tiles", ctypes.c_int64), ("kernel_ms", ctypes.c_float), ("sim_ms", ctypes.c_float)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class ScbError(RuntimeError):
@@ -77,6 +78,9 @@ def load(path=None):
     lib.scb_ctx_sync.argtypes = [vp]
     lib.scb_ctx_event_record.argtypes = [vp, ctypes.c_int]
     lib.scb_ctx_event_elapsed_ms.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.scb_ctx_flush_l2.argtypes = [vp]
+    lib.scb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
+    lib.scb_host_free.argtypes = [vp]
     lib.scb_eval_local_search.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, ctypes.c_int,
                                           i32p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     lib.scb_hamming_argmin.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p]
@@ -86,7 +90,8 @@ def load(path=None):
     lib.scb_set_legacy_geometry.restype = None
     for name in ("scb_ctx_create", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info", "scb_eval_population",
                  "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev", "scb_ctx_stream",
-                 "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms", "scb_eval_local_search",
+                 "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms", "scb_ctx_flush_l2", "scb_host_alloc",
+                 "scb_host_free", "scb_eval_local_search",
                  "scb_hamming_argmin", "scb_attractors"):
         getattr(lib, name).restype = ctypes.c_int
     _libs[path] = lib

@@ -69,7 +69,7 @@ struct scb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t evRun0 = nullptr, evRun1 = nullptr;
+    cudaEvent_t evRun0 = nullptr, evRun1 = nullptr, evSim0 = nullptr, evSim1 = nullptr;
     int numSM = 0;
     size_t smemLimit = 0;
     int N = 0, C = 0, W = 0, Wpad = 0;
@@ -94,6 +94,7 @@ struct scb_ctx {
     DevBuf<ScbDiag> dDiag;
     DevBuf<uint32_t> dAttr;
     DevBuf<int32_t> dDist, dDecider, dDeciderDist;
+    DevBuf<unsigned char> dFlush;
     /* current population */
     int P = 0, indLen = 0, tpi = 0;
     int lastMode = -1;
@@ -217,7 +218,9 @@ int scb_ctx_create(scb_ctx **out, int device, int nodeNum, int lenSamples, const
     auto bail = [&](int rc) { scb_ctx_destroy(c); return rc; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
-    if (cudaEventCreate(&c->evRun0) != cudaSuccess || cudaEventCreate(&c->evRun1) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreate(&c->evRun0) != cudaSuccess || cudaEventCreate(&c->evRun1) != cudaSuccess ||
+        cudaEventCreate(&c->evSim0) != cudaSuccess || cudaEventCreate(&c->evSim1) != cudaSuccess)
+        return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
     int rc;
     if ((rc = c->dX.ensure((size_t)c->N * c->Wpad))) return bail(rc);
     if ((rc = c->dDiag.ensure(1))) return bail(rc);
@@ -268,7 +271,9 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
-    c->dDecider.release(); c->dDeciderDist.release();
+    c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
+    if (c->evSim0) cudaEventDestroy(c->evSim0);
+    if (c->evSim1) cudaEventDestroy(c->evSim1);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->evRun0) cudaEventDestroy(c->evRun0);
     if (c->evRun1) cudaEventDestroy(c->evRun1);
@@ -397,10 +402,12 @@ int scb_pop_run(scb_ctx *c, int mode)
     const long long items = (long long)P * sa.tiles;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, c->ctas));
     const dim3 block((unsigned)c->warps * 32);
+    CK(cudaEventRecord(c->evSim0, st));
     if (c->K == 4) SCB_LAUNCH(scb_k_sim<4>, dim3(grid), block, c->smemSim, st, sa);
     else if (c->K == 2) SCB_LAUNCH(scb_k_sim<2>, dim3(grid), block, c->smemSim, st, sa);
     else SCB_LAUNCH(scb_k_sim<1>, dim3(grid), block, c->smemSim, st, sa);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->evSim1, st));
 
     ScbResolveArgs ra;
     ra.s = sa; ra.itemCursor = c->dCounters.p + 2;
@@ -440,6 +447,7 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
         stats->tiles = (int64_t)d.tiles;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->evRun0, c->evRun1) == cudaSuccess) stats->kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, c->evSim0, c->evSim1) == cudaSuccess) stats->sim_ms = ms;
     }
     if (d.bad_index_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules reference an input outside [0,%d)", d.bad_index_nodes, c->N);
     if (d.term_overflow_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules span more than 7 AND-terms or leave the bit-string", d.term_overflow_nodes);
@@ -499,6 +507,29 @@ int scb_ctx_event_elapsed_ms(scb_ctx *c, int s0, int s1, float *ms)
     if (s0 < 0 || s0 >= 8 || s1 < 0 || s1 >= 8 || !ms) return fail(SCB_ERR_INVALID, "bad event slot");
     CK(cudaEventSynchronize(c->ev[s1]));
     CK(cudaEventElapsedTime(ms, c->ev[s0], c->ev[s1]));
+    return SCB_OK;
+}
+
+int scb_ctx_flush_l2(scb_ctx *c)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    const size_t bytes = (size_t)256 << 20;              /* > 126 MB of L2 */
+    if ((rc = c->dFlush.ensure(bytes))) return rc;
+    CK(cudaMemsetAsync(c->dFlush.p, 0x5a, bytes, c->stream));
+    return SCB_OK;
+}
+
+int scb_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return fail(SCB_ERR_INVALID, "bad argument");
+    CK(cudaMallocHost(ptr, (size_t)bytes));
+    return SCB_OK;
+}
+
+int scb_host_free(void *ptr)
+{
+    if (ptr) CK(cudaFreeHost(ptr));
     return SCB_OK;
 }
 

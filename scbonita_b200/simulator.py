@@ -167,6 +167,9 @@ class Simulator:
         _lib.check(self.lib, self.lib.scb_ctx_event_elapsed_ms(self._ctx, int(slot0), int(slot1), ctypes.byref(ms)))
         return float(ms.value)
 
+    def flush_l2(self):
+        _lib.check(self.lib, self.lib.scb_ctx_flush_l2(self._ctx))
+
     def result_device_pointer(self, mode=MODE_SUM):
         p, n = ctypes.c_void_p(), ctypes.c_int64()
         _lib.check(self.lib, self.lib.scb_pop_result_dev(self._ctx, int(mode), ctypes.byref(p), ctypes.byref(n)))
@@ -240,3 +243,23 @@ class Simulator:
         rc = self.lib.scb_hamming_argmin(self._ctx, _ptr(at), A, _ptr(dist), _ptr(dec), _ptr(dd))
         _lib.check(self.lib, rc)
         return dist, dec, dd
+
+
+class PinnedArray:
+    """A numpy array in pinned host memory handed out by the library (scb_host_alloc), so that uploads are
+    truly asynchronous.  Keep the object alive while ``.array`` is in use; ``close()`` frees it."""
+
+    def __init__(self, shape, dtype, lib_path=None):
+        self.lib = _lib.load(lib_path)
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        self._ptr = ctypes.c_void_p()
+        _lib.check(self.lib, self.lib.scb_host_alloc(ctypes.byref(self._ptr), max(count * dtype.itemsize, 1)))
+        buf = (ctypes.c_char * max(count * dtype.itemsize, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def close(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            self.lib.scb_host_free(self._ptr)
+            self._ptr = None

@@ -63,32 +63,39 @@ void emu_launch_impl(const std::function<void()> &body, dim3 grid, dim3 block, s
     const int nthr = (int)block.x;
     const int nblk = (int)(grid.x * grid.y);
     if (nthr % 32 != 0) abort();
-    std::vector<std::unique_ptr<BlockCtx>> blocks;
-    std::vector<std::thread> threads;
-    for (int b = 0; b < nblk; ++b) {
-        auto bc = std::make_unique<BlockCtx>(nthr);
-        for (int w = 0; w < nthr / 32; ++w) {
-            bc->warps.push_back(std::make_unique<WarpCtx>(32));
-            memset(bc->warps.back()->slot, 0, sizeof(bc->warps.back()->slot));
+    /* blocks run in waves of a few at a time (like CTAs on a small GPU); no kernel here needs all blocks
+     * of a grid to be resident at once */
+    const int wave = 4;
+    for (int b0 = 0; b0 < nblk; b0 += wave) {
+        const int nb = nblk - b0 < wave ? nblk - b0 : wave;
+        std::vector<std::unique_ptr<BlockCtx>> blocks;
+        std::vector<std::thread> threads;
+        for (int b = 0; b < nb; ++b) {
+            auto bc = std::make_unique<BlockCtx>(nthr);
+            for (int w = 0; w < nthr / 32; ++w) {
+                bc->warps.push_back(std::make_unique<WarpCtx>(32));
+                memset(bc->warps.back()->slot, 0, sizeof(bc->warps.back()->slot));
+            }
+            bc->smem = (unsigned char *)aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
+            memset(bc->smem, 0xCD, smem);          /* shared memory starts undefined */
+            blocks.push_back(std::move(bc));
         }
-        bc->smem = (unsigned char *)aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
-        memset(bc->smem, 0xCD, smem);          /* shared memory starts undefined */
-        blocks.push_back(std::move(bc));
+        for (int b = 0; b < nb; ++b)
+            for (int t = 0; t < nthr; ++t) {
+                BlockCtx *bc = blocks[b].get();
+                const int gb = b0 + b;
+                threads.emplace_back([=, &body]() {
+                    threadIdx = dim3(t); blockIdx = dim3(gb % grid.x, gb / grid.x); blockDim = block; gridDim = grid;
+                    tl_block = bc; tl_warp = bc->warps[t / 32].get();
+                    body();
+                    /* a thread that returns early must not leave the others stuck at a barrier */
+                    bc->warps[t / 32]->bar.arrive_and_drop();
+                    bc->bar.arrive_and_drop();
+                });
+            }
+        for (auto &th : threads) th.join();
+        for (auto &bc : blocks) free(bc->smem);
     }
-    for (int b = 0; b < nblk; ++b)
-        for (int t = 0; t < nthr; ++t) {
-            BlockCtx *bc = blocks[b].get();
-            threads.emplace_back([=, &body]() {
-                threadIdx = dim3(t); blockIdx = dim3(b % grid.x, b / grid.x); blockDim = block; gridDim = grid;
-                tl_block = bc; tl_warp = bc->warps[t / 32].get();
-                body();
-                /* a thread that returns early must not leave the others stuck at a barrier */
-                bc->warps[t / 32]->bar.arrive_and_drop();
-                bc->bar.arrive_and_drop();
-            });
-        }
-    for (auto &th : threads) th.join();
-    for (auto &bc : blocks) free(bc->smem);
 }
 
 /* ---- runtime API ------------------------------------------------------------------------ */

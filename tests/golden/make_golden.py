@@ -1,0 +1,97 @@
+"""Generates the golden vectors under tests/golden/ (run in the build container, where /root/reference and
+oracle/_ref exist):   python tests/golden/make_golden.py
+
+* sim_*.npz -- seeded inputs in the reference's int32 layouts plus the outputs of the UNMODIFIED reference
+  C (oracle/_ref/simulator.so driven with the reference's own ctypes convention): errors[] of scSyncBool
+  for localSearch = 0 (cellwise) and 1 (nodewise), for every individual.
+* hamming_kat.npz -- the reference's own packaged known answer for the distance / decider stage:
+  src/scBONITA/data/hsa00010.graphml_processed.graphml_attractorDistance.csv (100 cells x 51 attractors +
+  deciderDistance + decider) together with the pickled binarized matrix it was computed from.  The script
+  asserts that sum|attractor - cell| recomputed from the matrix reproduces the CSV before writing it.
+"""
+import ast
+import csv
+import os
+import pickle
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from common import Problem, oracle_model, ring_problem  # noqa: E402
+
+REF_DATA = "/root/reference/src/scBONITA/data"
+
+
+def ref_outputs(pr):
+    ref = oracle.RefSimulator(pr.n_cells)
+    m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+    bm = ref.dense(pr.bin_rows.astype(np.int32), pr.node_positions)
+    cw, nw = [], []
+    for p in range(pr.individuals.shape[0]):
+        an = None if pr.pop_an is None else pr.pop_an[p]
+        ai = None if pr.pop_ai is None else pr.pop_ai[p]
+        cw.append(ref.sync_bool(m, pr.individuals[p], bm, pr.n_cells, 0, and_nodes=an, and_inv=ai)[:pr.n_cells].copy())
+        nw.append(ref.sync_bool(m, pr.individuals[p], bm, pr.n_cells, 1, and_nodes=an, and_inv=ai)[:pr.n].copy())
+    return np.array(cw, np.int32), np.array(nw, np.int32)
+
+
+def save_sim(name, pr):
+    cw, nw = ref_outputs(pr)
+    per_ind = pr.pop_an is not None
+    np.savez_compressed(
+        os.path.join(HERE, name), and_len=pr.net.and_len, parse=pr.net.parse, and_nodes=pr.net.and_nodes,
+        and_inv=pr.net.and_inv, node_positions=pr.node_positions, ind_len=pr.net.ind_len, knockouts=pr.ko,
+        knockins=pr.ki, n_cells=pr.n_cells, bin_rows=np.packbits(pr.bin_rows, axis=1), individuals=pr.individuals,
+        pop_and_nodes=pr.pop_an if per_ind else np.zeros(1, np.int32),
+        pop_and_inv=pr.pop_ai if per_ind else np.zeros(1, np.int32), ref_cellwise=cw, ref_nodewise=nw)
+    print(name, "fitness", cw.sum(axis=1))
+
+
+def hamming_kat():
+    import networkx as nx
+
+    class _U(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module in ("singleCell", "ruleMaker", "__main__"):
+                return type(name, (object,), {})
+            return super().find_class(module, name)
+
+    sc = _U(open(os.path.join(REF_DATA, "trainingData.csvscTest.pickle"), "rb")).load()
+    genes = [str(g) for g in sc.geneList]
+    n_cells = len(sc.sampleList)
+    graph = nx.read_graphml(os.path.join(REF_DATA, "hsa00010.graphml_processed.graphml"))
+    node_list = [n for n in graph.nodes() if n in genes]           # ruleMaker.__init__ keeps graph order
+    pos = np.array([genes.index(n) for n in node_list], np.int32)
+    dense = np.asarray(sc.binMat[: len(genes), :n_cells].todense()).astype(np.int32)
+    with open(os.path.join(REF_DATA, "hsa00010.graphml_processed.graphml_attractorDistance.csv")) as f:
+        rows = list(csv.reader(f))
+    header = rows[0][1:]
+    attractors = np.array([ast.literal_eval(h) for h in header[:-2]], np.int32)
+    body = np.array([[int(float(x)) for x in r[1:]] for r in rows[1:]], np.int64)
+    dist, dd, dec = body[:, :-2].astype(np.int32), body[:, -2].astype(np.int32), body[:, -1]
+    assert attractors.shape[1] == len(node_list), (attractors.shape, len(node_list))
+    mine = np.abs(attractors[None, :, :] - dense[pos].T[:, None, :]).sum(axis=2)
+    assert np.array_equal(mine, dist), "packaged distances do not reproduce"
+    assert np.array_equal(mine.min(axis=1), dd)
+    # `decider` holds the column label (attractor string) or index depending on pandas; derive first-min index
+    decider = mine.argmin(axis=1).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "hamming_kat.npz"), attractors=attractors, bin_mat=dense,
+                        node_positions=pos, n_cells=n_cells, dist=dist, decider=decider, decider_distance=dd)
+    print("hamming_kat: %d cells x %d attractors reproduce the packaged CSV" % dist.shape)
+    return rows
+
+
+if __name__ == "__main__":
+    oracle.build(ref=True)
+    save_sim("sim_kegg60.npz", Problem.synthetic(60, 700, 4))
+    save_sim("sim_hsa47_noknock.npz", Problem.synthetic(47, 100, 3, knock=False))
+    save_sim("sim_n200.npz", Problem.synthetic(200, 130, 3))
+    save_sim("sim_ring45_chain12.npz", ring_problem([45], 12, 1500))
+    save_sim("sim_ring60_undefined_lead.npz", ring_problem([60], 0, 200, lead_found=True))
+    hamming_kat()

@@ -1,0 +1,331 @@
+"""Parity of the CUDA path with the oracle, bit for bit.
+
+Every test runs against two builds of the SAME sources (scbonita_b200/csrc):
+  * ``emu``  -- g++ + the host-thread emulator (tests/emu), on CPU, small sizes;
+  * ``cuda`` -- the product library on a B200 (marked ``gpu``), through the C-ABI, larger sizes.
+The oracle (oracle/) is only the checker.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from common import EMU_LIB, GOLDEN, Problem, oracle_model, ring_problem, tables
+from scbonita_b200 import _lib, simulator
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def backend(request):
+    if request.param == "emu":
+        return "emu", request.getfixturevalue("emu_lib")
+    return "cuda", request.getfixturevalue("cuda_lib")
+
+
+def big(backend, small, large):
+    return large if backend[0] == "cuda" else small
+
+
+# ---- seeded synthetic shapes ------------------------------------------------------------------
+@pytest.mark.parametrize("n,cells,pop", [(20, 200, 3), (60, 1100, 4), (200, 1300, 3), (230, 500, 2), (5, 40, 4), (1, 70, 2)])
+def test_synthetic_matches_oracle(backend, n, cells, pop):
+    cells = big(backend, cells, cells * 9 + 17)
+    pop = big(backend, pop, pop * 4)
+    pr = Problem.synthetic(n, cells, pop)
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim)
+
+
+@pytest.mark.parametrize("opts", [dict(early_exit=0, snapshots=0), dict(early_exit=1, snapshots=0),
+                                  dict(early_exit=0, snapshots=1), dict(words=1), dict(words=2, check_every=3),
+                                  dict(warps=4), dict(period_search=24), dict(check_every=1)])
+def test_every_schedule_gives_identical_integers(backend, opts):
+    """Early exit, snapshot resolution and tile geometry are optimisations: results must not move."""
+    pr = Problem.synthetic(60, big(backend, 2100, 21000), big(backend, 5, 24))
+    with pr.simulator(backend[1], **opts) as sim:
+        pr.check(sim)
+
+
+def test_no_knockouts(backend):
+    pr = Problem.synthetic(47, big(backend, 100, 5000), 4, knock=False)
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim)
+
+
+def test_shared_tables(backend):
+    """tablesPerIndividual = 0: one [N][7][3] model for the whole population."""
+    pr = Problem.synthetic(60, big(backend, 600, 6000), 5)
+    pr.pop_an = pr.pop_ai = None
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim)
+
+
+def test_uint8_matrix(backend):
+    pr = Problem.synthetic(30, 777, 3)
+    sim = simulator.Simulator(pr.bm.astype(np.uint8), tables(pr.net, pr.node_positions), lib_path=backend[1])
+    if backend[0] == "emu":
+        sim.set_option(_lib.OPT_MAX_CTAS, 2)
+    with sim:
+        pr.check(sim)
+
+
+# ---- golden vectors from the unmodified reference ---------------------------------------------
+@pytest.mark.parametrize("name", sorted(f for f in os.listdir(GOLDEN) if f.startswith("sim_")))
+def test_golden_vectors(backend, name):
+    g = np.load(os.path.join(GOLDEN, name))
+    C = int(g["n_cells"])
+    pos = g["node_positions"]
+    bm = np.zeros((int(pos.max()) + 1, C), np.int32)
+    bm[pos] = np.unpackbits(g["bin_rows"], axis=1)[:, :C]
+    model = simulator.ModelTables(g["and_len"], g["parse"], g["and_nodes"], g["and_inv"], pos, int(g["ind_len"]))
+    per_ind = g["pop_and_nodes"].ndim == 4
+    an = g["pop_and_nodes"] if per_ind else None
+    ai = g["pop_and_inv"] if per_ind else None
+    sim = simulator.Simulator(bm, model, lib_path=backend[1])
+    if backend[0] == "emu":
+        sim.set_option(_lib.OPT_MAX_CTAS, 3)
+    with sim:
+        cw = sim.evaluate_population(g["individuals"], g["knockouts"], g["knockins"], an, ai, mode=simulator.MODE_CELLWISE)
+        nw = sim.evaluate_population(g["individuals"], g["knockouts"], g["knockins"], an, ai, mode=simulator.MODE_NODEWISE)
+        fit = sim.evaluate_population(g["individuals"], g["knockouts"], g["knockins"], an, ai, mode=simulator.MODE_SUM)
+    assert np.array_equal(cw, g["ref_cellwise"])
+    assert np.array_equal(nw, g["ref_nodewise"])
+    assert np.array_equal(fit, g["ref_cellwise"].sum(axis=1))
+
+
+# ---- attractor-found semantics ---------------------------------------------------
+@pytest.mark.parametrize("rings,chain,cells", [([60], 0, 300), ([45], 12, 2500), ([3, 5], 4, 1500), ([49], 0, 200),
+                                               ([50], 0, 200), ([7, 11, 13], 20, 3000), ([2, 3, 4], 0, 1100)])
+@pytest.mark.parametrize("opts", [dict(), dict(early_exit=0, snapshots=0), dict(words=1)])
+def test_cycles_not_found_and_fill_forward(backend, rings, chain, cells, opts):
+    pr = ring_problem(rings, chain, cells)
+    with pr.simulator(backend[1], **opts) as sim:
+        st = pr.check(sim)
+    assert st["undefined_leading"] == 0
+
+
+def test_leading_not_found_cells_are_counted_and_defined_as_zero(backend):
+    """The reference reads uninitialised stack for not-found cells before the first found one; the oracle
+    and the library both define them as 0 and count them."""
+    pr = ring_problem([60], 0, 2300, gate_density=0.97, lead_found=False, seed=3)
+    o = pr.oracle()
+    with pr.simulator(backend[1]) as sim:
+        st = pr.check(sim)
+    first_found = int(np.argmax(pr.bin_rows[0] == 0)) if (pr.bin_rows[0] == 0).any() else pr.n_cells
+    assert st["undefined_leading"] >= 1
+    assert st["undefined_leading"] <= first_found
+    assert int(o["not_found"][0]) == st["not_found_cells"]
+
+
+def test_fill_forward_across_chunk_boundaries(backend):
+    """Runs of not-found cells longer than a 1024-cell chunk: the value comes from an earlier chunk."""
+    pr = ring_problem([55], 0, 4000, gate_density=0.5, seed=11)
+    pr.bin_rows[0, 900:3300] = 1          # gate on: 2400 consecutive not-found cells
+    pr.bm[pr.node_positions[0]] = pr.bin_rows[0]
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim)
+
+
+# ---- reference quirks, hand-built tables ------------------------------------------------------------
+def _random_tables(rng, n, max_distinct=3, weird_flags=True):
+    """Arbitrary reference-format tables (not only what ruleMaker generates): random term counts, repeated
+    inputs, flags outside {0,1} (constant-TRUE literals, Q3), zero-input nodes (Q2)."""
+    class Net:
+        pass
+    net = Net()
+    net.n = n
+    net.and_len = np.zeros(n, np.int32)
+    net.parse = np.zeros(n + 1, np.int32)
+    net.and_nodes = np.zeros((n, 7, 3), np.int32)
+    net.and_inv = np.zeros((n, 7, 3), np.int32)
+    cnt = 0
+    for i in range(n):
+        net.parse[i] = cnt
+        kind = rng.integers(0, 10)
+        if kind == 0:
+            net.and_len[i] = 0
+            net.and_nodes[i, 0] = [rng.integers(0, n), 0, 0]
+        elif kind <= 2:
+            net.and_len[i] = 1
+            net.and_nodes[i, 0] = [rng.integers(0, n), -1, -1]
+            net.and_inv[i, 0] = [rng.choice([0, 1, 1, 0, 5, -1]) if weird_flags else rng.integers(0, 2), -1, -1]
+            cnt += 1
+        else:
+            nt = int(rng.integers(2, 8))
+            pool = rng.choice(n, size=min(n, max_distinct), replace=False)
+            net.and_len[i] = nt
+            for a in range(nt):
+                k = int(rng.integers(1, 4))
+                ins = list(rng.choice(pool, size=k)) + [-1] * (3 - k)
+                fl = [int(rng.choice([0, 1, 0, 1, 7, -3])) if weird_flags else int(rng.integers(0, 2)) for _ in range(k)] + [-1] * (3 - k)
+                net.and_nodes[i, a] = ins
+                net.and_inv[i, a] = fl
+            cnt += nt
+    net.parse[n] = cnt
+    net.ind_len = cnt
+    return net
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_arbitrary_tables(backend, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(3, 40))
+    net = _random_tables(rng, n)
+    cells = big(backend, 300, 3000)
+    pop = 4
+    rows = (rng.random((n, cells)) < 0.4).astype(np.uint8)
+    inds = rng.integers(0, 2, size=(pop, max(net.ind_len, 1))).astype(np.int32)[:, :net.ind_len]
+    for i in range(n):          # at least one selected term per multi-term node (Q9 contract)
+        s, e = net.parse[i], net.parse[i + 1]
+        if net.and_len[i] >= 2:
+            inds[:, s] |= (inds[:, s:e].sum(axis=1) == 0)
+    ko = (rng.random(n) < 0.1).astype(np.int32) * rng.choice([1, 2], size=n)      # 2 does not knock (Q5)
+    ki = (rng.random(n) < 0.1).astype(np.int32) * rng.choice([1, 3], size=n)
+    pr = Problem(net, rows, rng.permutation(n + 5)[:n].astype(np.int32), inds, ko=ko.astype(np.int32), ki=ki.astype(np.int32))
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim)
+
+
+def test_empty_rule_is_defined_as_zero_and_counted(backend):
+    """Q9: a multi-term node with no selected term reads uninitialised memory in the reference."""
+    rng = np.random.default_rng(5)
+    net = _random_tables(rng, 12, weird_flags=False)
+    rows = (rng.random((12, 100)) < 0.5).astype(np.uint8)
+    inds = np.zeros((2, net.ind_len), np.int32)
+    inds[1] = 1
+    pr = Problem(net, rows, np.arange(12, dtype=np.int32), inds)
+    with pr.simulator(backend[1]) as sim:
+        st = pr.check(sim)
+    assert st["empty_rule_nodes"] == int((net.and_len >= 2).sum())
+
+
+# ---- error behaviour ------------------------------------------------------------------------------------
+def test_more_than_three_distinct_inputs_is_refused(backend):
+    rng = np.random.default_rng(9)
+    net = _random_tables(rng, 12, max_distinct=5, weird_flags=False)
+    rows = (rng.random((12, 64)) < 0.5).astype(np.uint8)
+    inds = np.ones((1, net.ind_len), np.int32)
+    pr = Problem(net, rows, np.arange(12, dtype=np.int32), inds)
+    with pr.simulator(backend[1]) as sim:
+        with pytest.raises(simulator.ScbError) as ei:
+            sim.evaluate_population(pr.individuals)
+        assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
+def test_bad_input_index_is_refused(backend):
+    pr = Problem.synthetic(10, 64, 1)
+    pr.net.and_nodes = pr.net.and_nodes.copy()
+    i = int(np.argmax(pr.net.and_len >= 1))
+    pr.net.and_nodes[i, 0, 0] = 10
+    pr.pop_an = pr.pop_ai = None
+    with pr.simulator(backend[1]) as sim:
+        with pytest.raises(simulator.ScbError) as ei:
+            sim.evaluate_population(pr.individuals, pr.ko * 0, pr.ki * 0)
+        assert ei.value.code == _lib.ERR_INVALID
+
+
+def test_non_binary_matrix_is_refused(backend):
+    pr = Problem.synthetic(8, 64, 1)
+    bm = pr.bm.copy()
+    bm[pr.node_positions[3], 5] = 2
+    with pytest.raises(simulator.ScbError) as ei:
+        simulator.Simulator(bm, tables(pr.net, pr.node_positions), lib_path=backend[1])
+    assert ei.value.code == _lib.ERR_INVALID
+
+
+# ---- callers: local search, per-individual entry point, legacy symbol -------------------------------------
+def test_evaluate_by_node_mirrors_reference_returns(backend):
+    pr = Problem.synthetic(30, 400, 2, knock=True)
+    pr.pop_an = pr.pop_ai = None
+    o = pr.oracle()
+    with pr.simulator(backend[1]) as sim:
+        # KOlist = [0]*N used as indices -> node 0 knocked out and in (Q4)
+        assert sim.evaluate_by_node(pr.individuals[0].tolist(), [0] * pr.n, [0] * pr.n) == [int(o["fitness"][0])]
+        assert sim.evaluate_by_node(pr.individuals[1].tolist(), [0] * pr.n, [0] * pr.n, localSearch=True) == o["nodewise"][1].tolist()
+
+
+def test_check_node_possibilities(backend):
+    pr = Problem.synthetic(25, big(backend, 300, 4000), 1)
+    pr.pop_an = pr.pop_ai = None
+    m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+    with pr.simulator(backend[1]) as sim:
+        for node in range(pr.n):
+            start, end = int(pr.net.parse[node]), int(pr.net.parse[node + 1])
+            truth, equivs, minny, errs = sim.check_node_possibilities(node, pr.individuals[0].tolist(), [0] * pr.n, [0] * pr.n)
+            if end == start:
+                assert errs == 0.0
+                continue
+            want = []
+            for v in range(1, 2 ** (end - start)):
+                ind = pr.individuals[0].copy()
+                ind[start:end] = [(v >> j) & 1 for j in range(end - start)]          # ruleMaker.__bitList
+                e, _ = oracle.sync_bool(m, ind, pr.bm, pr.n_cells, 1)
+                want.append(int(e[node]))
+            assert errs == want
+            assert minny == min(want)
+            assert equivs == [[(v >> j) & 1 for j in range(end - start)] for v in range(1, 2 ** (end - start)) if want[v - 1] == min(want)]
+            assert truth == equivs[0]
+
+
+def test_legacy_scSyncBool_symbol(backend):
+    """The reference's own calling convention: 17 x c_void_p, ints smuggled as pointers (ruleMaker.py:1117-1219)."""
+    pr = Problem.synthetic(20, 150, 1)
+    lib = _lib.load(backend[1])
+    o = pr.oracle()
+    stride = 256
+    lib.scb_set_legacy_geometry(20000, stride)
+    bm = np.zeros((pr.bm.shape[0], stride), np.int32)
+    bm[:, :150] = pr.bm
+    V = ctypes.c_void_p
+    vals = np.zeros((100, 64), np.int32)
+    arr = [np.ascontiguousarray(a, np.int32) for a in (pr.individuals[0], pr.net.and_len, pr.net.parse, pr.pop_an[0],
+                                                       pr.pop_ai[0], pr.ko, pr.ki, pr.node_positions)]
+    ind, al, parse, an, ai, ko, ki, pos = arr
+    fn = lib.scSyncBool
+    fn.restype = None
+    fn.argtypes = None
+    for local, want in ((0, o["cellwise"][0]), (1, o["nodewise"][0])):
+        errors = np.full(max(pr.n, 150) + 3, 7 if local else -1, np.int32)
+        fn(V(vals.ctypes.data), V(ind.ctypes.data), V(len(ind)), V(pr.n), V(al.ctypes.data), V(parse.ctypes.data),
+           V(an.ctypes.data), V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data), V(150),
+           V(bm.ctypes.data), V(pos.ctypes.data), V(errors.ctypes.data), V(local), V(0))
+        if local:
+            assert np.array_equal(errors[:pr.n], want + 7)           # accumulates (simulator.c:477-479)
+            assert (errors[pr.n:] == 7).all()
+        else:
+            assert np.array_equal(errors[:150], want)                # assigns (simulator.c:481)
+            assert (errors[150:] == -1).all()
+    lib.scb_set_legacy_geometry(20000, 15000)
+
+
+# ---- attractor companion ----------------------------------------------------------------------------------
+def test_hamming_matches_oracle_and_reference_kat(backend):
+    g = np.load(os.path.join(GOLDEN, "hamming_kat.npz"))
+    n = g["attractors"].shape[1]
+    model = simulator.ModelTables(np.zeros(n), np.zeros(n + 1), np.zeros((n, 7, 3)), np.zeros((n, 7, 3)), g["node_positions"], 0)
+    with simulator.Simulator(g["bin_mat"], model, n_cells=int(g["n_cells"]), lib_path=backend[1]) as sim:
+        dist, dec, dd = sim.hamming_argmin(g["attractors"])
+    assert np.array_equal(dist, g["dist"])
+    assert np.array_equal(dec, g["decider"])
+    assert np.array_equal(dd, g["decider_distance"])
+
+
+@pytest.mark.parametrize("n,cells,A", [(47, 333, 7), (300, 1000, 40), (33, 64, 1)])
+def test_hamming_random(backend, n, cells, A):
+    rng = np.random.default_rng(n + A)
+    cells = big(backend, cells, cells * 20)
+    rows = (rng.random((n, cells)) < 0.3).astype(np.int32)
+    pos = rng.permutation(n).astype(np.int32)
+    bm = np.zeros((n, cells), np.int32)
+    bm[pos] = rows
+    attr = (rng.random((A, n)) < 0.4).astype(np.int32)
+    if A > 3:
+        attr[3] = attr[1]             # ties: first minimum wins (pandas idxmin)
+    model = simulator.ModelTables(np.zeros(n), np.zeros(n + 1), np.zeros((n, 7, 3)), np.zeros((n, 7, 3)), pos, 0)
+    with simulator.Simulator(bm, model, lib_path=backend[1]) as sim:
+        dist, dec, dd = sim.hamming_argmin(attr)
+    wd, wdec, wdd = oracle.hamming_argmin(attr, bm, pos, cells)
+    assert np.array_equal(dist, wd) and np.array_equal(dec, wdec) and np.array_equal(dd, wdd)
