@@ -90,6 +90,10 @@ struct scb_ctx {
     DevBuf<int32_t> dNodewise, dCellwise;
     DevBuf<unsigned int> dCounters;      /* [0] K2 work head, [1] resolve count, [2] K3 work head */
     DevBuf<uint2> dItems;
+    DevBuf<uint4> dFillItems;
+    DevBuf<int32_t> dChunkLast;
+    DevBuf<uint32_t> dResolveT;
+    unsigned resolveTCap = 0;
     DevBuf<uint32_t> dZ;
     DevBuf<ScbDiag> dDiag;
     DevBuf<uint32_t> dAttr;
@@ -139,6 +143,7 @@ int pick_geometry(scb_ctx *c)
     CK(cudaFuncSetAttribute(scb_k_sim<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_sim<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
 #endif
     int occ = 1;
@@ -151,7 +156,7 @@ int pick_geometry(scb_ctx *c)
     if (c->optMaxCtas > 0) ctas = std::min(ctas, c->optMaxCtas);
     c->ctas = ctas;
     int occR = 1;
-    c->resWarps = std::min(8, std::max(1, (N + 3) / 4));
+    c->resWarps = std::min(16, std::max(1, (N + 3) / 4));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve, c->resWarps * 32, c->smemRes));
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
@@ -224,7 +229,7 @@ int scb_ctx_create(scb_ctx **out, int device, int nodeNum, int lenSamples, const
     int rc;
     if ((rc = c->dX.ensure((size_t)c->N * c->Wpad))) return bail(rc);
     if ((rc = c->dDiag.ensure(1))) return bail(rc);
-    if ((rc = c->dCounters.ensure(4))) return bail(rc);
+    if ((rc = c->dCounters.ensure(8))) return bail(rc);
 
     /* stage the N gene rows the network uses (row i = gene nodePositions[i]) and pack them */
     const size_t rowBytes = (size_t)lenSamples * elemBytes;
@@ -270,7 +275,7 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
-    c->dItems.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
+    c->dItems.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
     if (c->evSim1) cudaEventDestroy(c->evSim1);
@@ -346,7 +351,14 @@ int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, co
     if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
     if ((rc = c->dFitness.ensure(P))) return rc;
     const size_t chunks = (size_t)c->Wpad / 32;
-    if ((rc = c->dItems.ensure((size_t)P * chunks))) return rc;
+    if ((rc = c->dItems.ensure((size_t)P * chunks)) || (rc = c->dFillItems.ensure((size_t)P * chunks)) ||
+        (rc = c->dChunkLast.ensure((size_t)P * chunks))) return rc;
+    {   /* S_99 hand-over slots for the resolver: at most 64 MiB */
+        const size_t per = (size_t)N * 32;
+        const size_t want = std::min<size_t>((size_t)P * chunks, std::max<size_t>(64, ((size_t)64 << 20) / (per * 4)));
+        if ((rc = c->dResolveT.ensure(want * per))) return rc;
+        c->resolveTCap = (unsigned)(c->dResolveT.cap / per);
+    }
     cudaStream_t st = c->stream;
     if (indLen > 0) CK(cudaMemcpyAsync(c->dInd.p, individuals, (size_t)P * indLen * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dAndLen.p, andLenList, (size_t)N * 4, cudaMemcpyHostToDevice, st));
@@ -375,7 +387,7 @@ int scb_pop_run(scb_ctx *c, int mode)
     CK(cudaEventRecord(c->evRun0, st));
     CK(cudaMemsetAsync(c->dFitness.p, 0, (size_t)P * 8, st));
     if (mode == SCB_MODE_NODEWISE) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
-    CK(cudaMemsetAsync(c->dCounters.p, 0, 4 * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(c->dCounters.p, 0, 8 * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
 
     ScbCompileArgs ca;
@@ -395,6 +407,9 @@ int scb_pop_run(scb_ctx *c, int mode)
     sa.fitness = c->dFitness.p; sa.nodewise = c->dNodewise.p; sa.cellwise = c->dCellwise.p;
     sa.workCounter = c->dCounters.p; sa.resolveCount = c->dCounters.p + 1;
     sa.resolveItems = c->dItems.p; sa.resolveCap = (unsigned)std::min<size_t>(c->dItems.cap, 0xffffffffu);
+    sa.resolveT = c->dResolveT.p; sa.resolveTCap = c->resolveTCap;
+    sa.chunkLast = c->dChunkLast.p; sa.chunksPerInd = (c->C + 1023) / 1024;
+    sa.fillCount = c->dCounters.p + 3; sa.fillItems = c->dFillItems.p;
     sa.zscratch = c->dZ.p; sa.zstride = (unsigned long long)N * WT;
     sa.flags = (c->optEarly ? SCB_KF_EARLY : 0u) | (c->optSnap ? SCB_KF_SNAP : 0u);
     sa.chkEvery = c->optChk; sa.snapLo = c->snapLo; sa.snapHi = c->snapHi; sa.periodSearch = c->optSearch;
@@ -412,6 +427,9 @@ int scb_pop_run(scb_ctx *c, int mode)
     ScbResolveArgs ra;
     ra.s = sa; ra.itemCursor = c->dCounters.p + 2;
     SCB_LAUNCH(scb_k_resolve, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+    CK(cudaGetLastError());
+    ra.itemCursor = c->dCounters.p + 4;
+    SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->evRun1, st));
     c->lastMode = mode; c->ran = true;

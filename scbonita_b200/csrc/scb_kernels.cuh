@@ -479,14 +479,34 @@ __global__ void scb_k_sim(ScbSimArgs A)
             if (lane < K) {
                 const unsigned msk = (LPC == 32) ? 0xffffffffu : (((1u << LPC) - 1u) << (lane * LPC));
                 const int cb = (bal & msk) != 0u;
+                const int q = tile * K + lane;                 /* chunk index within the individual */
                 sh[4 + lane] = cb;
+                sh[8 + lane] = -1;
                 if (cb) {
                     const unsigned idx = atomicAdd(A.resolveCount, 1u);
-                    if (idx < A.resolveCap) A.resolveItems[idx] = make_uint2((unsigned)p, (unsigned)(tile * K + lane));
+                    if (idx < A.resolveCap) A.resolveItems[idx] = make_uint2((unsigned)p, (unsigned)q);
+                    if (idx < A.resolveTCap) sh[8 + lane] = (int)idx;
+                } else if (q < A.chunksPerInd) {
+                    /* every valid cell of the chunk is found: its last valid cell can feed a later fill-forward */
+                    const long long rem = (long long)A.C - (long long)q * 1024;
+                    A.chunkLast[(long long)p * A.chunksPerInd + q] = (int)(rem >= 1024 ? 1023 : rem - 1);
                 }
             }
         }
         __syncthreads();
+        /* hand S_99 of the queued chunks to the resolver (t == 99 here, so src holds S_99) */
+        if (!allfound) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int w = lane * K + k, j = w / 32;
+                const int slot = sh[8 + j];
+                if (slot < 0) continue;
+                uint32_t *T = A.resolveT + (unsigned long long)slot * N * 32 + (w & 31);
+                for (int row = warp; row < N; row += S)
+                    T[(long long)row * 32] = *reinterpret_cast<const uint32_t *>(sm + srcOff + (uint32_t)row * ROWB + (uint32_t)w * 4u);
+            }
+            __syncthreads();          /* the cellwise epilogue reuses the S_99 buffer */
+        }
 
         /* ---- errors: e = S_98 xor S_0 on valid cells of proven chunks ---------------------- */
         ScbVec<K> ok;
@@ -546,14 +566,18 @@ __global__ void scb_k_sim(ScbSimArgs A)
  * ---------------------------------------------------------------------------------------- */
 struct ScbResolveArgs {
     ScbSimArgs s;
-    unsigned int *itemCursor;     /* persistent work counter for K3 */
+    unsigned int *itemCursor;     /* persistent work counter of the launch */
 };
 
-/* simulate chunk q of individual p exactly.  On return: buffer A rows hold S_98, buffer B rows
- * hold e = S_98 xor S_0 (all nodes), Fm[32] = found & valid per word.  All threads call it. */
+/* simulate chunk q of the individual whose program is in `desc`.
+ *   how = 0: pass a (99 plain steps -> T = S_99), then pass b (98 steps comparing every S_j with T)
+ *   how = 1: T is read from Tglob ([N][32] words, written by K2), pass b only
+ *   how = 2: 98 plain steps only (Fm is not computed)
+ * On return: buffer A rows hold S_98, buffer B rows hold e = (S_98 xor S_0) & valid for every node,
+ * Fm[32] = found & valid per word (how != 2), vm[32] = valid masks.  All threads call it. */
 SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uint4 *desc, int4 cnt,
-                               uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q,
-                               int tid, int nthr)
+                               uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
+                               const uint32_t *Tglob, int tid, int nthr)
 {
     const int N = A.N;
     const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
@@ -563,14 +587,20 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
     unsigned char *bufA = sm, *bufB = sm + BUFB, *bufT = sm + 2u * BUFB;
     ScbVec<1> d2, dz;
 
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = (how == 0 ? 0 : 1); pass < 2; ++pass) {
+        const bool cmp = pass == 1 && how != 2;
         for (int row = warp; row < N; row += S) {
             const ScbVec<1> v = scb_ldg<1>(A.X + (long long)row * A.Wpad + w0 + lane);
             scb_st<1>(bufA + (uint32_t)row * ROWB + laneOff, v);
+            if (pass == 1 && how == 1) {
+                ScbVec<1> tv;
+                tv.v[0] = Tglob[(long long)row * 32 + lane];
+                scb_st<1>(bufT + (uint32_t)row * ROWB + laneOff, tv);
+            }
         }
-        if (tid < 32) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; if (pass == 0) Fm[tid] = 0u; }
+        if (tid < 32) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; Fm[tid] = 0u; }
         __syncthreads();
-        if (pass == 1) {
+        if (cmp) {
             /* j = 0: compare S_0 with T on every row */
             uint32_t d = 0u;
             for (int row = warp; row < N; row += S)
@@ -584,12 +614,12 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
         uint32_t srcOff = 0u, dstOff = BUFB;
         for (int tn = 1; tn <= last; ++tn) {
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
-            if (pass == 1) f |= SCB_SF_TCMP;
+            if (cmp) f |= SCB_SF_TCMP;
             d2.v[0] = 0u; dz.v[0] = 0u;
             scb_step<1>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, nullptr, bufT + laneOff, d2, dz);
-            if (pass == 1 && dz.v[0]) atomicOr(&dmz[lane], dz.v[0]);
+            if (cmp && dz.v[0]) atomicOr(&dmz[lane], dz.v[0]);
             __syncthreads();
-            if (pass == 1) {
+            if (cmp) {
                 if (tid < 32) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
                 __syncthreads();
             }
@@ -613,6 +643,8 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
     __syncthreads();
 }
 
+/* K3 phase 1: exact found mask and error sums of every queued chunk; leading not-found cells that must
+ * copy a cell of an earlier chunk are queued for phase 2. */
 __global__ void scb_k_resolve(ScbResolveArgs R)
 {
     SCB_DYN_SMEM(smraw);
@@ -624,10 +656,8 @@ __global__ void scb_k_resolve(ScbResolveArgs R)
     uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
     uint32_t *Fm = dmz + 32;
     uint32_t *vm = Fm + 32;
-    uint32_t *F0 = vm + 32;                                /* found & valid of the item's own chunk */
-    uint32_t *V0 = F0 + 32;                                /* valid mask of the item's own chunk    */
-    int *sh = reinterpret_cast<int *>(V0 + 32);            /* [0] item, [2] pending cells, [3] look-back value */
-    int *srcc = sh + 8;                                    /* [1024] source cell of each cell       */
+    int *sh = reinterpret_cast<int *>(vm + 32 + 64);       /* [0] item, [2] pending cells, [3] not-found cells */
+    int *srcc = sh + 8;                                    /* [1024] source cell of each cell */
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
     const unsigned char *bufB = sm + BUFB;
@@ -642,33 +672,31 @@ __global__ void scb_k_resolve(ScbResolveArgs R)
         const int p = (int)A.resolveItems[it].x, q = (int)A.resolveItems[it].y;
         const int4 cnt = A.counts[p];
         scb_load_program<1>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+        if (tid == 0) { sh[2] = 0; sh[3] = 0; }
         __syncthreads();
-        scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, q, tid, nthr);
-        if (tid < 32) { F0[tid] = Fm[tid]; V0[tid] = vm[tid]; }
-        if (tid == 0) sh[2] = 0;
-        __syncthreads();
+        const bool haveT = it < A.resolveTCap;
+        scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, q, haveT ? 1 : 0,
+                          A.resolveT + (unsigned long long)it * N * 32, tid, nthr);
 
-        /* source cell of every cell: itself when found, else the nearest earlier found cell of
-         * the chunk (fill-forward), -1 when that lies in an earlier chunk, -2 for padding */
-        unsigned nfHere = 0;
+        /* source cell of every cell: itself when found, else the nearest earlier found cell of the chunk
+         * (the reference's fill-forward), -1 when that lies in an earlier chunk, -2 padding */
         for (int i = tid; i < 1024; i += nthr) {
             const int w = i >> 5, b = i & 31;
             int s = -2;
-            if ((V0[w] >> b) & 1u) {
-                if ((F0[w] >> b) & 1u) s = i;
+            if ((vm[w] >> b) & 1u) {
+                if ((Fm[w] >> b) & 1u) s = i;
                 else {
-                    ++nfHere;
                     s = -1;
-                    const uint32_t m = F0[w] & ((1u << b) - 1u);
+                    const uint32_t m = Fm[w] & ((1u << b) - 1u);
                     if (m) s = w * 32 + (31 - __clz((int)m));
                     else for (int ww = w - 1; ww >= 0; --ww)
-                        if (F0[ww]) { s = ww * 32 + (31 - __clz((int)F0[ww])); break; }
+                        if (Fm[ww]) { s = ww * 32 + (31 - __clz((int)Fm[ww])); break; }
+                    atomicAdd(reinterpret_cast<unsigned int *>(&sh[3]), 1u);
                     if (s == -1) atomicAdd(reinterpret_cast<unsigned int *>(&sh[2]), 1u);
                 }
             }
             srcc[i] = s;
         }
-        if (nfHere) atomicAdd(&A.diag->not_found_cells, (unsigned long long)nfHere);
         __syncthreads();
 
         /* per-node sums: found cells plus the copies made by not-found cells */
@@ -677,8 +705,8 @@ __global__ void scb_k_resolve(ScbResolveArgs R)
             const uint32_t dsto = desc[j].w & 0xFFFFFFu;
             const int node = (int)(dsto / ROWB);
             const uint32_t e = *reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)lane * 4u);
-            unsigned c = (unsigned)__popc(e & F0[lane]);
-            uint32_t nfb = ~F0[lane] & V0[lane];
+            unsigned c = (unsigned)__popc(e & Fm[lane]);
+            uint32_t nfb = ~Fm[lane] & vm[lane];
             while (nfb) {
                 const int b = __ffs((int)nfb) - 1;
                 nfb &= nfb - 1u;
@@ -703,42 +731,82 @@ __global__ void scb_k_resolve(ScbResolveArgs R)
                 A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
             }
         }
-        __syncthreads();
-
-        /* leading not-found cells: copy the last found cell of an earlier chunk */
-        const int pend = sh[2];
-        if (pend > 0) {
-            int qq = q - 1, sw = -1, sb = -1;
-            for (; qq >= 0; --qq) {
-                scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, qq, tid, nthr);
-                for (int w = 31; w >= 0; --w) if (Fm[w]) { sw = w; sb = 31 - __clz((int)Fm[w]); break; }
-                if (sw >= 0) break;
-                __syncthreads();
+        if (tid == 0) {
+            int lastFound = -1;
+            for (int w = 31; w >= 0; --w) if (Fm[w]) { lastFound = w * 32 + (31 - __clz((int)Fm[w])); break; }
+            A.chunkLast[(long long)p * A.chunksPerInd + q] = lastFound;
+            if (sh[2] > 0) {
+                const unsigned idx = atomicAdd(A.fillCount, 1u);
+                A.fillItems[idx] = make_uint4((unsigned)p, (unsigned)q, (unsigned)sh[2], 0u);
             }
-            int n1 = 0;
-            if (sw >= 0) {
-                unsigned add = 0;
-                for (int j = warp; j < N; j += S) {
-                    const uint32_t dsto = desc[j].w & 0xFFFFFFu;
-                    const int node = (int)(dsto / ROWB);
-                    const unsigned bit = (*reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)sw * 4u) >> sb) & 1u;
-                    if (lane == 0 && bit) {
-                        add += (unsigned)pend;
-                        if (A.mode == 1) atomicAdd(&A.nodewise[(long long)p * N + node], pend);
-                    }
-                }
-                if (lane == 0 && add) atomicAdd(&A.fitness[p], (unsigned long long)add);
-                if (A.mode == 2)
-                    for (int row = 0; row < N; ++row)
-                        n1 += (int)((*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + (uint32_t)sw * 4u) >> sb) & 1u);
-            } else if (tid == 0) {
-                atomicAdd(&A.diag->undefined_leading, (unsigned long long)pend);
-            }
-            if (A.mode == 2)
-                for (int i = tid; i < 1024; i += nthr)
-                    if (srcc[i] == -1) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
+            if (sh[3] > 0) atomicAdd(&A.diag->not_found_cells, (unsigned long long)sh[3]);
+            atomicAdd(&A.diag->resolver_chunks, 1ull);
         }
-        if (tid == 0) atomicAdd(&A.diag->resolver_chunks, 1ull);
+        __syncthreads();
+    }
+}
+
+/* K3 phase 2: chunks that start with not-found cells copy the last found cell of the nearest earlier
+ * chunk that has one (chunkLast, complete after phase 1); its error column is recomputed with 98 plain
+ * steps.  No earlier found cell at all: the reference's value is uninitialised memory -> defined as 0. */
+__global__ void scb_k_fill(ScbResolveArgs R)
+{
+    SCB_DYN_SMEM(smraw);
+    const ScbSimArgs &A = R.s;
+    const int N = A.N;
+    const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
+    unsigned char *sm = smraw;
+    uint4 *desc = reinterpret_cast<uint4 *>(smraw + 3u * BUFB);
+    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
+    uint32_t *Fm = dmz + 32;
+    uint32_t *vm = Fm + 32;
+    int *sh = reinterpret_cast<int *>(vm + 32 + 64);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    const unsigned char *bufB = sm + BUFB;
+    const unsigned nItems = *A.fillCount;
+
+    for (;;) {
+        if (tid == 0) sh[0] = (int)atomicAdd(R.itemCursor, 1u);
+        __syncthreads();
+        const unsigned it = (unsigned)sh[0];
+        if (it >= nItems) break;
+        const int p = (int)A.fillItems[it].x, q = (int)A.fillItems[it].y, pend = (int)A.fillItems[it].z;
+        int qq = q - 1, cell = -1;
+        for (; qq >= 0; --qq) {
+            cell = A.chunkLast[(long long)p * A.chunksPerInd + qq];
+            if (cell >= 0) break;
+        }
+        if (qq < 0) {
+            if (tid == 0) atomicAdd(&A.diag->undefined_leading, (unsigned long long)pend);
+            if (A.mode == 2)
+                for (int i = tid; i < pend; i += nthr) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = 0;
+            __syncthreads();
+            continue;
+        }
+        const int4 cnt = A.counts[p];
+        scb_load_program<1>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+        __syncthreads();
+        scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, qq, 2, nullptr, tid, nthr);
+        const int sw = cell >> 5, sb = cell & 31;
+        unsigned add = 0;
+        for (int j = warp; j < N; j += S) {
+            const uint32_t dsto = desc[j].w & 0xFFFFFFu;
+            const int node = (int)(dsto / ROWB);
+            const unsigned bit = (*reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)sw * 4u) >> sb) & 1u;
+            if (lane == 0 && bit) {
+                add += (unsigned)pend;
+                if (A.mode == 1) atomicAdd(&A.nodewise[(long long)p * N + node], pend);
+            }
+        }
+        if (lane == 0 && add) atomicAdd(&A.fitness[p], (unsigned long long)add);
+        if (A.mode == 2) {
+            int n1 = 0;
+            for (int row = 0; row < N; ++row)
+                n1 += (int)((*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + (uint32_t)sw * 4u) >> sb) & 1u);
+            /* the pending cells are the first `pend` valid cells of chunk q */
+            for (int i = tid; i < pend; i += nthr) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
+        }
         __syncthreads();
     }
 }

@@ -96,6 +96,12 @@ struct ScbSimArgs {
     unsigned int *resolveCount;   /* number of chunks queued for the exact resolver */
     uint2 *resolveItems;          /* (individual, chunk) */
     unsigned int resolveCap;
+    uint32_t *resolveT;           /* S_99 of queued chunks: [resolveTCap][N][32] words (saves K3 a pass) */
+    unsigned int resolveTCap;
+    int32_t *chunkLast;           /* [P][chunksPerInd]: last found valid cell of each chunk, -1 none */
+    int chunksPerInd;
+    unsigned int *fillCount;      /* chunks whose leading not-found cells copy an earlier chunk's cell */
+    uint4 *fillItems;             /* (individual, chunk, pending cells, first pending-free cell) */
     uint32_t *zscratch;           /* snapshot scratch, zstride words per CTA */
     unsigned long long zstride;
     unsigned int flags;           /* SCB_KF_* */
