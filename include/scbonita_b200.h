@@ -62,6 +62,8 @@ extern "C" {
 #define SCB_OPT_WORDS        5  /* 32-bit words per lane (0 = auto: 4, 2 or 1 by node count)          */
 #define SCB_OPT_CHECK_EVERY  6  /* period-<=2 check cadence in steps (default 4)                      */
 #define SCB_OPT_PERIOD_SEARCH 7 /* extra snapshot-compare steps spent looking for a tile-wide period  */
+#define SCB_OPT_SNAP_LO      8  /* bit t (t < 64): take a snapshot when computing S_t                 */
+#define SCB_OPT_SNAP_HI      9  /* bit t-64 for steps 64..98 (default: snapshots at 32 and 64)        */
 
 typedef struct scb_ctx scb_ctx;
 

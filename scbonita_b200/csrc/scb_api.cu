@@ -75,7 +75,7 @@ struct scb_ctx {
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
     int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 4, optSearch = 0;
-    unsigned long long snapLo = (1ull << 16) | (1ull << 32), snapHi = 1ull;   /* steps 16, 32, 64 */
+    unsigned long long snapLo = (1ull << 32), snapHi = 1ull;   /* snapshots when computing S_32 and S_64 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
     size_t smemSim = 0, smemRes = 0;
@@ -132,11 +132,11 @@ int pick_geometry(scb_ctx *c)
     int S = c->optWarps;
     if (S == 0) {
         S = 32 / occGuess;
-        S = std::min(16, std::max(2, S));
+        S = std::min(24, std::max(2, S));
         S = std::min(S, std::max(1, (N + 3) / 4));
     }
     S = std::max(S, K);                 /* the mask arrays need 32*K threads */
-    S = std::min(S, 32);
+    S = std::min(S, 24);                /* __launch_bounds__(768) */
     c->warps = S;
 #ifndef SCB_EMU
     CK(cudaFuncSetAttribute(scb_k_sim<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
@@ -301,8 +301,10 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
         case SCB_OPT_PERIOD_SEARCH:
             if (value < 0 || value > 99) return fail(SCB_ERR_INVALID, "period search must be in [0,99]");
             c->optSearch = (int)value; return SCB_OK;
+        case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
+        case SCB_OPT_SNAP_HI: c->snapHi = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_WARPS:
-            if (value < 0 || value > 32) return fail(SCB_ERR_INVALID, "warps must be in [0,32]");
+            if (value < 0 || value > 24) return fail(SCB_ERR_INVALID, "warps must be in [0,24]");
             c->optWarps = (int)value; break;
         case SCB_OPT_MAX_CTAS:
             if (value < 0) return fail(SCB_ERR_INVALID, "max CTAs must be >= 0");
@@ -395,7 +397,10 @@ int scb_pop_run(scb_ctx *c, int mode)
     ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
     ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = c->dKo.p; ca.ki = c->dKi.p;
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
-    SCB_LAUNCH(scb_k_compile, dim3((unsigned)((P + 3) / 4)), dim3(128), 0, st, ca);
+    {
+        const int cthr = std::min(256, ((N + 31) / 32) * 32);
+        SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), st, ca);
+    }
     CK(cudaGetLastError());
 
     ScbSimArgs sa;

@@ -93,42 +93,14 @@ SCB_DEV unsigned scb_warp_sum(unsigned v)
     return v;
 }
 
-/* ---- truth-table application: one LOP3 per word with the table as an immediate ---------- */
+/* ---- truth-table application: one LOP3 per word with the table as an immediate ----------
+ * The table is per-node runtime data, LOP3's table is an immediate.  A C++ switch over the 256
+ * tables compiles to a 7-deep compare/branch tree; the generated inline PTX (scb_lut_ptx.inc)
+ * uses brx.idx instead, which ptxas lowers to one LDC (jump table in the constant bank) + BRX. */
 #if defined(__CUDA_ARCH__)
-template <int LUT> SCB_DEV uint32_t scb_lop3(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
-    return r;
-}
-template <int K, int LUT> SCB_DEV void scb_lop3v(ScbVec<K> &r, const ScbVec<K> &a, const ScbVec<K> &b, const ScbVec<K> &c)
-{
-#pragma unroll
-    for (int k = 0; k < K; ++k) r.v[k] = scb_lop3<LUT>(a.v[k], b.v[k], c.v[k]);
-}
-#define SCB_C1(L) case (L): scb_lop3v<K, (L)>(r, a, b, c); break;
-#define SCB_C4(L) SCB_C1(L) SCB_C1((L) + 1) SCB_C1((L) + 2) SCB_C1((L) + 3)
-#define SCB_C16(L) SCB_C4(L) SCB_C4((L) + 4) SCB_C4((L) + 8) SCB_C4((L) + 12)
-#define SCB_C64(L) SCB_C16(L) SCB_C16((L) + 16) SCB_C16((L) + 32) SCB_C16((L) + 48)
+#include "scb_lut_ptx.inc"
 #endif
 
-/* three-input node: any of the 256 tables */
-template <int K> SCB_DEV ScbVec<K> scb_apply3(unsigned lut, const ScbVec<K> &a, const ScbVec<K> &b, const ScbVec<K> &c)
-{
-    ScbVec<K> r;
-#if defined(__CUDA_ARCH__)
-    switch (lut) {
-        SCB_C64(0) SCB_C64(64) SCB_C64(128) SCB_C64(192)
-        default:
-#pragma unroll
-            for (int k = 0; k < K; ++k) r.v[k] = 0;
-    }
-#else
-    for (int k = 0; k < K; ++k) r.v[k] = scb_lut_apply(lut, a.v[k], b.v[k], c.v[k]);
-#endif
-    return r;
-}
-/* two-input node: lut4 bit (x0<<1)|x1 */
 SCB_HD inline unsigned scb_expand2(unsigned l4)
 {
     return ((l4 & 1u) ? 0x03u : 0u) | ((l4 & 2u) ? 0x0Cu : 0u) | ((l4 & 4u) ? 0x30u : 0u) | ((l4 & 8u) ? 0xC0u : 0u);
@@ -137,22 +109,39 @@ SCB_HD inline unsigned scb_compress2(unsigned l8)
 {
     return ((l8 >> 0) & 1u) | (((l8 >> 2) & 1u) << 1) | (((l8 >> 4) & 1u) << 2) | (((l8 >> 6) & 1u) << 3);
 }
+
+/* three-input node: any of the 256 tables (lut8, lop3 convention) */
+template <int K> SCB_DEV ScbVec<K> scb_apply3(unsigned lut, const ScbVec<K> &a, const ScbVec<K> &b, const ScbVec<K> &c)
+{
+    ScbVec<K> r;
+#if defined(__CUDA_ARCH__)
+    if (K == 4)
+        asm(SCB_LUT3_PTX_K4 : "=r"(r.v[0]), "=r"(r.v[1 % K]), "=r"(r.v[2 % K]), "=r"(r.v[3 % K])
+            : "r"(a.v[0]), "r"(a.v[1 % K]), "r"(a.v[2 % K]), "r"(a.v[3 % K]), "r"(b.v[0]), "r"(b.v[1 % K]), "r"(b.v[2 % K]),
+              "r"(b.v[3 % K]), "r"(c.v[0]), "r"(c.v[1 % K]), "r"(c.v[2 % K]), "r"(c.v[3 % K]), "r"(lut));
+    else if (K == 2)
+        asm(SCB_LUT3_PTX_K2 : "=r"(r.v[0]), "=r"(r.v[1 % K])
+            : "r"(a.v[0]), "r"(a.v[1 % K]), "r"(b.v[0]), "r"(b.v[1 % K]), "r"(c.v[0]), "r"(c.v[1 % K]), "r"(lut));
+    else
+        asm(SCB_LUT3_PTX_K1 : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]), "r"(c.v[0]), "r"(lut));
+#else
+    for (int k = 0; k < K; ++k) r.v[k] = scb_lut_apply(lut, a.v[k], b.v[k], c.v[k]);
+#endif
+    return r;
+}
+/* two-input node: lut4 bit (x0<<1)|x1 */
 template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, const ScbVec<K> &b)
 {
     ScbVec<K> r;
 #if defined(__CUDA_ARCH__)
-    const ScbVec<K> &c = b;
-    switch (l4) {
-        SCB_C1(0x00) case 1: scb_lop3v<K, 0x03>(r, a, b, c); break;
-        case 2: scb_lop3v<K, 0x0C>(r, a, b, c); break;  case 3: scb_lop3v<K, 0x0F>(r, a, b, c); break;
-        case 4: scb_lop3v<K, 0x30>(r, a, b, c); break;  case 5: scb_lop3v<K, 0x33>(r, a, b, c); break;
-        case 6: scb_lop3v<K, 0x3C>(r, a, b, c); break;  case 7: scb_lop3v<K, 0x3F>(r, a, b, c); break;
-        case 8: scb_lop3v<K, 0xC0>(r, a, b, c); break;  case 9: scb_lop3v<K, 0xC3>(r, a, b, c); break;
-        case 10: scb_lop3v<K, 0xCC>(r, a, b, c); break; case 11: scb_lop3v<K, 0xCF>(r, a, b, c); break;
-        case 12: scb_lop3v<K, 0xF0>(r, a, b, c); break; case 13: scb_lop3v<K, 0xF3>(r, a, b, c); break;
-        case 14: scb_lop3v<K, 0xFC>(r, a, b, c); break;
-        default: scb_lop3v<K, 0xFF>(r, a, b, c); break;
-    }
+    if (K == 4)
+        asm(SCB_LUT2_PTX_K4 : "=r"(r.v[0]), "=r"(r.v[1 % K]), "=r"(r.v[2 % K]), "=r"(r.v[3 % K])
+            : "r"(a.v[0]), "r"(a.v[1 % K]), "r"(a.v[2 % K]), "r"(a.v[3 % K]), "r"(b.v[0]), "r"(b.v[1 % K]), "r"(b.v[2 % K]),
+              "r"(b.v[3 % K]), "r"(l4));
+    else if (K == 2)
+        asm(SCB_LUT2_PTX_K2 : "=r"(r.v[0]), "=r"(r.v[1 % K]) : "r"(a.v[0]), "r"(a.v[1 % K]), "r"(b.v[0]), "r"(b.v[1 % K]), "r"(l4));
+    else
+        asm(SCB_LUT2_PTX_K1 : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]), "r"(l4));
 #else
     for (int k = 0; k < K; ++k) r.v[k] = scb_lut_apply(scb_expand2(l4), a.v[k], b.v[k], b.v[k]);
 #endif
@@ -160,67 +149,50 @@ template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, c
 }
 
 /* ------------------------------------------------------------------------------------------
- * K0: rule compiler.  One warp per individual; two passes (count, then stable scatter by
- * arity) so that the program order is deterministic.
+ * K0: rule compiler.  One CTA per individual, one thread per node; the program is written sorted
+ * by arity (stable in node order, so the layout is deterministic).
+ * dynamic shared memory: N * 16 (descriptors) + N (arity) + 64
  * ---------------------------------------------------------------------------------------- */
+SCB_HD inline size_t scb_compile_smem_bytes(int N) { return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64; }
+
 __global__ void scb_k_compile(ScbCompileArgs A)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (p >= A.P) return;
-    const int N = A.N;
+    SCB_DYN_SMEM(smraw);
+    const int N = A.N, p = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    uint4 *sd = reinterpret_cast<uint4 *>(smraw);
+    unsigned int *cn = reinterpret_cast<unsigned int *>(sd + N);          /* [0..3] class counts, [4..7] flag counts */
+    unsigned char *sar = reinterpret_cast<unsigned char *>(cn + 8);
     const int32_t *ind = A.individuals + (long long)p * A.indLen;
     const long long toff = A.tablesPerIndividual ? (long long)p * N * (SCB_MAX_TERMS * SCB_MAX_IN) : 0;
     const int32_t *an = A.an + toff, *ai = A.ai + toff;
-    const unsigned lt = (1u << lane) - 1u;
-
-    int c3 = 0, c2 = 0, c1 = 0, c0 = 0;
-    unsigned nUns = 0, nEmp = 0, nBad = 0, nTerm = 0;
-    for (int base = 0; base < N; base += 32) {
-        const int i = base + lane;
-        int ar = -1; unsigned fl = 0;
-        if (i < N) {
-            ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki);
-            ar = f.arity; fl = f.flags;
-        }
-        c3 += __popc(__ballot_sync(0xffffffffu, ar == 3));
-        c2 += __popc(__ballot_sync(0xffffffffu, ar == 2));
-        c1 += __popc(__ballot_sync(0xffffffffu, ar == 1));
-        c0 += __popc(__ballot_sync(0xffffffffu, ar == 0));
-        nUns += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_UNSUPPORTED) != 0));
-        nEmp += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_EMPTY) != 0));
-        nBad += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_BADIDX) != 0));
-        nTerm += __popc(__ballot_sync(0xffffffffu, (fl & SCB_NF_TERMS) != 0));
+    if (tid < 8) cn[tid] = 0u;
+    __syncthreads();
+    for (int i = tid; i < N; i += nthr) {
+        const ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki);
+        sd[i] = make_uint4((unsigned)f.in[0], (unsigned)f.in[1], (unsigned)f.in[2], (unsigned)i | (f.lut << 24));
+        sar[i] = (unsigned char)f.arity;
+        atomicAdd(&cn[3 - f.arity], 1u);
+        if (f.flags & SCB_NF_UNSUPPORTED) atomicAdd(&cn[4], 1u);
+        if (f.flags & SCB_NF_EMPTY) atomicAdd(&cn[5], 1u);
+        if (f.flags & SCB_NF_BADIDX) atomicAdd(&cn[6], 1u);
+        if (f.flags & SCB_NF_TERMS) atomicAdd(&cn[7], 1u);
     }
-    int o3 = 0, o2 = c3, o1 = c3 + c2, o0 = c3 + c2 + c1;
+    __syncthreads();
+    const int c3 = (int)cn[0], c2 = (int)cn[1], c1 = (int)cn[2], c0 = (int)cn[3];
     uint4 *out = A.descs + (long long)p * A.Npad;
-    for (int base = 0; base < N; base += 32) {
-        const int i = base + lane;
-        int ar = -1;
-        ScbNodeFn f = scb_const_fn(0, 0);
-        if (i < N) {
-            f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki);
-            ar = f.arity;
-        }
-        const unsigned b3 = __ballot_sync(0xffffffffu, ar == 3);
-        const unsigned b2 = __ballot_sync(0xffffffffu, ar == 2);
-        const unsigned b1 = __ballot_sync(0xffffffffu, ar == 1);
-        const unsigned b0 = __ballot_sync(0xffffffffu, ar == 0);
-        int pos = -1;
-        if (ar == 3) pos = o3 + __popc(b3 & lt);
-        else if (ar == 2) pos = o2 + __popc(b2 & lt);
-        else if (ar == 1) pos = o1 + __popc(b1 & lt);
-        else if (ar == 0) pos = o0 + __popc(b0 & lt);
-        if (pos >= 0)
-            out[pos] = make_uint4((unsigned)f.in[0], (unsigned)f.in[1], (unsigned)f.in[2], (unsigned)i | (f.lut << 24));
-        o3 += __popc(b3); o2 += __popc(b2); o1 += __popc(b1); o0 += __popc(b0);
+    for (int i = tid; i < N; i += nthr) {
+        const int ar = sar[i];
+        int before = 0;
+        for (int j = 0; j < i; ++j) before += (sar[j] == ar);
+        const int off = ar == 3 ? 0 : ar == 2 ? c3 : ar == 1 ? c3 + c2 : c3 + c2 + c1;
+        out[off + before] = sd[i];
     }
-    if (lane == 0) {
+    if (tid == 0) {
         A.counts[p] = make_int4(c3, c2, c1, c0);
-        if (nUns) atomicAdd(&A.diag->unsupported_nodes, (unsigned long long)nUns);
-        if (nEmp) atomicAdd(&A.diag->empty_rule_nodes, (unsigned long long)nEmp);
-        if (nBad) atomicAdd(&A.diag->bad_index_nodes, (unsigned long long)nBad);
-        if (nTerm) atomicAdd(&A.diag->term_overflow_nodes, (unsigned long long)nTerm);
+        if (cn[4]) atomicAdd(&A.diag->unsupported_nodes, (unsigned long long)cn[4]);
+        if (cn[5]) atomicAdd(&A.diag->empty_rule_nodes, (unsigned long long)cn[5]);
+        if (cn[6]) atomicAdd(&A.diag->bad_index_nodes, (unsigned long long)cn[6]);
+        if (cn[7]) atomicAdd(&A.diag->term_overflow_nodes, (unsigned long long)cn[7]);
     }
 }
 
@@ -282,56 +254,79 @@ SCB_DEV void scb_load_program(uint4 *desc, const uint4 *g, int4 cnt, int N, int 
  *   zg       : lane-adjusted pointer into the global snapshot (ZCMP / ZSNAP)
  *   tsm      : lane-adjusted pointer into the shared-memory target state (TCMP)
  * d2 / dz accumulate, per word, the cells whose new state differs from S_{t-1} ... */
-template <int K>
+template <int K, bool PLAIN>
 SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 *desc, int4 cnt,
-                      int warp, int S, unsigned flags, unsigned char *zg, const unsigned char *tsm,
+                      int warp, int S, unsigned flagsRt, unsigned char *zg, const unsigned char *tsm,
                       ScbVec<K> &d2, ScbVec<K> &dz)
 {
+    /* PLAIN steps (no compare, no snapshot, no constant rows: the majority) are a separate
+     * instantiation so that their loop carries no flag tests */
+    const unsigned flags = PLAIN ? 0u : flagsRt;
+    /* SCB_PRE issues the loads a compare needs before the node's own work (the old S_{t-2} row from
+     * shared memory) and, one node ahead, the snapshot row from global memory, so that the L2 latency
+     * of the snapshot is covered by a whole node's processing. */
+#define SCB_PRE(dsto, dstoNext)                                                                   \
+        ScbVec<K> o2, zc = zn;                                                                    \
+        if (flags & SCB_SF_CMP2) o2 = scb_ld<K>(dst + (dsto));                                    \
+        if (flags & SCB_SF_TCMP) zc = scb_ld<K>(tsm + (dsto));                                    \
+        if (flags & SCB_SF_ZCMP) zn = scb_ldcg<K>(zg + (dstoNext));
 #define SCB_POST(r, dsto)                                                                         \
     do {                                                                                          \
-        if (flags & SCB_SF_CMP2) { ScbVec<K> o = scb_ld<K>(dst + (dsto));                         \
-            _Pragma("unroll") for (int k = 0; k < K; ++k) d2.v[k] |= (r).v[k] ^ o.v[k]; }         \
-        if (flags & SCB_SF_ZCMP) { ScbVec<K> z = scb_ldcg<K>(zg + (dsto));                        \
-            _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ z.v[k]; }         \
-        if (flags & SCB_SF_TCMP) { ScbVec<K> z = scb_ld<K>(tsm + (dsto));                         \
-            _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ z.v[k]; }         \
+        if (flags & SCB_SF_CMP2) {                                                                \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) d2.v[k] |= (r).v[k] ^ o2.v[k]; }        \
+        if (flags & (SCB_SF_ZCMP | SCB_SF_TCMP)) {                                                \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ zc.v[k]; }        \
         scb_st<K>(dst + (dsto), (r));                                                             \
         if (flags & SCB_SF_ZSNAP) scb_stcg<K>(zg + (dsto), (r));                                  \
     } while (0)
 
     int j = warp;
     const int e3 = cnt.x, e2 = cnt.x + cnt.y, e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
+    if (j >= e0) return;
+    /* the next node's descriptor is fetched while the current node is processed */
+    uint4 d = desc[j];
+    ScbVec<K> zn;
+#pragma unroll
+    for (int k = 0; k < K; ++k) zn.v[k] = 0u;
+    if ((flags & SCB_SF_ZCMP) && j < e1) zn = scb_ldcg<K>(zg + (d.w & 0xFFFFFFu));
     for (; j < e3; j += S) {
-        const uint4 d = desc[j];
+        const uint4 dn = desc[j + S < e0 ? j + S : j];
+        SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
         const ScbVec<K> a = scb_ld<K>(src + d.x), b = scb_ld<K>(src + d.y), c = scb_ld<K>(src + d.z);
         ScbVec<K> r = scb_apply3<K>(d.w >> 24, a, b, c);
         SCB_POST(r, d.w & 0xFFFFFFu);
+        d = dn;
     }
     for (; j < e2; j += S) {
-        const uint4 d = desc[j];
+        const uint4 dn = desc[j + S < e0 ? j + S : j];
+        SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
         const ScbVec<K> a = scb_ld<K>(src + d.x), b = scb_ld<K>(src + d.y);
         ScbVec<K> r = scb_apply2<K>(d.w >> 24, a, b);
         SCB_POST(r, d.w & 0xFFFFFFu);
+        d = dn;
     }
     for (; j < e1; j += S) {
-        const uint4 d = desc[j];
+        const uint4 dn = desc[j + S < e0 ? j + S : j];
+        SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
         ScbVec<K> r = scb_ld<K>(src + d.x);
         const uint32_t inv = (d.w >> 24) ? 0xffffffffu : 0u;
 #pragma unroll
         for (int k = 0; k < K; ++k) r.v[k] ^= inv;
         SCB_POST(r, d.w & 0xFFFFFFu);
+        d = dn;
     }
     if (flags & SCB_SF_CONST) {
         for (; j < e0; j += S) {
-            const uint4 d = desc[j];
+            const uint4 dc = desc[j];
             ScbVec<K> r;
-            const uint32_t val = (d.w >> 24) ? 0xffffffffu : 0u;
+            const uint32_t val = (dc.w >> 24) ? 0xffffffffu : 0u;
 #pragma unroll
             for (int k = 0; k < K; ++k) r.v[k] = val;
-            scb_st<K>(dst + (d.w & 0xFFFFFFu), r);
+            scb_st<K>(dst + (dc.w & 0xFFFFFFu), r);
         }
     }
 #undef SCB_POST
+#undef SCB_PRE
 }
 
 /* valid-cell mask of word w (cells w*32 .. w*32+31 below C) */
@@ -357,7 +352,7 @@ SCB_DEV uint32_t scb_valid_mask(long long w, int C)
  *       at t = 99 are queued, as 1024-cell chunks, for K3, and K2 leaves them out of its sums.
  * ---------------------------------------------------------------------------------------- */
 template <int K>
-__global__ void scb_k_sim(ScbSimArgs A)
+__global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
 {
     SCB_DYN_SMEM(smraw);
     const int N = A.N;
@@ -415,7 +410,8 @@ __global__ void scb_k_sim(ScbSimArgs A)
             ScbVec<K> d2, dz;
 #pragma unroll
             for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
-            scb_step<K>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, zg, nullptr, d2, dz);
+            if (f == 0u) scb_step<K, true>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, 0u, zg, nullptr, d2, dz);
+            else scb_step<K, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, zg, nullptr, d2, dz);
             if (f & SCB_SF_CMP2) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
@@ -616,7 +612,8 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
             if (cmp) f |= SCB_SF_TCMP;
             d2.v[0] = 0u; dz.v[0] = 0u;
-            scb_step<1>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, nullptr, bufT + laneOff, d2, dz);
+            if (f == 0u) scb_step<1, true>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, 0u, nullptr, bufT + laneOff, d2, dz);
+            else scb_step<1, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, nullptr, bufT + laneOff, d2, dz);
             if (cmp && dz.v[0]) atomicOr(&dmz[lane], dz.v[0]);
             __syncthreads();
             if (cmp) {
