@@ -65,6 +65,8 @@ template <class T> struct DevBuf {
 
 }  // namespace
 
+struct SimGeom { int K = 0, warps = 0, ctas = 0; size_t smem = 0; };
+
 struct scb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -78,6 +80,8 @@ struct scb_ctx {
     unsigned long long snapLo = (1ull << 32), snapHi = 1ull;   /* snapshots when computing S_32 and S_64 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
+    SimGeom main, tail;
+    int mainTiles = 0, tailTiles = 0;
     size_t smemSim = 0, smemRes = 0;
     int resWarps = 8, resCtas = 0;
     bool geomValid = false;
@@ -109,6 +113,32 @@ struct scb_ctx {
 
 namespace {
 
+/* launch geometry of the simulator kernel for one tile width (K words per lane) */
+int sim_geometry(scb_ctx *c, int K, int optWarps, SimGeom *g)
+{
+    const int N = c->N;
+    g->K = K;
+    g->smem = scb_smem_bytes(N, K, 2);
+    const int occGuess = (int)std::max<size_t>(1, (c->smemLimit + 1024) / (g->smem + 1024));
+    int S = optWarps;
+    if (S == 0) {
+        S = 32 / occGuess;
+        S = std::min(24, std::max(2, S));
+        S = std::min(S, std::max(1, (N + 3) / 4));
+    }
+    S = std::max(S, K);                 /* the mask arrays need 32*K threads */
+    S = std::min(S, 24);                /* __launch_bounds__(768) */
+    g->warps = S;
+    int occ = 1;
+    if (K == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<4>, S * 32, g->smem));
+    else if (K == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<2>, S * 32, g->smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<1>, S * 32, g->smem));
+    if (occ < 1) return fail(SCB_ERR_UNSUPPORTED, "simulator kernel does not fit on an SM (N=%d, K=%d, warps=%d)", N, K, S);
+    g->ctas = c->numSM * occ;
+    if (c->optMaxCtas > 0) g->ctas = std::min(g->ctas, c->optMaxCtas);
+    return SCB_OK;
+}
+
 int pick_geometry(scb_ctx *c)
 {
     const int N = c->N;
@@ -117,7 +147,6 @@ int pick_geometry(scb_ctx *c)
     if (K == 0) {
         K = 4;
         while (K >= 1 && scb_smem_bytes(N, K, 2) > c->smemLimit) K >>= 1;
-        /* small matrices: prefer narrower tiles so that there are enough tiles to fill the GPU */
         if (K < 1)
             return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the %zu-byte shared-memory state buffers", N, c->smemLimit);
     } else if (scb_smem_bytes(N, K, 2) > c->smemLimit) {
@@ -125,19 +154,6 @@ int pick_geometry(scb_ctx *c)
     }
     if (scb_smem_bytes(N, 1, 3) > c->smemLimit)
         return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the resolver's three state buffers", N);
-    c->K = K;
-    c->smemSim = scb_smem_bytes(N, K, 2);
-    c->smemRes = scb_smem_bytes(N, 1, 3);
-    int occGuess = (int)std::max<size_t>(1, (c->smemLimit + 1024) / (c->smemSim + 1024));
-    int S = c->optWarps;
-    if (S == 0) {
-        S = 32 / occGuess;
-        S = std::min(24, std::max(2, S));
-        S = std::min(S, std::max(1, (N + 3) / 4));
-    }
-    S = std::max(S, K);                 /* the mask arrays need 32*K threads */
-    S = std::min(S, 24);                /* __launch_bounds__(768) */
-    c->warps = S;
 #ifndef SCB_EMU
     CK(cudaFuncSetAttribute(scb_k_sim<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_sim<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
@@ -146,22 +162,32 @@ int pick_geometry(scb_ctx *c)
     CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
 #endif
-    int occ = 1;
-    if (K == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<4>, S * 32, c->smemSim));
-    else if (K == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<2>, S * 32, c->smemSim));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<1>, S * 32, c->smemSim));
-    if (occ < 1) return fail(SCB_ERR_UNSUPPORTED, "simulator kernel does not fit on an SM (N=%d, K=%d, warps=%d)", N, K, S);
-    c->occ = occ;
-    int ctas = c->numSM * occ;
-    if (c->optMaxCtas > 0) ctas = std::min(ctas, c->optMaxCtas);
-    c->ctas = ctas;
+    int rc = sim_geometry(c, K, c->optWarps, &c->main);
+    if (rc) return rc;
+    /* the words left over after the full tiles get a narrower tile (less padding to simulate) */
+    const int WT = 32 * K;
+    c->mainTiles = c->W / WT;
+    const int rem = c->W - c->mainTiles * WT;
+    c->tailTiles = 0;
+    if (rem > 0) {
+        int Kt = 1;
+        while (32 * Kt < rem) Kt <<= 1;
+        if (Kt >= K || c->mainTiles == 0) c->mainTiles += 1;          /* no narrower width fits: one more full tile */
+        else {
+            if ((rc = sim_geometry(c, Kt, 0, &c->tail))) return rc;
+            c->tailTiles = 1;
+        }
+    }
+    c->K = K; c->warps = c->main.warps; c->ctas = c->main.ctas; c->smemSim = c->main.smem;
+    c->smemRes = scb_smem_bytes(N, 1, 3);
     int occR = 1;
     c->resWarps = std::min(16, std::max(1, (N + 3) / 4));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve, c->resWarps * 32, c->smemRes));
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
-    int rc = c->dZ.ensure((size_t)c->ctas * N * 32 * K);
-    if (rc) return rc;
+    size_t zwords = (size_t)c->main.ctas * N * 32 * K;
+    if (c->tailTiles) zwords = std::max(zwords, (size_t)c->tail.ctas * N * 32 * c->tail.K);
+    if ((rc = c->dZ.ensure(zwords))) return rc;
     c->geomValid = true;
     return SCB_OK;
 }
@@ -405,28 +431,36 @@ int scb_pop_run(scb_ctx *c, int mode)
 
     ScbSimArgs sa;
     memset(&sa, 0, sizeof(sa));
-    const int WT = 32 * c->K;
     sa.X = c->dX.p; sa.N = N; sa.C = c->C; sa.Wpad = c->Wpad;
-    sa.tiles = (c->W + WT - 1) / WT; sa.P = P; sa.Npad = N; sa.mode = mode;
+    sa.P = P; sa.Npad = N; sa.mode = mode;
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
     sa.fitness = c->dFitness.p; sa.nodewise = c->dNodewise.p; sa.cellwise = c->dCellwise.p;
-    sa.workCounter = c->dCounters.p; sa.resolveCount = c->dCounters.p + 1;
+    sa.resolveCount = c->dCounters.p + 1;
     sa.resolveItems = c->dItems.p; sa.resolveCap = (unsigned)std::min<size_t>(c->dItems.cap, 0xffffffffu);
     sa.resolveT = c->dResolveT.p; sa.resolveTCap = c->resolveTCap;
     sa.chunkLast = c->dChunkLast.p; sa.chunksPerInd = (c->C + 1023) / 1024;
     sa.fillCount = c->dCounters.p + 3; sa.fillItems = c->dFillItems.p;
-    sa.zscratch = c->dZ.p; sa.zstride = (unsigned long long)N * WT;
+    sa.zscratch = c->dZ.p;
     sa.flags = (c->optEarly ? SCB_KF_EARLY : 0u) | (c->optSnap ? SCB_KF_SNAP : 0u);
     sa.chkEvery = c->optChk; sa.snapLo = c->snapLo; sa.snapHi = c->snapHi; sa.periodSearch = c->optSearch;
     sa.diag = c->dDiag.p;
-    const long long items = (long long)P * sa.tiles;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, c->ctas));
-    const dim3 block((unsigned)c->warps * 32);
     CK(cudaEventRecord(c->evSim0, st));
-    if (c->K == 4) SCB_LAUNCH(scb_k_sim<4>, dim3(grid), block, c->smemSim, st, sa);
-    else if (c->K == 2) SCB_LAUNCH(scb_k_sim<2>, dim3(grid), block, c->smemSim, st, sa);
-    else SCB_LAUNCH(scb_k_sim<1>, dim3(grid), block, c->smemSim, st, sa);
-    CK(cudaGetLastError());
+    for (int part = 0; part < 2; ++part) {
+        const SimGeom &g = part == 0 ? c->main : c->tail;
+        const int tiles = part == 0 ? c->mainTiles : c->tailTiles;
+        if (tiles <= 0) continue;
+        sa.tiles = tiles;
+        sa.wordBase = part == 0 ? 0 : c->mainTiles * 32 * c->K;
+        sa.workCounter = c->dCounters.p + (part == 0 ? 0 : 5);
+        sa.zstride = (unsigned long long)N * 32 * g.K;
+        const long long items = (long long)P * tiles;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, g.ctas));
+        const dim3 block((unsigned)g.warps * 32);
+        if (g.K == 4) SCB_LAUNCH(scb_k_sim<4>, dim3(grid), block, g.smem, st, sa);
+        else if (g.K == 2) SCB_LAUNCH(scb_k_sim<2>, dim3(grid), block, g.smem, st, sa);
+        else SCB_LAUNCH(scb_k_sim<1>, dim3(grid), block, g.smem, st, sa);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(c->evSim1, st));
 
     ScbResolveArgs ra;

@@ -379,12 +379,24 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         const unsigned item = (unsigned)sh[0];
         if (item >= total) break;
         const int p = (int)(item / (unsigned)A.tiles), tile = (int)(item % (unsigned)A.tiles);
-        const int w0 = tile * WT;
+        const int w0 = A.wordBase + tile * WT;
         const int4 cnt = A.counts[p];
         scb_load_program<K>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
-        for (int row = warp; row < N; row += S) {
-            const ScbVec<K> v = scb_ldg<K>(A.X + (long long)row * A.Wpad + w0 + lane * K);
-            scb_st<K>(sm + (uint32_t)row * ROWB + laneOff, v);
+        {   /* S_0 tile: four rows in flight per warp */
+            const uint32_t *xs = A.X + w0 + lane * K;
+            int row = warp;
+            for (; row + 3 * S < N; row += 4 * S) {
+                const ScbVec<K> v0 = scb_ldg<K>(xs + (long long)row * A.Wpad);
+                const ScbVec<K> v1 = scb_ldg<K>(xs + (long long)(row + S) * A.Wpad);
+                const ScbVec<K> v2 = scb_ldg<K>(xs + (long long)(row + 2 * S) * A.Wpad);
+                const ScbVec<K> v3 = scb_ldg<K>(xs + (long long)(row + 3 * S) * A.Wpad);
+                scb_st<K>(sm + (uint32_t)row * ROWB + laneOff, v0);
+                scb_st<K>(sm + (uint32_t)(row + S) * ROWB + laneOff, v1);
+                scb_st<K>(sm + (uint32_t)(row + 2 * S) * ROWB + laneOff, v2);
+                scb_st<K>(sm + (uint32_t)(row + 3 * S) * ROWB + laneOff, v3);
+            }
+            for (; row < N; row += S)
+                scb_st<K>(sm + (uint32_t)row * ROWB + laneOff, scb_ldg<K>(xs + (long long)row * A.Wpad));
         }
         if (tid < WT) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); Rm[tid] = 0u; dm2[tid] = 0u; dmz[tid] = 0u; }
         if (tid == 0) { sh[1] = 0; sh[2] = 0; }
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             if (lane < K) {
                 const unsigned msk = (LPC == 32) ? 0xffffffffu : (((1u << LPC) - 1u) << (lane * LPC));
                 const int cb = (bal & msk) != 0u;
-                const int q = tile * K + lane;                 /* chunk index within the individual */
+                const int q = w0 / 32 + lane;                  /* chunk index within the individual */
                 sh[4 + lane] = cb;
                 sh[8 + lane] = -1;
                 if (cb) {
@@ -511,21 +523,32 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         const unsigned char *fin = sm + finOff + laneOff;
         unsigned char *oth = sm + (finOff ? 0u : BUFB) + laneOff;
         unsigned total32 = 0;
-        for (int j = warp; j < N; j += S) {
-            const uint32_t dsto = desc[j].w & 0xFFFFFFu;
-            const int node = (int)(dsto / ROWB);
-            const ScbVec<K> s98 = scb_ld<K>(fin + dsto);
-            const ScbVec<K> s0 = scb_ldg<K>(A.X + (long long)node * A.Wpad + w0 + lane * K);
-            ScbVec<K> e;
-            unsigned c = 0;
+        for (int j0 = warp; j0 < N; j0 += 2 * S) {
+            /* two nodes in flight per warp: the S_0 rows come from L2 */
+            const int j1 = j0 + S;
+            const bool two = j1 < N;
+            const uint32_t dsto0 = desc[j0].w & 0xFFFFFFu, dsto1 = desc[two ? j1 : j0].w & 0xFFFFFFu;
+            const int node0 = (int)(dsto0 / ROWB), node1 = (int)(dsto1 / ROWB);
+            const ScbVec<K> x0 = scb_ldg<K>(A.X + (long long)node0 * A.Wpad + w0 + lane * K);
+            const ScbVec<K> x1 = scb_ldg<K>(A.X + (long long)node1 * A.Wpad + w0 + lane * K);
+            const ScbVec<K> s0 = scb_ld<K>(fin + dsto0), s1 = scb_ld<K>(fin + dsto1);
+            ScbVec<K> e0, e1;
+            unsigned c0 = 0, c1 = 0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) { e.v[k] = (s98.v[k] ^ s0.v[k]) & ok.v[k]; c += (unsigned)__popc(e.v[k]); }
-            total32 += c;
+            for (int k = 0; k < K; ++k) {
+                e0.v[k] = (s0.v[k] ^ x0.v[k]) & ok.v[k]; c0 += (unsigned)__popc(e0.v[k]);
+                e1.v[k] = (s1.v[k] ^ x1.v[k]) & ok.v[k]; c1 += (unsigned)__popc(e1.v[k]);
+            }
+            if (!two) c1 = 0;
+            total32 += c0 + c1;
             if (A.mode == 1) {
-                c = scb_warp_sum(c);
-                if (lane == 0 && c) atomicAdd(&A.nodewise[(long long)p * N + node], (int)c);
+                c0 = scb_warp_sum(c0);
+                c1 = scb_warp_sum(c1);
+                if (lane == 0 && c0) atomicAdd(&A.nodewise[(long long)p * N + node0], (int)c0);
+                if (lane == 0 && c1) atomicAdd(&A.nodewise[(long long)p * N + node1], (int)c1);
             } else if (A.mode == 2) {
-                scb_st<K>(oth + dsto, e);
+                scb_st<K>(oth + dsto0, e0);
+                if (two) scb_st<K>(oth + dsto1, e1);
             }
         }
         total32 = scb_warp_sum(total32);

@@ -87,6 +87,7 @@ struct ScbPackArgs {
 struct ScbSimArgs {
     const uint32_t *X;            /* packed S_0: [N][Wpad] node-major, 32 cells per word */
     int N, C, Wpad, tiles, P, Npad, mode;
+    int wordBase;                 /* first word of this launch's tile range (tail tiles use a narrower K) */
     const uint4 *descs;
     const int4 *counts;
     unsigned long long *fitness;  /* [P] */
