@@ -164,20 +164,12 @@ int pick_geometry(scb_ctx *c)
 #endif
     int rc = sim_geometry(c, K, c->optWarps, &c->main);
     if (rc) return rc;
-    /* the words left over after the full tiles get a narrower tile (less padding to simulate) */
+    /* One launch covers all tiles; the last, partly filled tile is made cheap inside the kernel by
+     * idling the lanes that hold no valid word (a separate narrow-tile launch was measured slower:
+     * its few long-running tiles leave most SMs idle).  The tail geometry stays available. */
     const int WT = 32 * K;
-    c->mainTiles = c->W / WT;
-    const int rem = c->W - c->mainTiles * WT;
+    c->mainTiles = (c->W + WT - 1) / WT;
     c->tailTiles = 0;
-    if (rem > 0) {
-        int Kt = 1;
-        while (32 * Kt < rem) Kt <<= 1;
-        if (Kt >= K || c->mainTiles == 0) c->mainTiles += 1;          /* no narrower width fits: one more full tile */
-        else {
-            if ((rc = sim_geometry(c, Kt, 0, &c->tail))) return rc;
-            c->tailTiles = 1;
-        }
-    }
     c->K = K; c->warps = c->main.warps; c->ctas = c->main.ctas; c->smemSim = c->main.smem;
     c->smemRes = scb_smem_bytes(N, 1, 3);
     int occR = 1;

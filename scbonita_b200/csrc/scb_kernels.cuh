@@ -257,9 +257,11 @@ SCB_DEV void scb_load_program(uint4 *desc, const uint4 *g, int4 cnt, int N, int 
 template <int K, bool PLAIN>
 SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 *desc, int4 cnt,
                       int warp, int S, unsigned flagsRt, unsigned char *zg, const unsigned char *tsm,
-                      ScbVec<K> &d2, ScbVec<K> &dz)
+                      ScbVec<K> &d2, ScbVec<K> &dz, bool active = true)
 {
-    /* PLAIN steps (no compare, no snapshot, no constant rows: the majority) are a separate
+    /* `active` is false for lanes whose words lie entirely beyond the last cell (the padding of the last
+     * tile): they skip the step, which cuts the shared-memory wavefronts of a mostly empty tile.
+     * PLAIN steps (no compare, no snapshot, no constant rows: the majority) are a separate
      * instantiation so that their loop carries no flag tests */
     const unsigned flags = PLAIN ? 0u : flagsRt;
     /* SCB_PRE issues the loads a compare needs before the node's own work (the old S_{t-2} row from
@@ -282,7 +284,7 @@ SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 
 
     int j = warp;
     const int e3 = cnt.x, e2 = cnt.x + cnt.y, e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
-    if (j >= e0) return;
+    if (j >= e0 || !active) return;
     /* the next node's descriptor is fetched while the current node is processed */
     uint4 d = desc[j];
     ScbVec<K> zn;
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         if (tid == 0) { sh[1] = 0; sh[2] = 0; }
         __syncthreads();
 
+        const bool laneActive = ((long long)w0 + lane * K) * 32 < A.C;       /* the lane holds a valid cell */
         uint32_t srcOff = 0u, dstOff = BUFB, finOff = 0u;
         int t = 0, target = SCB_LAST, zs = -1, ncmp = 0, searchLeft = 0;
         bool allres = false, allfound = false, plainOnly = false, haveFin = false;
@@ -422,8 +425,8 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             ScbVec<K> d2, dz;
 #pragma unroll
             for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
-            if (f == 0u) scb_step<K, true>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, 0u, zg, nullptr, d2, dz);
-            else scb_step<K, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, zg, nullptr, d2, dz);
+            if (f == 0u) scb_step<K, true>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, 0u, zg, nullptr, d2, dz, laneActive);
+            else scb_step<K, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, zg, nullptr, d2, dz, laneActive);
             if (f & SCB_SF_CMP2) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
