@@ -164,6 +164,15 @@ int scb_attractors(scb_ctx *ctx, const int32_t *individual, int indLen,
                    const int32_t *knockouts, const int32_t *knockins, int semantics,
                    int maxStates, int32_t *res, int32_t *nStates, uint32_t *states);
 
+/* ---- importance score of one knock-out / knock-in pair (ruleMaker.__calcImportance calls the C function
+ * importanceScore 3 x N times per network, ruleMaker.py:1268-1412): same arithmetic as simulator.c:555-755
+ * on the context's packed matrix.  Fails with SCB_ERR_INVALID (score = NaN) when a cell has no attractor
+ * window, where the reference divides by zero. */
+int scb_importance_score(scb_ctx *ctx, const int32_t *individual, int indLen,
+                         const int32_t *andLenList, const int32_t *individualParse,
+                         const int32_t *andNodes, const int32_t *andNodeInvertList,
+                         const int32_t *knockouts, const int32_t *knockins, double *score);
+
 /* ---- the reference's exported symbols (drop-in ./simulator.so) --------------------------
  * Argument lists are exactly simulator.c:350, :555 and :487.  ctypes passes every argument as
  * c_void_p (ruleMaker.py:1117-1138), so integers arrive in 64-bit registers: they are

@@ -12,6 +12,7 @@
 #include "scb_kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -103,6 +104,9 @@ struct scb_ctx {
     DevBuf<uint32_t> dAttr;
     DevBuf<int32_t> dDist, dDecider, dDeciderDist;
     DevBuf<unsigned char> dFlush;
+    DevBuf<uint32_t> dTraj, dStates;
+    DevBuf<int32_t> dRes, dNStates;
+    DevBuf<unsigned long long> dNodeCnt;
     /* current population */
     int P = 0, indLen = 0, tpi = 0;
     int lastMode = -1;
@@ -160,6 +164,7 @@ int pick_geometry(scb_ctx *c)
     CK(cudaFuncSetAttribute(scb_k_sim<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
 #endif
     int rc = sim_geometry(c, K, c->optWarps, &c->main);
@@ -181,6 +186,22 @@ int pick_geometry(scb_ctx *c)
     if (c->tailTiles) zwords = std::max(zwords, (size_t)c->tail.ctas * N * 32 * c->tail.K);
     if ((rc = c->dZ.ensure(zwords))) return rc;
     c->geomValid = true;
+    return SCB_OK;
+}
+
+/* K0 on the uploaded population; `knock` is the array the rules read as knock-outs (the importance score
+ * passes its knock-in list through the same slot, simulator.c:674) */
+int launch_compile(scb_ctx *c, int sem, const int32_t *knock)
+{
+    const int N = c->N, P = c->P;
+    ScbCompileArgs ca;
+    ca.P = P; ca.N = N; ca.indLen = c->indLen; ca.tablesPerIndividual = c->tpi; ca.Npad = N; ca.sem = sem;
+    ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
+    ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p;
+    ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
+    const int cthr = std::min(256, ((N + 31) / 32) * 32);
+    SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
+    CK(cudaGetLastError());
     return SCB_OK;
 }
 
@@ -295,6 +316,7 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
+    c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dNodeCnt.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
     if (c->evSim1) cudaEventDestroy(c->evSim1);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -410,16 +432,7 @@ int scb_pop_run(scb_ctx *c, int mode)
     CK(cudaMemsetAsync(c->dCounters.p, 0, 8 * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
 
-    ScbCompileArgs ca;
-    ca.P = P; ca.N = N; ca.indLen = c->indLen; ca.tablesPerIndividual = c->tpi; ca.Npad = N;
-    ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
-    ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = c->dKo.p; ca.ki = c->dKi.p;
-    ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
-    {
-        const int cthr = std::min(256, ((N + 31) / 32) * 32);
-        SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), st, ca);
-    }
-    CK(cudaGetLastError());
+    if ((rc = launch_compile(c, SCB_SEM_C, c->dKo.p))) return rc;
 
     ScbSimArgs sa;
     memset(&sa, 0, sizeof(sa));

@@ -32,16 +32,47 @@ SCB_HD inline ScbNodeFn scb_const_fn(int v, unsigned flags)
     return f;
 }
 
+/* sem selects whose update rule is restated:
+ *   SCB_SEM_C      scSyncBool / cluster                   (simulator.c:377-416, :509-549)
+ *   SCB_SEM_PY     singleCell.__cluster                   (singleCell.py:1014-1055): a zero-input node holds its
+ *                  OWN value (:1032-1033) and the last node, unless knocked / single-input / zero-input, is
+ *                  never updated (:1037-1038) -- the caller blanks its recorded rows
+ *   SCB_SEM_IMPORTANCE importanceScore                    (simulator.c:600-622): `ko` is the knock array of the pass,
+ *                  any nonzero entry forces 0; every node with andLen != 0 is the single literal of its first
+ *                  term's first input, the individual is ignored */
+#define SCB_SEM_C 0
+#define SCB_SEM_PY 1
+#define SCB_SEM_IMPORTANCE 2
+
+SCB_HD inline ScbNodeFn scb_copy_fn(int src, int invert)
+{
+    ScbNodeFn f;
+    f.arity = 1; f.in[0] = src; f.in[1] = src; f.in[2] = src;
+    f.lut = invert ? 0x0Fu : 0xF0u; f.flags = 0;
+    return f;
+}
+
 SCB_HD inline ScbNodeFn scb_compile_node(int i, int N, int indLen, const int32_t *ind,
                                          const int32_t *andLen, const int32_t *parse,
                                          const int32_t *an, const int32_t *ai,
-                                         const int32_t *ko, const int32_t *ki)
+                                         const int32_t *ko, const int32_t *ki, int sem = SCB_SEM_C)
 {
-    if (ko[i] == 1) return scb_const_fn(0, 0);
-    if (ki[i] == 1) return scb_const_fn(1, 0);
     const int32_t *an_i = an + (long long)i * (SCB_MAX_TERMS * SCB_MAX_IN);
     const int32_t *ai_i = ai + (long long)i * (SCB_MAX_TERMS * SCB_MAX_IN);
     const int al = andLen[i];
+    if (sem == SCB_SEM_IMPORTANCE) {
+        if (ko[i]) return scb_const_fn(0, 0);                                   /* simulator.c:604 */
+        const int src = an_i[0];
+        if (src < 0 || src >= N) return scb_const_fn(0, SCB_NF_BADIDX);
+        if (al == 0) return scb_copy_fn(src, 0);                                /* :617 */
+        const int fl = ai_i[0];                                                 /* :611 */
+        if (fl != 0 && fl != 1) return scb_const_fn(1, 0);
+        return scb_copy_fn(src, fl);
+    }
+    if (ko[i] == 1) return scb_const_fn(0, 0);
+    if (ki[i] == 1) return scb_const_fn(1, 0);
+    if (sem == SCB_SEM_PY && al == 0) return scb_copy_fn(i, 0);
+    if (sem == SCB_SEM_PY && al != 1 && i == N - 1) return scb_copy_fn(i, 0);
     if (al == 1 || al == 0) {
         const int src = an_i[0];
         if (src < 0 || src >= N) return scb_const_fn(0, SCB_NF_BADIDX);

@@ -168,7 +168,7 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     if (tid < 8) cn[tid] = 0u;
     __syncthreads();
     for (int i = tid; i < N; i += nthr) {
-        const ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki);
+        const ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki, A.sem);
         sd[i] = make_uint4((unsigned)f.in[0], (unsigned)f.in[1], (unsigned)f.in[2], (unsigned)i | (f.lut << 24));
         sar[i] = (unsigned char)f.arity;
         atomicAdd(&cn[3 - f.arity], 1u);
@@ -325,6 +325,7 @@ SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 
 #pragma unroll
             for (int k = 0; k < K; ++k) r.v[k] = val;
             scb_st<K>(dst + (dc.w & 0xFFFFFFu), r);
+            if (flags & SCB_SF_ZSNAP) scb_stcg<K>(zg + (dc.w & 0xFFFFFFu), r);
         }
     }
 #undef SCB_POST
@@ -831,6 +832,160 @@ __global__ void scb_k_fill(ScbResolveArgs R)
             for (int i = tid; i < pend; i += nthr) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
         }
         __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K4: trajectories for attractor extraction (the `cluster` companion, simulator.c:487-552, and
+ * singleCell.__cluster, singleCell.py:990-1059).
+ *
+ * scb_k_traj   one CTA per 1024-cell tile (K = 1): runs `steps` states of one compiled program and
+ *              stores every state tile-locally, traj[tile][step][N][32] words (the snapshot-store
+ *              path of scb_step writes them).
+ * scb_k_window per tile: row-pair equality masks, the reference's scan order for the attractor
+ *              window, and the window's states gathered into cell-major packed words.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void scb_k_traj(ScbTrajArgs A)
+{
+    SCB_DYN_SMEM(smraw);
+    const int N = A.N;
+    const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
+    unsigned char *sm = smraw;
+    uint4 *desc = reinterpret_cast<uint4 *>(smraw + 2u * BUFB);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    const uint32_t laneOff = (uint32_t)lane * 4u;
+    const int4 cnt = A.counts[0];
+    scb_load_program<1>(desc, A.descs, cnt, N, tid, nthr);
+    for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
+        const int w0 = tile * 32;
+        uint32_t *tbase = A.traj + (unsigned long long)tile * A.steps * N * 32;
+        __syncthreads();
+        for (int row = warp; row < N; row += S) {
+            const uint32_t v = __ldg(A.X + (long long)row * A.Wpad + w0 + lane);
+            *reinterpret_cast<uint32_t *>(sm + (uint32_t)row * ROWB + laneOff) = v;
+            tbase[(long long)row * 32 + lane] = v;                         /* state 0 */
+        }
+        __syncthreads();
+        uint32_t srcOff = 0u, dstOff = BUFB;
+        ScbVec<1> d2, dz;
+        d2.v[0] = 0u; dz.v[0] = 0u;
+        for (int t = 1; t < A.steps; ++t) {
+            unsigned char *zg = reinterpret_cast<unsigned char *>(tbase + (unsigned long long)t * N * 32) + laneOff;
+            scb_step<1, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S,
+                               SCB_SF_ZSNAP | SCB_SF_CONST, zg, nullptr, d2, dz);
+            __syncthreads();
+            const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
+        }
+        if (A.zeroNode >= 0)
+            for (int i = tid; i < (A.steps - 1) * 32; i += nthr)
+                tbase[((unsigned long long)(1 + i / 32) * N + A.zeroNode) * 32 + (i & 31)] = 0u;
+    }
+}
+
+#define SCB_WIN_MAXPAIRS 128
+__global__ void scb_k_window(ScbWindowArgs A)
+{
+    SCB_DYN_SMEM(smraw);
+    uint32_t *eq = reinterpret_cast<uint32_t *>(smraw);                  /* [pairs][32] equality masks */
+    const int N = A.N, T = A.steps;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    /* pairs in the reference's scan order: i = T-1 .. 0, j = i-1 .. 0 (getAttractCycle2).  For the C
+     * semantics only i = T-1 can match first (a deterministic trajectory whose last state repeats no
+     * earlier one has no repeated pair at all), so only those T-1 pairs are evaluated. */
+    const int nPairs = A.sem == 0 ? T - 1 : T * (T - 1) / 2;
+    for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
+        const uint32_t *tbase = A.traj + (unsigned long long)tile * T * N * 32;
+        __syncthreads();
+        for (int pr = warp; pr < nPairs; pr += S) {
+            int i, j;
+            if (A.sem == 0) { i = T - 1; j = T - 2 - pr; }
+            else {
+                int r = pr; i = T - 1;
+                while (r >= i) { r -= i; --i; }
+                j = i - 1 - r;
+            }
+            uint32_t d = 0u;
+            const uint32_t *ri = tbase + (unsigned long long)i * N * 32 + lane, *rj = tbase + (unsigned long long)j * N * 32 + lane;
+            for (int n = 0; n < N; ++n) d |= ri[n * 32] ^ rj[n * 32];
+            eq[pr * 32 + lane] = ~d;
+        }
+        __syncthreads();
+        for (int cl = tid; cl < 1024; cl += nthr) {
+            const long long c = (long long)tile * 1024 + cl;
+            if (c >= A.C) continue;
+            const int w = cl >> 5, b = cl & 31;
+            int r0, r1, first, count;
+            int hit = -1;
+            for (int pr = 0; pr < nPairs; ++pr) if ((eq[pr * 32 + w] >> b) & 1u) { hit = pr; break; }
+            if (A.sem == 0) {
+                if (hit < 0) { r0 = 0; r1 = 0; first = 0; count = 0; }               /* simulator.c:307 res = {0,0} */
+                else { r1 = T - 1; r0 = T - 2 - hit; first = r0; count = r1 - r0; }   /* states [r0, r1) */
+            } else {
+                if (hit < 0) { r0 = -1; r1 = -1; first = T - 1; count = 1; }          /* vals[-1]: the last row */
+                else {
+                    int r = hit, i = T - 1;
+                    while (r >= i) { r -= i; --i; }
+                    r1 = i; r0 = i - 1 - r; first = r0; count = r1 - r0 + 1;          /* rows r0..r1 inclusive */
+                }
+            }
+            A.res[c * 2] = r0; A.res[c * 2 + 1] = r1; A.nStates[c] = count;
+            const int ns = count < A.maxStates ? count : A.maxStates;
+            for (int s = 0; s < ns; ++s) {
+                const uint32_t *row = tbase + (unsigned long long)(first + s) * N * 32 + w;
+                uint32_t *out = A.states + ((unsigned long long)c * A.maxStates + s) * A.NW;
+                for (int wq = 0; wq < A.NW; ++wq) {
+                    uint32_t acc = 0u;
+                    const int lim = (N - wq * 32) < 32 ? (N - wq * 32) : 32;
+                    for (int q = 0; q < lim; ++q) acc |= ((row[(wq * 32 + q) * 32] >> b) & 1u) << q;
+                    out[wq] = acc;
+                }
+            }
+        }
+    }
+}
+
+/* K6: the reduction of importanceScore (simulator.c:641-648): for every cell whose attractor window has
+ * length 1 the two window rows (98 and 99) are added node by node; longer windows add
+ * (int)(state / length) = 0; a cell without a window divides by zero in the reference (counted here). */
+struct ScbImportanceArgs {
+    const uint32_t *traj;
+    const int32_t *res;           /* [C][2] from scb_k_window (C semantics) */
+    int N, C, tiles, steps;
+    unsigned long long *nodeCnt;  /* [N] accumulated */
+    unsigned long long *notFound; /* [1] */
+};
+
+__global__ void scb_k_importance_reduce(ScbImportanceArgs A)
+{
+    SCB_DYN_SMEM(smraw);
+    uint32_t *fp = reinterpret_cast<uint32_t *>(smraw);                   /* [32] fixed-point cell masks */
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t m = 0u;
+            unsigned nf = 0;
+            for (int b = 0; b < 32; ++b) {
+                const long long c = (long long)tile * 1024 + lane * 32 + b;
+                if (c >= A.C) continue;
+                const int r0 = A.res[c * 2], r1 = A.res[c * 2 + 1];
+                if (r1 - r0 == 1) m |= 1u << b;
+                if (r1 - r0 == 0) ++nf;
+            }
+            fp[lane] = m;
+            nf = scb_warp_sum(nf);
+            if (lane == 0 && nf) atomicAdd(A.notFound, (unsigned long long)nf);
+        }
+        __syncthreads();
+        const uint32_t *t98 = A.traj + ((unsigned long long)tile * A.steps + (A.steps - 2)) * A.N * 32;
+        const uint32_t *t99 = t98 + (unsigned long long)A.N * 32;
+        for (int n = warp; n < A.N; n += S) {
+            unsigned c = (unsigned)__popc(t98[n * 32 + lane] & fp[lane]) + (unsigned)__popc(t99[n * 32 + lane] & fp[lane]);
+            c = scb_warp_sum(c);
+            if (lane == 0 && c) atomicAdd(&A.nodeCnt[n], (unsigned long long)c);
+        }
     }
 }
 

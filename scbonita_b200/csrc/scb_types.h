@@ -65,6 +65,7 @@ struct ScbDiag {                      /* device-side counters, zeroed per evalua
 
 struct ScbCompileArgs {
     int P, N, indLen, tablesPerIndividual, Npad;
+    int sem;                      /* SCB_SEM_* (scb_compile.h) */
     const int32_t *individuals;   /* [P][indLen] */
     const int32_t *andLen;        /* [N] */
     const int32_t *parse;         /* [N] */
@@ -110,6 +111,24 @@ struct ScbSimArgs {
     unsigned long long snapLo, snapHi;  /* bit t set: take a snapshot when computing S_t */
     int periodSearch;             /* snapshot-compare steps kept after all cells resolved */
     ScbDiag *diag;
+};
+
+/* K4: trajectories of one individual for every cell, stored tile-local: traj[tile][step][N][32] words */
+struct ScbTrajArgs {
+    const uint32_t *X;            /* [N][Wpad] */
+    int N, C, Wpad, tiles, steps;
+    const uint4 *descs;           /* one compiled program */
+    const int4 *counts;
+    uint32_t *traj;
+    int zeroNode;                 /* >= 0: rows of this node are recorded as 0 for steps >= 1 */
+};
+
+struct ScbWindowArgs {
+    const uint32_t *traj;
+    int N, C, tiles, steps, sem, maxStates, NW;
+    int32_t *res;                 /* [C][2] */
+    int32_t *nStates;             /* [C] */
+    uint32_t *states;             /* [C][maxStates][NW] */
 };
 
 struct ScbHammingArgs {

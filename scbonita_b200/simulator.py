@@ -195,9 +195,17 @@ class Simulator:
         """ruleMaker.__evaluateByNode (ruleMaker.py:1077-1221).  ``cFunction`` is accepted and
         ignored (the reference passes the ctypes symbol).  Returns ``errors[:nodeNum]`` as a
         list when ``localSearch`` else ``[sum(errors)]``."""
-        if importanceScores:
-            raise NotImplementedError("importanceScore is served by the legacy symbol (see INTEGRATION.md)")
         knockouts, knockins = self._knock(KOlist, KIlist)
+        if importanceScores and not localSearch:
+            # ruleMaker.py:1172-1194: cFunction is importanceScore, the result a one-element float list
+            m = self.model
+            ind = _i32(individual)
+            score = np.zeros(1, dtype=np.float64)
+            rc = self.lib.scb_importance_score(self._ctx, _ptr(ind), m.ind_len, _ptr(m.and_len_list),
+                                               _ptr(m.individual_parse), _ptr(m.and_nodes),
+                                               _ptr(m.and_node_invert_list), _ptr(knockouts), _ptr(knockins), _ptr(score))
+            _lib.check(self.lib, rc)
+            return score.tolist()
         if localSearch:
             out = self.evaluate_population(individual, knockouts, knockins, and_nodes, and_inv, MODE_NODEWISE)
             return out[0].tolist()
@@ -231,6 +239,42 @@ class Simulator:
         return equivs[0], equivs, minny, ind_errors
 
     # -- attractor companion ------------------------------------------------------------------
+    def attractors(self, individual, knockouts=None, knockins=None, semantics="python", max_states=10):
+        """Per-cell attractor window and its states (singleCell.py:1162-1192 runs this one cell at a time in
+        pure Python).  ``semantics``: "python" = singleCell.__cluster with simSteps 10 (rows res[0]..res[1]
+        inclusive; [-1,-1] yields the last row), "c" = simulator.c cluster with simSteps 100 (rows
+        [res[0], res[1])).  Returns (res[C][2], n_states[C], states[C][max_states][N] as 0/1 uint8)."""
+        m = self.model
+        sem = {"c": 0, "python": 1}[semantics]
+        ind = _i32(individual)
+        ko = _i32(knockouts if knockouts is not None else np.zeros(m.n))
+        ki = _i32(knockins if knockins is not None else np.zeros(m.n))
+        nw = (m.n + 31) // 32
+        res = np.zeros((self.n_cells, 2), dtype=np.int32)
+        nst = np.zeros(self.n_cells, dtype=np.int32)
+        packed = np.zeros((self.n_cells, max(max_states, 1), nw), dtype=np.uint32)
+        rc = self.lib.scb_attractors(self._ctx, _ptr(ind), m.ind_len, _ptr(m.and_len_list), _ptr(m.individual_parse),
+                                     _ptr(m.and_nodes), _ptr(m.and_node_invert_list), _ptr(ko), _ptr(ki), sem,
+                                     int(max_states), _ptr(res), _ptr(nst), _ptr(packed))
+        _lib.check(self.lib, rc)
+        bits = np.unpackbits(packed.view(np.uint8), axis=-1, bitorder="little")[..., :m.n]
+        return res, nst, bits
+
+    def attractor_set(self, individual, knockouts=None, knockins=None, remove_zero=True):
+        """The unique attractor states of all cells, as assignAttractors collects them
+        (singleCell.py:1189-1207), in first-seen order (the reference's order is Python set order)."""
+        _, nst, bits = self.attractors(individual, knockouts, knockins, "python", 10)
+        seen, out = set(), []
+        for c in range(self.n_cells):
+            for s in range(min(int(nst[c]), 10)):
+                key = bits[c, s].tobytes()
+                if key not in seen:
+                    seen.add(key)
+                    out.append(bits[c, s].astype(np.int32))
+        if remove_zero:
+            out = [a for a in out if a.sum() > 0]
+        return np.array(out, dtype=np.int32).reshape(-1, self.model.n)
+
     def hamming_argmin(self, attractors, want_dist=True):
         """singleCell.py:1211-1238: returns (dist[C][A] or None, decider[C], deciderDistance[C])."""
         at = _i32(attractors)

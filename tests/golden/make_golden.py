@@ -87,6 +87,65 @@ def hamming_kat():
     return rows
 
 
+
+
+# ---------------------------------------------------------------------------------------------
+# Python attractor path (singleCell.__cluster, singleCell.py:990-1059) run from the reference itself
+# ---------------------------------------------------------------------------------------------
+def import_reference_single_cell():
+    """Imports /root/reference/src/scBONITA/singleCell.py with stand-ins for the plotting / GA / KEGG
+    packages that are not installed here (none of them takes part in __cluster)."""
+    from unittest.mock import MagicMock
+    for name in ("deap", "deap.base", "deap.creator", "deap.gp", "deap.tools", "deap.algorithms", "seaborn",
+                 "matplotlib", "matplotlib.pyplot", "matplotlib.patches", "statsmodels", "statsmodels.stats",
+                 "statsmodels.stats.multitest", "bioservices", "bioservices.kegg", "bs4", "requests"):
+        sys.modules.setdefault(name, MagicMock())
+    sys.path.insert(0, "/root/reference/src/scBONITA")
+    import singleCell as ref_sc
+    return ref_sc
+
+
+def ragged(net, pop_an, pop_ai):
+    """andNodeList / andNodeInvertList as ruleMaker keeps them (ragged lists, bools)."""
+    an, ai = [], []
+    for i in range(net.n):
+        k = int(net.and_len[i])
+        an.append([[int(x) for x in pop_an[i, a] if x > -1] for a in range(k)])
+        ai.append([[bool(f) for x, f in zip(pop_an[i, a], pop_ai[i, a]) if x > -1] for a in range(k)])
+    return an, ai
+
+
+def save_py_cluster(name, n, cells, seed):
+    from scbonita_b200 import synth
+    ref_sc = import_reference_single_cell()
+    pr = synth.make_problem(n, cells, 1, knock=False, net_seed=seed, cell_seed=seed + 1, pop_seed=seed + 2)
+    bm = np.zeros((n, cells), np.int32)
+    bm[pr.node_positions] = pr.bin_rows
+
+    stub = object.__new__(ref_sc.singleCell)          # the real class, without running its __init__
+    stub.maxNodes = n + 5
+    stub.nodeList = list(range(n))
+    an, ai = ragged(pr.net, pr.pop_and_nodes[0], pr.pop_and_inv[0])
+    ko = np.zeros(n, np.intc)
+    ki = np.zeros(n, np.intc)
+    ki[n // 2] = 1
+    all_vals, all_res = [], []
+    for c in range(cells):
+        vals = np.full((10, n), 0, dtype=np.intc)
+        res = np.full(2, 2, dtype=np.intc)
+        res = ref_sc.singleCell._singleCell__cluster(stub, vals, res, c, pr.individuals[0], pr.net.ind_len, n,
+                                                     pr.net.and_len, pr.net.parse, an, ai, 10, ko, ki, bm,
+                                                     list(pr.node_positions))
+        all_vals.append(vals.copy())
+        all_res.append([int(res[0]), int(res[1])])
+    np.savez_compressed(os.path.join(HERE, name), and_len=pr.net.and_len, parse=pr.net.parse,
+                        and_nodes=pr.pop_and_nodes[0], and_inv=pr.pop_and_inv[0], node_positions=pr.node_positions,
+                        ind_len=pr.net.ind_len, knockouts=ko, knockins=ki, n_cells=cells,
+                        bin_rows=np.packbits(pr.bin_rows, axis=1), individual=pr.individuals[0],
+                        ref_vals=np.array(all_vals, np.int8), ref_res=np.array(all_res, np.int32))
+    print(name, "res histogram", {tuple(r): all_res.count(r) for r in map(list, set(map(tuple, all_res)))})
+
+
 if __name__ == "__main__":
     oracle.build(ref=True)
     save_sim("sim_kegg60.npz", Problem.synthetic(60, 700, 4))
@@ -95,3 +154,5 @@ if __name__ == "__main__":
     save_sim("sim_ring45_chain12.npz", ring_problem([45], 12, 1500))
     save_sim("sim_ring60_undefined_lead.npz", ring_problem([60], 0, 200, lead_found=True))
     hamming_kat()
+    save_py_cluster("pycluster_n24.npz", 24, 70, 501)
+    save_py_cluster("pycluster_n40.npz", 40, 50, 777)

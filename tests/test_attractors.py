@@ -1,0 +1,170 @@
+"""Attractor companion: trajectories + windows (K4) against the oracle and against vectors produced by the
+reference's own Python (singleCell.__cluster) and C (`cluster`)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from common import GOLDEN, Problem, oracle_model, tables
+from scbonita_b200 import _lib, simulator
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def backend(request):
+    if request.param == "emu":
+        return "emu", request.getfixturevalue("emu_lib")
+    return "cuda", request.getfixturevalue("cuda_lib")
+
+
+def _sim(pr, backend):
+    sim = simulator.Simulator(pr.bm, tables(pr.net, pr.node_positions), lib_path=backend[1])
+    if backend[0] == "emu":
+        sim.set_option(_lib.OPT_MAX_CTAS, 3)
+    return sim
+
+
+@pytest.mark.parametrize("name", ["pycluster_n24.npz", "pycluster_n40.npz"])
+def test_python_semantics_against_reference_python(backend, name):
+    """Golden vectors come from the reference's own singleCell.__cluster (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    C = int(g["n_cells"]); pos = g["node_positions"]; n = len(pos)
+    bm = np.zeros((n, C), np.int32)
+    bm[pos] = np.unpackbits(g["bin_rows"], axis=1)[:, :C]
+    model = simulator.ModelTables(g["and_len"], g["parse"], g["and_nodes"], g["and_inv"], pos, int(g["ind_len"]))
+    with simulator.Simulator(bm, model, lib_path=backend[1]) as sim:
+        res, nst, bits = sim.attractors(g["individual"], g["knockouts"], g["knockins"], "python", 10)
+    assert np.array_equal(res, g["ref_res"])
+    vals = g["ref_vals"]
+    for c in range(C):
+        r0, r1 = g["ref_res"][c]
+        rows = list(range(r0, r1 + 1)) if r0 >= 0 else [9]          # range(-1, 0) -> vals[-1]
+        assert nst[c] == len(rows)
+        assert np.array_equal(bits[c, :len(rows)], vals[c, rows].astype(np.uint8)), c
+
+
+@pytest.mark.parametrize("n,cells", [(30, 300), (61, 1500), (7, 40)])
+def test_python_semantics_against_oracle(backend, n, cells):
+    pr = Problem.synthetic(n, cells, 1, knock=False)
+    ki = np.zeros(n, np.int32); ki[n // 3] = 1
+    ko = np.zeros(n, np.int32); ko[min(n - 1, 2)] = 1
+    m = oracle_model(pr.net, pr.node_positions, ko, ki)
+    m.and_nodes, m.and_inv = pr.pop_an[0], pr.pop_ai[0]
+    vals, wres, _ = oracle.py_cluster(m, pr.individuals[0], pr.bm, cells)
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_an[0], pr.pop_ai[0], pr.node_positions, pr.net.ind_len)
+    sim = simulator.Simulator(pr.bm, model, lib_path=backend[1])
+    with sim:
+        res, nst, bits = sim.attractors(pr.individuals[0], ko, ki, "python", 10)
+    assert np.array_equal(res, wres)
+    for c in range(cells):
+        r0, r1 = wres[c]
+        rows = list(range(r0, r1 + 1)) if r0 >= 0 else [9]
+        assert nst[c] == len(rows)
+        assert np.array_equal(bits[c, :len(rows)], vals[c, rows].astype(np.uint8)), c
+
+
+@pytest.mark.parametrize("n,cells", [(30, 64), (12, 100)])
+def test_c_semantics_against_oracle(backend, n, cells):
+    """C `cluster` (simulator.c:487-552): window (99 - period, 99) or (0, 0); states [res0, res1)."""
+    pr = Problem.synthetic(n, cells, 1, knock=False)
+    m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+    m.and_nodes, m.and_inv = pr.pop_an[0], pr.pop_ai[0]
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_an[0], pr.pop_ai[0], pr.node_positions, pr.net.ind_len)
+    with simulator.Simulator(pr.bm, model, lib_path=backend[1]) as sim:
+        res, nst, bits = sim.attractors(pr.individuals[0], pr.ko, pr.ki, "c", 12)
+    for c in range(cells):
+        traj, wres = oracle.c_cluster(m, pr.individuals[0], pr.bm, c)
+        assert tuple(res[c]) == tuple(wres), c
+        k = int(wres[1] - wres[0])
+        assert nst[c] == k
+        kk = min(k, 12)
+        assert np.array_equal(bits[c, :kk], traj[wres[0]:wres[0] + kk].astype(np.uint8)), c
+
+
+def test_legacy_cluster_symbol(backend):
+    """The reference's `cluster` argument list (simulator.c:487), one cell per call, trajectory left in simData."""
+    pr = Problem.synthetic(20, 40, 1, knock=False)
+    lib = _lib.load(backend[1])
+    m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+    m.and_nodes, m.and_inv = pr.pop_an[0], pr.pop_ai[0]
+    stride, nstride = 64, 32
+    lib.scb_set_legacy_geometry(nstride, stride)
+    bm = np.zeros((pr.bm.shape[0], stride), np.int32)
+    bm[:, :40] = pr.bm
+    V = ctypes.c_void_p
+    arr = [np.ascontiguousarray(a, np.int32) for a in (pr.individuals[0], pr.net.and_len, pr.net.parse, pr.pop_an[0],
+                                                       pr.pop_ai[0], pr.ko, pr.ki, pr.node_positions)]
+    ind, al, parse, an, ai, ko, ki, pos = arr
+    fn = lib.cluster
+    fn.restype = None
+    fn.argtypes = None
+    for cell in (0, 7, 39):
+        vals = np.zeros((100, nstride), np.int32)
+        res = np.full(2, 2, np.int32)
+        fn(V(vals.ctypes.data), V(res.ctypes.data), V(cell), V(ind.ctypes.data), V(len(ind)), V(pr.n), V(al.ctypes.data),
+           V(parse.ctypes.data), V(an.ctypes.data), V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data),
+           V(bm.ctypes.data), V(pos.ctypes.data))
+        traj, wres = oracle.c_cluster(m, pr.individuals[0], pr.bm, cell)
+        assert tuple(res) == tuple(wres)
+        assert np.array_equal(vals[:, pr.node_positions], traj)
+    lib.scb_set_legacy_geometry(20000, 15000)
+
+
+def test_attractor_set_then_decider(backend):
+    """assignAttractors end to end on the device: unique attractor states, then distance + first-min decider."""
+    pr = Problem.synthetic(25, 400, 1, knock=False)
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_an[0], pr.pop_ai[0], pr.node_positions, pr.net.ind_len)
+    m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+    m.and_nodes, m.and_inv = pr.pop_an[0], pr.pop_ai[0]
+    vals, wres, _ = oracle.py_cluster(m, pr.individuals[0], pr.bm, 400)
+    want = set()
+    for c in range(400):
+        r0, r1 = wres[c]
+        for r in (range(r0, r1 + 1) if r0 >= 0 else [9]):
+            want.add(tuple(int(x) for x in vals[c, r]))
+    want = {a for a in want if sum(a) > 0}
+    with simulator.Simulator(pr.bm, model, lib_path=backend[1]) as sim:
+        attrs = sim.attractor_set(pr.individuals[0])
+        assert {tuple(int(x) for x in a) for a in attrs} == want
+        dist, dec, dd = sim.hamming_argmin(attrs)
+    wd, wdec, wdd = oracle.hamming_argmin(attrs, pr.bm, pr.node_positions, 400)
+    assert np.array_equal(dist, wd) and np.array_equal(dec, wdec) and np.array_equal(dd, wdd)
+
+
+@pytest.mark.parametrize("n,cells,seed", [(12, 30, None), (20, 200, 4242), (9, 64, 99)])
+def test_legacy_importanceScore_symbol(backend, n, cells, seed):
+    """importanceScore (simulator.c:555-755): double result bit-identical to the oracle restatement, which is
+    itself checked against the unmodified reference in tests/test_oracle.py."""
+    pr = Problem.synthetic(n, cells, 1, knock=False, net_seed=seed)
+    lib = _lib.load(backend[1])
+    stride = 256
+    lib.scb_set_legacy_geometry(64, stride)
+    bm = np.zeros((pr.bm.shape[0], stride), np.int32)
+    bm[:, :cells] = pr.bm
+    ko = np.zeros(n, np.int32); ko[1 % n] = 1
+    ki = np.zeros(n, np.int32); ki[(n - 1)] = 1
+    m = oracle_model(pr.net, pr.node_positions, ko, ki)
+    m.and_nodes, m.and_inv = pr.pop_an[0], pr.pop_ai[0]
+    try:
+        want = oracle.importance_score(m, pr.individuals[0], pr.bm, cells)
+    except ValueError:
+        want = float("nan")
+    V = ctypes.c_void_p
+    arr = [np.ascontiguousarray(a, np.int32) for a in (pr.individuals[0], pr.net.and_len, pr.net.parse, pr.pop_an[0],
+                                                       pr.pop_ai[0], ko, ki, pr.node_positions)]
+    ind, al, parse, an, ai, ko_, ki_, pos = arr
+    score = np.zeros(1, np.float64)
+    fn = lib.importanceScore
+    fn.restype = None
+    fn.argtypes = None
+    fn(V(0), V(ind.ctypes.data), V(len(ind)), V(n), V(al.ctypes.data), V(parse.ctypes.data), V(an.ctypes.data),
+       V(ai.ctypes.data), V(100), V(ko_.ctypes.data), V(ki_.ctypes.data), V(cells), V(bm.ctypes.data), V(pos.ctypes.data),
+       V(score.ctypes.data))
+    lib.scb_set_legacy_geometry(20000, 15000)
+    if np.isnan(want):
+        assert np.isnan(score[0])
+    else:
+        assert score[0].tobytes() == np.float64(want).tobytes(), (score[0], want)
