@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -167,7 +167,9 @@ def run_ours(args, wl, rank, world, local_rank):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    pr, bm = build_problem(wl, seed_shift=rank)
+    # weak scaling: every rank scores a population of the same size drawn with the same seeds, so that the
+    # per-rank work is identical and the measured efficiency reflects the collective, not sampling noise
+    pr, bm = build_problem(wl)
     model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.net.and_nodes, pr.net.and_inv,
                                   pr.node_positions, pr.net.ind_len)
     sim = simulator.Simulator(bm, model, device=local_rank)
@@ -296,6 +298,7 @@ def run_ours(args, wl, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl["name"], "population_per_gpu": P, "cells": C, "nodes": N,
+                       "population_seeds": "identical on every rank",
                        "sharding": "individuals sharded over %d rank(s), packed matrix replicated, all-gather of int64 fitness" % world,
                        "l2": "flushed (256 MiB memset) between timed steps", "geometry": info,
                        "options": args.opt},
@@ -321,6 +324,11 @@ def run_ours(args, wl, rank, world, local_rank):
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner,
+    # ...) is sent to stderr by pointing fd 1 at fd 2 until the line is written
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -1,0 +1,31 @@
+"""bench.py's own arm runs end to end (on the emulator build, tiny shape) and prints the contracted JSON keys."""
+import argparse
+import json
+
+import bench
+from scbonita_b200 import _lib
+
+
+def test_bench_line_has_contract_keys(emu_lib, monkeypatch, capsys):
+    monkeypatch.setattr(_lib, "DEFAULT_PATH", emu_lib)
+    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="ours", workload="T0", opt=["max_ctas=2"],
+                              no_cpu_baseline=False)
+    bench.run_ours(args, bench.WORKLOADS["T0"], 0, 1, 0)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in line, key
+    assert line["config"]["workload"].startswith("T0")
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["value"] > 0 and line["e2e"]["value"] > 0
+    assert line["gpu_launches"] == 5 * 2
+
+
+def test_reference_arm_line(capsys):
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", workload="T0", opt=[], no_cpu_baseline=False)
+    bench.run_reference(args, bench.WORKLOADS["T0"], 0)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "reference"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
