@@ -146,6 +146,15 @@ int scb_eval_local_search(scb_ctx *ctx, const int32_t *individual, int indLen,
                           const int32_t *knockouts, const int32_t *knockins, int node,
                           int32_t *nodeErrors, int maxVariants, int *nVariants);
 
+/* The whole local search of one individual in one launch: the 2^k - 1 variants of EVERY node (the loop over
+ * nodes at singleCell.py:478-510).  nodeErrors[offsets[i] + v - 1] = errors[i] of variant v of node i;
+ * offsets has nodeNum + 1 entries (prefix sums of 2^k_i - 1, 0 for nodes without rule bits). */
+int scb_eval_local_search_all(scb_ctx *ctx, const int32_t *individual, int indLen,
+                              const int32_t *andLenList, const int32_t *individualParse,
+                              const int32_t *andNodes, const int32_t *andNodeInvertList,
+                              const int32_t *knockouts, const int32_t *knockins,
+                              int32_t *nodeErrors, int maxVariants, int32_t *offsets);
+
 /* ---- attractor companion (singleCell.assignAttractors, singleCell.py:1211-1238):
  * dist[c][a] = sum_i |attractors[a][i] - cell c's observed state|, decider = first minimum
  * (pandas idxmin), deciderDistance = the minimum.  dist may be NULL. */

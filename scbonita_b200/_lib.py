@@ -24,7 +24,7 @@ SYMBOLS = (
     "scb_eval_population", "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
     "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
-    "scb_eval_local_search", "scb_hamming_argmin", "scb_attractors", "scb_importance_score",
+    "scb_eval_local_search", "scb_eval_local_search_all", "scb_hamming_argmin", "scb_attractors", "scb_importance_score",
     "scb_set_legacy_geometry", "scSyncBool", "importanceScore", "cluster",
 )
 
@@ -84,6 +84,9 @@ def load(path=None):
     lib.scb_host_free.argtypes = [vp]
     lib.scb_eval_local_search.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, ctypes.c_int,
                                           i32p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.scb_eval_local_search_all.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, i32p,
+                                              ctypes.c_int, i32p]
+    lib.scb_eval_local_search_all.restype = ctypes.c_int
     lib.scb_hamming_argmin.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p]
     lib.scb_attractors.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, ctypes.c_int,
                                    ctypes.c_int, i32p, i32p, vp]

@@ -627,6 +627,49 @@ int scb_eval_local_search(scb_ctx *c, const int32_t *individual, int indLen, con
     return SCB_OK;
 }
 
+/* All nodes at once (the driver loop singleCell.py:478-510 calls __checkNodePossibilities node by node, or through a
+ * ThreadPool): the variants of every node with 1 <= k <= 7 rule bits are scored in ONE launch.
+ * offsets[i] .. offsets[i+1] index nodeErrors for node i (offsets has N + 1 entries; nodes with k == 0 get none). */
+int scb_eval_local_search_all(scb_ctx *c, const int32_t *individual, int indLen, const int32_t *andLenList,
+                              const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                              const int32_t *knockouts, const int32_t *knockins, int32_t *nodeErrors, int maxVariants,
+                              int32_t *offsets)
+{
+    if (!c) return fail(SCB_ERR_INVALID, "null context");
+    if (!individual || !individualParse || !nodeErrors || !offsets) return fail(SCB_ERR_INVALID, "null argument");
+    const int N = c->N;
+    int total = 0;
+    for (int node = 0; node < N; ++node) {
+        const int start = individualParse[node];
+        const int end = (node == N - 1) ? indLen : individualParse[node + 1];
+        const int k = end - start;
+        if (k < 0 || k > SCB_MAX_TERMS || start < 0 || end > indLen) return fail(SCB_ERR_INVALID, "node %d has %d rule bits", node, k);
+        offsets[node] = total;
+        total += k > 0 ? (1 << k) - 1 : 0;
+    }
+    offsets[N] = total;
+    if (maxVariants < total) return fail(SCB_ERR_INVALID, "nodeErrors holds %d entries, %d needed", maxVariants, total);
+    if (total == 0) return SCB_OK;
+    std::vector<int32_t> pop((size_t)total * indLen);
+    for (int node = 0; node < N; ++node) {
+        const int start = individualParse[node];
+        const int nv = offsets[node + 1] - offsets[node];
+        const int k = (node == N - 1 ? indLen : individualParse[node + 1]) - start;
+        for (int v = 1; v <= nv; ++v) {
+            int32_t *row = pop.data() + (size_t)(offsets[node] + v - 1) * indLen;
+            memcpy(row, individual, (size_t)indLen * 4);
+            for (int j = 0; j < k; ++j) row[start + j] = (v >> j) & 1;            /* __bitList, ruleMaker.py:796-802 */
+        }
+    }
+    std::vector<int32_t> nodewise((size_t)total * N);
+    int rc = scb_eval_population(c, total, pop.data(), indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0,
+                                 knockouts, knockins, SCB_MODE_NODEWISE, nodewise.data(), nullptr);
+    if (rc) return rc;
+    for (int node = 0; node < N; ++node)
+        for (int v = offsets[node]; v < offsets[node + 1]; ++v) nodeErrors[v] = nodewise[(size_t)v * N + node];
+    return SCB_OK;
+}
+
 int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t *dist, int32_t *decider,
                        int32_t *deciderDistance)
 {

@@ -238,6 +238,36 @@ class Simulator:
         equivs = [ind_options[i] for i in range(nv) if ind_errors[i] <= minny]
         return equivs[0], equivs, minny, ind_errors
 
+    def local_search(self, indy, KOlist, KIlist):
+        """The loop over nodes of singleCell.__scoreNodes (singleCell.py:478-510) in one launch: returns, per node,
+        the same 4-tuple ``__checkNodePossibilities`` returns."""
+        m = self.model
+        knockouts, knockins = self._knock(KOlist, KIlist)
+        ind = _i32(indy)
+        ends = [m.ind_len if i == m.n - 1 else int(m.individual_parse[i + 1]) for i in range(m.n)]
+        ks = [ends[i] - int(m.individual_parse[i]) for i in range(m.n)]
+        total = sum((1 << k) - 1 for k in ks if k > 0)
+        errs = np.zeros(max(total, 1), dtype=np.int32)
+        offs = np.zeros(m.n + 1, dtype=np.int32)
+        rc = self.lib.scb_eval_local_search_all(self._ctx, _ptr(ind), m.ind_len, _ptr(m.and_len_list),
+                                                _ptr(m.individual_parse), _ptr(m.and_nodes),
+                                                _ptr(m.and_node_invert_list), _ptr(knockouts), _ptr(knockins),
+                                                _ptr(errs), int(errs.shape[0]), _ptr(offs))
+        _lib.check(self.lib, rc)
+        out = []
+        for i in range(m.n):
+            start, k = int(m.individual_parse[i]), ks[i]
+            truth = list(indy[start:start + k])
+            if k == 0:
+                out.append((truth, [truth], [truth], 0.0))
+                continue
+            ind_errors = errs[offs[i]:offs[i + 1]].tolist()
+            options = [[(v >> j) & 1 for j in range(k)] for v in range(1, (1 << k))]
+            minny = min(ind_errors)
+            equivs = [options[v] for v in range(len(options)) if ind_errors[v] <= minny]
+            out.append((equivs[0], equivs, minny, ind_errors))
+        return out
+
     # -- attractor companion ------------------------------------------------------------------
     def attractors(self, individual, knockouts=None, knockins=None, semantics="python", max_states=10):
         """Per-cell attractor window and its states (singleCell.py:1162-1192 runs this one cell at a time in

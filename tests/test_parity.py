@@ -270,6 +270,15 @@ def test_check_node_possibilities(backend):
             assert truth == equivs[0]
 
 
+def test_local_search_all_nodes_in_one_launch(backend):
+    pr = Problem.synthetic(25, big(backend, 300, 4000), 1)
+    pr.pop_an = pr.pop_ai = None
+    with pr.simulator(backend[1]) as sim:
+        every = sim.local_search(pr.individuals[0].tolist(), [0] * pr.n, [0] * pr.n)
+        for node in range(pr.n):
+            assert every[node] == sim.check_node_possibilities(node, pr.individuals[0].tolist(), [0] * pr.n, [0] * pr.n)
+
+
 def test_legacy_scSyncBool_symbol(backend):
     """The reference's own calling convention: 17 x c_void_p, ints smuggled as pointers (ruleMaker.py:1117-1219)."""
     pr = Problem.synthetic(20, 150, 1)
