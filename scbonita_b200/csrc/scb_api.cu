@@ -83,8 +83,8 @@ struct scb_ctx {
     int K = 0, warps = 0, ctas = 0, occ = 1;
     SimGeom main, tail;
     int mainTiles = 0, tailTiles = 0;
-    size_t smemSim = 0, smemRes = 0;
-    int resWarps = 8, resCtas = 0;
+    size_t smemSim = 0, smemRes = 0, smemFill = 0;
+    int resWarps = 8, resCtas = 0, resGroup = 1, fillWarps = 8, fillCtas = 0;
     bool geomValid = false;
     /* device data */
     DevBuf<uint32_t> dX;
@@ -156,13 +156,14 @@ int pick_geometry(scb_ctx *c)
     } else if (scb_smem_bytes(N, K, 2) > c->smemLimit) {
         return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d with %d words per lane exceeds shared memory", N, K);
     }
-    if (scb_smem_bytes(N, 1, 3) > c->smemLimit)
+    if (scb_resolve_smem_bytes(N, 1) > c->smemLimit)
         return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the resolver's three state buffers", N);
 #ifndef SCB_EMU
     CK(cudaFuncSetAttribute(scb_k_sim<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_sim<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_sim<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute(scb_k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_resolve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
@@ -176,12 +177,21 @@ int pick_geometry(scb_ctx *c)
     c->mainTiles = (c->W + WT - 1) / WT;
     c->tailTiles = 0;
     c->K = K; c->warps = c->main.warps; c->ctas = c->main.ctas; c->smemSim = c->main.smem;
-    c->smemRes = scb_smem_bytes(N, 1, 3);
+    /* resolver: two adjacent chunks per item when the simulator tile holds >= 2 chunks and three 64-word
+     * state buffers fit; the fill-forward kernel always works on single chunks */
+    c->resGroup = (K >= 2 && scb_resolve_smem_bytes(N, 2) <= c->smemLimit) ? 2 : 1;
+    c->smemRes = scb_resolve_smem_bytes(N, c->resGroup);
+    c->smemFill = scb_resolve_smem_bytes(N, 1);
     int occR = 1;
-    c->resWarps = std::min(16, std::max(1, (N + 3) / 4));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve, c->resWarps * 32, c->smemRes));
+    c->resWarps = std::min(c->resGroup == 2 ? 24 : 16, std::max(c->resGroup, (N + 3) / 4));
+    if (c->resGroup == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<2>, c->resWarps * 32, c->smemRes));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<1>, c->resWarps * 32, c->smemRes));
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
+    c->fillWarps = std::min(16, std::max(1, (N + 3) / 4));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_fill, c->fillWarps * 32, c->smemFill));
+    c->fillCtas = c->numSM * std::max(1, occR);
+    if (c->optMaxCtas > 0) c->fillCtas = std::min(c->fillCtas, c->optMaxCtas);
     size_t zwords = (size_t)c->main.ctas * N * 32 * K;
     if (c->tailTiles) zwords = std::max(zwords, (size_t)c->tail.ctas * N * 32 * c->tail.K);
     if ((rc = c->dZ.ensure(zwords))) return rc;
@@ -396,7 +406,8 @@ int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, co
     if ((rc = c->dItems.ensure((size_t)P * chunks)) || (rc = c->dFillItems.ensure((size_t)P * chunks)) ||
         (rc = c->dChunkLast.ensure((size_t)P * chunks))) return rc;
     {   /* S_99 hand-over slots for the resolver: at most 64 MiB */
-        const size_t per = (size_t)N * 32;
+        if (!c->geomValid && (rc = pick_geometry(c))) return rc;
+        const size_t per = (size_t)N * 32 * c->resGroup;
         const size_t want = std::min<size_t>((size_t)P * chunks, std::max<size_t>(64, ((size_t)64 << 20) / (per * 4)));
         if ((rc = c->dResolveT.ensure(want * per))) return rc;
         c->resolveTCap = (unsigned)(c->dResolveT.cap / per);
@@ -442,7 +453,8 @@ int scb_pop_run(scb_ctx *c, int mode)
     sa.fitness = c->dFitness.p; sa.nodewise = c->dNodewise.p; sa.cellwise = c->dCellwise.p;
     sa.resolveCount = c->dCounters.p + 1;
     sa.resolveItems = c->dItems.p; sa.resolveCap = (unsigned)std::min<size_t>(c->dItems.cap, 0xffffffffu);
-    sa.resolveT = c->dResolveT.p; sa.resolveTCap = c->resolveTCap;
+    sa.resolveT = c->dResolveT.p; sa.resolveGroup = c->resGroup;
+    sa.resolveTCap = (unsigned)(c->dResolveT.cap / ((size_t)N * 32 * c->resGroup));
     sa.chunkLast = c->dChunkLast.p; sa.chunksPerInd = (c->C + 1023) / 1024;
     sa.fillCount = c->dCounters.p + 3; sa.fillItems = c->dFillItems.p;
     sa.zscratch = c->dZ.p;
@@ -470,10 +482,11 @@ int scb_pop_run(scb_ctx *c, int mode)
 
     ScbResolveArgs ra;
     ra.s = sa; ra.itemCursor = c->dCounters.p + 2;
-    SCB_LAUNCH(scb_k_resolve, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+    if (c->resGroup == 2) SCB_LAUNCH(scb_k_resolve<2>, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+    else SCB_LAUNCH(scb_k_resolve<1>, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
     CK(cudaGetLastError());
     ra.itemCursor = c->dCounters.p + 4;
-    SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+    SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->fillCtas), dim3((unsigned)c->fillWarps * 32), c->smemFill, st, ra);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->evRun1, st));
     c->lastMode = mode; c->ran = true;

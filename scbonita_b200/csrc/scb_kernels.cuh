@@ -50,6 +50,40 @@ template <int K> SCB_DEV void scb_st(unsigned char *p, const ScbVec<K> &r)
     else if (K == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(r.v[0], r.v[1 % K]);
     else *reinterpret_cast<uint32_t *>(p) = r.v[0];
 }
+/* Shared-memory accesses of the hot loop go through 32-bit shared-window addresses (ld.shared / st.shared):
+ * with generic pointers the compiler re-derives the window base (S2R + LEA) and does 64-bit address
+ * arithmetic for every access.  Under the emulator an "address" is simply a host pointer. */
+#if defined(__CUDA_ARCH__)
+typedef uint32_t scb_saddr;
+SCB_DEV scb_saddr scb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int K> SCB_DEV ScbVec<K> scb_lds(scb_saddr a)
+{
+    ScbVec<K> r;
+    if (K == 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1 % K]), "=r"(r.v[2 % K]), "=r"(r.v[3 % K]) : "r"(a));
+    else if (K == 2) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.v[0]), "=r"(r.v[1 % K]) : "r"(a));
+    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r.v[0]) : "r"(a));
+    return r;
+}
+template <int K> SCB_DEV void scb_sts(scb_saddr a, const ScbVec<K> &r)
+{
+    if (K == 4) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(r.v[0]), "r"(r.v[1 % K]), "r"(r.v[2 % K]), "r"(r.v[3 % K]) : "memory");
+    else if (K == 2) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(r.v[0]), "r"(r.v[1 % K]) : "memory");
+    else asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(r.v[0]) : "memory");
+}
+SCB_DEV uint4 scb_lds_desc(scb_saddr a)
+{
+    uint4 d;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(a));
+    return d;
+}
+#else
+typedef unsigned char *scb_saddr;
+SCB_DEV scb_saddr scb_smem_addr(const void *p) { return reinterpret_cast<unsigned char *>(const_cast<void *>(p)); }
+template <int K> SCB_DEV ScbVec<K> scb_lds(scb_saddr a) { return scb_ld<K>(a); }
+template <int K> SCB_DEV void scb_sts(scb_saddr a, const ScbVec<K> &r) { scb_st<K>(a, r); }
+SCB_DEV uint4 scb_lds_desc(scb_saddr a) { return *reinterpret_cast<const uint4 *>(a); }
+#endif
+
 /* global memory, L2 only (the snapshot scratch is written and re-read by the same thread) */
 template <int K> SCB_DEV ScbVec<K> scb_ldcg(const unsigned char *p)
 {
@@ -255,8 +289,8 @@ SCB_DEV void scb_load_program(uint4 *desc, const uint4 *g, int4 cnt, int N, int 
  *   tsm      : lane-adjusted pointer into the shared-memory target state (TCMP)
  * d2 / dz accumulate, per word, the cells whose new state differs from S_{t-1} ... */
 template <int K, bool PLAIN>
-SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 *desc, int4 cnt,
-                      int warp, int S, unsigned flagsRt, unsigned char *zg, const unsigned char *tsm,
+SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
+                      int warp, int S, unsigned flagsRt, unsigned char *zg, scb_saddr tsm,
                       ScbVec<K> &d2, ScbVec<K> &dz, bool active = true)
 {
     /* `active` is false for lanes whose words lie entirely beyond the last cell (the padding of the last
@@ -269,8 +303,8 @@ SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 
      * of the snapshot is covered by a whole node's processing. */
 #define SCB_PRE(dsto, dstoNext)                                                                   \
         ScbVec<K> o2, zc = zn;                                                                    \
-        if (flags & SCB_SF_CMP2) o2 = scb_ld<K>(dst + (dsto));                                    \
-        if (flags & SCB_SF_TCMP) zc = scb_ld<K>(tsm + (dsto));                                    \
+        if (flags & SCB_SF_CMP2) o2 = scb_lds<K>(dst + (dsto));                                   \
+        if (flags & SCB_SF_TCMP) zc = scb_lds<K>(tsm + (dsto));                                   \
         if (flags & SCB_SF_ZCMP) zn = scb_ldcg<K>(zg + (dstoNext));
 #define SCB_POST(r, dsto)                                                                         \
     do {                                                                                          \
@@ -278,7 +312,7 @@ SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 
             _Pragma("unroll") for (int k = 0; k < K; ++k) d2.v[k] |= (r).v[k] ^ o2.v[k]; }        \
         if (flags & (SCB_SF_ZCMP | SCB_SF_TCMP)) {                                                \
             _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ zc.v[k]; }        \
-        scb_st<K>(dst + (dsto), (r));                                                             \
+        scb_sts<K>(dst + (dsto), (r));                                                            \
         if (flags & SCB_SF_ZSNAP) scb_stcg<K>(zg + (dsto), (r));                                  \
     } while (0)
 
@@ -286,31 +320,37 @@ SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 
     const int e3 = cnt.x, e2 = cnt.x + cnt.y, e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
     if (j >= e0 || !active) return;
     /* the next node's descriptor is fetched while the current node is processed */
-    uint4 d = desc[j];
+    const uint32_t dstep = 16u * (uint32_t)S;
+    scb_saddr dp = desc + 16u * (uint32_t)j;
+    const scb_saddr dlast = desc + 16u * (uint32_t)(e0 - 1);
+    uint4 d = scb_lds_desc(dp);
     ScbVec<K> zn;
 #pragma unroll
     for (int k = 0; k < K; ++k) zn.v[k] = 0u;
     if ((flags & SCB_SF_ZCMP) && j < e1) zn = scb_ldcg<K>(zg + (d.w & 0xFFFFFFu));
     for (; j < e3; j += S) {
-        const uint4 dn = desc[j + S < e0 ? j + S : j];
+        dp = (dp + dstep <= dlast) ? dp + dstep : dp;
+        const uint4 dn = scb_lds_desc(dp);
         SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
-        const ScbVec<K> a = scb_ld<K>(src + d.x), b = scb_ld<K>(src + d.y), c = scb_ld<K>(src + d.z);
+        const ScbVec<K> a = scb_lds<K>(src + d.x), b = scb_lds<K>(src + d.y), c = scb_lds<K>(src + d.z);
         ScbVec<K> r = scb_apply3<K>(d.w >> 24, a, b, c);
         SCB_POST(r, d.w & 0xFFFFFFu);
         d = dn;
     }
     for (; j < e2; j += S) {
-        const uint4 dn = desc[j + S < e0 ? j + S : j];
+        dp = (dp + dstep <= dlast) ? dp + dstep : dp;
+        const uint4 dn = scb_lds_desc(dp);
         SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
-        const ScbVec<K> a = scb_ld<K>(src + d.x), b = scb_ld<K>(src + d.y);
+        const ScbVec<K> a = scb_lds<K>(src + d.x), b = scb_lds<K>(src + d.y);
         ScbVec<K> r = scb_apply2<K>(d.w >> 24, a, b);
         SCB_POST(r, d.w & 0xFFFFFFu);
         d = dn;
     }
     for (; j < e1; j += S) {
-        const uint4 dn = desc[j + S < e0 ? j + S : j];
+        dp = (dp + dstep <= dlast) ? dp + dstep : dp;
+        const uint4 dn = scb_lds_desc(dp);
         SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
-        ScbVec<K> r = scb_ld<K>(src + d.x);
+        ScbVec<K> r = scb_lds<K>(src + d.x);
         const uint32_t inv = (d.w >> 24) ? 0xffffffffu : 0u;
 #pragma unroll
         for (int k = 0; k < K; ++k) r.v[k] ^= inv;
@@ -319,12 +359,12 @@ SCB_DEV void scb_step(const unsigned char *src, unsigned char *dst, const uint4 
     }
     if (flags & SCB_SF_CONST) {
         for (; j < e0; j += S) {
-            const uint4 dc = desc[j];
+            const uint4 dc = scb_lds_desc(desc + 16u * (uint32_t)j);
             ScbVec<K> r;
             const uint32_t val = (dc.w >> 24) ? 0xffffffffu : 0u;
 #pragma unroll
             for (int k = 0; k < K; ++k) r.v[k] = val;
-            scb_st<K>(dst + (dc.w & 0xFFFFFFu), r);
+            scb_sts<K>(dst + (dc.w & 0xFFFFFFu), r);
             if (flags & SCB_SF_ZSNAP) scb_stcg<K>(zg + (dc.w & 0xFFFFFFu), r);
         }
     }
@@ -373,6 +413,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
     const uint32_t laneOff = (uint32_t)lane * 4u * K;
     const bool early = (A.flags & SCB_KF_EARLY) != 0, useZ = (A.flags & SCB_KF_SNAP) != 0;
     unsigned char *zg = reinterpret_cast<unsigned char *>(A.zscratch + (unsigned long long)blockIdx.x * A.zstride) + laneOff;
+    const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
     const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
     unsigned long long stepsDone = 0, tilesDone = 0;
 
@@ -381,7 +422,9 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         __syncthreads();
         const unsigned item = (unsigned)sh[0];
         if (item >= total) break;
-        const int p = (int)(item / (unsigned)A.tiles), tile = (int)(item % (unsigned)A.tiles);
+        /* tile-major order: the long tiles of a hard individual are spread over the whole launch and the last
+         * items to be handed out are the cheap, partly filled tail tiles, which keeps the end of the launch level */
+        const int p = (int)(item % (unsigned)A.P), tile = (int)(item / (unsigned)A.P);
         const int w0 = A.wordBase + tile * WT;
         const int4 cnt = A.counts[p];
         scb_load_program<K>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
@@ -426,8 +469,8 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             ScbVec<K> d2, dz;
 #pragma unroll
             for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
-            if (f == 0u) scb_step<K, true>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, 0u, zg, nullptr, d2, dz, laneActive);
-            else scb_step<K, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, zg, nullptr, d2, dz, laneActive);
+            if (f == 0u) scb_step<K, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, zg, sa, d2, dz, laneActive);
+            else scb_step<K, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, zg, sa, d2, dz, laneActive);
             if (f & SCB_SF_CMP2) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
@@ -488,34 +531,44 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             }
             const unsigned bal = __ballot_sync(0xffffffffu, bad);
             const int LPC = 32 / K;                          /* lanes per chunk */
+            const int KR = A.resolveGroup;                   /* chunks per resolver item (1 or 2, <= K) */
             if (lane < K) {
                 const unsigned msk = (LPC == 32) ? 0xffffffffu : (((1u << LPC) - 1u) << (lane * LPC));
                 const int cb = (bal & msk) != 0u;
                 const int q = w0 / 32 + lane;                  /* chunk index within the individual */
                 sh[4 + lane] = cb;
                 sh[8 + lane] = -1;
-                if (cb) {
-                    const unsigned idx = atomicAdd(A.resolveCount, 1u);
-                    if (idx < A.resolveCap) A.resolveItems[idx] = make_uint2((unsigned)p, (unsigned)q);
-                    if (idx < A.resolveTCap) sh[8 + lane] = (int)idx;
-                } else if (q < A.chunksPerInd) {
+                if (!cb && q < A.chunksPerInd) {
                     /* every valid cell of the chunk is found: its last valid cell can feed a later fill-forward */
                     const long long rem = (long long)A.C - (long long)q * 1024;
                     A.chunkLast[(long long)p * A.chunksPerInd + q] = (int)(rem >= 1024 ? 1023 : rem - 1);
                 }
             }
+            __syncwarp();
+            if (lane < K / KR) {
+                /* one resolver item per group of KR adjacent chunks that holds an unproven chunk */
+                unsigned bad = 0u;
+                for (int j = 0; j < KR; ++j) if (sh[4 + lane * KR + j]) bad |= 1u << j;
+                if (bad) {
+                    const unsigned idx = atomicAdd(A.resolveCount, 1u);
+                    if (idx < A.resolveCap)
+                        A.resolveItems[idx] = make_uint2((unsigned)p, (unsigned)(w0 / 32 + lane * KR) | (bad << 24));
+                    if (idx < A.resolveTCap) for (int j = 0; j < KR; ++j) sh[8 + lane * KR + j] = (int)idx;
+                }
+            }
         }
         __syncthreads();
-        /* hand S_99 of the queued chunks to the resolver (t == 99 here, so src holds S_99) */
+        /* hand S_99 of the queued groups to the resolver (t == 99 here, so src holds S_99) */
         if (!allfound) {
+            const int GW = 32 * A.resolveGroup;               /* words per group */
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int w = lane * K + k, j = w / 32;
                 const int slot = sh[8 + j];
                 if (slot < 0) continue;
-                uint32_t *T = A.resolveT + (unsigned long long)slot * N * 32 + (w & 31);
+                uint32_t *T = A.resolveT + (unsigned long long)slot * N * GW + (w % GW);
                 for (int row = warp; row < N; row += S)
-                    T[(long long)row * 32] = *reinterpret_cast<const uint32_t *>(sm + srcOff + (uint32_t)row * ROWB + (uint32_t)w * 4u);
+                    T[(long long)row * GW] = *reinterpret_cast<const uint32_t *>(sm + srcOff + (uint32_t)row * ROWB + (uint32_t)w * 4u);
             }
             __syncthreads();          /* the cellwise epilogue reuses the S_99 buffer */
         }
@@ -592,45 +645,52 @@ struct ScbResolveArgs {
     unsigned int *itemCursor;     /* persistent work counter of the launch */
 };
 
-/* simulate chunk q of the individual whose program is in `desc`.
+/* simulate KR adjacent chunks (first chunk q) of the individual whose program is in `desc`.
  *   how = 0: pass a (99 plain steps -> T = S_99), then pass b (98 steps comparing every S_j with T)
- *   how = 1: T is read from Tglob ([N][32] words, written by K2), pass b only
+ *   how = 1: T is read from Tglob ([N][32*KR] words, written by K2), pass b only
  *   how = 2: 98 plain steps only (Fm is not computed)
  * On return: buffer A rows hold S_98, buffer B rows hold e = (S_98 xor S_0) & valid for every node,
- * Fm[32] = found & valid per word (how != 2), vm[32] = valid masks.  All threads call it. */
+ * Fm[32*KR] = found & valid per word (how != 2), vm[32*KR] = valid masks.  All threads call it. */
+template <int KR>
 SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uint4 *desc, int4 cnt,
                                uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
                                const uint32_t *Tglob, int tid, int nthr)
 {
     const int N = A.N;
-    const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
+    const uint32_t ROWB = 128u * KR, BUFB = (uint32_t)N * ROWB;
+    const int GW = 32 * KR;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
-    const uint32_t laneOff = (uint32_t)lane * 4u;
+    const uint32_t laneOff = (uint32_t)lane * 4u * KR;
     const int w0 = q * 32;
     unsigned char *bufA = sm, *bufB = sm + BUFB, *bufT = sm + 2u * BUFB;
-    ScbVec<1> d2, dz;
+    const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
+    ScbVec<KR> d2, dz;
 
     for (int pass = (how == 0 ? 0 : 1); pass < 2; ++pass) {
         const bool cmp = pass == 1 && how != 2;
         for (int row = warp; row < N; row += S) {
-            const ScbVec<1> v = scb_ldg<1>(A.X + (long long)row * A.Wpad + w0 + lane);
-            scb_st<1>(bufA + (uint32_t)row * ROWB + laneOff, v);
-            if (pass == 1 && how == 1) {
-                ScbVec<1> tv;
-                tv.v[0] = Tglob[(long long)row * 32 + lane];
-                scb_st<1>(bufT + (uint32_t)row * ROWB + laneOff, tv);
-            }
+            const ScbVec<KR> v = scb_ldg<KR>(A.X + (long long)row * A.Wpad + w0 + lane * KR);
+            scb_st<KR>(bufA + (uint32_t)row * ROWB + laneOff, v);
+            if (pass == 1 && how == 1)
+                scb_st<KR>(bufT + (uint32_t)row * ROWB + laneOff,
+                           scb_ld<KR>(reinterpret_cast<const unsigned char *>(Tglob + (long long)row * GW + lane * KR)));
         }
-        if (tid < 32) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; Fm[tid] = 0u; }
+        if (tid < GW) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; Fm[tid] = 0u; }
         __syncthreads();
         if (cmp) {
             /* j = 0: compare S_0 with T on every row */
-            uint32_t d = 0u;
-            for (int row = warp; row < N; row += S)
-                d |= scb_ld<1>(bufA + (uint32_t)row * ROWB + laneOff).v[0] ^ scb_ld<1>(bufT + (uint32_t)row * ROWB + laneOff).v[0];
-            if (d) atomicOr(&dmz[lane], d);
+            ScbVec<KR> d;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) d.v[k] = 0u;
+            for (int row = warp; row < N; row += S) {
+                const ScbVec<KR> x = scb_ld<KR>(bufA + (uint32_t)row * ROWB + laneOff), y = scb_ld<KR>(bufT + (uint32_t)row * ROWB + laneOff);
+#pragma unroll
+                for (int k = 0; k < KR; ++k) d.v[k] |= x.v[k] ^ y.v[k];
+            }
+#pragma unroll
+            for (int k = 0; k < KR; ++k) if (d.v[k]) atomicOr(&dmz[lane * KR + k], d.v[k]);
             __syncthreads();
-            if (tid < 32) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
+            if (tid < GW) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
             __syncthreads();
         }
         const int last = pass == 0 ? SCB_LAST : SCB_LAST - 1;
@@ -638,13 +698,17 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
         for (int tn = 1; tn <= last; ++tn) {
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
             if (cmp) f |= SCB_SF_TCMP;
-            d2.v[0] = 0u; dz.v[0] = 0u;
-            if (f == 0u) scb_step<1, true>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, 0u, nullptr, bufT + laneOff, d2, dz);
-            else scb_step<1, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S, f, nullptr, bufT + laneOff, d2, dz);
-            if (cmp && dz.v[0]) atomicOr(&dmz[lane], dz.v[0]);
+#pragma unroll
+            for (int k = 0; k < KR; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
+            if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz);
+            else scb_step<KR, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz);
+            if (cmp) {
+#pragma unroll
+                for (int k = 0; k < KR; ++k) if (dz.v[k]) atomicOr(&dmz[lane * KR + k], dz.v[k]);
+            }
             __syncthreads();
             if (cmp) {
-                if (tid < 32) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
+                if (tid < GW) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
                 __syncthreads();
             }
             const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
@@ -652,36 +716,46 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
         if (pass == 0) {
             /* S_99 sits in buffer B (99 is odd): T = B */
             for (int row = warp; row < N; row += S)
-                scb_st<1>(bufT + (uint32_t)row * ROWB + laneOff, scb_ld<1>(bufB + (uint32_t)row * ROWB + laneOff));
+                scb_st<KR>(bufT + (uint32_t)row * ROWB + laneOff, scb_ld<KR>(bufB + (uint32_t)row * ROWB + laneOff));
             __syncthreads();
         }
     }
     /* S_98 in buffer A (98 is even).  e rows -> buffer B */
     for (int row = warp; row < N; row += S) {
-        ScbVec<1> e;
-        e.v[0] = (scb_ld<1>(bufA + (uint32_t)row * ROWB + laneOff).v[0]
-                  ^ __ldg(A.X + (long long)row * A.Wpad + w0 + lane)) & vm[lane];
-        scb_st<1>(bufB + (uint32_t)row * ROWB + laneOff, e);
+        const ScbVec<KR> s98 = scb_ld<KR>(bufA + (uint32_t)row * ROWB + laneOff);
+        const ScbVec<KR> x0 = scb_ldg<KR>(A.X + (long long)row * A.Wpad + w0 + lane * KR);
+        ScbVec<KR> e;
+#pragma unroll
+        for (int k = 0; k < KR; ++k) e.v[k] = (s98.v[k] ^ x0.v[k]) & vm[lane * KR + k];
+        scb_st<KR>(bufB + (uint32_t)row * ROWB + laneOff, e);
     }
-    if (tid < 32) Fm[tid] &= vm[tid];
+    if (tid < GW) Fm[tid] &= vm[tid];
     __syncthreads();
 }
 
-/* K3 phase 1: exact found mask and error sums of every queued chunk; leading not-found cells that must
- * copy a cell of an earlier chunk are queued for phase 2. */
-__global__ void scb_k_resolve(ScbResolveArgs R)
+/* shared-memory carve-up of the resolver kernels (after the three state buffers) */
+SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR)
+{
+    return (size_t)3 * N * 128 * KR + (size_t)N * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 4 + 256;
+}
+
+/* K3 phase 1: exact found mask and error sums of every queued group of KR chunks; leading not-found cells that
+ * must copy a cell of an earlier chunk are queued for phase 2.  Only the chunks K2 flagged are summed here. */
+template <int KR>
+__global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
 {
     SCB_DYN_SMEM(smraw);
     const ScbSimArgs &A = R.s;
     const int N = A.N;
-    const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
+    const uint32_t ROWB = 128u * KR, BUFB = (uint32_t)N * ROWB;
+    const int GW = 32 * KR, GC = 1024 * KR;
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + 3u * BUFB);
     uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
-    uint32_t *Fm = dmz + 32;
-    uint32_t *vm = Fm + 32;
-    int *sh = reinterpret_cast<int *>(vm + 32 + 64);       /* [0] item, [2] pending cells, [3] not-found cells */
-    int *srcc = sh + 8;                                    /* [1024] source cell of each cell */
+    uint32_t *Fm = dmz + GW;
+    uint32_t *vm = Fm + GW;
+    int *sh = reinterpret_cast<int *>(vm + GW);            /* [0] item, [2] pending cells, [3] not-found cells */
+    int *srcc = sh + 16;                                   /* [GC] source cell of each cell */
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
     const unsigned char *bufB = sm + BUFB;
@@ -693,18 +767,20 @@ __global__ void scb_k_resolve(ScbResolveArgs R)
         __syncthreads();
         const unsigned it = (unsigned)sh[0];
         if (it >= nItems) break;
-        const int p = (int)A.resolveItems[it].x, q = (int)A.resolveItems[it].y;
+        const int p = (int)A.resolveItems[it].x;
+        const int q = (int)(A.resolveItems[it].y & 0xFFFFFFu);
+        const unsigned flagged = A.resolveItems[it].y >> 24;       /* bit j: chunk q + j was left out by K2 */
         const int4 cnt = A.counts[p];
-        scb_load_program<1>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+        scb_load_program<KR>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
         if (tid == 0) { sh[2] = 0; sh[3] = 0; }
         __syncthreads();
         const bool haveT = it < A.resolveTCap;
-        scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, q, haveT ? 1 : 0,
-                          A.resolveT + (unsigned long long)it * N * 32, tid, nthr);
+        scb_resolve_chunk<KR>(A, sm, desc, cnt, dmz, Fm, vm, q, haveT ? 1 : 0,
+                              A.resolveT + (unsigned long long)it * N * GW, tid, nthr);
 
-        /* source cell of every cell: itself when found, else the nearest earlier found cell of the chunk
+        /* source cell of every cell: itself when found, else the nearest earlier found cell of the group
          * (the reference's fill-forward), -1 when that lies in an earlier chunk, -2 padding */
-        for (int i = tid; i < 1024; i += nthr) {
+        for (int i = tid; i < GC; i += nthr) {
             const int w = i >> 5, b = i & 31;
             int s = -2;
             if ((vm[w] >> b) & 1u) {
@@ -715,27 +791,35 @@ __global__ void scb_k_resolve(ScbResolveArgs R)
                     if (m) s = w * 32 + (31 - __clz((int)m));
                     else for (int ww = w - 1; ww >= 0; --ww)
                         if (Fm[ww]) { s = ww * 32 + (31 - __clz((int)Fm[ww])); break; }
-                    atomicAdd(reinterpret_cast<unsigned int *>(&sh[3]), 1u);
-                    if (s == -1) atomicAdd(reinterpret_cast<unsigned int *>(&sh[2]), 1u);
+                    if ((flagged >> (i >> 10)) & 1u) {
+                        atomicAdd(reinterpret_cast<unsigned int *>(&sh[3]), 1u);
+                        if (s == -1) atomicAdd(reinterpret_cast<unsigned int *>(&sh[2]), 1u);
+                    }
                 }
             }
             srcc[i] = s;
         }
         __syncthreads();
 
-        /* per-node sums: found cells plus the copies made by not-found cells */
+        /* per-node sums over the flagged chunks: found cells plus the copies made by not-found cells */
         unsigned tot = 0;
         for (int j = warp; j < N; j += S) {
             const uint32_t dsto = desc[j].w & 0xFFFFFFu;
             const int node = (int)(dsto / ROWB);
-            const uint32_t e = *reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)lane * 4u);
-            unsigned c = (unsigned)__popc(e & Fm[lane]);
-            uint32_t nfb = ~Fm[lane] & vm[lane];
-            while (nfb) {
-                const int b = __ffs((int)nfb) - 1;
-                nfb &= nfb - 1u;
-                const int s = srcc[lane * 32 + b];
-                if (s >= 0) c += (*reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)(s >> 5) * 4u) >> (s & 31)) & 1u;
+            unsigned c = 0;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                const int w = lane * KR + k;
+                if (!((flagged >> (w >> 5)) & 1u)) continue;
+                const uint32_t e = *reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)w * 4u);
+                c += (unsigned)__popc(e & Fm[w]);
+                uint32_t nfb = ~Fm[w] & vm[w];
+                while (nfb) {
+                    const int b = __ffs((int)nfb) - 1;
+                    nfb &= nfb - 1u;
+                    const int sc = srcc[w * 32 + b];
+                    if (sc >= 0) c += (*reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)(sc >> 5) * 4u) >> (sc & 31)) & 1u;
+                }
             }
             tot += c;
             if (A.mode == 1) {
@@ -746,25 +830,28 @@ __global__ void scb_k_resolve(ScbResolveArgs R)
         tot = scb_warp_sum(tot);
         if (lane == 0 && tot) atomicAdd(&A.fitness[p], (unsigned long long)tot);
         if (A.mode == 2) {
-            for (int i = tid; i < 1024; i += nthr) {
-                const int s = srcc[i];
-                if (s < 0) continue;
+            for (int i = tid; i < GC; i += nthr) {
+                const int sc = srcc[i];
+                if (sc < 0 || !((flagged >> (i >> 10)) & 1u)) continue;
                 int n1 = 0;
                 for (int row = 0; row < N; ++row)
-                    n1 += (int)((*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + (uint32_t)(s >> 5) * 4u) >> (s & 31)) & 1u);
+                    n1 += (int)((*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + (uint32_t)(sc >> 5) * 4u) >> (sc & 31)) & 1u);
                 A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
             }
         }
         if (tid == 0) {
-            int lastFound = -1;
-            for (int w = 31; w >= 0; --w) if (Fm[w]) { lastFound = w * 32 + (31 - __clz((int)Fm[w])); break; }
-            A.chunkLast[(long long)p * A.chunksPerInd + q] = lastFound;
+            for (int j = 0; j < KR; ++j) {
+                if (!((flagged >> j) & 1u)) continue;
+                int lastFound = -1;
+                for (int w = j * 32 + 31; w >= j * 32; --w) if (Fm[w]) { lastFound = (w - j * 32) * 32 + (31 - __clz((int)Fm[w])); break; }
+                A.chunkLast[(long long)p * A.chunksPerInd + q + j] = lastFound;
+            }
             if (sh[2] > 0) {
                 const unsigned idx = atomicAdd(A.fillCount, 1u);
                 A.fillItems[idx] = make_uint4((unsigned)p, (unsigned)q, (unsigned)sh[2], 0u);
             }
             if (sh[3] > 0) atomicAdd(&A.diag->not_found_cells, (unsigned long long)sh[3]);
-            atomicAdd(&A.diag->resolver_chunks, 1ull);
+            atomicAdd(&A.diag->resolver_chunks, (unsigned long long)__popc(flagged));
         }
         __syncthreads();
     }
@@ -784,7 +871,7 @@ __global__ void scb_k_fill(ScbResolveArgs R)
     uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
     uint32_t *Fm = dmz + 32;
     uint32_t *vm = Fm + 32;
-    int *sh = reinterpret_cast<int *>(vm + 32 + 64);
+    int *sh = reinterpret_cast<int *>(vm + 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
     const unsigned char *bufB = sm + BUFB;
@@ -811,7 +898,7 @@ __global__ void scb_k_fill(ScbResolveArgs R)
         const int4 cnt = A.counts[p];
         scb_load_program<1>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
         __syncthreads();
-        scb_resolve_chunk(A, sm, desc, cnt, dmz, Fm, vm, qq, 2, nullptr, tid, nthr);
+        scb_resolve_chunk<1>(A, sm, desc, cnt, dmz, Fm, vm, qq, 2, nullptr, tid, nthr);
         const int sw = cell >> 5, sb = cell & 31;
         unsigned add = 0;
         for (int j = warp; j < N; j += S) {
@@ -856,6 +943,7 @@ __global__ void scb_k_traj(ScbTrajArgs A)
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
     const uint32_t laneOff = (uint32_t)lane * 4u;
     const int4 cnt = A.counts[0];
+    const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
     scb_load_program<1>(desc, A.descs, cnt, N, tid, nthr);
     for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
         const int w0 = tile * 32;
@@ -872,8 +960,8 @@ __global__ void scb_k_traj(ScbTrajArgs A)
         d2.v[0] = 0u; dz.v[0] = 0u;
         for (int t = 1; t < A.steps; ++t) {
             unsigned char *zg = reinterpret_cast<unsigned char *>(tbase + (unsigned long long)t * N * 32) + laneOff;
-            scb_step<1, false>(sm + srcOff + laneOff, sm + dstOff + laneOff, desc, cnt, warp, S,
-                               SCB_SF_ZSNAP | SCB_SF_CONST, zg, nullptr, d2, dz);
+            scb_step<1, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S,
+                               SCB_SF_ZSNAP | SCB_SF_CONST, zg, sa, d2, dz);
             __syncthreads();
             const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
         }

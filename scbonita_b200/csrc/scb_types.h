@@ -98,7 +98,8 @@ struct ScbSimArgs {
     unsigned int *resolveCount;   /* number of chunks queued for the exact resolver */
     uint2 *resolveItems;          /* (individual, chunk) */
     unsigned int resolveCap;
-    uint32_t *resolveT;           /* S_99 of queued chunks: [resolveTCap][N][32] words (saves K3 a pass) */
+    int resolveGroup;             /* adjacent chunks per resolver item (1 or 2; <= K of the launch) */
+    uint32_t *resolveT;           /* S_99 of queued groups: [resolveTCap][N][32*resolveGroup] words (saves K3 a pass) */
     unsigned int resolveTCap;
     int32_t *chunkLast;           /* [P][chunksPerInd]: last found valid cell of each chunk, -1 none */
     int chunksPerInd;
