@@ -129,6 +129,7 @@ int sim_geometry(scb_ctx *c, int K, int optWarps, SimGeom *g)
         S = 32 / occGuess;
         S = std::min(24, std::max(2, S));
         S = std::min(S, std::max(1, (N + 3) / 4));
+        if (occGuess == 1) S = std::min(S, std::max(8, N / 10));       /* ~10 nodes per warp measured best */
     }
     S = std::max(S, K);                 /* the mask arrays need 32*K threads */
     S = std::min(S, 24);                /* __launch_bounds__(768) */
