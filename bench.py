@@ -105,26 +105,40 @@ def build_problem(wl, seed_shift=0):
 # reference arm: the unmodified reference C on the host cores
 # ---------------------------------------------------------------------------------------------
 def reference_sample(pr, cells, n_ind, threads):
-    """Times n_ind individuals x `cells` cells of the workload through oracle/_ref (the reference's own
-    scSyncBool via its ctypes convention), `threads` concurrent calls (ctypes releases the GIL; this is how
-    the reference parallelises local search, singleCell.py:490-492).  Returns (seconds, CRE)."""
+    """Times n_ind individuals x `cells` cells of the workload on the host cores.  Returns (seconds, CRE, kind).
+
+    kind "reference": oracle/_ref, the UNMODIFIED reference scSyncBool driven with its own ctypes convention,
+    `threads` concurrent calls (ctypes releases the GIL; this is how the reference parallelises local search,
+    singleCell.py:490-492).  If the prebuilt reference library is not on this box, kind "port": the scalar C
+    restatement oracle/scb_oracle.c (same loops, runtime strides), also one call per thread."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
-    ref = oracle.RefSimulator(cells)
     m = oracle.Model(pr.net.and_len, pr.net.parse, pr.net.and_nodes, pr.net.and_inv, pr.node_positions,
                      pr.net.ind_len, pr.knockouts, pr.knockins)
-    bm = ref.dense(pr.bin_rows[:, :cells].astype(np.int32), pr.node_positions)
+    try:
+        ref = oracle.RefSimulator(cells)
+        bm = ref.dense(pr.bin_rows[:, :cells].astype(np.int32), pr.node_positions)
+        kind = "reference"
 
-    def one(p):
-        p = p % pr.individuals.shape[0]
-        return ref.sync_bool(m, pr.individuals[p], bm, cells, 0, and_nodes=pr.pop_and_nodes[p],
-                             and_inv=pr.pop_and_inv[p]).sum()
+        def one(p):
+            p = p % pr.individuals.shape[0]
+            return ref.sync_bool(m, pr.individuals[p], bm, cells, 0, and_nodes=pr.pop_and_nodes[p],
+                                 and_inv=pr.pop_and_inv[p]).sum()
+    except (FileNotFoundError, OSError):
+        bm = np.zeros((pr.net.n, cells), np.int32)
+        bm[pr.node_positions] = pr.bin_rows[:, :cells]
+        kind = "port"
+
+        def one(p):
+            p = p % pr.individuals.shape[0]
+            return oracle.sync_bool(m, pr.individuals[p], bm, cells, 0, and_nodes=pr.pop_and_nodes[p],
+                                    and_inv=pr.pop_and_inv[p])[0].sum()
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(one, range(n_ind)))
     dt = time.perf_counter() - t0
-    return dt, float(n_ind) * cells * pr.net.n * STEPS_PER_CELL
+    return dt, float(n_ind) * cells * pr.net.n * STEPS_PER_CELL, kind
 
 
 def run_reference(args, wl, rank):
@@ -134,20 +148,21 @@ def run_reference(args, wl, rank):
     cores = len(os.sched_getaffinity(0))
     threads = min(cores, 64)
     cells = min(wl["cells"], 12_500)
-    sample = "%d individuals x %d cells x %d nodes per step, %d concurrent scSyncBool calls (oracle/_ref, gcc -O3)" % (
-        threads, cells, wl["nodes"], threads)
     for _ in range(args.warmup):
         reference_sample(pr, cells, threads, threads)
-    tot_t, tot_u = 0.0, 0.0
+    tot_t, tot_u, kind = 0.0, 0.0, "reference"
     for _ in range(args.steps):
-        dt, u = reference_sample(pr, cells, threads, threads)
+        dt, u, kind = reference_sample(pr, cells, threads, threads)
         tot_t += dt; tot_u += u
+    sample = "%d individuals x %d cells x %d nodes per step, %d concurrent scSyncBool calls (%s, gcc -O3)" % (
+        threads, cells, wl["nodes"], threads,
+        "oracle/_ref = the unmodified reference C" if kind == "reference" else "oracle/scb_oracle.c restatement")
     value = tot_u / tot_t
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -274,6 +289,14 @@ def run_ours(args, wl, rank, world, local_rank):
         # algorithmic HBM bytes of one K2 launch: packed matrix N*C/8, rule programs 16 B/node, fitness 8 B
         alg_bytes = N * C / 8.0 + P * N * 16.0 + P * 8.0
         hbm_ach = alg_bytes / (k2_ms * 1e-3) / 1e9
+        traffic = None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed `ncu --set full` capture
+            with open(os.path.join(ROOT, "profiles", "r1", "k2_dram_traffic.json")) as f:
+                t = json.load(f)
+            if t.get("workload") == args.workload:
+                traffic = t["dram_bytes_per_launch"]
+        except Exception:
+            pass
         # binding resource: shared-memory bandwidth, 128 B/clk/SM.  Executed traffic of one launch =
         # executed (tile, step) pairs x nodes x 128*K bytes x (inputs + 1 store); inputs/node from the network
         sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
@@ -287,10 +310,11 @@ def run_ours(args, wl, rank, world, local_rank):
             try:
                 cores = min(len(os.sched_getaffinity(0)), 64)
                 cells = min(C, 12_500)
-                dt, u = reference_sample(pr, cells, cores, cores)
-                cpu = {"value": u / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-                       "sample": "%d individuals x %d cells x %d nodes, %d concurrent scSyncBool calls of the "
-                                 "unmodified reference C (oracle/_ref), %.1f s" % (cores, cells, N, cores, dt)}
+                dt, u, kind = reference_sample(pr, cells, cores, cores)
+                cpu = {"value": u / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                       "sample": "%d individuals x %d cells x %d nodes, %d concurrent scSyncBool calls of %s, %.1f s" % (
+                           cores, cells, N, cores, "the unmodified reference C (oracle/_ref)" if kind == "reference"
+                           else "the C restatement (oracle/scb_oracle.c)", dt)}
             except Exception as exc:           # oracle/_ref absent on this box
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % exc}
         line = {
@@ -307,7 +331,8 @@ def run_ours(args, wl, rank, world, local_rank):
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": 5 * args.steps,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": hbm_ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                         "frac": hbm_ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                         "peak_source": peak_kind,
                          "kernel": "scb_k_sim<%d>" % info["words_per_lane"], "kernel_ms": k2_ms,
                          "note": "the path is shared-memory/issue bound, not HBM bound (SURVEY 8d): see roofline_binding"},
             "roofline_binding": {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
