@@ -77,8 +77,8 @@ struct scb_ctx {
     size_t smemLimit = 0;
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
-    int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 4, optSearch = 0;
-    unsigned long long snapLo = (1ull << 32), snapHi = 1ull;   /* snapshots when computing S_32 and S_64 */
+    int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 6, optSearch = 0, optMinGap = 8;
+    unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
     SimGeom main, tail;
@@ -352,6 +352,9 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
         case SCB_OPT_PERIOD_SEARCH:
             if (value < 0 || value > 99) return fail(SCB_ERR_INVALID, "period search must be in [0,99]");
             c->optSearch = (int)value; return SCB_OK;
+        case SCB_OPT_SNAP_MIN_GAP:
+            if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "snapshot gap must be in [1,99]");
+            c->optMinGap = (int)value; return SCB_OK;
         case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_SNAP_HI: c->snapHi = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_WARPS:
@@ -461,6 +464,7 @@ int scb_pop_run(scb_ctx *c, int mode)
     sa.zscratch = c->dZ.p;
     sa.flags = (c->optEarly ? SCB_KF_EARLY : 0u) | (c->optSnap ? SCB_KF_SNAP : 0u);
     sa.chkEvery = c->optChk; sa.snapLo = c->snapLo; sa.snapHi = c->snapHi; sa.periodSearch = c->optSearch;
+    sa.snapMinGap = c->optMinGap;
     sa.diag = c->dDiag.p;
     CK(cudaEventRecord(c->evSim0, st));
     for (int part = 0; part < 2; ++part) {

@@ -417,11 +417,13 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
     const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
     unsigned long long stepsDone = 0, tilesDone = 0;
 
-    for (;;) {
-        if (tid == 0) sh[0] = (int)atomicAdd(A.workCounter, 1u);
-        __syncthreads();
-        const unsigned item = (unsigned)sh[0];
+    if (tid == 0) sh[12] = (int)atomicAdd(A.workCounter, 1u);
+    __syncthreads();
+    for (unsigned iter = 0;; ++iter) {
+        const unsigned item = (unsigned)sh[12 + (iter & 1u)];
         if (item >= total) break;
+        /* the next item is requested now and read after this tile's last barrier: the atomic's latency is hidden */
+        if (tid == 0) sh[12 + ((iter + 1u) & 1u)] = (int)atomicAdd(A.workCounter, 1u);
         /* tile-major order: the long tiles of a hard individual are spread over the whole launch and the last
          * items to be handed out are the cheap, partly filled tail tiles, which keeps the end of the launch level */
         const int p = (int)(item % (unsigned)A.P), tile = (int)(item / (unsigned)A.P);
@@ -458,7 +460,9 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             if (!plainOnly) {
                 if (!allres) {
                     if (tn == SCB_LAST || (early && tn >= 3 && (tn % A.chkEvery) == 0)) f |= SCB_SF_CMP2;
-                    if (useZ && zs >= 0) f |= SCB_SF_ZCMP;
+                    /* a cell of period L matches the snapshot at every multiple of L, so the first compares after a
+                     * snapshot can be skipped without losing any cell: only the proof comes a little later */
+                    if (useZ && zs >= 0 && (tn - zs >= A.snapMinGap || tn == SCB_LAST)) f |= SCB_SF_ZCMP;
                     const bool snapNow = tn < 64 ? ((A.snapLo >> tn) & 1ull) != 0ull
                                                  : ((A.snapHi >> (tn - 64)) & 1ull) != 0ull;
                     if (useZ && snapNow && tn < SCB_LAST) f |= SCB_SF_ZSNAP;

@@ -111,6 +111,7 @@ struct ScbSimArgs {
     int chkEvery;                 /* cadence of the period<=2 check */
     unsigned long long snapLo, snapHi;  /* bit t set: take a snapshot when computing S_t */
     int periodSearch;             /* snapshot-compare steps kept after all cells resolved */
+    int snapMinGap;               /* first snapshot compare this many steps after the snapshot */
     ScbDiag *diag;
 };
 

@@ -41,7 +41,8 @@ def test_synthetic_matches_oracle(backend, n, cells, pop):
 
 @pytest.mark.parametrize("opts", [dict(early_exit=0, snapshots=0), dict(early_exit=1, snapshots=0),
                                   dict(early_exit=0, snapshots=1), dict(words=1), dict(words=2, check_every=3),
-                                  dict(warps=4), dict(period_search=24), dict(check_every=1)])
+                                  dict(warps=4), dict(period_search=24), dict(check_every=1), dict(snap_min_gap=1, check_every=4),
+                                  dict(snap_min_gap=20, snap_lo=1 << 20, snap_hi=0)])
 def test_every_schedule_gives_identical_integers(backend, opts):
     """Early exit, snapshot resolution and tile geometry are optimisations: results must not move."""
     pr = Problem.synthetic(60, big(backend, 2100, 21000), big(backend, 5, 24))
