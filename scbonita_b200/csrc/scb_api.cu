@@ -189,7 +189,7 @@ int pick_geometry(scb_ctx *c)
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<1>, c->resWarps * 32, c->smemRes));
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
-    c->fillWarps = std::min(16, std::max(1, (N + 3) / 4));
+    c->fillWarps = std::min(24, std::max(1, (N + 3) / 4));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_fill, c->fillWarps * 32, c->smemFill));
     c->fillCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->fillCtas = std::min(c->fillCtas, c->optMaxCtas);

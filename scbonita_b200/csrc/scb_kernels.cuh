@@ -658,8 +658,11 @@ struct ScbResolveArgs {
 template <int KR>
 SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uint4 *desc, int4 cnt,
                                uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
-                               const uint32_t *Tglob, int tid, int nthr)
+                               const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr, int onlyLane = -1)
 {
+    /* D: [2][warps][32*KR] per-step difference words of every warp (double buffered by step parity), so that the
+     * per-step "equal to T" reduction needs no atomics and no barrier of its own.
+     * onlyLane >= 0: only that lane's words are simulated (the fill-forward needs a single cell). */
     const int N = A.N;
     const uint32_t ROWB = 128u * KR, BUFB = (uint32_t)N * ROWB;
     const int GW = 32 * KR;
@@ -704,16 +707,22 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
             if (cmp) f |= SCB_SF_TCMP;
 #pragma unroll
             for (int k = 0; k < KR; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
-            if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz);
-            else scb_step<KR, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz);
+            const bool act = onlyLane < 0 || lane == onlyLane;
+            if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
+            else scb_step<KR, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             if (cmp) {
+                uint32_t *Dw = D + ((size_t)(tn & 1) * S + warp) * GW + lane * KR;
 #pragma unroll
-                for (int k = 0; k < KR; ++k) if (dz.v[k]) atomicOr(&dmz[lane * KR + k], dz.v[k]);
+                for (int k = 0; k < KR; ++k) Dw[k] = dz.v[k];
             }
             __syncthreads();
-            if (cmp) {
-                if (tid < GW) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
-                __syncthreads();
+            if (cmp && tid < GW) {
+                /* these threads fold step tn while the others already run step tn + 1; buffer (tn & 1) is not
+                 * written again before the barrier of step tn + 1, which these threads take part in */
+                const uint32_t *Dr = D + (size_t)(tn & 1) * S * GW + tid;
+                uint32_t acc = 0u;
+                for (int w = 0; w < S; ++w) acc |= Dr[(size_t)w * GW];
+                Fm[tid] |= ~acc;
             }
             const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
         }
@@ -740,7 +749,8 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
 /* shared-memory carve-up of the resolver kernels (after the three state buffers) */
 SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR)
 {
-    return (size_t)3 * N * 128 * KR + (size_t)N * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 4 + 256;
+    return (size_t)3 * N * 128 * KR + (size_t)N * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 4
+           + (size_t)2 * 24 * 32 * KR * 4 + 256;                       /* + D[2][<=24 warps][32*KR] */
 }
 
 /* K3 phase 1: exact found mask and error sums of every queued group of KR chunks; leading not-found cells that
@@ -760,6 +770,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
     uint32_t *vm = Fm + GW;
     int *sh = reinterpret_cast<int *>(vm + GW);            /* [0] item, [2] pending cells, [3] not-found cells */
     int *srcc = sh + 16;                                   /* [GC] source cell of each cell */
+    uint32_t *Dbuf = reinterpret_cast<uint32_t *>(srcc + GC);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
     const unsigned char *bufB = sm + BUFB;
@@ -780,7 +791,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
         __syncthreads();
         const bool haveT = it < A.resolveTCap;
         scb_resolve_chunk<KR>(A, sm, desc, cnt, dmz, Fm, vm, q, haveT ? 1 : 0,
-                              A.resolveT + (unsigned long long)it * N * GW, tid, nthr);
+                              A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf);
 
         /* source cell of every cell: itself when found, else the nearest earlier found cell of the group
          * (the reference's fill-forward), -1 when that lies in an earlier chunk, -2 padding */
@@ -902,8 +913,8 @@ __global__ void scb_k_fill(ScbResolveArgs R)
         const int4 cnt = A.counts[p];
         scb_load_program<1>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
         __syncthreads();
-        scb_resolve_chunk<1>(A, sm, desc, cnt, dmz, Fm, vm, qq, 2, nullptr, tid, nthr);
         const int sw = cell >> 5, sb = cell & 31;
+        scb_resolve_chunk<1>(A, sm, desc, cnt, dmz, Fm, vm, qq, 2, nullptr, tid, nthr, nullptr, sw);
         unsigned add = 0;
         for (int j = warp; j < N; j += S) {
             const uint32_t dsto = desc[j].w & 0xFFFFFFu;
