@@ -96,6 +96,13 @@ int scb_device_count(void);
 int scb_ctx_create(scb_ctx **ctx, int device, int nodeNum, int lenSamples,
                    const void *binMat, int elemBytes, int64_t rowStride,
                    const int32_t *nodePositions);
+/* The same from a CSR matrix (scipy.sparse.csr_matrix: indptr[nRows+1], indices, data), which is how the
+ * reference stores binMat (singleCell.py:25-90): only the slices of the N gene rows are copied, there is no
+ * dense detour (the reference densifies 20000 x 15000 on every evaluation, ruleMaker.py:1109-1111).
+ * data may be NULL (stored element = 1); values must be 0 or 1; columns >= lenSamples are ignored. */
+int scb_ctx_create_csr(scb_ctx **ctx, int device, int nodeNum, int lenSamples,
+                       const int32_t *indptr, const int32_t *indices, const double *data,
+                       int nRows, const int32_t *nodePositions);
 int scb_ctx_destroy(scb_ctx *ctx);
 int scb_ctx_set_option(scb_ctx *ctx, int key, int64_t value);
 int scb_ctx_info(scb_ctx *ctx, int *nodeNum, int *lenSamples, int *wordsPerLane, int *warps,

@@ -20,7 +20,7 @@ OPT_SNAP_LO, OPT_SNAP_HI, OPT_SNAP_MIN_GAP = 8, 9, 10
 # every symbol include/scbonita_b200.h declares (tests check that the library exports them all)
 SYMBOLS = (
     "scb_last_error", "scb_version", "scb_device_count",
-    "scb_ctx_create", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info",
+    "scb_ctx_create", "scb_ctx_create_csr", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info",
     "scb_eval_population", "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
     "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
@@ -66,6 +66,9 @@ def load(path=None):
     lib.scb_device_count.restype = ctypes.c_int
     lib.scb_ctx_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
                                    ctypes.c_int64, i32p]
+    lib.scb_ctx_create_csr.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p, i32p, vp,
+                                       ctypes.c_int, i32p]
+    lib.scb_ctx_create_csr.restype = ctypes.c_int
     lib.scb_ctx_destroy.argtypes = [vp]
     lib.scb_ctx_set_option.argtypes = [vp, ctypes.c_int, ctypes.c_int64]
     lib.scb_ctx_info.argtypes = [vp] + [ctypes.POINTER(ctypes.c_int)] * 6
@@ -94,7 +97,7 @@ def load(path=None):
     lib.scb_importance_score.restype = ctypes.c_int
     lib.scb_set_legacy_geometry.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.scb_set_legacy_geometry.restype = None
-    for name in ("scb_ctx_create", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info", "scb_eval_population",
+    for name in ("scb_ctx_create", "scb_ctx_create_csr", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info", "scb_eval_population",
                  "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev", "scb_ctx_stream",
                  "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms", "scb_ctx_flush_l2", "scb_host_alloc",
                  "scb_host_free", "scb_eval_local_search",

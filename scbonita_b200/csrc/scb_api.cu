@@ -317,6 +317,87 @@ int scb_ctx_create(scb_ctx **out, int device, int nodeNum, int lenSamples, const
     return SCB_OK;
 }
 
+/* Context from a CSR matrix: only the index/value slices of the N gene rows the network uses
+ * are copied to the device; no dense detour. */
+int scb_ctx_create_csr(scb_ctx **out, int device, int nodeNum, int lenSamples, const int32_t *indptr,
+                       const int32_t *indices, const double *data, int nRows, const int32_t *nodePositions)
+{
+    if (!out) return fail(SCB_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    if (nodeNum <= 0 || lenSamples <= 0) return fail(SCB_ERR_INVALID, "nodeNum and lenSamples must be positive");
+    if (nodeNum > 65535) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > 65535", nodeNum);
+    if (!indptr || !indices || !nodePositions) return fail(SCB_ERR_INVALID, "null CSR / nodePositions pointer");
+    long long nnz = 0;
+    for (int i = 0; i < nodeNum; ++i) {
+        const int r = nodePositions[i];
+        if (r < 0 || r >= nRows) return fail(SCB_ERR_INVALID, "nodePositions[%d] = %d outside the %d CSR rows", i, r, nRows);
+        if (indptr[r + 1] < indptr[r]) return fail(SCB_ERR_INVALID, "CSR indptr is not monotone at row %d", r);
+        nnz += indptr[r + 1] - indptr[r];
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(SCB_ERR_CUDA, "no CUDA device available");
+    if (device < 0 || device >= ndev) return fail(SCB_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    scb_ctx *c = new (std::nothrow) scb_ctx();
+    if (!c) return fail(SCB_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return fail(SCB_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    c->numSM = prop.multiProcessorCount;
+    c->smemLimit = prop.sharedMemPerBlockOptin;
+    c->N = nodeNum; c->C = lenSamples;
+    c->W = (lenSamples + 31) / 32;
+    c->Wpad = ((c->W + 127) / 128) * 128;
+    auto bail = [&](int rc) { scb_ctx_destroy(c); return rc; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaStreamCreate failed"));
+    for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreate(&c->evRun0) != cudaSuccess || cudaEventCreate(&c->evRun1) != cudaSuccess ||
+        cudaEventCreate(&c->evSim0) != cudaSuccess || cudaEventCreate(&c->evSim1) != cudaSuccess)
+        return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
+    int rc;
+    if ((rc = c->dX.ensure((size_t)c->N * c->Wpad))) return bail(rc);
+    if ((rc = c->dDiag.ensure(1))) return bail(rc);
+    if ((rc = c->dCounters.ensure(8))) return bail(rc);
+    /* gather the selected rows' slices on the host (pointer arithmetic only), one H2D each */
+    std::vector<int32_t> rowOf((size_t)std::max<long long>(nnz, 1)), col((size_t)std::max<long long>(nnz, 1));
+    std::vector<double> val(data ? (size_t)std::max<long long>(nnz, 1) : 0);
+    long long k = 0;
+    for (int i = 0; i < nodeNum; ++i) {
+        const int r = nodePositions[i];
+        for (int e = indptr[r]; e < indptr[r + 1]; ++e, ++k) {
+            rowOf[k] = i; col[k] = indices[e];
+            if (data) val[k] = data[e];
+        }
+    }
+    DevBuf<int32_t> dRow, dCol;
+    DevBuf<double> dVal;
+    if ((rc = dRow.ensure(rowOf.size())) || (rc = dCol.ensure(col.size())) || (data && (rc = dVal.ensure(val.size())))) {
+        dRow.release(); dCol.release(); dVal.release();
+        return bail(rc);
+    }
+    cudaError_t ce = cudaMemsetAsync(c->dX.p, 0, (size_t)c->N * c->Wpad * 4, c->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), c->stream);
+    if (ce == cudaSuccess && nnz) ce = cudaMemcpyAsync(dRow.p, rowOf.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess && nnz) ce = cudaMemcpyAsync(dCol.p, col.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess && nnz && data) ce = cudaMemcpyAsync(dVal.p, val.data(), (size_t)nnz * 8, cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess && nnz) {
+        ScbPackCsrArgs pa;
+        pa.rowOfNnz = dRow.p; pa.col = dCol.p; pa.val = data ? dVal.p : nullptr; pa.nnz = nnz;
+        pa.C = c->C; pa.Wpad = c->Wpad; pa.X = c->dX.p; pa.diag = c->dDiag.p;
+        SCB_LAUNCH(scb_k_pack_csr, dim3((unsigned)((nnz + 255) / 256)), dim3(256), 0, c->stream, pa);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&c->hDiag, c->dDiag.p, sizeof(ScbDiag), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    dRow.release(); dCol.release(); dVal.release();
+    if (ce != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "CSR pack failed: %s", cudaGetErrorString(ce)));
+    if (c->hDiag.nonbinary_cells)
+        return bail(fail(SCB_ERR_INVALID, "the CSR matrix holds %llu values other than 0/1 in the network's rows", c->hDiag.nonbinary_cells));
+    if ((rc = pick_geometry(c))) return bail(rc);
+    *out = c;
+    return SCB_OK;
+}
+
 int scb_ctx_destroy(scb_ctx *c)
 {
     if (!c) return SCB_OK;

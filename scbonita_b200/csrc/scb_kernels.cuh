@@ -257,6 +257,30 @@ __global__ void scb_k_pack(ScbPackArgs A)
     if (lane == 0 && bad) atomicAdd(&A.diag->nonbinary_cells, (unsigned long long)bad);
 }
 
+/* K1b: bit-pack straight from a CSR matrix (the reference keeps binMat as scipy CSR and densifies it on every
+ * evaluation, ruleMaker.py:1109-1111).  One thread per stored element of the selected rows: the bit of
+ * (row i, column c) is OR-ed into X[i][c/32].  X must be zeroed first. */
+struct ScbPackCsrArgs {
+    const int32_t *rowOfNnz;      /* [nnz] node index of each stored element */
+    const int32_t *col;           /* [nnz] */
+    const double *val;            /* [nnz] or null (structure only: stored => 1) */
+    long long nnz;
+    int C, Wpad;
+    uint32_t *X;
+    ScbDiag *diag;
+};
+
+__global__ void scb_k_pack_csr(ScbPackCsrArgs A)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.nnz) return;
+    const int c = A.col[e];
+    const double v = A.val ? A.val[e] : 1.0;
+    if (c < 0 || c >= A.C) return;                  /* columns beyond lenSamples are not part of the data set */
+    if (v != 0.0 && v != 1.0) { atomicAdd(&A.diag->nonbinary_cells, 1ull); return; }
+    if (v == 1.0) atomicOr(&A.X[(long long)A.rowOfNnz[e] * A.Wpad + (c >> 5)], 1u << (c & 31));
+}
+
 /* ------------------------------------------------------------------------------------------
  * shared pieces of K2 / K3
  * ---------------------------------------------------------------------------------------- */

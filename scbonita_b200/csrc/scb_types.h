@@ -136,7 +136,7 @@ struct ScbWindowArgs {
 struct ScbHammingArgs {
     const uint32_t *X;            /* [N][Wpad] */
     int N, C, Wpad, A;
-    const uint32_t *attr;         /* [A][N] as 0/1 words?  no: packed [A][ceil(N/32)] node bits */
+    const uint32_t *attr;         /* [A][ceil(N/32)]: bit i%32 of word i/32 = node i of the attractor */
     int32_t *dist;                /* [C][A] or null */
     int32_t *decider;             /* [C] */
     int32_t *deciderDistance;     /* [C] */

@@ -55,6 +55,20 @@ class Simulator:
     def __init__(self, bin_mat, model, n_cells=None, device=0, lib_path=None):
         self.lib = _lib.load(lib_path)
         self.model = model
+        if hasattr(bin_mat, "indptr") and hasattr(bin_mat, "indices"):
+            # scipy.sparse CSR, the form the reference keeps binMat in: no dense detour
+            csr = bin_mat.tocsr() if hasattr(bin_mat, "tocsr") else bin_mat
+            self.n_cells = int(csr.shape[1] if n_cells is None else n_cells)
+            if int(model.node_positions.max(initial=0)) >= csr.shape[0]:
+                raise ValueError("nodePositions exceed the rows of bin_mat")
+            indptr, indices = _i32(csr.indptr), _i32(csr.indices)
+            data = np.ascontiguousarray(csr.data, dtype=np.float64)
+            self._ctx = ctypes.c_void_p()
+            rc = self.lib.scb_ctx_create_csr(ctypes.byref(self._ctx), int(device), model.n, self.n_cells, _ptr(indptr),
+                                             _ptr(indices), _ptr(data), int(csr.shape[0]), _ptr(model.node_positions))
+            _lib.check(self.lib, rc)
+            self.last_stats = None
+            return
         bm = np.asarray(bin_mat)
         if bm.dtype == np.uint8 or bm.dtype == np.bool_:
             bm = np.ascontiguousarray(bm, dtype=np.uint8)

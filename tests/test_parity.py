@@ -339,3 +339,22 @@ def test_hamming_random(backend, n, cells, A):
         dist, dec, dd = sim.hamming_argmin(attr)
     wd, wdec, wdd = oracle.hamming_argmin(attr, bm, pos, cells)
     assert np.array_equal(dist, wd) and np.array_equal(dec, wdec) and np.array_equal(dd, wdd)
+
+
+def test_csr_matrix_ingest(backend):
+    """the context is built straight from scipy CSR (how the reference stores binMat)."""
+    import scipy.sparse as sp
+    pr = Problem.synthetic(40, big(backend, 1500, 15000), 3)
+    big_rows = np.zeros((pr.bm.shape[0] + 7, pr.n_cells + 100), np.float64)      # extra genes / extra columns
+    big_rows[:pr.bm.shape[0], :pr.n_cells] = pr.bm
+    big_rows[:, pr.n_cells:] = 1.0                                               # beyond lenSamples: ignored
+    csr = sp.csr_matrix(big_rows)
+    sim = simulator.Simulator(csr, tables(pr.net, pr.node_positions), n_cells=pr.n_cells, lib_path=backend[1])
+    if backend[0] == "emu":
+        sim.set_option(_lib.OPT_MAX_CTAS, 2)
+    with sim:
+        pr.check(sim)
+    bad = sp.csr_matrix(np.where(big_rows > 0, 2.0, 0.0))
+    with pytest.raises(simulator.ScbError) as ei:
+        simulator.Simulator(bad, tables(pr.net, pr.node_positions), n_cells=pr.n_cells, lib_path=backend[1])
+    assert ei.value.code == _lib.ERR_INVALID
