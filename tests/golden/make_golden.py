@@ -96,7 +96,10 @@ def import_reference_single_cell():
     """Imports /root/reference/src/scBONITA/singleCell.py with stand-ins for the plotting / GA / KEGG
     packages that are not installed here (none of them takes part in __cluster)."""
     from unittest.mock import MagicMock
-    for name in ("deap", "deap.base", "deap.creator", "deap.gp", "deap.tools", "deap.algorithms", "seaborn",
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import deap_standin
+    deap_standin.install()                       # functional stand-in for the GA containers (deap is not installed)
+    for name in ("seaborn",
                  "matplotlib", "matplotlib.pyplot", "matplotlib.patches", "statsmodels", "statsmodels.stats",
                  "statsmodels.stats.multitest", "bioservices", "bioservices.kegg", "bs4", "requests"):
         sys.modules.setdefault(name, MagicMock())

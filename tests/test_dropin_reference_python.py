@@ -87,3 +87,40 @@ def test_unmodified_reference_importance_call(model, emu_lib):
     want = sc._ruleMaker__evaluateByNode(ind, [3], [], ref.importanceScore, importanceScores=True)
     got = sc._ruleMaker__evaluateByNode(ind, [3], [], ours.importanceScore, importanceScores=True)
     assert np.float64(got[0]).tobytes() == np.float64(want[0]).tobytes(), (got, want)
+
+
+def _run_reference_ga(sc, so_path, tmp_path, seed):
+    """ruleMaker.__eaMuPlusLambdaAdaptive loads "./simulator.so" relative to the working directory
+    (ruleMaker.py:979): the drop-in is literally a file swap."""
+    import random
+    import copy
+    workdir = tmp_path / ("run_" + os.path.basename(so_path))
+    workdir.mkdir()
+    os.symlink(so_path, workdir / "simulator.so")
+    model = copy.deepcopy(sc)
+    model._ruleMaker__makeToolBox(None)
+    model.params.popSize, model.params.lambd, model.params.mu, model.params.generations = 8, 8, 4, 2
+    random.seed(seed)
+    np.random.seed(seed)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        population, logbook = model._ruleMaker__eaMuPlusLambdaAdaptive(None, "graph", verbose=False)
+    finally:
+        os.chdir(cwd)
+    return [list(ind[1]) for ind in population], [list(ind.fitness.values) for ind in population], \
+           [(rec["gen"], rec["nevals"], float(rec["min"]), float(rec["max"])) for rec in logbook]
+
+
+def test_unmodified_reference_ga_run_is_reproduced(model, emu_lib, tmp_path, capsys):
+    """The whole GA driver (population init, adaptive mutation, NSGA-II selection, logbook), unmodified, with only
+    ./simulator.so swapped: same final population, same fitness values, same logbook."""
+    sc, _ = model
+    if not hasattr(sc, "params") or not hasattr(sc.params, "popSize"):
+        pytest.skip("reference model has no GA parameters")
+    want = _run_reference_ga(sc, os.path.join(ROOT, "oracle", "_ref", "simulator.so"), tmp_path, 20260)
+    got = _run_reference_ga(sc, emu_lib, tmp_path, 20260)
+    capsys.readouterr()
+    assert got[2] == want[2]          # logbook: gen, nevals, min, max
+    assert got[1] == want[1]          # fitness of the survivors
+    assert got[0] == want[0]          # their rule bit-strings

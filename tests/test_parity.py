@@ -358,3 +358,36 @@ def test_csr_matrix_ingest(backend):
     with pytest.raises(simulator.ScbError) as ei:
         simulator.Simulator(bad, tables(pr.net, pr.node_positions), n_cells=pr.n_cells, lib_path=backend[1])
     assert ei.value.code == _lib.ERR_INVALID
+
+
+def test_legacy_symbol_is_reentrant(backend):
+    """The reference's parallel local search calls scSyncBool from a ThreadPool (singleCell.py:487-497; ctypes
+    releases the GIL): concurrent calls must not interfere."""
+    from multiprocessing.pool import ThreadPool
+    pr = Problem.synthetic(20, 150, 6)
+    lib = _lib.load(backend[1])
+    o = pr.oracle()
+    stride = 256
+    lib.scb_set_legacy_geometry(20000, stride)
+    bm = np.zeros((pr.bm.shape[0], stride), np.int32)
+    bm[:, :150] = pr.bm
+    V = ctypes.c_void_p
+    al, parse, ko, ki, pos = [np.ascontiguousarray(a, np.int32) for a in (pr.net.and_len, pr.net.parse, pr.ko, pr.ki, pr.node_positions)]
+    fn = lib.scSyncBool
+    fn.restype = None
+    fn.argtypes = None
+
+    def one(p):
+        ind, an, ai = [np.ascontiguousarray(a, np.int32) for a in (pr.individuals[p], pr.pop_an[p], pr.pop_ai[p])]
+        errors = np.zeros(pr.n + 150, np.int32)
+        vals = np.zeros((100, 64), np.int32)
+        fn(V(vals.ctypes.data), V(ind.ctypes.data), V(len(ind)), V(pr.n), V(al.ctypes.data), V(parse.ctypes.data),
+           V(an.ctypes.data), V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data), V(150),
+           V(bm.ctypes.data), V(pos.ctypes.data), V(errors.ctypes.data), V(1), V(0))
+        return errors[:pr.n].copy()
+
+    with ThreadPool(4) as pool:
+        got = pool.map(one, list(range(6)) * 2)
+    lib.scb_set_legacy_geometry(20000, 15000)
+    for p, e in zip(list(range(6)) * 2, got):
+        assert np.array_equal(e, o["nodewise"][p]), p
