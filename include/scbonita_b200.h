@@ -82,6 +82,9 @@ typedef struct scb_stats {
     int64_t tiles;                /* tiles simulated (individuals x cell tiles)                       */
     float   kernel_ms;            /* device time of the last evaluation (CUDA events on the stream)   */
     float   sim_ms;               /* of which the simulator kernel K2 alone                           */
+    int64_t cyc_prologue;         /* SM clocks summed over the K2 CTAs: work fetch + program + S_0 tile load */
+    int64_t cyc_steps;            /*   ... the synchronous steps                                      */
+    int64_t cyc_epilogue;         /*   ... chunk flags, error reduction, outputs                      */
 } scb_stats;
 
 const char *scb_last_error(void);

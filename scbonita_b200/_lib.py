@@ -34,7 +34,8 @@ class Stats(ctypes.Structure):
                 ("empty_rule_nodes", ctypes.c_int64), ("unsupported_nodes", ctypes.c_int64),
                 ("bad_index_nodes", ctypes.c_int64), ("term_overflow_nodes", ctypes.c_int64),
                 ("resolver_chunks", ctypes.c_int64), ("steps_executed", ctypes.c_int64),
-                ("tiles", ctypes.c_int64), ("kernel_ms", ctypes.c_float), ("sim_ms", ctypes.c_float)]
+                ("tiles", ctypes.c_int64), ("kernel_ms", ctypes.c_float), ("sim_ms", ctypes.c_float),
+                ("cyc_prologue", ctypes.c_int64), ("cyc_steps", ctypes.c_int64), ("cyc_epilogue", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

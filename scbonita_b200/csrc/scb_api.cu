@@ -606,6 +606,9 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
         stats->resolver_chunks = (int64_t)d.resolver_chunks;
         stats->steps_executed = (int64_t)d.steps_executed;
         stats->tiles = (int64_t)d.tiles;
+        stats->cyc_prologue = (int64_t)d.cyc_prologue;
+        stats->cyc_steps = (int64_t)d.cyc_steps;
+        stats->cyc_epilogue = (int64_t)d.cyc_epilogue;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->evRun0, c->evRun1) == cudaSuccess) stats->kernel_ms = ms;
         if (cudaEventElapsedTime(&ms, c->evSim0, c->evSim1) == cudaSuccess) stats->sim_ms = ms;

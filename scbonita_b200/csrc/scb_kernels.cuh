@@ -121,6 +121,15 @@ template <int K> SCB_DEV ScbVec<K> scb_ldg(const uint32_t *p)
 #endif
 }
 
+SCB_DEV long long scb_clock()
+{
+#if defined(__CUDA_ARCH__) && defined(SCB_PHASE_CLOCKS)
+    return clock64();          /* per-phase cycle counters of K2 (build with -DSCB_PHASE_CLOCKS); off by default */
+#else
+    return 0;
+#endif
+}
+
 SCB_DEV unsigned scb_warp_sum(unsigned v)
 {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -440,6 +449,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
     const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
     const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
     unsigned long long stepsDone = 0, tilesDone = 0;
+    long long cycPro = 0, cycStep = 0, cycEpi = 0;
 
     if (tid == 0) sh[12] = (int)atomicAdd(A.workCounter, 1u);
     __syncthreads();
@@ -451,6 +461,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         /* tile-major order: the long tiles of a hard individual are spread over the whole launch and the last
          * items to be handed out are the cheap, partly filled tail tiles, which keeps the end of the launch level */
         const int p = (int)(item % (unsigned)A.P), tile = (int)(item / (unsigned)A.P);
+        const long long c0 = scb_clock();
         const int w0 = A.wordBase + tile * WT;
         const int4 cnt = A.counts[p];
         scb_load_program<K>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
@@ -475,6 +486,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         __syncthreads();
 
         const bool laneActive = ((long long)w0 + lane * K) * 32 < A.C;       /* the lane holds a valid cell */
+        const long long c1 = scb_clock();
         uint32_t srcOff = 0u, dstOff = BUFB, finOff = 0u;
         int t = 0, target = SCB_LAST, zs = -1, ncmp = 0, searchLeft = 0;
         bool allres = false, allfound = false, plainOnly = false, haveFin = false;
@@ -549,6 +561,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         if (!haveFin) finOff = (t == SCB_LAST) ? dstOff : srcOff;
         if (allres) allfound = true;
         stepsDone += (unsigned long long)t; ++tilesDone;
+        const long long c2 = scb_clock();
 
         /* ---- chunk flags: a 32-word chunk with an unproven valid cell goes to K3 ---------- */
         if (warp == 0) {
@@ -652,10 +665,14 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             }
         }
         __syncthreads();
+        cycPro += c1 - c0; cycStep += c2 - c1; cycEpi += scb_clock() - c2;
     }
     if (tid == 0 && tilesDone) {
         atomicAdd(&A.diag->steps_executed, stepsDone);
         atomicAdd(&A.diag->tiles, tilesDone);
+        atomicAdd(&A.diag->cyc_prologue, (unsigned long long)cycPro);
+        atomicAdd(&A.diag->cyc_steps, (unsigned long long)cycStep);
+        atomicAdd(&A.diag->cyc_epilogue, (unsigned long long)cycEpi);
     }
 }
 

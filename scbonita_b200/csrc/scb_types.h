@@ -57,6 +57,7 @@ struct ScbDiag {                      /* device-side counters, zeroed per evalua
     unsigned long long resolver_chunks;
     unsigned long long steps_executed;
     unsigned long long tiles;
+    unsigned long long cyc_prologue, cyc_steps, cyc_epilogue;   /* SM clocks of thread 0 of every K2 CTA, per phase */
 };
 
 /* One compiled node: d.x, d.y, d.z = input node indices, d.w = node index | lut8 << 24.
