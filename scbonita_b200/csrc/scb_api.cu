@@ -78,6 +78,7 @@ struct scb_ctx {
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
     int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 6, optSearch = 0, optMinGap = 8;
+    int optTmem = 1;
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
@@ -135,9 +136,9 @@ int sim_geometry(scb_ctx *c, int K, int optWarps, SimGeom *g)
     S = std::min(S, 24);                /* __launch_bounds__(768) */
     g->warps = S;
     int occ = 1;
-    if (K == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<4>, S * 32, g->smem));
-    else if (K == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<2>, S * 32, g->smem));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scb_k_sim<1>, S * 32, g->smem));
+    if (K == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (scb_k_sim<4, false>), S * 32, g->smem));
+    else if (K == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (scb_k_sim<2, false>), S * 32, g->smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (scb_k_sim<1, false>), S * 32, g->smem));
     if (occ < 1) return fail(SCB_ERR_UNSUPPORTED, "simulator kernel does not fit on an SM (N=%d, K=%d, warps=%d)", N, K, S);
     g->ctas = c->numSM * occ;
     if (c->optMaxCtas > 0) g->ctas = std::min(g->ctas, c->optMaxCtas);
@@ -160,9 +161,12 @@ int pick_geometry(scb_ctx *c)
     if (scb_resolve_smem_bytes(N, 1) > c->smemLimit)
         return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the resolver's three state buffers", N);
 #ifndef SCB_EMU
-    CK(cudaFuncSetAttribute(scb_k_sim<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute(scb_k_sim<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute(scb_k_sim<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute((scb_k_sim<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute((scb_k_sim<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute((scb_k_sim<4, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute((scb_k_sim<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute((scb_k_sim<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute((scb_k_sim<4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
@@ -436,6 +440,7 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
         case SCB_OPT_SNAP_MIN_GAP:
             if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "snapshot gap must be in [1,99]");
             c->optMinGap = (int)value; return SCB_OK;
+        case SCB_OPT_TMEM: c->optTmem = value != 0; return SCB_OK;
         case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_SNAP_HI: c->snapHi = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_WARPS:
@@ -556,12 +561,30 @@ int scb_pop_run(scb_ctx *c, int mode)
         sa.wordBase = part == 0 ? 0 : c->mainTiles * 32 * c->K;
         sa.workCounter = c->dCounters.p + (part == 0 ? 0 : 5);
         sa.zstride = (unsigned long long)N * 32 * g.K;
+        {   /* snapshot in tensor memory when the columns of all co-resident CTAs fit into the SM's 512 */
+            const int npw = (N + g.warps - 1) / g.warps;
+            const int need = g.K * ((g.warps + 3) / 4) * npw;
+            int cols = 32;
+            while (cols < need) cols <<= 1;
+            const int ctasPerSm = std::max(1, g.ctas / std::max(1, c->numSM));
+            sa.tmemCols = (c->optTmem && c->optSnap && cols <= 512 && cols * ctasPerSm <= 512) ? cols : 0;
+            sa.tmemSlotsPerWarp = npw;
+        }
         const long long items = (long long)P * tiles;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, g.ctas));
         const dim3 block((unsigned)g.warps * 32);
-        if (g.K == 4) SCB_LAUNCH(scb_k_sim<4>, dim3(grid), block, g.smem, st, sa);
-        else if (g.K == 2) SCB_LAUNCH(scb_k_sim<2>, dim3(grid), block, g.smem, st, sa);
-        else SCB_LAUNCH(scb_k_sim<1>, dim3(grid), block, g.smem, st, sa);
+#ifdef SCB_EMU
+        sa.tmemCols = 0;                            /* the emulator has no tensor memory */
+#endif
+        if (sa.tmemCols > 0) {
+            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, true>), dim3(grid), block, g.smem, st, sa);
+            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, true>), dim3(grid), block, g.smem, st, sa);
+            else SCB_LAUNCH((scb_k_sim<1, true>), dim3(grid), block, g.smem, st, sa);
+        } else {
+            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, false>), dim3(grid), block, g.smem, st, sa);
+            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, false>), dim3(grid), block, g.smem, st, sa);
+            else SCB_LAUNCH((scb_k_sim<1, false>), dim3(grid), block, g.smem, st, sa);
+        }
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c->evSim1, st));

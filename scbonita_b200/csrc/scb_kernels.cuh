@@ -84,6 +84,56 @@ template <int K> SCB_DEV void scb_sts(scb_saddr a, const ScbVec<K> &r) { scb_st<
 SCB_DEV uint4 scb_lds_desc(scb_saddr a) { return *reinterpret_cast<const uint4 *>(a); }
 #endif
 
+/* ---- tensor memory as a scratchpad --------------------------------------------------------------------
+ * The simulator uses no tensor cores, so the SM's 256 KB of TMEM (128 lanes x 512 columns x 32 bit) is free.
+ * K2 keeps its snapshot S_s there instead of in global memory: a warp owns the 32 lanes of its quarter
+ * (warp % 4), lane l of the warp maps to TMEM lane 32*(warp%4)+l, and every node the warp updates gets K
+ * consecutive columns.  tcgen05.st / tcgen05.ld (.32x32b.xK) then move exactly one state row segment
+ * (K words per lane) between registers and TMEM, on a datapath that does not compete with LDS/STS. */
+#define SCB_TMEM_OFF 0xffffffffu
+#if defined(__CUDA_ARCH__)
+SCB_DEV void scb_tmem_alloc(uint32_t smemSlotAddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemSlotAddr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+SCB_DEV void scb_tmem_dealloc(uint32_t base, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "r"(ncols) : "memory");
+}
+SCB_DEV void scb_tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+SCB_DEV void scb_tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int K> SCB_DEV void scb_tmem_st(uint32_t taddr, const ScbVec<K> &r)
+{
+    if (K == 4) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" :: "r"(taddr), "r"(r.v[0]), "r"(r.v[1 % K]), "r"(r.v[2 % K]), "r"(r.v[3 % K]) : "memory");
+    else if (K == 2) asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(taddr), "r"(r.v[0]), "r"(r.v[1 % K]) : "memory");
+    else asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(r.v[0]) : "memory");
+}
+/* asynchronous: the registers may only be read after scb_tmem_wait_ld, which is tied to them as an operand */
+template <int K> SCB_DEV void scb_tmem_ld(uint32_t taddr, ScbVec<K> &r)
+{
+    if (K == 4) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1 % K]), "=r"(r.v[2 % K]), "=r"(r.v[3 % K]) : "r"(taddr) : "memory");
+    else if (K == 2) asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r.v[0]), "=r"(r.v[1 % K]) : "r"(taddr) : "memory");
+    else asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r.v[0]) : "r"(taddr) : "memory");
+}
+template <int K> SCB_DEV void scb_tmem_wait_ld(ScbVec<K> &r)
+{
+    if (K == 4) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r.v[0]), "+r"(r.v[1 % K]), "+r"(r.v[2 % K]), "+r"(r.v[3 % K]) :: "memory");
+    else if (K == 2) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r.v[0]), "+r"(r.v[1 % K]) :: "memory");
+    else asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r.v[0]) :: "memory");
+}
+SCB_DEV void scb_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else
+SCB_DEV void scb_tmem_alloc(uint32_t, uint32_t) {}
+SCB_DEV void scb_tmem_dealloc(uint32_t, uint32_t) {}
+SCB_DEV void scb_tmem_fence_before() {}
+SCB_DEV void scb_tmem_fence_after() {}
+template <int K> SCB_DEV void scb_tmem_st(uint32_t, const ScbVec<K> &) {}
+template <int K> SCB_DEV void scb_tmem_ld(uint32_t, ScbVec<K> &) {}
+template <int K> SCB_DEV void scb_tmem_wait_ld(ScbVec<K> &) {}
+SCB_DEV void scb_tmem_wait_st() {}
+#endif
+
 /* global memory, L2 only (the snapshot scratch is written and re-read by the same thread) */
 template <int K> SCB_DEV ScbVec<K> scb_ldcg(const unsigned char *p)
 {
@@ -321,11 +371,13 @@ SCB_DEV void scb_load_program(uint4 *desc, const uint4 *g, int4 cnt, int N, int 
  *   zg       : lane-adjusted pointer into the global snapshot (ZCMP / ZSNAP)
  *   tsm      : lane-adjusted pointer into the shared-memory target state (TCMP)
  * d2 / dz accumulate, per word, the cells whose new state differs from S_{t-1} ... */
-template <int K, bool PLAIN>
+template <int K, bool PLAIN, bool TM = false>
 SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
                       int warp, int S, unsigned flagsRt, unsigned char *zg, scb_saddr tsm,
-                      ScbVec<K> &d2, ScbVec<K> &dz, bool active = true)
+                      ScbVec<K> &d2, ScbVec<K> &dz, bool active = true, uint32_t tm = SCB_TMEM_OFF)
 {
+    /* TM: the snapshot lives in tensor memory; tm is the address of this warp's first slot and the warp's n-th
+     * node (in the order of this loop) uses columns tm + K*n.  Otherwise it lives in global scratch (zg). */
     /* `active` is false for lanes whose words lie entirely beyond the last cell (the padding of the last
      * tile): they skip the step, which cuts the shared-memory wavefronts of a mostly empty tile.
      * PLAIN steps (no compare, no snapshot, no constant rows: the majority) are a separate
@@ -338,20 +390,31 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
         ScbVec<K> o2, zc = zn;                                                                    \
         if (flags & SCB_SF_CMP2) o2 = scb_lds<K>(dst + (dsto));                                   \
         if (flags & SCB_SF_TCMP) zc = scb_lds<K>(tsm + (dsto));                                   \
-        if (flags & SCB_SF_ZCMP) zn = scb_ldcg<K>(zg + (dstoNext));
+        if (flags & SCB_SF_ZCMP) {                                                                \
+            if (TM) scb_tmem_ld<K>(tmc, zc);                                                      \
+            else zn = scb_ldcg<K>(zg + (dstoNext));                                               \
+        }
 #define SCB_POST(r, dsto)                                                                         \
     do {                                                                                          \
         if (flags & SCB_SF_CMP2) {                                                                \
             _Pragma("unroll") for (int k = 0; k < K; ++k) d2.v[k] |= (r).v[k] ^ o2.v[k]; }        \
         if (flags & (SCB_SF_ZCMP | SCB_SF_TCMP)) {                                                \
+            if (TM && (flags & SCB_SF_ZCMP)) scb_tmem_wait_ld<K>(zc);                             \
             _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ zc.v[k]; }        \
         scb_sts<K>(dst + (dsto), (r));                                                            \
-        if (flags & SCB_SF_ZSNAP) scb_stcg<K>(zg + (dsto), (r));                                  \
+        if (flags & SCB_SF_ZSNAP) {                                                               \
+            if (TM) scb_tmem_st<K>(tmc, (r));                                                     \
+            else scb_stcg<K>(zg + (dsto), (r));                                                   \
+        }                                                                                         \
+        if (TM) tmc += (uint32_t)K;                                                               \
     } while (0)
 
     int j = warp;
     const int e3 = cnt.x, e2 = cnt.x + cnt.y, e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
-    if (j >= e0 || !active) return;
+    /* lanes without valid cells sit out the plain steps; compare / snapshot steps keep the warp converged
+     * because the tensor-memory instructions are warp-collective (their garbage is masked by the valid mask) */
+    if (j >= e0 || ((PLAIN || !TM) && !active)) return;
+    uint32_t tmc = tm;
     /* the next node's descriptor is fetched while the current node is processed */
     const uint32_t dstep = 16u * (uint32_t)S;
     scb_saddr dp = desc + 16u * (uint32_t)j;
@@ -360,7 +423,7 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
     ScbVec<K> zn;
 #pragma unroll
     for (int k = 0; k < K; ++k) zn.v[k] = 0u;
-    if ((flags & SCB_SF_ZCMP) && j < e1) zn = scb_ldcg<K>(zg + (d.w & 0xFFFFFFu));
+    if ((flags & SCB_SF_ZCMP) && !TM && j < e1) zn = scb_ldcg<K>(zg + (d.w & 0xFFFFFFu));
     for (; j < e3; j += S) {
         dp = (dp + dstep <= dlast) ? dp + dstep : dp;
         const uint4 dn = scb_lds_desc(dp);
@@ -398,9 +461,10 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
 #pragma unroll
             for (int k = 0; k < K; ++k) r.v[k] = val;
             scb_sts<K>(dst + (dc.w & 0xFFFFFFu), r);
-            if (flags & SCB_SF_ZSNAP) scb_stcg<K>(zg + (dc.w & 0xFFFFFFu), r);
+            if ((flags & SCB_SF_ZSNAP) && !TM) scb_stcg<K>(zg + (dc.w & 0xFFFFFFu), r);
         }
     }
+    if (TM && (flags & SCB_SF_ZSNAP)) scb_tmem_wait_st();
 #undef SCB_POST
 #undef SCB_PRE
 }
@@ -427,7 +491,7 @@ SCB_DEV uint32_t scb_valid_mask(long long w, int C)
  *       are, the tile runs plain steps to S_98.  Cells still unproven after the last compare
  *       at t = 99 are queued, as 1024-cell chunks, for K3, and K2 leaves them out of its sums.
  * ---------------------------------------------------------------------------------------- */
-template <int K>
+template <int K, bool TM>
 __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
 {
     SCB_DYN_SMEM(smraw);
@@ -447,6 +511,18 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
     const bool early = (A.flags & SCB_KF_EARLY) != 0, useZ = (A.flags & SCB_KF_SNAP) != 0;
     unsigned char *zg = reinterpret_cast<unsigned char *>(A.zscratch + (unsigned long long)blockIdx.x * A.zstride) + laneOff;
     const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
+    /* snapshot in tensor memory: warp 0 allocates the columns, every warp derives the address of its slots */
+    uint32_t tm = SCB_TMEM_OFF;
+#if defined(__CUDA_ARCH__)
+    if (TM) {
+        if (warp == 0) scb_tmem_alloc((uint32_t)__cvta_generic_to_shared(&sh[14]), (uint32_t)A.tmemCols);
+        scb_tmem_fence_before();
+        __syncthreads();
+        scb_tmem_fence_after();
+        const uint32_t tbase = (uint32_t)sh[14];
+        tm = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(K * (warp >> 2) * A.tmemSlotsPerWarp);
+    }
+#endif
     const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
     unsigned long long stepsDone = 0, tilesDone = 0;
     long long cycPro = 0, cycStep = 0, cycEpi = 0;
@@ -510,7 +586,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
 #pragma unroll
             for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
             if (f == 0u) scb_step<K, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, zg, sa, d2, dz, laneActive);
-            else scb_step<K, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, zg, sa, d2, dz, laneActive);
+            else scb_step<K, false, TM>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, zg, sa, d2, dz, laneActive, tm);
             if (f & SCB_SF_CMP2) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
@@ -667,6 +743,13 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         __syncthreads();
         cycPro += c1 - c0; cycStep += c2 - c1; cycEpi += scb_clock() - c2;
     }
+#if defined(__CUDA_ARCH__)
+    if (TM) {
+        scb_tmem_fence_before();
+        __syncthreads();
+        if (warp == 0) scb_tmem_dealloc((uint32_t)sh[14], (uint32_t)A.tmemCols);
+    }
+#endif
     if (tid == 0 && tilesDone) {
         atomicAdd(&A.diag->steps_executed, stepsDone);
         atomicAdd(&A.diag->tiles, tilesDone);

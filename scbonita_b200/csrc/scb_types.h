@@ -113,6 +113,8 @@ struct ScbSimArgs {
     unsigned long long snapLo, snapHi;  /* bit t set: take a snapshot when computing S_t */
     int periodSearch;             /* snapshot-compare steps kept after all cells resolved */
     int snapMinGap;               /* first snapshot compare this many steps after the snapshot */
+    int tmemCols;                 /* > 0: the snapshot lives in tensor memory, this many columns per CTA */
+    int tmemSlotsPerWarp;         /* node slots reserved per warp (ceil(N / warps)) */
     ScbDiag *diag;
 };
 
