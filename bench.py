@@ -185,6 +185,16 @@ def run_ours(args, wl, rank, world, local_rank):
     # weak scaling: every rank scores a population of the same size drawn with the same seeds, so that the
     # per-rank work is identical and the measured efficiency reflects the collective, not sampling noise
     pr, bm = build_problem(wl)
+    if args.scaling == "strong" and world > 1:
+        # fixed global population: every rank scores its contiguous block (scbonita_b200.distributed.shard_bounds)
+        from scbonita_b200.distributed import shard_bounds
+        lo, hi = shard_bounds(wl["population"], rank, world)
+        width = -(-wl["population"] // world)
+        lo = min(lo, wl["population"] - width)          # equal block sizes for the all-gather
+        pr.individuals = pr.individuals[lo:lo + width]
+        pr.pop_and_nodes = pr.pop_and_nodes[lo:lo + width]
+        pr.pop_and_inv = pr.pop_and_inv[lo:lo + width]
+        wl = dict(wl, population=width)
     model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.net.and_nodes, pr.net.and_inv,
                                   pr.node_positions, pr.net.ind_len)
     sim = simulator.Simulator(bm, model, device=local_rank)
@@ -319,7 +329,7 @@ def run_ours(args, wl, rank, world, local_rank):
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % exc}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl["name"], "population_per_gpu": P, "cells": C, "nodes": N,
                        "population_seeds": "identical on every rank",
@@ -362,6 +372,8 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--opt", action="append", default=[], help="library option, e.g. early_exit=0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): 500 individuals per GPU; strong: the 500 individuals split over the GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

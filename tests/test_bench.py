@@ -9,7 +9,7 @@ from scbonita_b200 import _lib
 def test_bench_line_has_contract_keys(emu_lib, monkeypatch, capsys):
     monkeypatch.setattr(_lib, "DEFAULT_PATH", emu_lib)
     args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="ours", workload="T0", opt=["max_ctas=2"],
-                              no_cpu_baseline=False)
+                              no_cpu_baseline=False, scaling="weak")
     bench.run_ours(args, bench.WORKLOADS["T0"], 0, 1, 0)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -24,7 +24,7 @@ def test_bench_line_has_contract_keys(emu_lib, monkeypatch, capsys):
 
 
 def test_reference_arm_line(capsys):
-    args = argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", workload="T0", opt=[], no_cpu_baseline=False)
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", workload="T0", opt=[], no_cpu_baseline=False, scaling="weak")
     bench.run_reference(args, bench.WORKLOADS["T0"], 0)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "reference"
