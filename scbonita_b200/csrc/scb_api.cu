@@ -193,9 +193,10 @@ int pick_geometry(scb_ctx *c)
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<1>, c->resWarps * 32, c->smemRes));
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
-    c->fillWarps = std::min(24, std::max(1, (N + 3) / 4));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_fill, c->fillWarps * 32, c->smemFill));
-    c->fillCtas = c->numSM * std::max(1, occR);
+    /* fill-forward: one warp per item, two N-word state vectors per warp */
+    c->fillWarps = 4;
+    c->smemFill = (size_t)c->fillWarps * 2 * N * 4;
+    c->fillCtas = c->numSM * 4;
     if (c->optMaxCtas > 0) c->fillCtas = std::min(c->fillCtas, c->optMaxCtas);
     size_t zwords = (size_t)c->main.ctas * N * 32 * K;
     if (c->tailTiles) zwords = std::max(zwords, (size_t)c->tail.ctas * N * 32 * c->tail.K);

@@ -996,30 +996,26 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
     }
 }
 
-/* K3 phase 2: chunks that start with not-found cells copy the last found cell of the nearest earlier
- * chunk that has one (chunkLast, complete after phase 1); its error column is recomputed with 98 plain
- * steps.  No earlier found cell at all: the reference's value is uninitialised memory -> defined as 0. */
+/* K3 phase 2: chunks that start with not-found cells copy the last found cell of the nearest earlier chunk that
+ * has one (chunkLast, complete after phase 1).  Only that ONE cell's error column is needed, so each item is
+ * handled by a single warp that simulates the 32-cell word holding the cell with the NODES spread over its lanes
+ * (98 synchronous steps on a [N]-word state in shared memory, generic truth-table lookup): tens of microseconds
+ * instead of a full chunk re-simulation.  No earlier found cell at all: the reference's value is uninitialised
+ * memory -> defined as 0 and counted.
+ * dynamic shared memory: warps * 2 * N * 4 bytes. */
 __global__ void scb_k_fill(ScbResolveArgs R)
 {
     SCB_DYN_SMEM(smraw);
     const ScbSimArgs &A = R.s;
     const int N = A.N;
-    const uint32_t ROWB = 128u, BUFB = (uint32_t)N * ROWB;
-    unsigned char *sm = smraw;
-    uint4 *desc = reinterpret_cast<uint4 *>(smraw + 3u * BUFB);
-    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
-    uint32_t *Fm = dmz + 32;
-    uint32_t *vm = Fm + 32;
-    int *sh = reinterpret_cast<int *>(vm + 32);
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
-    const unsigned char *bufB = sm + BUFB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *st = reinterpret_cast<uint32_t *>(smraw) + (size_t)warp * 2 * N;      /* this warp's two state vectors */
     const unsigned nItems = *A.fillCount;
 
     for (;;) {
-        if (tid == 0) sh[0] = (int)atomicAdd(R.itemCursor, 1u);
-        __syncthreads();
-        const unsigned it = (unsigned)sh[0];
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(R.itemCursor, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= nItems) break;
         const int p = (int)A.fillItems[it].x, q = (int)A.fillItems[it].y, pend = (int)A.fillItems[it].z;
         int qq = q - 1, cell = -1;
@@ -1028,36 +1024,43 @@ __global__ void scb_k_fill(ScbResolveArgs R)
             if (cell >= 0) break;
         }
         if (qq < 0) {
-            if (tid == 0) atomicAdd(&A.diag->undefined_leading, (unsigned long long)pend);
+            if (lane == 0) atomicAdd(&A.diag->undefined_leading, (unsigned long long)pend);
             if (A.mode == 2)
-                for (int i = tid; i < pend; i += nthr) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = 0;
-            __syncthreads();
+                for (int i = lane; i < pend; i += 32) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = 0;
             continue;
         }
+        const int word = qq * 32 + (cell >> 5), sb = cell & 31;
         const int4 cnt = A.counts[p];
-        scb_load_program<1>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
-        __syncthreads();
-        const int sw = cell >> 5, sb = cell & 31;
-        scb_resolve_chunk<1>(A, sm, desc, cnt, dmz, Fm, vm, qq, 2, nullptr, tid, nthr, nullptr, sw);
-        unsigned add = 0;
-        for (int j = warp; j < N; j += S) {
-            const uint32_t dsto = desc[j].w & 0xFFFFFFu;
-            const int node = (int)(dsto / ROWB);
-            const unsigned bit = (*reinterpret_cast<const uint32_t *>(bufB + dsto + (uint32_t)sw * 4u) >> sb) & 1u;
-            if (lane == 0 && bit) {
-                add += (unsigned)pend;
-                if (A.mode == 1) atomicAdd(&A.nodewise[(long long)p * N + node], pend);
+        const uint4 *desc = A.descs + (long long)p * A.Npad;
+        const int e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
+        uint32_t *cur = st, *nxt = st + N;
+        for (int i = lane; i < N; i += 32) cur[i] = A.X[(long long)i * A.Wpad + word];
+        __syncwarp();
+        for (int t = 1; t <= SCB_LAST - 1; ++t) {
+            for (int j = lane; j < e1; j += 32) {
+                const uint4 d = desc[j];
+                nxt[d.w & 0xFFFFFFu] = scb_lut_apply(d.w >> 24, cur[d.x], cur[d.y], cur[d.z]);
             }
+            if (t <= 2)
+                for (int j = e1 + lane; j < e0; j += 32) {
+                    const uint4 d = desc[j];
+                    nxt[d.w & 0xFFFFFFu] = (d.w >> 24) ? 0xffffffffu : 0u;
+                }
+            __syncwarp();
+            uint32_t *x = cur; cur = nxt; nxt = x;
         }
-        if (lane == 0 && add) atomicAdd(&A.fitness[p], (unsigned long long)add);
-        if (A.mode == 2) {
-            int n1 = 0;
-            for (int row = 0; row < N; ++row)
-                n1 += (int)((*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + (uint32_t)sw * 4u) >> sb) & 1u);
-            /* the pending cells are the first `pend` valid cells of chunk q */
-            for (int i = tid; i < pend; i += nthr) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
+        /* cur = S_98 of the word; error bits of the source cell, node by node */
+        unsigned bits = 0;
+        for (int i = lane; i < N; i += 32) {
+            const unsigned bit = ((cur[i] ^ A.X[(long long)i * A.Wpad + word]) >> sb) & 1u;
+            bits += bit;
+            if (bit && A.mode == 1) atomicAdd(&A.nodewise[(long long)p * N + i], pend);
         }
-        __syncthreads();
+        bits = scb_warp_sum(bits);
+        if (lane == 0 && bits) atomicAdd(&A.fitness[p], (unsigned long long)bits * (unsigned long long)pend);
+        if (A.mode == 2)
+            for (int i = lane; i < pend; i += 32) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = (int)bits;
+        __syncwarp();
     }
 }
 
