@@ -371,7 +371,7 @@ SCB_DEV void scb_load_program(uint4 *desc, const uint4 *g, int4 cnt, int N, int 
  *   zg       : lane-adjusted pointer into the global snapshot (ZCMP / ZSNAP)
  *   tsm      : lane-adjusted pointer into the shared-memory target state (TCMP)
  * d2 / dz accumulate, per word, the cells whose new state differs from S_{t-1} ... */
-template <int K, bool PLAIN, bool TM = false>
+template <int K, bool PLAIN, bool TM = false, unsigned FIXED = 0u>
 SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
                       int warp, int S, unsigned flagsRt, unsigned char *zg, scb_saddr tsm,
                       ScbVec<K> &d2, ScbVec<K> &dz, bool active = true, uint32_t tm = SCB_TMEM_OFF)
@@ -382,7 +382,8 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
      * tile): they skip the step, which cuts the shared-memory wavefronts of a mostly empty tile.
      * PLAIN steps (no compare, no snapshot, no constant rows: the majority) are a separate
      * instantiation so that their loop carries no flag tests */
-    const unsigned flags = PLAIN ? 0u : flagsRt;
+    /* FIXED != 0: the flags are a compile-time constant (the resolver's compare-with-target steps) */
+    const unsigned flags = PLAIN ? 0u : (FIXED ? FIXED : flagsRt);
     /* SCB_PRE issues the loads a compare needs before the node's own work (the old S_{t-2} row from
      * shared memory) and, one node ahead, the snapshot row from global memory, so that the L2 latency
      * of the snapshot is covered by a whole node's processing. */
@@ -833,6 +834,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
             for (int k = 0; k < KR; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
             const bool act = onlyLane < 0 || lane == onlyLane;
             if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
+            else if (f == SCB_SF_TCMP) scb_step<KR, false, false, SCB_SF_TCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             else scb_step<KR, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             if (cmp) {
                 uint32_t *Dw = D + ((size_t)(tn & 1) * S + warp) * GW + lane * KR;
@@ -1002,14 +1004,15 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
  * (98 synchronous steps on a [N]-word state in shared memory, generic truth-table lookup): tens of microseconds
  * instead of a full chunk re-simulation.  No earlier found cell at all: the reference's value is uninitialised
  * memory -> defined as 0 and counted.
- * dynamic shared memory: warps * 2 * N * 4 bytes. */
+ * dynamic shared memory: warps * (16 + 2 * 4) * N bytes (the item's program, then two state vectors). */
 __global__ void scb_k_fill(ScbResolveArgs R)
 {
     SCB_DYN_SMEM(smraw);
     const ScbSimArgs &A = R.s;
     const int N = A.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *st = reinterpret_cast<uint32_t *>(smraw) + (size_t)warp * 2 * N;      /* this warp's two state vectors */
+    uint4 *sdesc = reinterpret_cast<uint4 *>(smraw + (size_t)warp * 24 * N);        /* this warp's copy of the program */
+    uint32_t *st = reinterpret_cast<uint32_t *>(sdesc + N);                          /* and its two state vectors */
     const unsigned nItems = *A.fillCount;
 
     for (;;) {
@@ -1031,15 +1034,16 @@ __global__ void scb_k_fill(ScbResolveArgs R)
         }
         const int word = qq * 32 + (cell >> 5), sb = cell & 31;
         const int4 cnt = A.counts[p];
-        const uint4 *desc = A.descs + (long long)p * A.Npad;
+        const uint4 *gdesc = A.descs + (long long)p * A.Npad;
         const int e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
         uint32_t *cur = st, *nxt = st + N;
-        for (int i = lane; i < N; i += 32) cur[i] = A.X[(long long)i * A.Wpad + word];
+        for (int i = lane; i < N; i += 32) { cur[i] = A.X[(long long)i * A.Wpad + word]; sdesc[i] = gdesc[i]; }
+        const uint4 *desc = sdesc;
         __syncwarp();
         for (int t = 1; t <= SCB_LAST - 1; ++t) {
             for (int j = lane; j < e1; j += 32) {
                 const uint4 d = desc[j];
-                nxt[d.w & 0xFFFFFFu] = scb_lut_apply(d.w >> 24, cur[d.x], cur[d.y], cur[d.z]);
+                nxt[d.w & 0xFFFFFFu] = scb_lut_apply_mux(d.w >> 24, cur[d.x], cur[d.y], cur[d.z]);
             }
             if (t <= 2)
                 for (int j = e1 + lane; j < e0; j += 32) {
