@@ -170,6 +170,7 @@ int pick_geometry(scb_ctx *c)
     CK(cudaFuncSetAttribute(scb_k_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK(cudaFuncSetAttribute(scb_k_compile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
 #endif

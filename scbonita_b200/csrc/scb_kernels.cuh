@@ -244,9 +244,14 @@ template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, c
 /* ------------------------------------------------------------------------------------------
  * K0: rule compiler.  One CTA per individual, one thread per node; the program is written sorted
  * by arity (stable in node order, so the layout is deterministic).
- * dynamic shared memory: N * 16 (descriptors) + N (arity) + 64
+ * The individual's two [N][7][3] tables are first staged in shared memory with coalesced loads (a thread's
+ * own 2 x 84 bytes would otherwise be fetched as scattered 4-byte reads).
+ * dynamic shared memory: N * 16 (descriptors) + N (arity) + 64 + 2 * N * 21 * 4 (tables)
  * ---------------------------------------------------------------------------------------- */
-SCB_HD inline size_t scb_compile_smem_bytes(int N) { return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64; }
+SCB_HD inline size_t scb_compile_smem_bytes(int N)
+{
+    return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4;
+}
 
 __global__ void scb_k_compile(ScbCompileArgs A)
 {
@@ -257,7 +262,10 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     unsigned char *sar = reinterpret_cast<unsigned char *>(cn + 8);
     const int32_t *ind = A.individuals + (long long)p * A.indLen;
     const long long toff = A.tablesPerIndividual ? (long long)p * N * (SCB_MAX_TERMS * SCB_MAX_IN) : 0;
-    const int32_t *an = A.an + toff, *ai = A.ai + toff;
+    const int TBL = N * SCB_MAX_TERMS * SCB_MAX_IN;
+    int32_t *an = reinterpret_cast<int32_t *>(smraw + (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64);
+    int32_t *ai = an + TBL;
+    for (int i = tid; i < TBL; i += nthr) { an[i] = A.an[toff + i]; ai[i] = A.ai[toff + i]; }
     if (tid < 8) cn[tid] = 0u;
     __syncthreads();
     for (int i = tid; i < N; i += nthr) {
