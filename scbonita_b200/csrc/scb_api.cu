@@ -196,7 +196,7 @@ int pick_geometry(scb_ctx *c)
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
     /* fill-forward: one warp per item, two N-word state vectors per warp */
     c->fillWarps = 4;
-    c->smemFill = (size_t)c->fillWarps * 24 * N;
+    c->smemFill = (size_t)c->fillWarps * scb_fill_smem_per_warp(N);
     c->fillCtas = c->numSM * 4;
     if (c->optMaxCtas > 0) c->fillCtas = std::min(c->fillCtas, c->optMaxCtas);
     size_t zwords = (size_t)c->main.ctas * N * 32 * K;

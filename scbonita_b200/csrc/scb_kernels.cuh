@@ -1013,13 +1013,15 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
  * instead of a full chunk re-simulation.  No earlier found cell at all: the reference's value is uninitialised
  * memory -> defined as 0 and counted.
  * dynamic shared memory: warps * (16 + 2 * 4) * N bytes (the item's program, then two state vectors). */
+SCB_HD inline size_t scb_fill_smem_per_warp(int N) { return (((size_t)24 * N) + 15) & ~(size_t)15; }
+
 __global__ void scb_k_fill(ScbResolveArgs R)
 {
     SCB_DYN_SMEM(smraw);
     const ScbSimArgs &A = R.s;
     const int N = A.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint4 *sdesc = reinterpret_cast<uint4 *>(smraw + (size_t)warp * 24 * N);        /* this warp's copy of the program */
+    uint4 *sdesc = reinterpret_cast<uint4 *>(smraw + (size_t)warp * scb_fill_smem_per_warp(N));   /* this warp's copy of the program */
     uint32_t *st = reinterpret_cast<uint32_t *>(sdesc + N);                          /* and its two state vectors */
     const unsigned nItems = *A.fillCount;
 

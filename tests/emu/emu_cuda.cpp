@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -60,12 +61,16 @@ uint32_t emu_shfl(uint32_t v, int srcLane)
 
 void emu_launch_impl(const std::function<void()> &body, dim3 grid, dim3 block, size_t smem)
 {
+    /* one launch at a time, process-wide: host threads that launch concurrently (the re-entrancy tests) would
+     * otherwise multiply the number of live std::threads */
+    static std::mutex launchMutex;
+    std::lock_guard<std::mutex> lock(launchMutex);
     const int nthr = (int)block.x;
     const int nblk = (int)(grid.x * grid.y);
     if (nthr % 32 != 0) abort();
     /* blocks run in waves of a few at a time (like CTAs on a small GPU); no kernel here needs all blocks
      * of a grid to be resident at once */
-    const int wave = 4;
+    const int wave = nthr > 512 ? 2 : 4;
     for (int b0 = 0; b0 < nblk; b0 += wave) {
         const int nb = nblk - b0 < wave ? nblk - b0 : wave;
         std::vector<std::unique_ptr<BlockCtx>> blocks;
