@@ -339,7 +339,7 @@ def run_ours(args, wl, rank, world, local_rank):
             "ga_generations_per_sec": 1e3 / ms_per_step,
             "e2e": {"value": units_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": 5 * args.steps,
+            "gpu_launches": 4 * args.steps,      # K0 compile, K2 simulate, K3 resolve, K3 fill per generation
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                          "peak_source": peak_kind,
