@@ -78,7 +78,7 @@ struct scb_ctx {
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
     int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 6, optSearch = 0, optMinGap = 8;
-    int optTmem = 1;
+    int optTmem = 1, optFuse = 1;
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
@@ -99,6 +99,7 @@ struct scb_ctx {
     DevBuf<uint4> dFillItems;
     DevBuf<int32_t> dChunkLast;
     DevBuf<uint32_t> dResolveT;
+    DevBuf<unsigned int> dReady;
     unsigned resolveTCap = 0;
     DevBuf<uint32_t> dZ;
     DevBuf<ScbDiag> dDiag;
@@ -412,7 +413,7 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
-    c->dItems.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
+    c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
     c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dNodeCnt.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
@@ -443,6 +444,7 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
             if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "snapshot gap must be in [1,99]");
             c->optMinGap = (int)value; return SCB_OK;
         case SCB_OPT_TMEM: c->optTmem = value != 0; return SCB_OK;
+        case SCB_OPT_FUSE: c->optFuse = value != 0; return SCB_OK;
         case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_SNAP_HI: c->snapHi = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_WARPS:
@@ -495,6 +497,7 @@ int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, co
     if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
     if ((rc = c->dFitness.ensure(P))) return rc;
     const size_t chunks = (size_t)c->Wpad / 32;
+    if ((rc = c->dReady.ensure((size_t)P * chunks))) return rc;
     if ((rc = c->dItems.ensure((size_t)P * chunks)) || (rc = c->dFillItems.ensure((size_t)P * chunks)) ||
         (rc = c->dChunkLast.ensure((size_t)P * chunks))) return rc;
     {   /* S_99 hand-over slots for the resolver: at most 64 MiB */
@@ -554,6 +557,11 @@ int scb_pop_run(scb_ctx *c, int mode)
     sa.chkEvery = c->optChk; sa.snapLo = c->snapLo; sa.snapHi = c->snapHi; sa.periodSearch = c->optSearch;
     sa.snapMinGap = c->optMinGap;
     sa.diag = c->dDiag.p;
+    /* the simulator resolves queued groups in its own tail when a single launch covers all tiles */
+    const bool fuse = c->optFuse && c->tailTiles == 0;
+    sa.fuseResolve = fuse ? 1 : 0;
+    sa.tilesDone = c->dCounters.p + 6; sa.readyFlags = c->dReady.p; sa.resolveCursor = c->dCounters.p + 2;
+    if (fuse) CK(cudaMemsetAsync(c->dReady.p, 0, (size_t)sa.resolveCap * sizeof(unsigned int), st));
     CK(cudaEventRecord(c->evSim0, st));
     for (int part = 0; part < 2; ++part) {
         const SimGeom &g = part == 0 ? c->main : c->tail;
@@ -575,17 +583,19 @@ int scb_pop_run(scb_ctx *c, int mode)
         const long long items = (long long)P * tiles;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, g.ctas));
         const dim3 block((unsigned)g.warps * 32);
+        const size_t smemLaunch = fuse ? std::max(g.smem, c->smemRes) : g.smem;
+        sa.smemBytes = (unsigned)smemLaunch;
 #ifdef SCB_EMU
         sa.tmemCols = 0;                            /* the emulator has no tensor memory */
 #endif
         if (sa.tmemCols > 0) {
-            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, true>), dim3(grid), block, g.smem, st, sa);
-            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, true>), dim3(grid), block, g.smem, st, sa);
-            else SCB_LAUNCH((scb_k_sim<1, true>), dim3(grid), block, g.smem, st, sa);
+            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, true>), dim3(grid), block, smemLaunch, st, sa);
+            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, true>), dim3(grid), block, smemLaunch, st, sa);
+            else SCB_LAUNCH((scb_k_sim<1, true>), dim3(grid), block, smemLaunch, st, sa);
         } else {
-            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, false>), dim3(grid), block, g.smem, st, sa);
-            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, false>), dim3(grid), block, g.smem, st, sa);
-            else SCB_LAUNCH((scb_k_sim<1, false>), dim3(grid), block, g.smem, st, sa);
+            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, false>), dim3(grid), block, smemLaunch, st, sa);
+            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, false>), dim3(grid), block, smemLaunch, st, sa);
+            else SCB_LAUNCH((scb_k_sim<1, false>), dim3(grid), block, smemLaunch, st, sa);
         }
         CK(cudaGetLastError());
     }
@@ -593,8 +603,10 @@ int scb_pop_run(scb_ctx *c, int mode)
 
     ScbResolveArgs ra;
     ra.s = sa; ra.itemCursor = c->dCounters.p + 2;
-    if (c->resGroup == 2) SCB_LAUNCH(scb_k_resolve<2>, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
-    else SCB_LAUNCH(scb_k_resolve<1>, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+    if (!fuse) {
+        if (c->resGroup == 2) SCB_LAUNCH(scb_k_resolve<2>, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+        else SCB_LAUNCH(scb_k_resolve<1>, dim3((unsigned)c->resCtas), dim3((unsigned)c->resWarps * 32), c->smemRes, st, ra);
+    }
     CK(cudaGetLastError());
     ra.itemCursor = c->dCounters.p + 4;
     SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->fillCtas), dim3((unsigned)c->fillWarps * 32), c->smemFill, st, ra);

@@ -171,6 +171,16 @@ template <int K> SCB_DEV ScbVec<K> scb_ldg(const uint32_t *p)
 #endif
 }
 
+SCB_DEV unsigned scb_ld_volatile(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+SCB_DEV void scb_backoff()
+{
+#if defined(__CUDA_ARCH__)
+    __nanosleep(256);
+#elif defined(SCB_EMU)
+    emu_yield();
+#endif
+}
+
 SCB_DEV long long scb_clock()
 {
 #if defined(__CUDA_ARCH__) && defined(SCB_PHASE_CLOCKS)
@@ -500,6 +510,8 @@ SCB_DEV uint32_t scb_valid_mask(long long w, int C)
  *       are, the tile runs plain steps to S_98.  Cells still unproven after the last compare
  *       at t = 99 are queued, as 1024-cell chunks, for K3, and K2 leaves them out of its sums.
  * ---------------------------------------------------------------------------------------- */
+template <int KR> SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it);
+
 template <int K, bool TM>
 __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
 {
@@ -675,10 +687,13 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
                 /* one resolver item per group of KR adjacent chunks that holds an unproven chunk */
                 unsigned bad = 0u;
                 for (int j = 0; j < KR; ++j) if (sh[4 + lane * KR + j]) bad |= 1u << j;
+                sh[16 + lane] = -1;
                 if (bad) {
                     const unsigned idx = atomicAdd(A.resolveCount, 1u);
-                    if (idx < A.resolveCap)
+                    if (idx < A.resolveCap) {
                         A.resolveItems[idx] = make_uint2((unsigned)p, (unsigned)(w0 / 32 + lane * KR) | (bad << 24));
+                        sh[16 + lane] = (int)idx;
+                    }
                     if (idx < A.resolveTCap) for (int j = 0; j < KR; ++j) sh[8 + lane * KR + j] = (int)idx;
                 }
             }
@@ -697,7 +712,13 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
                     T[(long long)row * GW] = *reinterpret_cast<const uint32_t *>(sm + srcOff + (uint32_t)row * ROWB + (uint32_t)w * 4u);
             }
             __syncthreads();          /* the cellwise epilogue reuses the S_99 buffer */
+            /* publish the queued groups: everything a resolver needs (item, S_99) is in memory */
+            if (A.fuseResolve && tid < K / A.resolveGroup && sh[16 + tid] >= 0) {
+                __threadfence();
+                atomicExch(&A.readyFlags[sh[16 + tid]], 1u);
+            }
         }
+        if (A.fuseResolve && tid == 0) { __threadfence(); atomicAdd(A.tilesDone, 1u); }
 
         /* ---- errors: e = S_98 xor S_0 on valid cells of proven chunks ---------------------- */
         ScbVec<K> ok;
@@ -759,6 +780,34 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         if (warp == 0) scb_tmem_dealloc((uint32_t)sh[14], (uint32_t)A.tmemCols);
     }
 #endif
+    /* ---- in-kernel resolver: a CTA that found the tile queue empty takes tickets for resolver items.  An item
+     * is processed as soon as its producer has published it; a ticket beyond the final count ends the CTA.  All
+     * producers are running CTAs of this launch (the queue is empty), so waiting for them cannot deadlock. ---- */
+    if (A.fuseResolve) {
+        int *slot = reinterpret_cast<int *>(smraw + A.smemBytes - 64);
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned my = atomicAdd(A.resolveCursor, 1u);
+                int got = -1;
+                for (;;) {
+                    if (my < A.resolveCap && scb_ld_volatile(&A.readyFlags[my]) != 0u) { got = (int)my; break; }
+                    if (scb_ld_volatile(A.tilesDone) >= total) {
+                        __threadfence();
+                        if (my >= scb_ld_volatile(A.resolveCount) || my >= A.resolveCap) break;
+                    }
+                    scb_backoff();
+                }
+                __threadfence();
+                slot[0] = got;
+            }
+            __syncthreads();
+            const int it = slot[0];
+            if (it < 0) break;
+            if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it);
+            else scb_resolve_item<1>(A, smraw, (unsigned)it);
+        }
+    }
     if (tid == 0 && tilesDone) {
         atomicAdd(&A.diag->steps_executed, stepsDone);
         atomicAdd(&A.diag->tiles, tilesDone);
@@ -890,10 +939,8 @@ SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR)
 /* K3 phase 1: exact found mask and error sums of every queued group of KR chunks; leading not-found cells that
  * must copy a cell of an earlier chunk are queued for phase 2.  Only the chunks K2 flagged are summed here. */
 template <int KR>
-__global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
+SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it)
 {
-    SCB_DYN_SMEM(smraw);
-    const ScbSimArgs &A = R.s;
     const int N = A.N;
     const uint32_t ROWB = 128u * KR, BUFB = (uint32_t)N * ROWB;
     const int GW = 32 * KR, GC = 1024 * KR;
@@ -902,20 +949,13 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
     uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
     uint32_t *Fm = dmz + GW;
     uint32_t *vm = Fm + GW;
-    int *sh = reinterpret_cast<int *>(vm + GW);            /* [0] item, [2] pending cells, [3] not-found cells */
+    int *sh = reinterpret_cast<int *>(vm + GW);            /* [2] pending cells, [3] not-found cells */
     int *srcc = sh + 16;                                   /* [GC] source cell of each cell */
     uint32_t *Dbuf = reinterpret_cast<uint32_t *>(srcc + GC);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
     const unsigned char *bufB = sm + BUFB;
-    unsigned nItems = *A.resolveCount;
-    if (nItems > A.resolveCap) nItems = A.resolveCap;
-
-    for (;;) {
-        if (tid == 0) sh[0] = (int)atomicAdd(R.itemCursor, 1u);
-        __syncthreads();
-        const unsigned it = (unsigned)sh[0];
-        if (it >= nItems) break;
+    {
         const int p = (int)A.resolveItems[it].x;
         const int q = (int)(A.resolveItems[it].y & 0xFFFFFFu);
         const unsigned flagged = A.resolveItems[it].y >> 24;       /* bit j: chunk q + j was left out by K2 */
@@ -1003,6 +1043,25 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
             atomicAdd(&A.diag->resolver_chunks, (unsigned long long)__popc(flagged));
         }
         __syncthreads();
+    }
+}
+
+/* K3 phase 1 as a kernel of its own (used when the simulator does not resolve in its own tail) */
+template <int KR>
+__global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
+{
+    SCB_DYN_SMEM(smraw);
+    const ScbSimArgs &A = R.s;
+    int *slot = reinterpret_cast<int *>(smraw + scb_resolve_smem_bytes(A.N, KR) - 64);
+    unsigned nItems = *A.resolveCount;
+    if (nItems > A.resolveCap) nItems = A.resolveCap;
+    for (;;) {
+        if (threadIdx.x == 0) slot[0] = (int)atomicAdd(R.itemCursor, 1u);
+        __syncthreads();
+        const unsigned it = (unsigned)slot[0];
+        __syncthreads();
+        if (it >= nItems) break;
+        scb_resolve_item<KR>(A, smraw, it);
     }
 }
 

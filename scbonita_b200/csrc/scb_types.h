@@ -113,6 +113,11 @@ struct ScbSimArgs {
     unsigned long long snapLo, snapHi;  /* bit t set: take a snapshot when computing S_t */
     int periodSearch;             /* snapshot-compare steps kept after all cells resolved */
     int snapMinGap;               /* first snapshot compare this many steps after the snapshot */
+    int fuseResolve;              /* != 0: CTAs that run out of tiles resolve queued groups in the same launch */
+    unsigned int *tilesDone;      /* tiles completed (all their resolver items are published) */
+    unsigned int *readyFlags;     /* [resolveCap] item i is complete in memory */
+    unsigned int *resolveCursor;  /* ticket counter of the in-kernel resolver */
+    unsigned int smemBytes;       /* dynamic shared memory of the launch (the item slot sits in its last 64 bytes) */
     int tmemCols;                 /* > 0: the snapshot lives in tensor memory, this many columns per CTA */
     int tmemSlotsPerWarp;         /* node slots reserved per warp (ceil(N / warps)) */
     ScbDiag *diag;

@@ -33,6 +33,7 @@ thread_local WarpCtx *tl_warp = nullptr;
 }  // namespace
 
 unsigned char *emu_dyn_smem() { return tl_block->smem; }
+void emu_yield() { std::this_thread::yield(); }
 void __syncthreads() { tl_block->bar.arrive_and_wait(); }
 void __syncwarp(unsigned) { tl_warp->bar.arrive_and_wait(); }
 

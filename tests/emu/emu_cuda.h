@@ -33,6 +33,9 @@ static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}
 extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 unsigned char *emu_dyn_smem();
+void emu_yield();
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 void __syncthreads();
 void __syncwarp(unsigned mask = 0xffffffffu);
 unsigned __ballot_sync(unsigned mask, int pred);

@@ -42,7 +42,7 @@ def test_synthetic_matches_oracle(backend, n, cells, pop):
 @pytest.mark.parametrize("opts", [dict(early_exit=0, snapshots=0), dict(early_exit=1, snapshots=0),
                                   dict(early_exit=0, snapshots=1), dict(words=1), dict(words=2, check_every=3),
                                   dict(warps=4), dict(period_search=24), dict(check_every=1), dict(snap_min_gap=1, check_every=4),
-                                  dict(snap_min_gap=20, snap_lo=1 << 20, snap_hi=0)])
+                                  dict(snap_min_gap=20, snap_lo=1 << 20, snap_hi=0), dict(fuse=0), dict(fuse=0, early_exit=0, snapshots=0)])
 def test_every_schedule_gives_identical_integers(backend, opts):
     """Early exit, snapshot resolution and tile geometry are optimisations: results must not move."""
     pr = Problem.synthetic(60, big(backend, 2100, 21000), big(backend, 5, 24))
@@ -100,7 +100,7 @@ def test_golden_vectors(backend, name):
 # ---- attractor-found semantics ---------------------------------------------------
 @pytest.mark.parametrize("rings,chain,cells", [([60], 0, 300), ([45], 12, 2500), ([3, 5], 4, 1500), ([49], 0, 200),
                                                ([50], 0, 200), ([7, 11, 13], 20, 3000), ([2, 3, 4], 0, 1100)])
-@pytest.mark.parametrize("opts", [dict(), dict(early_exit=0, snapshots=0), dict(words=1)])
+@pytest.mark.parametrize("opts", [dict(), dict(early_exit=0, snapshots=0), dict(words=1), dict(fuse=0)])
 def test_cycles_not_found_and_fill_forward(backend, rings, chain, cells, opts):
     pr = ring_problem(rings, chain, cells)
     with pr.simulator(backend[1], **opts) as sim:
