@@ -288,13 +288,22 @@ def run_ours(args, wl, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
     fit = h_out.copy()
+    # roofline pass: the simulator kernel K2 timed on its own.  In the default configuration the same launch also
+    # resolves queued groups in its tail (K3 work), so K2's own duration is taken with that fusion switched off.
+    fused_default = "fuse=0" not in args.opt
+    if fused_default:
+        sim.set_option(_lib.OPT_FUSE, 0)
+    _, sim_ms, stats = timed(step_resident, min(args.steps, 5), 2)
+    sim_steps = min(args.steps, 5)
+    if fused_default:
+        sim.set_option(_lib.OPT_FUSE, 1)
 
     if rank == 0:
         hbm_peak, sm_max, peak_kind = load_peaks()
         ms_per_step = total_ms / args.steps
         value = units_per_step / (ms_per_step * 1e-3)
         info = sim.info()
-        k2_ms = sim_ms / args.steps
+        k2_ms = sim_ms / sim_steps
         per_gpu_units = float(P) * C * N * STEPS_PER_CELL
         # algorithmic HBM bytes of one K2 launch: packed matrix N*C/8, rule programs 16 B/node, fitness 8 B
         alg_bytes = N * C / 8.0 + P * N * 16.0 + P * 8.0
@@ -339,11 +348,13 @@ def run_ours(args, wl, rank, world, local_rank):
             "ga_generations_per_sec": 1e3 / ms_per_step,
             "e2e": {"value": units_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": 4 * args.steps,      # K0 compile, K2 simulate, K3 resolve, K3 fill per generation
+            "gpu_launches": (3 if fused_default else 4) * args.steps,   # K0 compile, K2 simulate (+ in-kernel K3), K3 fill
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                          "peak_source": peak_kind,
                          "kernel": "scb_k_sim<%d>" % info["words_per_lane"], "kernel_ms": k2_ms,
+                         "kernel_timing": "CUDA events around K2 on the library's stream, K2 run without the in-kernel "
+                                          "resolver tail (option fuse=0) so that the duration is K2's own",
                          "note": "the path is shared-memory/issue bound, not HBM bound (SURVEY 8d): see roofline_binding"},
             "roofline_binding": {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
                                  "frac": smem_ach / smem_peak, "sm_mhz": sm_mhz,

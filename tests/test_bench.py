@@ -20,7 +20,7 @@ def test_bench_line_has_contract_keys(emu_lib, monkeypatch, capsys):
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
     assert line["value"] > 0 and line["e2e"]["value"] > 0
-    assert line["gpu_launches"] == 4 * 2
+    assert line["gpu_launches"] == 3 * 2
 
 
 def test_reference_arm_line(capsys):
