@@ -171,7 +171,14 @@ template <int K> SCB_DEV ScbVec<K> scb_ldg(const uint32_t *p)
 #endif
 }
 
-SCB_DEV unsigned scb_ld_volatile(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+SCB_DEV unsigned scb_ld_volatile(const unsigned int *p)
+{
+#if defined(SCB_EMU)
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);          /* the host emulation needs a real atomic load */
+#else
+    return *reinterpret_cast<const volatile unsigned int *>(p);
+#endif
+}
 SCB_DEV void scb_backoff()
 {
 #if defined(__CUDA_ARCH__)
