@@ -77,3 +77,13 @@ def test_two_gpu_sharding_nccl(cuda_lib):
                           os.path.join(ROOT, "tests", "nccl_worker.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_c4_independent_pathways(cuda_lib):
+    """BASELINE config 4 in miniature: the same ~60 000 cells scored against several KEGG-shaped pathways of
+    different sizes, one context per pathway (independent work: pathways map to GPUs round-robin, no collective)."""
+    for n in (47, 60, 100, 159, 200, 300):
+        pr = Problem.synthetic(n, 60_000, 24)
+        with pr.simulator(cuda_lib) as sim:
+            fit = sim.evaluate_population(pr.individuals, pr.ko, pr.ki, pr.pop_an, pr.pop_ai, mode=simulator.MODE_SUM)
+        assert np.array_equal(fit, pr.oracle()["fitness"]), n

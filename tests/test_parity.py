@@ -30,7 +30,8 @@ def big(backend, small, large):
 
 
 # ---- seeded synthetic shapes ------------------------------------------------------------------
-@pytest.mark.parametrize("n,cells,pop", [(20, 200, 3), (60, 1100, 4), (200, 1300, 3), (230, 500, 2), (5, 40, 4), (1, 70, 2)])
+@pytest.mark.parametrize("n,cells,pop", [(20, 200, 3), (60, 1100, 4), (200, 1300, 3), (230, 500, 2), (460, 200, 2),
+                                        (5, 40, 4), (1, 70, 2)])
 def test_synthetic_matches_oracle(backend, n, cells, pop):
     cells = big(backend, cells, cells * 9 + 17)
     pop = big(backend, pop, pop * 4)
@@ -391,3 +392,15 @@ def test_legacy_symbol_is_reentrant(backend):
     lib.scb_set_legacy_geometry(20000, 15000)
     for p, e in zip(list(range(6)) * 2, got):
         assert np.array_equal(e, o["nodewise"][p]), p
+
+
+def test_network_too_large_for_on_chip_state_is_refused(backend):
+    """N beyond the shared-memory state buffers is refused loudly, never computed elsewhere."""
+    rng = np.random.default_rng(2)
+    n = 900
+    net = _random_tables(rng, n, weird_flags=False)
+    rows = (rng.random((n, 64)) < 0.5).astype(np.uint8)
+    pr = Problem(net, rows, np.arange(n, dtype=np.int32), np.ones((1, net.ind_len), np.int32))
+    with pytest.raises(simulator.ScbError) as ei:
+        pr.simulator(backend[1])
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
