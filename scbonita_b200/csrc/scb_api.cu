@@ -66,7 +66,7 @@ template <class T> struct DevBuf {
 
 }  // namespace
 
-struct SimGeom { int K = 0, warps = 0, ctas = 0; size_t smem = 0; };
+struct SimGeom { int K = 0, warps = 0, ctas = 0, tmemCols = 0, tmemSlotsPerWarp = 0; size_t smem = 0; };
 
 struct scb_ctx {
     int device = 0;
@@ -143,6 +143,14 @@ int sim_geometry(scb_ctx *c, int K, int optWarps, SimGeom *g)
     if (occ < 1) return fail(SCB_ERR_UNSUPPORTED, "simulator kernel does not fit on an SM (N=%d, K=%d, warps=%d)", N, K, S);
     g->ctas = c->numSM * occ;
     if (c->optMaxCtas > 0) g->ctas = std::min(g->ctas, c->optMaxCtas);
+    {   /* snapshot in tensor memory when the columns of all co-resident CTAs fit into the SM's 512 */
+        const int npw = (N + S - 1) / S;
+        const int need = K * ((S + 3) / 4) * npw;
+        int cols = 32;
+        while (cols < need) cols <<= 1;
+        g->tmemCols = (c->optTmem && c->optSnap && cols <= 512 && cols * occ <= 512) ? cols : 0;
+        g->tmemSlotsPerWarp = npw;
+    }
     return SCB_OK;
 }
 
@@ -188,11 +196,17 @@ int pick_geometry(scb_ctx *c)
      * state buffers fit; the fill-forward kernel always works on single chunks */
     c->resGroup = (K >= 2 && scb_resolve_smem_bytes(N, 2) <= c->smemLimit) ? 2 : 1;
     c->smemRes = scb_resolve_smem_bytes(N, c->resGroup);
+    /* inside the simulator launch the resolver can keep its target state in tensor memory and work on whole
+     * 4-chunk tiles with the simulator's own two-buffer layout */
+    if (c->optFuse && K == 4 && c->main.tmemCols > 0 && scb_resolve_smem_bytes(N, 4, true) <= c->smemLimit) {
+        c->resGroup = 4;
+        c->smemRes = scb_resolve_smem_bytes(N, 4, true);
+    }
     c->smemFill = scb_resolve_smem_bytes(N, 1);
     int occR = 1;
     c->resWarps = std::min(c->resGroup == 2 ? 24 : 16, std::max(c->resGroup, (N + 3) / 4));
     if (c->resGroup == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<2>, c->resWarps * 32, c->smemRes));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<1>, c->resWarps * 32, c->smemRes));
+    else if (c->resGroup == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<1>, c->resWarps * 32, c->smemRes));
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
     /* fill-forward: one warp per item, two N-word state vectors per warp */
@@ -433,7 +447,7 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
     std::lock_guard<std::mutex> lk(c->mu);
     switch (key) {
         case SCB_OPT_EARLY_EXIT: c->optEarly = value != 0; return SCB_OK;
-        case SCB_OPT_SNAPSHOTS: c->optSnap = value != 0; return SCB_OK;
+        case SCB_OPT_SNAPSHOTS: c->optSnap = value != 0; break;
         case SCB_OPT_CHECK_EVERY:
             if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "check cadence must be in [1,99]");
             c->optChk = (int)value; return SCB_OK;
@@ -443,8 +457,8 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
         case SCB_OPT_SNAP_MIN_GAP:
             if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "snapshot gap must be in [1,99]");
             c->optMinGap = (int)value; return SCB_OK;
-        case SCB_OPT_TMEM: c->optTmem = value != 0; return SCB_OK;
-        case SCB_OPT_FUSE: c->optFuse = value != 0; return SCB_OK;
+        case SCB_OPT_TMEM: c->optTmem = value != 0; break;
+        case SCB_OPT_FUSE: c->optFuse = value != 0; break;
         case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_SNAP_HI: c->snapHi = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_WARPS:
@@ -571,23 +585,12 @@ int scb_pop_run(scb_ctx *c, int mode)
         sa.wordBase = part == 0 ? 0 : c->mainTiles * 32 * c->K;
         sa.workCounter = c->dCounters.p + (part == 0 ? 0 : 5);
         sa.zstride = (unsigned long long)N * 32 * g.K;
-        {   /* snapshot in tensor memory when the columns of all co-resident CTAs fit into the SM's 512 */
-            const int npw = (N + g.warps - 1) / g.warps;
-            const int need = g.K * ((g.warps + 3) / 4) * npw;
-            int cols = 32;
-            while (cols < need) cols <<= 1;
-            const int ctasPerSm = std::max(1, g.ctas / std::max(1, c->numSM));
-            sa.tmemCols = (c->optTmem && c->optSnap && cols <= 512 && cols * ctasPerSm <= 512) ? cols : 0;
-            sa.tmemSlotsPerWarp = npw;
-        }
+        sa.tmemCols = g.tmemCols; sa.tmemSlotsPerWarp = g.tmemSlotsPerWarp;
         const long long items = (long long)P * tiles;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, g.ctas));
         const dim3 block((unsigned)g.warps * 32);
         const size_t smemLaunch = fuse ? std::max(g.smem, c->smemRes) : g.smem;
         sa.smemBytes = (unsigned)smemLaunch;
-#ifdef SCB_EMU
-        sa.tmemCols = 0;                            /* the emulator has no tensor memory */
-#endif
         if (sa.tmemCols > 0) {
             if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, true>), dim3(grid), block, smemLaunch, st, sa);
             else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, true>), dim3(grid), block, smemLaunch, st, sa);

@@ -123,6 +123,16 @@ template <int K> SCB_DEV void scb_tmem_wait_ld(ScbVec<K> &r)
     else asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r.v[0]) :: "memory");
 }
 SCB_DEV void scb_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#elif defined(SCB_EMU)
+/* host-thread emulator: tensor memory is a per-block array (tests/emu) */
+SCB_DEV void scb_tmem_alloc(uint32_t, uint32_t) {}
+SCB_DEV void scb_tmem_dealloc(uint32_t, uint32_t) {}
+SCB_DEV void scb_tmem_fence_before() {}
+SCB_DEV void scb_tmem_fence_after() {}
+template <int K> SCB_DEV void scb_tmem_st(uint32_t taddr, const ScbVec<K> &r) { for (int k = 0; k < K; ++k) *emu_tmem_cell(taddr, k) = r.v[k]; }
+template <int K> SCB_DEV void scb_tmem_ld(uint32_t taddr, ScbVec<K> &r) { for (int k = 0; k < K; ++k) r.v[k] = *emu_tmem_cell(taddr, k); }
+template <int K> SCB_DEV void scb_tmem_wait_ld(ScbVec<K> &) {}
+SCB_DEV void scb_tmem_wait_st() {}
 #else
 SCB_DEV void scb_tmem_alloc(uint32_t, uint32_t) {}
 SCB_DEV void scb_tmem_dealloc(uint32_t, uint32_t) {}
@@ -517,7 +527,7 @@ SCB_DEV uint32_t scb_valid_mask(long long w, int C)
  *       are, the tile runs plain steps to S_98.  Cells still unproven after the last compare
  *       at t = 99 are queued, as 1024-cell chunks, for K3, and K2 leaves them out of its sums.
  * ---------------------------------------------------------------------------------------- */
-template <int KR> SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it);
+template <int KR, bool TTM = false> SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it, uint32_t tm = SCB_TMEM_OFF);
 
 template <int K, bool TM>
 __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
@@ -541,16 +551,17 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
     const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
     /* snapshot in tensor memory: warp 0 allocates the columns, every warp derives the address of its slots */
     uint32_t tm = SCB_TMEM_OFF;
-#if defined(__CUDA_ARCH__)
+    uint32_t tmemBase = 0u;
     if (TM) {
+#if defined(__CUDA_ARCH__)
         if (warp == 0) scb_tmem_alloc((uint32_t)__cvta_generic_to_shared(&sh[14]), (uint32_t)A.tmemCols);
         scb_tmem_fence_before();
         __syncthreads();
         scb_tmem_fence_after();
-        const uint32_t tbase = (uint32_t)sh[14];
-        tm = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(K * (warp >> 2) * A.tmemSlotsPerWarp);
-    }
+        tmemBase = (uint32_t)sh[14];
 #endif
+        tm = tmemBase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(K * (warp >> 2) * A.tmemSlotsPerWarp);
+    }
     const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
     unsigned long long stepsDone = 0, tilesDone = 0;
     long long cycPro = 0, cycStep = 0, cycEpi = 0;
@@ -780,13 +791,6 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         __syncthreads();
         cycPro += c1 - c0; cycStep += c2 - c1; cycEpi += scb_clock() - c2;
     }
-#if defined(__CUDA_ARCH__)
-    if (TM) {
-        scb_tmem_fence_before();
-        __syncthreads();
-        if (warp == 0) scb_tmem_dealloc((uint32_t)sh[14], (uint32_t)A.tmemCols);
-    }
-#endif
     /* ---- in-kernel resolver: a CTA that found the tile queue empty takes tickets for resolver items.  An item
      * is processed as soon as its producer has published it; a ticket beyond the final count ends the CTA.  All
      * producers are running CTAs of this launch (the queue is empty), so waiting for them cannot deadlock. ---- */
@@ -811,10 +815,18 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             __syncthreads();
             const int it = slot[0];
             if (it < 0) break;
-            if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it);
+            if (TM && K == 4 && A.resolveGroup == 4) scb_resolve_item<4, true>(A, smraw, (unsigned)it, tm);
+            else if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it);
             else scb_resolve_item<1>(A, smraw, (unsigned)it);
         }
     }
+#if defined(__CUDA_ARCH__)
+    if (TM) {
+        scb_tmem_fence_before();
+        __syncthreads();
+        if (warp == 0) scb_tmem_dealloc(tmemBase, (uint32_t)A.tmemCols);
+    }
+#endif
     if (tid == 0 && tilesDone) {
         atomicAdd(&A.diag->steps_executed, stepsDone);
         atomicAdd(&A.diag->tiles, tilesDone);
@@ -844,11 +856,15 @@ struct ScbResolveArgs {
  *   how = 2: 98 plain steps only (Fm is not computed)
  * On return: buffer A rows hold S_98, buffer B rows hold e = (S_98 xor S_0) & valid for every node,
  * Fm[32*KR] = found & valid per word (how != 2), vm[32*KR] = valid masks.  All threads call it. */
-template <int KR>
+template <int KR, bool TTM = false>
 SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uint4 *desc, int4 cnt,
                                uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
-                               const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr, int onlyLane = -1)
+                               const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr, int onlyLane = -1,
+                               uint32_t tm = SCB_TMEM_OFF)
 {
+    /* TTM: the target state T = S_99 is kept in tensor memory (this warp's slots start at tm, one slot of KR
+     * columns per non-constant node in the order scb_step visits them) instead of a third shared-memory buffer,
+     * so that a whole 4-chunk tile fits; the per-step fold then goes through dmz with one extra barrier. */
     /* D: [2][warps][32*KR] per-step difference words of every warp (double buffered by step parity), so that the
      * per-step "equal to T" reduction needs no atomics and no barrier of its own.
      * onlyLane >= 0: only that lane's words are simulated (the fill-forward needs a single cell). */
@@ -867,17 +883,45 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
         for (int row = warp; row < N; row += S) {
             const ScbVec<KR> v = scb_ldg<KR>(A.X + (long long)row * A.Wpad + w0 + lane * KR);
             scb_st<KR>(bufA + (uint32_t)row * ROWB + laneOff, v);
-            if (pass == 1 && how == 1)
+            if (!TTM && pass == 1 && how == 1)
                 scb_st<KR>(bufT + (uint32_t)row * ROWB + laneOff,
                            scb_ld<KR>(reinterpret_cast<const unsigned char *>(Tglob + (long long)row * GW + lane * KR)));
         }
         if (tid < GW) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; Fm[tid] = 0u; }
+        if (TTM && pass == 1 && how == 1) {
+            /* T from the simulator's hand-over buffer into this warp's tensor-memory slots */
+            const int e1 = cnt.x + cnt.y + cnt.z;
+            uint32_t tmc = tm;
+            for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR) {
+                const int node = (int)((desc[j].w & 0xFFFFFFu) / ROWB);
+                scb_tmem_st<KR>(tmc, scb_ld<KR>(reinterpret_cast<const unsigned char *>(Tglob + (long long)node * GW + lane * KR)));
+            }
+            scb_tmem_wait_st();
+        }
         __syncthreads();
         if (cmp) {
             /* j = 0: compare S_0 with T on every row */
             ScbVec<KR> d;
 #pragma unroll
             for (int k = 0; k < KR; ++k) d.v[k] = 0u;
+            if (TTM) {
+                const int e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
+                uint32_t tmc = tm;
+                for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR) {
+                    ScbVec<KR> y;
+                    scb_tmem_ld<KR>(tmc, y);
+                    const ScbVec<KR> x = scb_ld<KR>(bufA + (desc[j].w & 0xFFFFFFu) + laneOff);
+                    scb_tmem_wait_ld<KR>(y);
+#pragma unroll
+                    for (int k = 0; k < KR; ++k) d.v[k] |= x.v[k] ^ y.v[k];
+                }
+                for (int j = e1 + warp; j < e0; j += S) {           /* constant rows: T holds the constant */
+                    const ScbVec<KR> x = scb_ld<KR>(bufA + (desc[j].w & 0xFFFFFFu) + laneOff);
+                    const uint32_t cv = (desc[j].w >> 24) ? 0xffffffffu : 0u;
+#pragma unroll
+                    for (int k = 0; k < KR; ++k) d.v[k] |= x.v[k] ^ cv;
+                }
+            } else
             for (int row = warp; row < N; row += S) {
                 const ScbVec<KR> x = scb_ld<KR>(bufA + (uint32_t)row * ROWB + laneOff), y = scb_ld<KR>(bufT + (uint32_t)row * ROWB + laneOff);
 #pragma unroll
@@ -893,10 +937,21 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
         uint32_t srcOff = 0u, dstOff = BUFB;
         for (int tn = 1; tn <= last; ++tn) {
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
-            if (cmp) f |= SCB_SF_TCMP;
+            if (cmp) f |= TTM ? SCB_SF_ZCMP : SCB_SF_TCMP;
 #pragma unroll
             for (int k = 0; k < KR; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
             const bool act = onlyLane < 0 || lane == onlyLane;
+            if (TTM && cmp) {
+                /* compare with T in tensor memory, fold through dmz */
+                scb_step<KR, false, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa, d2, dz, true, tm);
+#pragma unroll
+                for (int k = 0; k < KR; ++k) if (dz.v[k]) atomicOr(&dmz[lane * KR + k], dz.v[k]);
+                __syncthreads();
+                if (tid < GW) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
+                __syncthreads();
+                const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
+                continue;
+            }
             if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             else if (f == SCB_SF_TCMP) scb_step<KR, false, false, SCB_SF_TCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             else scb_step<KR, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
@@ -918,6 +973,13 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
         }
         if (pass == 0) {
             /* S_99 sits in buffer B (99 is odd): T = B */
+            if (TTM) {
+                const int e1 = cnt.x + cnt.y + cnt.z;
+                uint32_t tmc = tm;
+                for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR)
+                    scb_tmem_st<KR>(tmc, scb_ld<KR>(bufB + (desc[j].w & 0xFFFFFFu) + laneOff));
+                scb_tmem_wait_st();
+            } else
             for (int row = warp; row < N; row += S)
                 scb_st<KR>(bufT + (uint32_t)row * ROWB + laneOff, scb_ld<KR>(bufB + (uint32_t)row * ROWB + laneOff));
             __syncthreads();
@@ -937,27 +999,29 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
 }
 
 /* shared-memory carve-up of the resolver kernels (after the three state buffers) */
-SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR)
+SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR, bool ttm = false)
 {
-    return (size_t)3 * N * 128 * KR + (size_t)N * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 4
-           + (size_t)2 * 24 * 32 * KR * 4 + 256;                       /* + D[2][<=24 warps][32*KR] */
+    /* state buffers (three, or two when T lives in tensor memory) + program + dmz/Fm/vm + scalars +
+     * srcc[1024*KR] int16 + (shared-memory T only) D[2][<=24 warps][32*KR] + slack */
+    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + (size_t)N * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 2
+           + (ttm ? 0 : (size_t)2 * 24 * 32 * KR * 4) + 256;
 }
 
 /* K3 phase 1: exact found mask and error sums of every queued group of KR chunks; leading not-found cells that
  * must copy a cell of an earlier chunk are queued for phase 2.  Only the chunks K2 flagged are summed here. */
-template <int KR>
-SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it)
+template <int KR, bool TTM>
+SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it, uint32_t tm)
 {
     const int N = A.N;
     const uint32_t ROWB = 128u * KR, BUFB = (uint32_t)N * ROWB;
     const int GW = 32 * KR, GC = 1024 * KR;
     unsigned char *sm = smraw;
-    uint4 *desc = reinterpret_cast<uint4 *>(smraw + 3u * BUFB);
+    uint4 *desc = reinterpret_cast<uint4 *>(smraw + (TTM ? 2u : 3u) * BUFB);
     uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
     uint32_t *Fm = dmz + GW;
     uint32_t *vm = Fm + GW;
     int *sh = reinterpret_cast<int *>(vm + GW);            /* [2] pending cells, [3] not-found cells */
-    int *srcc = sh + 16;                                   /* [GC] source cell of each cell */
+    short *srcc = reinterpret_cast<short *>(sh + 16);      /* [GC] source cell of each cell */
     uint32_t *Dbuf = reinterpret_cast<uint32_t *>(srcc + GC);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
@@ -971,8 +1035,8 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
         if (tid == 0) { sh[2] = 0; sh[3] = 0; }
         __syncthreads();
         const bool haveT = it < A.resolveTCap;
-        scb_resolve_chunk<KR>(A, sm, desc, cnt, dmz, Fm, vm, q, haveT ? 1 : 0,
-                              A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf);
+        scb_resolve_chunk<KR, TTM>(A, sm, desc, cnt, dmz, Fm, vm, q, haveT ? 1 : 0,
+                                   A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf, -1, tm);
 
         /* source cell of every cell: itself when found, else the nearest earlier found cell of the group
          * (the reference's fill-forward), -1 when that lies in an earlier chunk, -2 padding */
@@ -993,7 +1057,7 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
                     }
                 }
             }
-            srcc[i] = s;
+            srcc[i] = (short)s;
         }
         __syncthreads();
 

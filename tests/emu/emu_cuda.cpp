@@ -26,7 +26,8 @@ struct BlockCtx {
     std::barrier<> bar;
     std::vector<std::unique_ptr<WarpCtx>> warps;
     unsigned char *smem;
-    explicit BlockCtx(int n) : bar(n), smem(nullptr) {}
+    std::vector<uint32_t> tmem;
+    explicit BlockCtx(int n) : bar(n), smem(nullptr), tmem(128 * 512, 0xDEADBEEFu) {}
 };
 thread_local BlockCtx *tl_block = nullptr;
 thread_local WarpCtx *tl_warp = nullptr;
@@ -34,6 +35,12 @@ thread_local WarpCtx *tl_warp = nullptr;
 
 unsigned char *emu_dyn_smem() { return tl_block->smem; }
 void emu_yield() { std::this_thread::yield(); }
+uint32_t *emu_tmem_cell(uint32_t taddr, int k)
+{
+    const unsigned lane = ((taddr >> 16) & 0xffffu) + (threadIdx.x & 31u), col = (taddr & 0xffffu) + (unsigned)k;
+    if (lane >= 128u || col >= 512u) abort();            /* out-of-range tensor-memory access */
+    return &tl_block->tmem[(size_t)lane * 512 + col];
+}
 void __syncthreads() { tl_block->bar.arrive_and_wait(); }
 void __syncwarp(unsigned) { tl_warp->bar.arrive_and_wait(); }
 

@@ -34,6 +34,8 @@ extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 unsigned char *emu_dyn_smem();
 void emu_yield();
+/* tensor memory of the emulated SM: 128 lanes x 512 columns of 32 bits per block; taddr = lane << 16 | column */
+uint32_t *emu_tmem_cell(uint32_t taddr, int k);
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 void __syncthreads();
