@@ -566,37 +566,13 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
     unsigned long long stepsDone = 0, tilesDone = 0;
     long long cycPro = 0, cycStep = 0, cycEpi = 0;
 
-    /* scalars that must survive a resolver item (which lays shared memory out differently) live in the last 64
-     * bytes of the launch's dynamic shared memory: [0] resolver item, [1],[2] prefetched tile items */
-    int *slot = reinterpret_cast<int *>(smraw + A.smemBytes - 64);
-    if (tid == 0) slot[1] = (int)atomicAdd(A.workCounter, 1u);
+    if (tid == 0) sh[12] = (int)atomicAdd(A.workCounter, 1u);
     __syncthreads();
     for (unsigned iter = 0;; ++iter) {
-        if (A.fuseResolve) {
-            /* resolver items are taken as soon as they are published, between tiles, so that their work is spread
-             * over the launch instead of piling up at its end */
-            for (;;) {
-                __syncthreads();
-                if (tid == 0) {
-                    int got = -1;
-                    const unsigned cur = scb_ld_volatile(A.resolveCursor);
-                    if (cur < A.resolveCap && scb_ld_volatile(&A.readyFlags[cur]) != 0u &&
-                        atomicCAS(A.resolveCursor, cur, cur + 1u) == cur) got = (int)cur;
-                    __threadfence();
-                    slot[0] = got;
-                }
-                __syncthreads();
-                const int it = slot[0];
-                if (it < 0) break;
-                if (TM && K == 4 && A.resolveGroup == 4) scb_resolve_item<4, true>(A, smraw, (unsigned)it, tm);
-                else if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it);
-                else scb_resolve_item<1>(A, smraw, (unsigned)it);
-            }
-        }
-        const unsigned item = (unsigned)slot[1 + (iter & 1u)];
+        const unsigned item = (unsigned)sh[12 + (iter & 1u)];
         if (item >= total) break;
         /* the next item is requested now and read after this tile's last barrier: the atomic's latency is hidden */
-        if (tid == 0) slot[1 + ((iter + 1u) & 1u)] = (int)atomicAdd(A.workCounter, 1u);
+        if (tid == 0) sh[12 + ((iter + 1u) & 1u)] = (int)atomicAdd(A.workCounter, 1u);
         /* tile-major order: the long tiles of a hard individual are spread over the whole launch and the last
          * items to be handed out are the cheap, partly filled tail tiles, which keeps the end of the launch level */
         const int p = (int)(item % (unsigned)A.P), tile = (int)(item / (unsigned)A.P);
@@ -819,6 +795,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
      * is processed as soon as its producer has published it; a ticket beyond the final count ends the CTA.  All
      * producers are running CTAs of this launch (the queue is empty), so waiting for them cannot deadlock. ---- */
     if (A.fuseResolve) {
+        int *slot = reinterpret_cast<int *>(smraw + A.smemBytes - 64);
         for (;;) {
             __syncthreads();
             if (tid == 0) {

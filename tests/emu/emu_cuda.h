@@ -37,7 +37,6 @@ void emu_yield();
 /* tensor memory of the emulated SM: 128 lanes x 512 columns of 32 bits per block; taddr = lane << 16 | column */
 uint32_t *emu_tmem_cell(uint32_t taddr, int k);
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 void __syncthreads();
 void __syncwarp(unsigned mask = 0xffffffffu);
