@@ -250,7 +250,7 @@ def test_evaluate_by_node_mirrors_reference_returns(backend):
 
 
 def test_check_node_possibilities(backend):
-    pr = Problem.synthetic(25, big(backend, 300, 4000), 1)
+    pr = Problem.synthetic(big(backend, 10, 25), big(backend, 200, 4000), 1)
     pr.pop_an = pr.pop_ai = None
     m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
     with pr.simulator(backend[1]) as sim:
@@ -273,7 +273,7 @@ def test_check_node_possibilities(backend):
 
 
 def test_local_search_all_nodes_in_one_launch(backend):
-    pr = Problem.synthetic(25, big(backend, 300, 4000), 1)
+    pr = Problem.synthetic(big(backend, 10, 25), big(backend, 200, 4000), 1)
     pr.pop_an = pr.pop_ai = None
     with pr.simulator(backend[1]) as sim:
         every = sim.local_search(pr.individuals[0].tolist(), [0] * pr.n, [0] * pr.n)
