@@ -128,7 +128,9 @@ int scb_eval_population(scb_ctx *ctx, int P, const int32_t *individuals, int ind
  * scb_pop_upload copies the reference-format tables to the device (async on the context's
  * stream); scb_pop_run launches rule compilation + simulation + resolver (async);
  * scb_pop_fetch waits and copies the result of `mode` to the host.  scb_pop_result_dev
- * exposes the device buffer (int64[P] / int32[P][N] / int32[P][C]) for a collective. */
+ * exposes the device buffer (int64[P] / int32[P][N] / int32[P][C]) for a collective.
+ * The host buffers given to scb_pop_upload must stay valid until scb_pop_fetch or scb_ctx_sync returns
+ * (with pinned memory, scb_host_alloc, the copy is truly asynchronous). */
 int scb_pop_upload(scb_ctx *ctx, int P, const int32_t *individuals, int indLen,
                    const int32_t *andLenList, const int32_t *individualParse,
                    const int32_t *andNodes, const int32_t *andNodeInvertList,

@@ -1,24 +1,32 @@
 /*
  * scb_kernels.cuh -- sm_100a kernels of the rule-inference fitness hot path.
  *
- *   K0  scb_k_compile   reference-format rule tables -> per-individual programs of 3-input
- *                       truth tables (scb_compile.h), sorted by arity
- *   K1  scb_k_pack      int32 / uint8 binarized matrix -> node-major 32-cells-per-word S_0
- *   K2  scb_k_sim<K>    the simulator: persistent CTAs, one (individual, cell tile) per work
- *                       item, state ping-pong in shared memory, one LOP3 per node per 32 cells
- *   K3  scb_k_resolve   exact second pass for the rare 1024-cell chunks K2 could not prove
- *                       "attractor found" for, incl. the reference's fill-forward
- *   K5  scb_k_hamming   cell x attractor Hamming distance + first-minimum argmin
+ *   K0  scb_k_compile    reference-format rule tables -> per-individual programs of 3-input truth tables
+ *                        (scb_compile.h), sorted by arity; one CTA per individual
+ *   K1  scb_k_pack       int32 / uint8 binarized matrix -> node-major 32-cells-per-word S_0
+ *   K1b scb_k_pack_csr   the same straight from a CSR matrix
+ *   K2  scb_k_sim<K,TM>  the simulator: persistent CTAs, one (individual, cell tile) per work item, state
+ *                        ping-pong in shared memory, one LOP3 per node per 32 cells reached through a brx.idx
+ *                        jump table, snapshot in tensor memory (TM); CTAs that run out of tiles resolve queued
+ *                        groups in the same launch
+ *   K3  scb_resolve_item / scb_k_resolve   exact second pass for the 1024-cell chunks K2 could not prove
+ *                        "attractor found" for (literally getAttractCycle2 on packed words);
+ *       scb_k_fill       the reference's fill-forward across chunks, one warp per item
+ *   K4  scb_k_traj + scb_k_window   trajectories, attractor windows and their states (C `cluster` and Python
+ *                        `__cluster` semantics)
+ *   K5  scb_k_hamming    cell x attractor Hamming distance + first-minimum argmin
+ *   K6  scb_k_importance_reduce   the reduction of importanceScore
  *
- * What is computed (reference simulator.c:350-485): per cell the
- * synchronous trajectory S_0..S_99; found <=> S_99 equals some earlier S_j; error bits
- * e = S_98 xor S_0 when found, else the previous cell's e.  The kernels never store the
- * trajectory: "found" is proven in flight by any observed repeat S_t == S_j (j < t <= 99),
- * which implies transient + period <= 99; cells without such a proof go to K3.
+ * What K2/K3 compute (reference simulator.c:350-485): per cell the synchronous trajectory
+ * S_0..S_99; found <=> S_99 equals some earlier S_j; error bits e = S_98 xor S_0 when found, else the previous
+ * cell's e.  The kernels never store the trajectory: "found" is proven in flight by any observed repeat
+ * S_t == S_j (j < t <= 99), which implies transient + period <= 99; cells without such a proof go to K3.
  *
- * Data layout in shared memory (per CTA): two state buffers [N][32*K] uint32 (row = node,
- * lane l owns words l*K .. l*K+K-1, so every access is a conflict-free LDS/STS.(32*K)),
- * followed by the CTA's program (uint4 per node) and a few 32*K-word masks.
+ * Data layout in shared memory (per CTA): two state buffers [N][32*K] uint32 (row = node, lane l owns words
+ * l*K .. l*K+K-1, so every access is a conflict-free LDS/STS.(32*K)), followed by the CTA's program (uint4 per
+ * node) and a few 32*K-word masks.
+ *
+ * The file also compiles with g++ -DSCB_EMU against tests/emu (host-thread emulator, test infrastructure).
  */
 #ifndef SCB_KERNELS_CUH
 #define SCB_KERNELS_CUH
