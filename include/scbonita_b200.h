@@ -66,6 +66,7 @@ extern "C" {
 #define SCB_OPT_SNAP_HI      9  /* bit t-64 for steps 64..98 (default: snapshots at 36 and 66)        */
 #define SCB_OPT_SNAP_MIN_GAP 10 /* first snapshot compare this many steps after a snapshot (default 8) */
 #define SCB_OPT_TMEM         11 /* 1 (default): keep the snapshot in tensor memory, 0: in global scratch    */
+#define SCB_OPT_TMA          13 /* 1 (default): load the S_0 tile with TMA bulk copies (cp.async.bulk + mbarrier)   */
 #define SCB_OPT_FUSE         12 /* 1 (default): CTAs that run out of tiles resolve queued groups in the same launch */
 
 typedef struct scb_ctx scb_ctx;

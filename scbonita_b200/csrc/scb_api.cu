@@ -78,7 +78,7 @@ struct scb_ctx {
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
     int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 6, optSearch = 0, optMinGap = 8;
-    int optTmem = 1, optFuse = 1;
+    int optTmem = 1, optFuse = 1, optTma = 1;
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
@@ -457,6 +457,7 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
         case SCB_OPT_SNAP_MIN_GAP:
             if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "snapshot gap must be in [1,99]");
             c->optMinGap = (int)value; return SCB_OK;
+        case SCB_OPT_TMA: c->optTma = value != 0; return SCB_OK;
         case SCB_OPT_TMEM: c->optTmem = value != 0; break;
         case SCB_OPT_FUSE: c->optFuse = value != 0; break;
         case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
@@ -574,6 +575,7 @@ int scb_pop_run(scb_ctx *c, int mode)
     /* the simulator resolves queued groups in its own tail when a single launch covers all tiles */
     const bool fuse = c->optFuse && c->tailTiles == 0;
     sa.fuseResolve = fuse ? 1 : 0;
+    sa.useTma = c->optTma;
     sa.tilesDone = c->dCounters.p + 6; sa.readyFlags = c->dReady.p; sa.resolveCursor = c->dCounters.p + 2;
     if (fuse) CK(cudaMemsetAsync(c->dReady.p, 0, (size_t)sa.resolveCap * sizeof(unsigned int), st));
     CK(cudaEventRecord(c->evSim0, st));

@@ -92,6 +92,30 @@ template <int K> SCB_DEV void scb_sts(scb_saddr a, const ScbVec<K> &r) { scb_st<
 SCB_DEV uint4 scb_lds_desc(scb_saddr a) { return *reinterpret_cast<const uint4 *>(a); }
 #endif
 
+/* ---- TMA bulk copies of the S_0 tile: one cp.async.bulk (SASS UBLKCP) per node row, completion on an mbarrier ---- */
+#if defined(__CUDA_ARCH__)
+SCB_DEV void scb_mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SCB_DEV void scb_mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+SCB_DEV void scb_bulk_g2s(uint32_t dstSmem, const void *srcGlobal, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dstSmem), "l"(srcGlobal), "r"(bytes), "r"(mbar) : "memory");
+}
+SCB_DEV void scb_mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nSCB_WAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra SCB_WAIT_DONE;\n"
+                 "bra SCB_WAIT_LOOP;\nSCB_WAIT_DONE:\n}" :: "r"(mbar), "r"(parity) : "memory");
+}
+SCB_DEV void scb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 /* ---- tensor memory as a scratchpad --------------------------------------------------------------------
  * The simulator uses no tensor cores, so the SM's 256 KB of TMEM (128 lanes x 512 columns x 32 bit) is free.
  * K2 keeps its snapshot S_s there instead of in global memory: a warp owns the 32 lanes of its quarter
@@ -570,6 +594,15 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
 #endif
         tm = tmemBase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(K * (warp >> 2) * A.tmemSlotsPerWarp);
     }
+#if defined(__CUDA_ARCH__)
+    /* mbarrier of the TMA tile loads: 8 bytes in the reserved tail of the launch's dynamic shared memory */
+    const uint32_t mbarAddr = (uint32_t)__cvta_generic_to_shared(smraw + A.smemBytes - 32);
+    uint32_t tmaParity = 0u;
+    if (A.useTma) {
+        if (tid == 0) scb_mbar_init(mbarAddr, 1u);
+        __syncthreads();
+    }
+#endif
     const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
     unsigned long long stepsDone = 0, tilesDone = 0;
     long long cycPro = 0, cycStep = 0, cycEpi = 0;
@@ -588,7 +621,22 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         const int w0 = A.wordBase + tile * WT;
         const int4 cnt = A.counts[p];
         scb_load_program<K>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
-        {   /* S_0 tile: four rows in flight per warp */
+        bool tileByTma = false;
+#if defined(__CUDA_ARCH__)
+        if (A.useTma) {
+            /* S_0 tile by TMA: one bulk copy per node row (a 128*K-byte segment of the packed matrix), issued by one
+             * thread, landing in buffer A while the other threads load the program; completion on the mbarrier */
+            tileByTma = true;
+            if (tid == 0) {
+                scb_fence_proxy_async();
+                scb_mbar_expect_tx(mbarAddr, (uint32_t)N * ROWB);
+                const uint32_t *xs = A.X + w0;
+                for (int row = 0; row < N; ++row)
+                    scb_bulk_g2s(sa + (uint32_t)row * ROWB, xs + (long long)row * A.Wpad, ROWB, mbarAddr);
+            }
+        }
+#endif
+        if (!tileByTma) {   /* S_0 tile: four rows in flight per warp */
             const uint32_t *xs = A.X + w0 + lane * K;
             int row = warp;
             for (; row + 3 * S < N; row += 4 * S) {
@@ -606,6 +654,9 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         }
         if (tid < WT) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); Rm[tid] = 0u; dm2[tid] = 0u; dmz[tid] = 0u; }
         if (tid == 0) { sh[1] = 0; sh[2] = 0; }
+#if defined(__CUDA_ARCH__)
+        if (tileByTma) { scb_mbar_wait(mbarAddr, tmaParity); tmaParity ^= 1u; }
+#endif
         __syncthreads();
 
         const bool laneActive = ((long long)w0 + lane * K) * 32 < A.C;       /* the lane holds a valid cell */

@@ -118,6 +118,7 @@ struct ScbSimArgs {
     unsigned int *readyFlags;     /* [resolveCap] item i is complete in memory */
     unsigned int *resolveCursor;  /* ticket counter of the in-kernel resolver */
     unsigned int smemBytes;       /* dynamic shared memory of the launch (the item slot sits in its last 64 bytes) */
+    int useTma;                   /* != 0: the S_0 tile is loaded with cp.async.bulk (TMA) row copies */
     int tmemCols;                 /* > 0: the snapshot lives in tensor memory, this many columns per CTA */
     int tmemSlotsPerWarp;         /* node slots reserved per warp (ceil(N / warps)) */
     ScbDiag *diag;
