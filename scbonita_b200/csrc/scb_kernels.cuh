@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
     const uint32_t mbarAddr = (uint32_t)__cvta_generic_to_shared(smraw + A.smemBytes - 32);
     uint32_t tmaParity = 0u;
     if (A.useTma) {
-        if (tid == 0) scb_mbar_init(mbarAddr, 1u);
+        if (tid == 0) scb_mbar_init(mbarAddr, (uint32_t)(S < N ? S : N));
         __syncthreads();
     }
 #endif
@@ -627,11 +627,13 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
             /* S_0 tile by TMA: one bulk copy per node row (a 128*K-byte segment of the packed matrix), issued by one
              * thread, landing in buffer A while the other threads load the program; completion on the mbarrier */
             tileByTma = true;
-            if (tid == 0) {
+            if (lane == 0 && warp < N) {
+                /* every warp's leader announces and issues the copies of its own rows (warp, warp + S, ...) */
+                const int nrows = (N - warp + S - 1) / S;
                 scb_fence_proxy_async();
-                scb_mbar_expect_tx(mbarAddr, (uint32_t)N * ROWB);
+                scb_mbar_expect_tx(mbarAddr, (uint32_t)nrows * ROWB);
                 const uint32_t *xs = A.X + w0;
-                for (int row = 0; row < N; ++row)
+                for (int row = warp; row < N; row += S)
                     scb_bulk_g2s(sa + (uint32_t)row * ROWB, xs + (long long)row * A.Wpad, ROWB, mbarAddr);
             }
         }
