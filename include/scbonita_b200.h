@@ -198,6 +198,16 @@ int scb_importance_score(scb_ctx *ctx, const int32_t *individual, int indLen,
                          const int32_t *andNodes, const int32_t *andNodeInvertList,
                          const int32_t *knockouts, const int32_t *knockins, double *score);
 
+/* The same for nItems knock-out / knock-in pairs in ONE simulator launch: knockouts and knockins are
+ * int32[nItems][N], scores double[nItems].  This is the loop over nodes of ruleMaker.__calcImportance
+ * (ruleMaker.py:1285-1300: one importanceScore call per node with KOlist = KIlist = [node]); every score is
+ * bit-identical to the single call.  Items whose cells lack an attractor window get NaN and the call returns
+ * SCB_ERR_INVALID (the other scores are valid). */
+int scb_importance_scores(scb_ctx *ctx, const int32_t *individual, int indLen,
+                          const int32_t *andLenList, const int32_t *individualParse,
+                          const int32_t *andNodes, const int32_t *andNodeInvertList,
+                          int nItems, const int32_t *knockouts, const int32_t *knockins, double *scores);
+
 /* ---- the reference's exported symbols (drop-in ./simulator.so) --------------------------
  * Argument lists are exactly simulator.c:350, :555 and :487.  ctypes passes every argument as
  * c_void_p (ruleMaker.py:1117-1138), so integers arrive in 64-bit registers: they are

@@ -108,9 +108,9 @@ struct scb_ctx {
     DevBuf<unsigned char> dFlush;
     DevBuf<uint32_t> dTraj, dStates;
     DevBuf<int32_t> dRes, dNStates;
-    DevBuf<unsigned long long> dNodeCnt;
     /* current population */
     int P = 0, indLen = 0, tpi = 0;
+    int koStride = 0;                    /* 0: shared knock-out array, N: one per program */
     int lastMode = -1;
     bool ran = false;
     ScbDiag hDiag = {};
@@ -229,7 +229,7 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock)
     ScbCompileArgs ca;
     ca.P = P; ca.N = N; ca.indLen = c->indLen; ca.tablesPerIndividual = c->tpi; ca.Npad = N; ca.sem = sem;
     ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
-    ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p;
+    ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p; ca.koStride = c->koStride;
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
     const int cthr = std::min(256, ((N + 31) / 32) * 32);
     SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
@@ -429,7 +429,7 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
-    c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dNodeCnt.release();
+    c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
     if (c->evSim1) cudaEventDestroy(c->evSim1);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -492,9 +492,11 @@ int scb_ctx_info(scb_ctx *c, int *nodeNum, int *lenSamples, int *wordsPerLane, i
     return SCB_OK;
 }
 
-int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, const int32_t *andLenList,
-                   const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
-                   int tablesPerIndividual, const int32_t *knockouts, const int32_t *knockins)
+/* scb_pop_upload with `indRows` bit-strings (P, or 1 when the programs do not read them) and `koRows` knock-out
+ * arrays (1 shared, or P: one per program, the batched importance score) */
+static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *individuals, int indLen, const int32_t *andLenList,
+                           const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                           int tablesPerIndividual, int koRows, const int32_t *knockouts, const int32_t *knockins)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
@@ -507,7 +509,7 @@ int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, co
     const size_t tbl = (size_t)N * SCB_MAX_TERMS * SCB_MAX_IN;
     const size_t ntab = tablesPerIndividual ? (size_t)P : 1;
     if ((rc = c->dInd.ensure((size_t)P * std::max(indLen, 1)))) return rc;
-    if ((rc = c->dAndLen.ensure(N)) || (rc = c->dParse.ensure(N)) || (rc = c->dKo.ensure(N)) || (rc = c->dKi.ensure(N))) return rc;
+    if ((rc = c->dAndLen.ensure(N)) || (rc = c->dParse.ensure(N)) || (rc = c->dKo.ensure((size_t)koRows * N)) || (rc = c->dKi.ensure(N))) return rc;
     if ((rc = c->dAn.ensure(ntab * tbl)) || (rc = c->dAi.ensure(ntab * tbl))) return rc;
     if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
     if ((rc = c->dFitness.ensure(P))) return rc;
@@ -523,37 +525,56 @@ int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, co
         c->resolveTCap = (unsigned)(c->dResolveT.cap / per);
     }
     cudaStream_t st = c->stream;
-    if (indLen > 0) CK(cudaMemcpyAsync(c->dInd.p, individuals, (size_t)P * indLen * 4, cudaMemcpyHostToDevice, st));
+    if (indLen > 0) CK(cudaMemcpyAsync(c->dInd.p, individuals, (size_t)indRows * indLen * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dAndLen.p, andLenList, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dParse.p, individualParse, (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->dKo.p, knockouts, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dKo.p, knockouts, (size_t)koRows * N * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dKi.p, knockins, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dAn.p, andNodes, ntab * tbl * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dAi.p, andNodeInvertList, ntab * tbl * 4, cudaMemcpyHostToDevice, st));
     c->P = P; c->indLen = indLen; c->tpi = tablesPerIndividual ? 1 : 0;
+    c->koStride = koRows > 1 ? N : 0;
     c->ran = false;
     return SCB_OK;
 }
 
+int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, const int32_t *andLenList,
+                   const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                   int tablesPerIndividual, const int32_t *knockouts, const int32_t *knockins)
+{
+    return pop_upload_impl(c, P, P, individuals, indLen, andLenList, individualParse, andNodes, andNodeInvertList,
+                           tablesPerIndividual, 1, knockouts, knockins);
+}
+
+static int pop_run_impl(scb_ctx *c, int mode, int sem);
+
 int scb_pop_run(scb_ctx *c, int mode)
+{
+    if (mode < 0 || mode > 2) return fail(SCB_ERR_INVALID, "unknown mode %d", mode);
+    return pop_run_impl(c, mode, SCB_SEM_C);
+}
+
+/* K0 + K2 + K3 on the uploaded population; mode may also be the internal SCB_MODE_IMPORTANCE (with
+ * sem = SCB_SEM_IMPORTANCE), whose per-node counts land in the nodewise buffer */
+static int pop_run_impl(scb_ctx *c, int mode, int sem)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
-    if (mode < 0 || mode > 2) return fail(SCB_ERR_INVALID, "unknown mode %d", mode);
     std::lock_guard<std::mutex> lk(c->mu);
     if (c->P <= 0) return fail(SCB_ERR_INVALID, "no population uploaded");
     if (!c->geomValid && (rc = pick_geometry(c))) return rc;
     const int N = c->N, P = c->P;
     cudaStream_t st = c->stream;
-    if (mode == SCB_MODE_NODEWISE && (rc = c->dNodewise.ensure((size_t)P * N))) return rc;
+    const bool wantNodewise = mode == SCB_MODE_NODEWISE || mode == SCB_MODE_IMPORTANCE;
+    if (wantNodewise && (rc = c->dNodewise.ensure((size_t)P * N))) return rc;
     if (mode == SCB_MODE_CELLWISE && (rc = c->dCellwise.ensure((size_t)P * c->C))) return rc;
     CK(cudaEventRecord(c->evRun0, st));
     CK(cudaMemsetAsync(c->dFitness.p, 0, (size_t)P * 8, st));
-    if (mode == SCB_MODE_NODEWISE) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
+    if (wantNodewise) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
     CK(cudaMemsetAsync(c->dCounters.p, 0, 8 * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
 
-    if ((rc = launch_compile(c, SCB_SEM_C, c->dKo.p))) return rc;
+    if ((rc = launch_compile(c, sem, c->dKo.p))) return rc;
 
     ScbSimArgs sa;
     memset(&sa, 0, sizeof(sa));

@@ -15,7 +15,8 @@
  *   K4  scb_k_traj + scb_k_window   trajectories, attractor windows and their states (C `cluster` and Python
  *                        `__cluster` semantics)
  *   K5  scb_k_hamming    cell x attractor Hamming distance + first-minimum argmin
- *   K6  scb_k_importance_reduce   the reduction of importanceScore
+ *   importanceScore (simulator.c:555-755) has no kernel of its own: K0 compiles its single-literal rules, K2/K3 run
+ *   in the SCB_MODE_IMPORTANCE output shape (per-node counts over fixed-point cells), one program per knock array
  *
  * What K2/K3 compute (reference simulator.c:350-485): per cell the synchronous trajectory
  * S_0..S_99; found <=> S_99 equals some earlier S_j; error bits e = S_98 xor S_0 when found, else the previous
@@ -328,7 +329,7 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     if (tid < 8) cn[tid] = 0u;
     __syncthreads();
     for (int i = tid; i < N; i += nthr) {
-        const ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko, A.ki, A.sem);
+        const ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko + (long long)p * A.koStride, A.ki, A.sem);
         sd[i] = make_uint4((unsigned)f.in[0], (unsigned)f.in[1], (unsigned)f.in[2], (unsigned)i | (f.lut << 24));
         sar[i] = (unsigned char)f.arity;
         atomicAdd(&cn[3 - f.arity], 1u);
@@ -739,6 +740,30 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         stepsDone += (unsigned long long)t; ++tilesDone;
         const long long c2 = scb_clock();
 
+        if (A.mode == SCB_MODE_IMPORTANCE) {
+            /* importanceScore adds rows res[0]..res[1] divided by the window length as integers (simulator.c:641-648):
+             * only cells with a window of length 1 (S_98 == S_99) contribute.  The two state buffers hold S_99 and
+             * S_98 (t == 99), or S_98 and S_97 of cells that are all proven periodic from step 97 or earlier, where
+             * S_97 == S_98 <=> S_98 == S_99: fixed point <=> the buffers agree on every node.  Such a cell is found
+             * (state 99 repeats state 98), so it needs no resolver; dmz keeps the mask for the epilogue. */
+            ScbVec<K> df;
+#pragma unroll
+            for (int k = 0; k < K; ++k) df.v[k] = 0u;
+            for (int row = warp; row < N; row += S) {
+                const ScbVec<K> a = scb_ld<K>(sm + (uint32_t)row * ROWB + laneOff), b = scb_ld<K>(sm + BUFB + (uint32_t)row * ROWB + laneOff);
+#pragma unroll
+                for (int k = 0; k < K; ++k) df.v[k] |= a.v[k] ^ b.v[k];
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) if (df.v[k]) atomicOr(&dm2[lane * K + k], df.v[k]);
+            __syncthreads();
+            if (tid < WT) {
+                const uint32_t fp = ~dm2[tid] & vm[tid];
+                dmz[tid] = fp; dm2[tid] = 0u; Rm[tid] |= fp;
+            }
+            __syncthreads();
+        }
+
         /* ---- chunk flags: a 32-word chunk with an unproven valid cell goes to K3 ---------- */
         if (warp == 0) {
             bool bad = false;
@@ -799,6 +824,25 @@ __global__ void __launch_bounds__(768, 1) scb_k_sim(ScbSimArgs A)
         }
         if (A.fuseResolve && tid == 0) { __threadfence(); atomicAdd(A.tilesDone, 1u); }
 
+        if (A.mode == SCB_MODE_IMPORTANCE) {
+            /* per node: fixed-point cells with the node set (every chunk is counted here; the resolver only
+             * decides whether the remaining cells have a window at all) */
+            const unsigned char *fin = sm + finOff + laneOff;
+            ScbVec<K> fpm;
+#pragma unroll
+            for (int k = 0; k < K; ++k) fpm.v[k] = dmz[lane * K + k];
+            for (int j = warp; j < N; j += S) {
+                const ScbVec<K> s = scb_ld<K>(fin + (uint32_t)j * ROWB);
+                unsigned c = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) c += (unsigned)__popc(s.v[k] & fpm.v[k]);
+                c = scb_warp_sum(c);
+                if (lane == 0 && c) atomicAdd(&A.nodewise[(long long)p * N + j], (int)c);
+            }
+            __syncthreads();
+            cycPro += c1 - c0; cycStep += c2 - c1; cycEpi += scb_clock() - c2;
+            continue;
+        }
         /* ---- errors: e = S_98 xor S_0 on valid cells of proven chunks ---------------------- */
         ScbVec<K> ok;
 #pragma unroll
@@ -1122,6 +1166,19 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
         }
         __syncthreads();
 
+        if (A.mode == SCB_MODE_IMPORTANCE) {
+            /* the simulator has counted every fixed-point cell; what is left to decide is whether the other cells
+             * of the flagged chunks have an attractor window at all (the reference divides by zero otherwise) */
+            if (tid == 0) {
+                if (sh[3] > 0) {
+                    atomicAdd(&A.fitness[p], (unsigned long long)sh[3]);
+                    atomicAdd(&A.diag->not_found_cells, (unsigned long long)sh[3]);
+                }
+                atomicAdd(&A.diag->resolver_chunks, (unsigned long long)__popc(flagged));
+            }
+            __syncthreads();
+            return;
+        }
         /* per-node sums over the flagged chunks: found cells plus the copies made by not-found cells */
         unsigned tot = 0;
         for (int j = warp; j < N; j += S) {
@@ -1377,49 +1434,6 @@ __global__ void scb_k_window(ScbWindowArgs A)
                     out[wq] = acc;
                 }
             }
-        }
-    }
-}
-
-/* K6: the reduction of importanceScore (simulator.c:641-648): for every cell whose attractor window has
- * length 1 the two window rows (98 and 99) are added node by node; longer windows add
- * (int)(state / length) = 0; a cell without a window divides by zero in the reference (counted here). */
-struct ScbImportanceArgs {
-    const uint32_t *traj;
-    const int32_t *res;           /* [C][2] from scb_k_window (C semantics) */
-    int N, C, tiles, steps;
-    unsigned long long *nodeCnt;  /* [N] accumulated */
-    unsigned long long *notFound; /* [1] */
-};
-
-__global__ void scb_k_importance_reduce(ScbImportanceArgs A)
-{
-    SCB_DYN_SMEM(smraw);
-    uint32_t *fp = reinterpret_cast<uint32_t *>(smraw);                   /* [32] fixed-point cell masks */
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
-    for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t m = 0u;
-            unsigned nf = 0;
-            for (int b = 0; b < 32; ++b) {
-                const long long c = (long long)tile * 1024 + lane * 32 + b;
-                if (c >= A.C) continue;
-                const int r0 = A.res[c * 2], r1 = A.res[c * 2 + 1];
-                if (r1 - r0 == 1) m |= 1u << b;
-                if (r1 - r0 == 0) ++nf;
-            }
-            fp[lane] = m;
-            nf = scb_warp_sum(nf);
-            if (lane == 0 && nf) atomicAdd(A.notFound, (unsigned long long)nf);
-        }
-        __syncthreads();
-        const uint32_t *t98 = A.traj + ((unsigned long long)tile * A.steps + (A.steps - 2)) * A.N * 32;
-        const uint32_t *t99 = t98 + (unsigned long long)A.N * 32;
-        for (int n = warp; n < A.N; n += S) {
-            unsigned c = (unsigned)__popc(t98[n * 32 + lane] & fp[lane]) + (unsigned)__popc(t99[n * 32 + lane] & fp[lane]);
-            c = scb_warp_sum(c);
-            if (lane == 0 && c) atomicAdd(&A.nodeCnt[n], (unsigned long long)c);
         }
     }
 }

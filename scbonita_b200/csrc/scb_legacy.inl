@@ -171,51 +171,79 @@ void cluster(void *simData, int32_t *resSubmit, intptr_t sampleIndex, const int3
 
 /* simulator.c:555-755, incl. its quirks: both passes force knocked nodes to 0 and accumulate into
  * the knock-OUT average (:674, :717), every node with andLen != 0 is a single literal, the individual is
- * ignored, (int)(state / window length) is an integer division.  The integer sums come from the device; the
- * last N divisions and additions are done here in the reference's order so that the double is bit-identical.
- * A cell without an attractor window makes the reference divide by zero (SIGFPE): SCB_ERR_INVALID, score = NaN. */
+ * ignored, (int)(state / window length) is an integer division, so only windows of length 1 (S_98 == S_99)
+ * contribute, with their two rows 98 and 99.  Batched: item k is the pair (knockouts[k][N], knockins[k][N]) --
+ * ruleMaker.__calcImportance makes 3 x N such calls per network (ruleMaker.py:1285-1300).  Every distinct knock
+ * array is one program of ONE simulator launch (K0 with the importance semantics, K2/K3 in their importance output
+ * shape); a pass whose knock-in array equals its knock-out array (what __calcImportance passes) is simulated once.
+ * The integer counts come from the device; the last N divisions and additions are done here in the reference's
+ * order so that every double is bit-identical.  A cell without an attractor window makes the reference divide
+ * by zero (SIGFPE): that item's score is NaN and the call returns SCB_ERR_INVALID. */
+int scb_importance_scores(scb_ctx *ctx, const int32_t *individual, int indLen, const int32_t *andLenList,
+                          const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                          int nItems, const int32_t *knockouts, const int32_t *knockins, double *scores)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!scores || !knockouts || !knockins) return fail(SCB_ERR_INVALID, "null argument");
+    if (nItems <= 0) return fail(SCB_ERR_INVALID, "nItems must be positive");
+    const int N = ctx->N, C = ctx->C;
+    for (int k = 0; k < nItems; ++k) scores[k] = 0.0;
+    std::vector<int32_t> knock;
+    std::vector<int> passOf((size_t)2 * nItems);
+    knock.reserve((size_t)2 * nItems * N);
+    for (int k = 0; k < nItems; ++k) {
+        const int32_t *ko = knockouts + (size_t)k * N, *ki = knockins + (size_t)k * N;
+        passOf[2 * k] = (int)(knock.size() / N);
+        knock.insert(knock.end(), ko, ko + N);
+        /* simulator.c:604 / :674 test the arrays for non-zero only */
+        bool same = true;
+        for (int i = 0; i < N && same; ++i) same = (ko[i] != 0) == (ki[i] != 0);
+        if (same) passOf[2 * k + 1] = passOf[2 * k];
+        else { passOf[2 * k + 1] = (int)(knock.size() / N); knock.insert(knock.end(), ki, ki + N); }
+    }
+    const int P = (int)(knock.size() / N);
+    rc = pop_upload_impl(ctx, P, 1, individual, indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0,
+                         P, knock.data(), knockins);
+    if (rc) return rc;
+    if ((rc = pop_run_impl(ctx, SCB_MODE_IMPORTANCE, SCB_SEM_IMPORTANCE))) return rc;
+    std::vector<int32_t> cnt((size_t)P * N);
+    std::vector<unsigned long long> noWindow((size_t)P);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CK(cudaMemcpyAsync(cnt.data(), ctx->dNodewise.p, cnt.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(noWindow.data(), ctx->dFitness.p, noWindow.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = check_compile_diag(ctx))) return rc;
+        ctx->ran = false;                       /* the buffers do not hold a population result */
+    }
+    unsigned long long bad = 0;
+    int badItems = 0;
+    for (int k = 0; k < nItems; ++k) {
+        const int pa = passOf[2 * k], pb = passOf[2 * k + 1];
+        const unsigned long long nf = noWindow[pa] + noWindow[pb];
+        if (nf) { scores[k] = nan(""); bad += nf; ++badItems; continue; }
+        double acc = 0.0;
+        for (int i = 0; i < N; ++i) {
+            /* rows 98 and 99 of every fixed-point cell, knock-out pass then knock-in pass (:641-648, :712-719) */
+            const long long sum = 2ll * cnt[(size_t)pa * N + i] + 2ll * cnt[(size_t)pb * N + i];
+            const double ki = 0.0 / C;                                   /* attractorAverage_ki stays 0 (:734-736) */
+            const double ko = (double)sum / C;                           /* :739-741 */
+            acc = acc + fabs(ki - ko);                                   /* :750 */
+        }
+        scores[k] = acc;
+    }
+    if (bad)
+        return fail(SCB_ERR_INVALID, "%llu cell passes of %d item(s) have no attractor window; the reference divides by "
+                                     "zero there (simulator.c:647)", bad, badItems);
+    return SCB_OK;
+}
+
 int scb_importance_score(scb_ctx *ctx, const int32_t *individual, int indLen, const int32_t *andLenList,
                          const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
                          const int32_t *knockouts, const int32_t *knockins, double *score)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
-    if (!score || !knockouts || !knockins) return fail(SCB_ERR_INVALID, "null argument");
-    score[0] = 0.0;
-    const int N = ctx->N, C = ctx->C;
-    std::vector<unsigned long long> cnt((size_t)N + 1, 0ull);
-    rc = scb_pop_upload(ctx, 1, individual, indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0,
-                        knockouts, knockins);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if ((rc = ctx->dNodeCnt.ensure((size_t)N + 1))) return rc;
-    CK(cudaMemsetAsync(ctx->dNodeCnt.p, 0, ((size_t)N + 1) * 8, ctx->stream));
-    const int tiles = (ctx->W + 31) / 32;
-    for (int pass = 0; pass < 2; ++pass) {
-        /* run_trajectories compiles with dKo as the knock array: the second pass swaps the knock-in list in */
-        if (pass == 1) CK(cudaMemcpyAsync(ctx->dKo.p, knockins, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if ((rc = run_trajectories(ctx, SCB_SEM_IMPORTANCE, SCB_STEPS, 0, -1))) return rc;
-        ScbImportanceArgs ia;
-        ia.traj = ctx->dTraj.p; ia.res = ctx->dRes.p; ia.N = N; ia.C = C; ia.tiles = tiles; ia.steps = SCB_STEPS;
-        ia.nodeCnt = ctx->dNodeCnt.p; ia.notFound = ctx->dNodeCnt.p + N;
-        SCB_LAUNCH(scb_k_importance_reduce, dim3((unsigned)std::max(1, std::min(tiles, ctx->numSM * 4))), dim3(256), 128, ctx->stream, ia);
-        CK(cudaGetLastError());
-    }
-    CK(cudaMemcpyAsync(cnt.data(), ctx->dNodeCnt.p, ((size_t)N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if ((rc = check_compile_diag(ctx))) return rc;
-    if (cnt[N]) {
-        score[0] = nan("");
-        return fail(SCB_ERR_INVALID, "%llu cell passes have no attractor window; the reference divides by zero there "
-                                     "(simulator.c:647)", cnt[N]);
-    }
-    double acc = 0.0;
-    for (int i = 0; i < N; ++i) {
-        const double ki = 0.0 / C;                                   /* attractorAverage_ki stays 0 (:734-736) */
-        const double ko = (double)cnt[i] / C;                        /* :739-741 */
-        acc = acc + fabs(ki - ko);                                   /* :750 */
-    }
-    score[0] = acc;
-    return SCB_OK;
+    return scb_importance_scores(ctx, individual, indLen, andLenList, individualParse, andNodes, andNodeInvertList, 1,
+                                 knockouts, knockins, score);
 }
 
 void importanceScore(void *simData, const int32_t *individual, intptr_t indLen, intptr_t nodeNum,

@@ -42,6 +42,11 @@
 #define SCB_SF_TCMP   8u   /* compare S_t with the target state held in shared memory     */
 #define SCB_SF_CONST 16u   /* also write the constant rows (steps 1 and 2 only)            */
 
+/* internal output shape of K2 / K3 next to the public SCB_MODE_* (0..2): the counts importanceScore needs,
+ * nodewise[p][i] = number of fixed-point cells (S_98 == S_99) with node i set, fitness[p] = cells without an
+ * attractor window (simulator.c:641-648) */
+#define SCB_MODE_IMPORTANCE 3
+
 /* kernel behaviour flags (ScbSimArgs.flags) */
 #define SCB_KF_EARLY  1u
 #define SCB_KF_SNAP   2u
@@ -72,6 +77,7 @@ struct ScbCompileArgs {
     const int32_t *parse;         /* [N] */
     const int32_t *an, *ai;       /* [P or 1][N][7][3] */
     const int32_t *ko, *ki;       /* [N] */
+    int koStride;                 /* 0: one shared `ko`; N: program p reads ko + p * N (batched importance scores) */
     uint4 *descs;                 /* [P][Npad] */
     int4 *counts;                 /* [P] */
     ScbDiag *diag;

@@ -226,6 +226,29 @@ class Simulator:
         out = self.evaluate_population(individual, knockouts, knockins, and_nodes, and_inv, MODE_SUM)
         return [int(out[0])]
 
+    def importance_scores(self, individual, KOlists, KIlists=None, strict=True):
+        """The loop over nodes of ruleMaker.__calcImportance (ruleMaker.py:1285-1300) in one launch: one
+        ``__evaluateByNode(individual, KOlist, KIlist, importanceScore, importanceScores=True)`` result per
+        (KOlist, KIlist) pair, each bit-identical to the single call.  ``KIlists`` defaults to ``KOlists``
+        (what ``__calcImportance`` passes: ``[node], [node]``).  Returns float64[len(KOlists)].  Where the reference
+        divides by zero (a cell without an attractor window) the score is NaN: an error when ``strict``."""
+        m = self.model
+        KIlists = KOlists if KIlists is None else KIlists
+        if len(KOlists) != len(KIlists) or len(KOlists) == 0:
+            raise ValueError("KOlists and KIlists must be non-empty and of equal length")
+        kos = np.zeros((len(KOlists), m.n), dtype=np.int32)
+        kis = np.zeros((len(KOlists), m.n), dtype=np.int32)
+        for k, (kol, kil) in enumerate(zip(KOlists, KIlists)):
+            kos[k], kis[k] = self._knock(kol, kil)
+        ind = _i32(individual)
+        scores = np.zeros(len(KOlists), dtype=np.float64)
+        rc = self.lib.scb_importance_scores(self._ctx, _ptr(ind), m.ind_len, _ptr(m.and_len_list),
+                                            _ptr(m.individual_parse), _ptr(m.and_nodes), _ptr(m.and_node_invert_list),
+                                            len(KOlists), _ptr(kos), _ptr(kis), _ptr(scores))
+        if not (rc == _lib.ERR_INVALID and not strict and np.isnan(scores).any()):
+            _lib.check(self.lib, rc)
+        return scores
+
     def check_node_possibilities(self, node, indy, KOlist, KIlist, scSyncBoolC=None):
         """ruleMaker.__checkNodePossibilities (ruleMaker.py:1235-1266): all 2^k - 1 rule bit-strings of
         ``node`` in one launch.  Returns ``(truth, equivs, minny, indErrors)``."""

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from common import GOLDEN, Problem, oracle_model, tables
+from common import GOLDEN, Problem, oracle_model, ring_problem, tables
 from scbonita_b200 import _lib, simulator
 
 BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
@@ -168,3 +168,88 @@ def test_legacy_importanceScore_symbol(backend, n, cells, seed):
         assert np.isnan(score[0])
     else:
         assert score[0].tobytes() == np.float64(want).tobytes(), (score[0], want)
+
+
+def _oracle_importance(pr, an, ai, individual, ko, ki):
+    m = oracle_model(pr.net, pr.node_positions, np.asarray(ko, np.int32), np.asarray(ki, np.int32))
+    m.and_nodes, m.and_inv = an, ai
+    try:
+        return oracle.importance_score(m, individual, pr.bm, pr.n_cells)
+    except ValueError:
+        return float("nan")
+
+
+def _same_doubles(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.array_equal(np.isnan(got), np.isnan(want)) and got[~np.isnan(got)].tobytes() == want[~np.isnan(want)].tobytes()
+
+
+@pytest.mark.parametrize("n,cells,seed", [(20, 200, 4242), (61, 1500, None), (33, 4200, 5)])
+def test_importance_scores_all_nodes_one_launch(backend, n, cells, seed):
+    """The loop over nodes of ruleMaker.__calcImportance (ruleMaker.py:1285-1300) as one batched call: every
+    score bit-identical to the oracle's importanceScore for KOlist = KIlist = [node]."""
+    pr = Problem.synthetic(n, cells, 1, knock=False, net_seed=seed)
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_an[0], pr.pop_ai[0], pr.node_positions, pr.net.ind_len)
+    want = []
+    for node in range(n):
+        k = np.zeros(n, np.int32); k[node] = 1
+        want.append(_oracle_importance(pr, pr.pop_an[0], pr.pop_ai[0], pr.individuals[0], k, k))
+    with simulator.Simulator(pr.bm, model, lib_path=backend[1]) as sim:
+        if backend[0] == "emu":
+            sim.set_option(_lib.OPT_MAX_CTAS, 3)
+        got = sim.importance_scores(pr.individuals[0], [[i] for i in range(n)], strict=False)
+        one = sim.evaluate_by_node(pr.individuals[0], [3], [3], importanceScores=True) if not np.isnan(want[3]) else None
+    assert _same_doubles(got, want), (got, want)
+    assert not np.isnan(np.asarray(want)).all()
+    if one is not None:
+        assert np.float64(one[0]).tobytes() == np.float64(want[3]).tobytes()
+
+
+def test_importance_scores_distinct_knockin_arrays(backend):
+    """Knock-in arrays that differ from the knock-out arrays: two simulated passes per item (simulator.c:674, :717),
+    non-0/1 knock values count as set (:604 tests for non-zero)."""
+    n, cells = 26, 900
+    pr = Problem.synthetic(n, cells, 1, knock=False, net_seed=77)
+    rng = np.random.default_rng(3)
+    items = 9
+    kos = (rng.random((items, n)) < 0.1).astype(np.int32) * rng.integers(1, 4, (items, n)).astype(np.int32)
+    kis = (rng.random((items, n)) < 0.1).astype(np.int32)
+    kis[4] = (kos[4] != 0)                                       # one item whose passes coincide
+    want = [_oracle_importance(pr, pr.pop_an[0], pr.pop_ai[0], pr.individuals[0], kos[k], kis[k]) for k in range(items)]
+    lib = _lib.load(backend[1])
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_an[0], pr.pop_ai[0], pr.node_positions, pr.net.ind_len)
+    with simulator.Simulator(pr.bm, model, lib_path=backend[1]) as sim:
+        if backend[0] == "emu":
+            sim.set_option(_lib.OPT_MAX_CTAS, 3)
+        ind = np.ascontiguousarray(pr.individuals[0], np.int32)
+        got = np.zeros(items, np.float64)
+        P = lambda a: ctypes.c_void_p(a.ctypes.data)
+        m = sim.model
+        rc = lib.scb_importance_scores(sim._ctx, P(ind), m.ind_len, P(m.and_len_list), P(m.individual_parse), P(m.and_nodes),
+                                       P(m.and_node_invert_list), items, P(kos), P(kis), P(got))
+    assert rc in (_lib.OK, _lib.ERR_INVALID)
+    assert (rc == _lib.ERR_INVALID) == bool(np.isnan(np.asarray(want)).any())
+    assert _same_doubles(got, want), (got, want)
+
+
+@pytest.mark.parametrize("rings,cells", [([40, 5], 1300), ([60, 7], 700)])
+def test_importance_scores_long_cycles(backend, rings, cells):
+    """Rings of period 80 (found only by the exact resolver: window length 80 adds (int)(state / 80) = 0) and of
+    period 120 (no attractor window in 100 rows: the reference divides by zero -> NaN for the items that leave
+    the ring alive, exact scores for the items that knock it)."""
+    pr = ring_problem(rings, 3, cells)
+    n = pr.n
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.net.and_nodes, pr.net.and_inv, pr.node_positions, pr.net.ind_len)
+    want = []
+    for node in range(n):
+        k = np.zeros(n, np.int32); k[node] = 1
+        want.append(_oracle_importance(pr, pr.net.and_nodes, pr.net.and_inv, pr.individuals[0], k, k))
+    with simulator.Simulator(pr.bm, model, lib_path=backend[1]) as sim:
+        if backend[0] == "emu":
+            sim.set_option(_lib.OPT_MAX_CTAS, 3)
+        got = sim.importance_scores(pr.individuals[0], [[i] for i in range(n)], strict=False)
+        if np.isnan(np.asarray(want)).any():
+            with pytest.raises(_lib.ScbError):
+                sim.importance_scores(pr.individuals[0], [[i] for i in range(n)])
+    assert _same_doubles(got, want), (got, want)
+    assert (~np.isnan(np.asarray(want))).any()
