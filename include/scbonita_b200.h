@@ -208,6 +208,10 @@ int scb_importance_scores(scb_ctx *ctx, const int32_t *individual, int indLen,
                           const int32_t *andNodes, const int32_t *andNodeInvertList,
                           int nItems, const int32_t *knockouts, const int32_t *knockins, double *scores);
 
+/* ---- measured on-box peaks for the roofline report (bench.py): kind 0 = 32-bit LOP3 ops/s, 1 = POPC ops/s,
+ * 2 = bytes/s of conflict-free 128-bit shared-memory loads, all SMs busy.  Not part of the reference's interface. */
+int scb_microbench(scb_ctx *ctx, int kind, double *perSecond);
+
 /* ---- the reference's exported symbols (drop-in ./simulator.so) --------------------------
  * Argument lists are exactly simulator.c:350, :555 and :487.  ctypes passes every argument as
  * c_void_p (ruleMaker.py:1117-1138), so integers arrive in 64-bit registers: they are

@@ -871,3 +871,4 @@ int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t
 }  /* extern "C" */
 
 #include "scb_legacy.inl"
+#include "scb_microbench.inl"

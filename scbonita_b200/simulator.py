@@ -194,6 +194,13 @@ class Simulator:
         _lib.check(self.lib, self.lib.scb_ctx_stream(self._ctx, ctypes.byref(p)))
         return p.value or 0
 
+    def microbench(self, kind):
+        """Measured peak of one on-chip resource with every SM busy: "lop3" / "popc" in thread-level ops per
+        second, "lds" in bytes per second of conflict-free 128-bit shared-memory loads (roofline denominators)."""
+        v = ctypes.c_double()
+        _lib.check(self.lib, self.lib.scb_microbench(self._ctx, {"lop3": 0, "popc": 1, "lds": 2}[kind], ctypes.byref(v)))
+        return v.value
+
     def evaluate_population(self, individuals, knockouts=None, knockins=None, and_nodes=None, and_inv=None,
                             mode=MODE_SUM):
         """Score P individuals in one launch.  Returns int64[P] (SUM), int32[P][N] (NODEWISE) or
