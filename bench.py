@@ -216,6 +216,10 @@ def run_ours(args, wl, rank, world, local_rank):
     h_an = pinned(np.ascontiguousarray(pr.pop_and_nodes, np.int32))
     h_ai = pinned(np.ascontiguousarray(pr.pop_and_inv, np.int32))
     h_out = pinned(np.zeros(P, np.int64))
+    # the same population in the compact form a GA driver can keep: upstream triples, not term tables
+    up, ui = simulator.upstream_from_tables(pr.net.and_len, pr.pop_and_nodes, pr.pop_and_inv)
+    h_up, h_ui = pinned(up), pinned(ui)
+    h2d_compact = h_ind.nbytes + h_up.nbytes + h_ui.nbytes + 4 * N * 4
     h2d = h_ind.nbytes + h_an.nbytes + h_ai.nbytes + 4 * N * 4
     d2h = h_out.nbytes
 
@@ -257,6 +261,13 @@ def run_ours(args, wl, rank, world, local_rank):
             gather()
         sim.fetch(simulator.MODE_SUM, out=h_out)
 
+    def step_e2e_compact():
+        sim.upload_compact(h_ind, h_up, h_ui, pr.knockouts, pr.knockins)
+        sim.run(simulator.MODE_SUM)
+        if gather:
+            gather()
+        sim.fetch(simulator.MODE_SUM, out=h_out)
+
     def timed(step, steps, warmup):
         for _ in range(warmup):
             step()
@@ -288,6 +299,10 @@ def run_ours(args, wl, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
     fit = h_out.copy()
+    e2e_compact_ms, _, _ = timed(step_e2e_compact, args.steps, max(args.warmup, 3))
+    if not np.array_equal(fit, h_out):
+        raise RuntimeError("compact and table uploads disagree")
+    sim.upload(h_ind, pr.knockouts, pr.knockins, h_an, h_ai)
     # roofline pass: the simulator kernel K2 timed on its own.  In the default configuration the same launch also
     # resolves queued groups in its tail (K3 work), so K2's own duration is taken with that fusion switched off.
     fused_default = "fuse=0" not in args.opt
@@ -361,6 +376,11 @@ def run_ours(args, wl, rank, world, local_rank):
             "ga_generations_per_sec": 1e3 / ms_per_step,
             "e2e": {"value": units_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e_compact": {"value": units_per_step / (e2e_compact_ms / args.steps * 1e-3), "unit": UNIT,
+                            "ms_per_step": e2e_compact_ms / args.steps, "h2d_bytes_per_step": int(h2d_compact),
+                            "d2h_bytes_per_step": int(d2h),
+                            "note": "same generation, population handed over as bit-strings + upstream triples "
+                                    "(scb_pop_upload_compact) instead of the reference's [N][7][3] tables"},
             "gpu_launches": (3 if fused_default else 4) * args.steps,   # K0 compile, K2 simulate (+ in-kernel K3), K3 fill
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,

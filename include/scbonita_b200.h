@@ -136,6 +136,16 @@ int scb_pop_upload(scb_ctx *ctx, int P, const int32_t *individuals, int indLen,
                    const int32_t *andLenList, const int32_t *individualParse,
                    const int32_t *andNodes, const int32_t *andNodeInvertList,
                    int tablesPerIndividual, const int32_t *knockouts, const int32_t *knockins);
+/* The same upload in the compact form a GA driver can keep per individual instead of a deep copy of the model
+ * (ruleMaker.py:650): upstream / upstreamInvert are int32[P][N][3] (perIndividual != 0) or one shared [N][3] --
+ * each node's at most three upstream nodes as a prefix, -1 after the last, and their inversion flags.  The
+ * [7][3] AND-term tables are rebuilt on the device in the reference's order [abc, ab, ac, a, bc, b, c]
+ * (ruleMaker.py:188-200, padded like __updateCpointers, :337-360); andLenList[i] must equal 2^k - 1 for a node
+ * with k upstream nodes, else scb_pop_fetch fails with SCB_ERR_INVALID.  24 instead of 168 bytes per node. */
+int scb_pop_upload_compact(scb_ctx *ctx, int P, const int32_t *individuals, int indLen,
+                           const int32_t *andLenList, const int32_t *individualParse,
+                           const int32_t *upstream, const int32_t *upstreamInvert,
+                           int perIndividual, const int32_t *knockouts, const int32_t *knockins);
 int scb_pop_run(scb_ctx *ctx, int mode);
 int scb_pop_fetch(scb_ctx *ctx, int mode, void *out, scb_stats *stats);
 int scb_pop_result_dev(scb_ctx *ctx, int mode, void **devPtr, int64_t *bytes);

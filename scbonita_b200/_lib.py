@@ -21,7 +21,7 @@ OPT_SNAP_LO, OPT_SNAP_HI, OPT_SNAP_MIN_GAP, OPT_TMEM, OPT_FUSE, OPT_TMA = 8, 9, 
 SYMBOLS = (
     "scb_last_error", "scb_version", "scb_device_count",
     "scb_ctx_create", "scb_ctx_create_csr", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info",
-    "scb_eval_population", "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
+    "scb_eval_population", "scb_pop_upload", "scb_pop_upload_compact", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
     "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
     "scb_eval_local_search", "scb_eval_local_search_all", "scb_hamming_argmin", "scb_attractors", "scb_importance_score",
@@ -77,6 +77,8 @@ def load(path=None):
     tables = [i32p, ctypes.c_int, i32p, i32p, i32p, i32p, ctypes.c_int, i32p, i32p]
     lib.scb_eval_population.argtypes = [vp, ctypes.c_int] + tables + [ctypes.c_int, vp, ctypes.POINTER(Stats)]
     lib.scb_pop_upload.argtypes = [vp, ctypes.c_int] + tables
+    lib.scb_pop_upload_compact.argtypes = [vp, ctypes.c_int] + tables
+    lib.scb_pop_upload_compact.restype = ctypes.c_int
     lib.scb_pop_run.argtypes = [vp, ctypes.c_int]
     lib.scb_pop_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Stats)]
     lib.scb_pop_result_dev.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]

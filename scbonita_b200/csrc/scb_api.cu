@@ -111,6 +111,7 @@ struct scb_ctx {
     /* current population */
     int P = 0, indLen = 0, tpi = 0;
     int koStride = 0;                    /* 0: shared knock-out array, N: one per program */
+    int compact = 0;                     /* dAn / dAi hold [P or 1][N][3] upstream triples instead of term tables */
     int lastMode = -1;
     bool ran = false;
     ScbDiag hDiag = {};
@@ -229,7 +230,7 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock)
     ScbCompileArgs ca;
     ca.P = P; ca.N = N; ca.indLen = c->indLen; ca.tablesPerIndividual = c->tpi; ca.Npad = N; ca.sem = sem;
     ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
-    ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p; ca.koStride = c->koStride;
+    ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p; ca.koStride = c->koStride; ca.compact = c->compact;
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
     const int cthr = std::min(256, ((N + 31) / 32) * 32);
     SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
@@ -496,7 +497,8 @@ int scb_ctx_info(scb_ctx *c, int *nodeNum, int *lenSamples, int *wordsPerLane, i
  * arrays (1 shared, or P: one per program, the batched importance score) */
 static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *individuals, int indLen, const int32_t *andLenList,
                            const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
-                           int tablesPerIndividual, int koRows, const int32_t *knockouts, const int32_t *knockins)
+                           int tablesPerIndividual, int koRows, const int32_t *knockouts, const int32_t *knockins,
+                           int compact = 0)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
@@ -506,7 +508,7 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
         return fail(SCB_ERR_INVALID, "null table pointer");
     std::lock_guard<std::mutex> lk(c->mu);
     const int N = c->N;
-    const size_t tbl = (size_t)N * SCB_MAX_TERMS * SCB_MAX_IN;
+    const size_t tbl = compact ? (size_t)N * SCB_MAX_IN : (size_t)N * SCB_MAX_TERMS * SCB_MAX_IN;
     const size_t ntab = tablesPerIndividual ? (size_t)P : 1;
     if ((rc = c->dInd.ensure((size_t)P * std::max(indLen, 1)))) return rc;
     if ((rc = c->dAndLen.ensure(N)) || (rc = c->dParse.ensure(N)) || (rc = c->dKo.ensure((size_t)koRows * N)) || (rc = c->dKi.ensure(N))) return rc;
@@ -534,6 +536,7 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
     CK(cudaMemcpyAsync(c->dAi.p, andNodeInvertList, ntab * tbl * 4, cudaMemcpyHostToDevice, st));
     c->P = P; c->indLen = indLen; c->tpi = tablesPerIndividual ? 1 : 0;
     c->koStride = koRows > 1 ? N : 0;
+    c->compact = compact ? 1 : 0;
     c->ran = false;
     return SCB_OK;
 }
@@ -544,6 +547,17 @@ int scb_pop_upload(scb_ctx *c, int P, const int32_t *individuals, int indLen, co
 {
     return pop_upload_impl(c, P, P, individuals, indLen, andLenList, individualParse, andNodes, andNodeInvertList,
                            tablesPerIndividual, 1, knockouts, knockins);
+}
+
+/* the population as the GA needs to keep it -- bit-strings plus each node's upstream triple
+ * (what ruleMaker.__update_upstream changes, ruleMaker.py:300-335) instead of a deep copy of the whole model per
+ * individual (ruleMaker.py:650).  K0 rebuilds the [7][3] term tables on the device. */
+int scb_pop_upload_compact(scb_ctx *c, int P, const int32_t *individuals, int indLen, const int32_t *andLenList,
+                           const int32_t *individualParse, const int32_t *upstream, const int32_t *upstreamInvert,
+                           int perIndividual, const int32_t *knockouts, const int32_t *knockins)
+{
+    return pop_upload_impl(c, P, P, individuals, indLen, andLenList, individualParse, upstream, upstreamInvert,
+                           perIndividual, 1, knockouts, knockins, 1);
 }
 
 static int pop_run_impl(scb_ctx *c, int mode, int sem);
@@ -677,7 +691,7 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
         if (cudaEventElapsedTime(&ms, c->evSim0, c->evSim1) == cudaSuccess) stats->sim_ms = ms;
     }
     if (d.bad_index_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules reference an input outside [0,%d)", d.bad_index_nodes, c->N);
-    if (d.term_overflow_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules span more than 7 AND-terms or leave the bit-string", d.term_overflow_nodes);
+    if (d.term_overflow_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules span more than 7 AND-terms, leave the bit-string, or (compact upload) disagree with andLenList", d.term_overflow_nodes);
     if (d.unsupported_nodes) return fail(SCB_ERR_UNSUPPORTED, "%llu (individual,node) rules use more than 3 distinct inputs", d.unsupported_nodes);
     return SCB_OK;
 }

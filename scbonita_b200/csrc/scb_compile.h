@@ -52,6 +52,33 @@ SCB_HD inline ScbNodeFn scb_copy_fn(int src, int invert)
     return f;
 }
 
+/* The AND-term tables of one node from its (at most three) upstream nodes, as the reference builds them:
+ * every non-empty subset of the inputs in itertools.product order over ((a, empty), (b, empty), (c, empty)),
+ * i.e. [abc, ab, ac, a, bc, b, c] (ruleMaker.py:188-200, :300-335), each term padded with -1 and the table
+ * padded to 7 terms with [0,0,0] (__updateCpointers, ruleMaker.py:337-360).  up[3] holds the inputs as a prefix
+ * (-1 after the last), upInv[3] their inversion flags.  Returns the number of terms, -1 for a malformed triple. */
+SCB_HD inline int scb_expand_terms(const int32_t *up, const int32_t *upInv, int32_t *an, int32_t *ai)
+{
+    int k = 0;
+    while (k < SCB_MAX_IN && up[k] >= 0) ++k;
+    bool bad = false;
+    for (int j = k; j < SCB_MAX_IN; ++j) bad = bad || up[j] >= 0;
+    for (int x = 0; x < SCB_MAX_TERMS * SCB_MAX_IN; ++x) { an[x] = 0; ai[x] = 0; }
+    if (bad) return -1;
+    const int nt = (1 << k) - 1;
+    for (int m = 0; m < nt; ++m) {
+        int w = 0;
+        for (int j = 0; j < k; ++j) {
+            if ((m >> (k - 1 - j)) & 1) continue;                 /* input j is "empty" in this term */
+            an[m * SCB_MAX_IN + w] = up[j];
+            ai[m * SCB_MAX_IN + w] = upInv[j];
+            ++w;
+        }
+        for (; w < SCB_MAX_IN; ++w) { an[m * SCB_MAX_IN + w] = -1; ai[m * SCB_MAX_IN + w] = -1; }
+    }
+    return nt;
+}
+
 SCB_HD inline ScbNodeFn scb_compile_node(int i, int N, int indLen, const int32_t *ind,
                                          const int32_t *andLen, const int32_t *parse,
                                          const int32_t *an, const int32_t *ai,

@@ -325,8 +325,19 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     const int TBL = N * SCB_MAX_TERMS * SCB_MAX_IN;
     int32_t *an = reinterpret_cast<int32_t *>(smraw + (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64);
     int32_t *ai = an + TBL;
-    for (int i = tid; i < TBL; i += nthr) { an[i] = A.an[toff + i]; ai[i] = A.ai[toff + i]; }
     if (tid < 8) cn[tid] = 0u;
+    __syncthreads();
+    if (A.compact) {
+        /* the GA keeps only each node's upstream triple per individual: 24 bytes per node over the
+         * bus instead of 168; the tables the reference would have marshalled are rebuilt here */
+        const long long uoff = A.tablesPerIndividual ? (long long)p * N * SCB_MAX_IN : 0;
+        for (int i = tid; i < N; i += nthr) {
+            const int nt = scb_expand_terms(A.an + uoff + i * SCB_MAX_IN, A.ai + uoff + i * SCB_MAX_IN,
+                                            an + i * (SCB_MAX_TERMS * SCB_MAX_IN), ai + i * (SCB_MAX_TERMS * SCB_MAX_IN));
+            if (nt != A.andLen[i]) atomicAdd(&cn[7], 1u);        /* triple and andLenList disagree */
+        }
+    } else
+    for (int i = tid; i < TBL; i += nthr) { an[i] = A.an[toff + i]; ai[i] = A.ai[toff + i]; }
     __syncthreads();
     for (int i = tid; i < N; i += nthr) {
         const ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko + (long long)p * A.koStride, A.ki, A.sem);

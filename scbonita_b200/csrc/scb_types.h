@@ -75,7 +75,8 @@ struct ScbCompileArgs {
     const int32_t *individuals;   /* [P][indLen] */
     const int32_t *andLen;        /* [N] */
     const int32_t *parse;         /* [N] */
-    const int32_t *an, *ai;       /* [P or 1][N][7][3] */
+    const int32_t *an, *ai;       /* [P or 1][N][7][3]; compact != 0: [P or 1][N][3] upstream nodes / inversion flags */
+    int compact;                  /* != 0: the term tables are expanded on the fly from the upstream triples */
     const int32_t *ko, *ki;       /* [N] */
     int koStride;                 /* 0: one shared `ko`; N: program p reads ko + p * N (batched importance scores) */
     uint4 *descs;                 /* [P][Npad] */

@@ -152,6 +152,28 @@ class Simulator:
                                      _ptr(m.individual_parse), _ptr(an), _ptr(ai), per_ind, _ptr(ko), _ptr(ki))
         _lib.check(self.lib, rc)
 
+    def upload_compact(self, individuals, upstream, upstream_inv, knockouts=None, knockins=None):
+        """H2D of one population in the compact form: ``upstream`` / ``upstream_inv`` are
+        [P][N][3] (every individual its own wiring, what ``__update_upstream`` changes, ruleMaker.py:300-335) or
+        one shared [N][3]; see :func:`upstream_from_tables`.  Then ``run`` / ``fetch`` as usual."""
+        m = self.model
+        inds = _i32(individuals)
+        if inds.ndim == 1:
+            inds = inds.reshape(1, -1)
+        if inds.shape[1] != m.ind_len:
+            raise ValueError("individuals must have %d bits" % m.ind_len)
+        up, ui = _i32(upstream), _i32(upstream_inv)
+        per_ind = int(up.ndim == 3)
+        if up.shape != ui.shape or up.shape[-2:] != (m.n, 3) or (per_ind and up.shape[0] != inds.shape[0]):
+            raise ValueError("upstream tables must be [P][N][3] or [N][3]")
+        ko = _i32(knockouts if knockouts is not None else np.zeros(m.n))
+        ki = _i32(knockins if knockins is not None else np.zeros(m.n))
+        self._keep = (inds, up, ui, ko, ki)
+        self._P = inds.shape[0]
+        rc = self.lib.scb_pop_upload_compact(self._ctx, inds.shape[0], _ptr(inds), m.ind_len, _ptr(m.and_len_list),
+                                             _ptr(m.individual_parse), _ptr(up), _ptr(ui), per_ind, _ptr(ko), _ptr(ki))
+        _lib.check(self.lib, rc)
+
     def run(self, mode=MODE_SUM):
         _lib.check(self.lib, self.lib.scb_pop_run(self._ctx, int(mode)))
 
@@ -361,6 +383,22 @@ class Simulator:
         rc = self.lib.scb_hamming_argmin(self._ctx, _ptr(at), A, _ptr(dist), _ptr(dec), _ptr(dd))
         _lib.check(self.lib, rc)
         return dist, dec, dd
+
+
+def upstream_from_tables(and_len_list, and_nodes, and_inv):
+    """The compact form of reference-format term tables: each node's upstream nodes and inversion flags,
+    int32[...][N][3] padded with -1.  The first AND-term of a node lists all of its inputs
+    (ruleMaker.py:188-200: itertools.product starts with the full set), so the triple is that term cut to
+    log2(andLen + 1) entries."""
+    al = np.asarray(and_len_list, dtype=np.int64)
+    an, ai = np.asarray(and_nodes, dtype=np.int32), np.asarray(and_inv, dtype=np.int32)
+    k = np.round(np.log2(al + 1)).astype(np.int64)                       # 0, 1, 3, 7 terms -> 0, 1, 2, 3 inputs
+    if not np.array_equal((1 << k) - 1, al):
+        raise ValueError("andLenList entries must be 0, 1, 3 or 7 for the compact form")
+    keep = np.arange(3)[None, :] < k[:, None]                            # [N][3]
+    up = np.where(keep, an[..., 0, :], -1).astype(np.int32)
+    ui = np.where(keep, ai[..., 0, :], -1).astype(np.int32)
+    return np.ascontiguousarray(up), np.ascontiguousarray(ui)
 
 
 class PinnedArray:

@@ -404,3 +404,58 @@ def test_network_too_large_for_on_chip_state_is_refused(backend):
     with pytest.raises(simulator.ScbError) as ei:
         pr.simulator(backend[1])
     assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
+# ---- compact population ------------------------------------------------------------
+def test_upstream_triples_rebuild_the_reference_tables():
+    """upstream_from_tables + the device-side expansion rule (scb_expand_terms, restated here in numpy) give back
+    exactly the [7][3] tables the reference marshals (ruleMaker.py:188-200, :337-360)."""
+    import itertools
+    pr = Problem.synthetic(80, 10, 6)
+    up, ui = simulator.upstream_from_tables(pr.net.and_len, pr.pop_an, pr.pop_ai)
+    assert up.shape == (6, 80, 3)
+    for p in range(6):
+        for i in range(80):
+            ins = [int(x) for x in up[p, i] if x >= 0]
+            fl = [int(x) for x in ui[p, i][:len(ins)]]
+            terms = [[(a, f) for (a, f) in t if a != "empty"] for t in
+                     itertools.product(*[((a, f), ("empty", 0)) for a, f in zip(ins, fl)])]
+            terms = [t for t in terms if t]
+            an = np.zeros((7, 3), np.int32); ai = np.zeros((7, 3), np.int32)
+            for m, t in enumerate(terms):
+                an[m] = [a for a, _ in t] + [-1] * (3 - len(t))
+                ai[m] = [f for _, f in t] + [-1] * (3 - len(t))
+            assert np.array_equal(an, pr.pop_an[p, i]) and np.array_equal(ai, pr.pop_ai[p, i]), (p, i)
+
+
+@pytest.mark.parametrize("n,cells,pop,shared", [(60, 700, 6, False), (200, 1300, 3, False), (33, 400, 5, True)])
+def test_compact_population_matches_oracle(backend, n, cells, pop, shared):
+    """The population handed over as bit-strings + upstream triples (24 instead of 168 bytes per node): identical
+    integers in every output shape."""
+    cells = big(backend, cells, cells * 9 + 5)
+    pop = big(backend, pop, pop * 6)
+    pr = Problem.synthetic(n, cells, pop)
+    if shared:
+        pr.pop_an = pr.pop_ai = None
+        up, ui = simulator.upstream_from_tables(pr.net.and_len, pr.net.and_nodes, pr.net.and_inv)
+    else:
+        up, ui = simulator.upstream_from_tables(pr.net.and_len, pr.pop_an, pr.pop_ai)
+    ref = pr.oracle()
+    with pr.simulator(backend[1]) as sim:
+        for mode, key in ((0, "fitness"), (1, "nodewise"), (2, "cellwise")):
+            sim.upload_compact(pr.individuals, up, ui, pr.ko, pr.ki)
+            sim.run(mode)
+            assert np.array_equal(sim.fetch(mode), ref[key]), key
+
+
+def test_compact_population_rejects_inconsistent_triples(backend):
+    pr = Problem.synthetic(30, 100, 2)
+    up, ui = simulator.upstream_from_tables(pr.net.and_len, pr.pop_an, pr.pop_ai)
+    i = int(np.argmax(pr.net.and_len == 7))
+    up[1, i, 2] = -1                                   # two inputs where andLenList says seven terms
+    with pr.simulator(backend[1]) as sim:
+        sim.upload_compact(pr.individuals, up, ui, pr.ko, pr.ki)
+        sim.run(0)
+        with pytest.raises(simulator.ScbError) as e:
+            sim.fetch(0)
+        assert e.value.code == _lib.ERR_INVALID
