@@ -67,6 +67,7 @@ extern "C" {
 #define SCB_OPT_SNAP_MIN_GAP 10 /* first snapshot compare this many steps after a snapshot (default 8) */
 #define SCB_OPT_TMEM         11 /* 1 (default): keep the snapshot in tensor memory, 0: in global scratch    */
 #define SCB_OPT_TMA          13 /* 1 (default): load the S_0 tile with TMA bulk copies (cp.async.bulk + mbarrier)   */
+#define SCB_OPT_STEADY       14 /* 1 (default): steps after the constants have spread run the constant-propagated program */
 #define SCB_OPT_FUSE         12 /* 1 (default): CTAs that run out of tiles resolve queued groups in the same launch */
 
 typedef struct scb_ctx scb_ctx;
@@ -88,6 +89,7 @@ typedef struct scb_stats {
     int64_t cyc_prologue;         /* SM clocks summed over the K2 CTAs: work fetch + program + S_0 tile load */
     int64_t cyc_steps;            /*   ... the synchronous steps                                      */
     int64_t cyc_epilogue;         /*   ... chunk flags, error reduction, outputs                      */
+    int64_t state_rows_moved;     /* state rows (128 x wordsPerLane bytes each) the simulator's steps loaded + stored */
 } scb_stats;
 
 const char *scb_last_error(void);

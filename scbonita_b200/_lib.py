@@ -10,12 +10,13 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_PATH = os.path.join(_HERE, "libscbonita_b200.so")
+# SCB_B200_LIB points the binding at another build of the same library (A/B measurements of kernel variants)
+DEFAULT_PATH = os.environ.get("SCB_B200_LIB") or os.path.join(_HERE, "libscbonita_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4
 MODE_SUM, MODE_NODEWISE, MODE_CELLWISE = 0, 1, 2
 OPT_EARLY_EXIT, OPT_SNAPSHOTS, OPT_WARPS, OPT_MAX_CTAS, OPT_WORDS, OPT_CHECK_EVERY, OPT_PERIOD_SEARCH = 1, 2, 3, 4, 5, 6, 7
-OPT_SNAP_LO, OPT_SNAP_HI, OPT_SNAP_MIN_GAP, OPT_TMEM, OPT_FUSE, OPT_TMA = 8, 9, 10, 11, 12, 13
+OPT_SNAP_LO, OPT_SNAP_HI, OPT_SNAP_MIN_GAP, OPT_TMEM, OPT_FUSE, OPT_TMA, OPT_STEADY = 8, 9, 10, 11, 12, 13, 14
 
 # every symbol include/scbonita_b200.h declares (tests check that the library exports them all)
 SYMBOLS = (
@@ -36,7 +37,8 @@ class Stats(ctypes.Structure):
                 ("bad_index_nodes", ctypes.c_int64), ("term_overflow_nodes", ctypes.c_int64),
                 ("resolver_chunks", ctypes.c_int64), ("steps_executed", ctypes.c_int64),
                 ("tiles", ctypes.c_int64), ("kernel_ms", ctypes.c_float), ("sim_ms", ctypes.c_float),
-                ("cyc_prologue", ctypes.c_int64), ("cyc_steps", ctypes.c_int64), ("cyc_epilogue", ctypes.c_int64)]
+                ("cyc_prologue", ctypes.c_int64), ("cyc_steps", ctypes.c_int64), ("cyc_epilogue", ctypes.c_int64),
+                ("state_rows_moved", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

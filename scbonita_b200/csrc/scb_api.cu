@@ -78,7 +78,7 @@ struct scb_ctx {
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
     int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 6, optSearch = 0, optMinGap = 8;
-    int optTmem = 1, optFuse = 1, optTma = 1;
+    int optTmem = 1, optFuse = 1, optTma = 1, optSteady = 1;
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
@@ -90,8 +90,9 @@ struct scb_ctx {
     /* device data */
     DevBuf<uint32_t> dX;
     DevBuf<int32_t> dInd, dAndLen, dParse, dAn, dAi, dKo, dKi;
-    DevBuf<uint4> dDescs;
-    DevBuf<int4> dCounts;
+    DevBuf<uint4> dDescs, dDescs2;
+    DevBuf<int4> dCounts, dCounts2;
+    DevBuf<int> dDepth;
     DevBuf<unsigned long long> dFitness;
     DevBuf<int32_t> dNodewise, dCellwise;
     DevBuf<unsigned int> dCounters;      /* [0] K2 work head, [1] resolve count, [2] K3 work head */
@@ -130,12 +131,12 @@ int sim_geometry(scb_ctx *c, int K, int optWarps, SimGeom *g)
     int S = optWarps;
     if (S == 0) {
         S = 32 / occGuess;
-        S = std::min(24, std::max(2, S));
+        S = std::min(SCB_SIM_MAX_WARPS, std::max(2, S));
         S = std::min(S, std::max(1, (N + 3) / 4));
         if (occGuess == 1) S = std::min(S, std::max(8, N / 10));       /* ~10 nodes per warp measured best */
     }
     S = std::max(S, K);                 /* the mask arrays need 32*K threads */
-    S = std::min(S, 24);                /* __launch_bounds__(768) */
+    S = std::min(S, SCB_SIM_MAX_WARPS); /* __launch_bounds__ of scb_k_sim */
     g->warps = S;
     int occ = 1;
     if (K == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (scb_k_sim<4, false>), S * 32, g->smem));
@@ -232,6 +233,7 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock)
     ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
     ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p; ca.koStride = c->koStride; ca.compact = c->compact;
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
+    ca.descs2 = c->dDescs2.p; ca.counts2 = c->dCounts2.p; ca.depth = c->dDepth.p;
     const int cthr = std::min(256, ((N + 31) / 32) * 32);
     SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
     CK(cudaGetLastError());
@@ -426,7 +428,7 @@ int scb_ctx_destroy(scb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
-    c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release();
+    c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dDescs2.release(); c->dCounts2.release(); c->dDepth.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
@@ -459,12 +461,13 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
             if (value < 1 || value > 99) return fail(SCB_ERR_INVALID, "snapshot gap must be in [1,99]");
             c->optMinGap = (int)value; return SCB_OK;
         case SCB_OPT_TMA: c->optTma = value != 0; return SCB_OK;
+        case SCB_OPT_STEADY: c->optSteady = value != 0; return SCB_OK;
         case SCB_OPT_TMEM: c->optTmem = value != 0; break;
         case SCB_OPT_FUSE: c->optFuse = value != 0; break;
         case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_SNAP_HI: c->snapHi = (unsigned long long)value; return SCB_OK;
         case SCB_OPT_WARPS:
-            if (value < 0 || value > 24) return fail(SCB_ERR_INVALID, "warps must be in [0,24]");
+            if (value < 0 || value > SCB_SIM_MAX_WARPS) return fail(SCB_ERR_INVALID, "warps must be in [0,%d]", SCB_SIM_MAX_WARPS);
             c->optWarps = (int)value; break;
         case SCB_OPT_MAX_CTAS:
             if (value < 0) return fail(SCB_ERR_INVALID, "max CTAs must be >= 0");
@@ -514,6 +517,7 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
     if ((rc = c->dAndLen.ensure(N)) || (rc = c->dParse.ensure(N)) || (rc = c->dKo.ensure((size_t)koRows * N)) || (rc = c->dKi.ensure(N))) return rc;
     if ((rc = c->dAn.ensure(ntab * tbl)) || (rc = c->dAi.ensure(ntab * tbl))) return rc;
     if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
+    if ((rc = c->dDescs2.ensure((size_t)P * N)) || (rc = c->dCounts2.ensure(P)) || (rc = c->dDepth.ensure(P))) return rc;
     if ((rc = c->dFitness.ensure(P))) return rc;
     const size_t chunks = (size_t)c->Wpad / 32;
     if ((rc = c->dReady.ensure((size_t)P * chunks))) return rc;
@@ -595,6 +599,10 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.X = c->dX.p; sa.N = N; sa.C = c->C; sa.Wpad = c->Wpad;
     sa.P = P; sa.Npad = N; sa.mode = mode;
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
+    sa.descs2 = c->dDescs2.p; sa.counts2 = c->dCounts2.p; sa.depth = c->dDepth.p; sa.useSteady = c->optSteady;
+    sa.firstSnap = 1000;
+    for (int t = SCB_LAST - 1; t >= 1; --t)
+        if (t < 64 ? ((c->snapLo >> t) & 1ull) : ((c->snapHi >> (t - 64)) & 1ull)) sa.firstSnap = t;
     sa.fitness = c->dFitness.p; sa.nodewise = c->dNodewise.p; sa.cellwise = c->dCellwise.p;
     sa.resolveCount = c->dCounters.p + 1;
     sa.resolveItems = c->dItems.p; sa.resolveCap = (unsigned)std::min<size_t>(c->dItems.cap, 0xffffffffu);
@@ -683,6 +691,7 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
         stats->resolver_chunks = (int64_t)d.resolver_chunks;
         stats->steps_executed = (int64_t)d.steps_executed;
         stats->tiles = (int64_t)d.tiles;
+        stats->state_rows_moved = (int64_t)d.rows_moved;
         stats->cyc_prologue = (int64_t)d.cyc_prologue;
         stats->cyc_steps = (int64_t)d.cyc_steps;
         stats->cyc_epilogue = (int64_t)d.cyc_epilogue;
@@ -693,6 +702,24 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
     if (d.bad_index_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules reference an input outside [0,%d)", d.bad_index_nodes, c->N);
     if (d.term_overflow_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules span more than 7 AND-terms, leave the bit-string, or (compact upload) disagree with andLenList", d.term_overflow_nodes);
     if (d.unsupported_nodes) return fail(SCB_ERR_UNSUPPORTED, "%llu (individual,node) rules use more than 3 distinct inputs", d.unsupported_nodes);
+    return SCB_OK;
+}
+
+/* test / diagnostics hook: the compiled programs of individual p of the last run (uint32[N][4] each: three input
+ * nodes, node | table << 24; counts = nodes of arity 3, 2, 1, 0) and the constant-propagation depth */
+int scb_debug_programs(scb_ctx *c, int p, uint32_t *descs, int32_t *counts, uint32_t *descs2, int32_t *counts2, int32_t *depth)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->ran || p < 0 || p >= c->P) return fail(SCB_ERR_INVALID, "no such individual in the last run");
+    const size_t n = (size_t)c->N;
+    CK(cudaStreamSynchronize(c->stream));
+    if (descs) CK(cudaMemcpy(descs, c->dDescs.p + p * n, n * 16, cudaMemcpyDeviceToHost));
+    if (counts) CK(cudaMemcpy(counts, c->dCounts.p + p, 16, cudaMemcpyDeviceToHost));
+    if (descs2) CK(cudaMemcpy(descs2, c->dDescs2.p + p * n, n * 16, cudaMemcpyDeviceToHost));
+    if (counts2) CK(cudaMemcpy(counts2, c->dCounts2.p + p, 16, cudaMemcpyDeviceToHost));
+    if (depth) CK(cudaMemcpy(depth, c->dDepth.p + p, 4, cudaMemcpyDeviceToHost));
     return SCB_OK;
 }
 

@@ -52,6 +52,28 @@ SCB_HD inline ScbNodeFn scb_copy_fn(int src, int invert)
     return f;
 }
 
+/* a table over vars[0..nv) -> the node function with the inputs the table does not depend on dropped
+ * (a node costs only the loads it needs); don't-care positions repeat the first kept input */
+SCB_HD inline ScbNodeFn scb_finish_fn(const int *vars, int nv, unsigned lut, unsigned flags)
+{
+    const bool dep[3] = { (((lut >> 4) ^ lut) & 0x0Fu) != 0,
+                          (((lut >> 2) ^ lut) & 0x33u) != 0,
+                          (((lut >> 1) ^ lut) & 0x55u) != 0 };
+    int keep[3] = {0, 0, 0}, nk = 0;
+    for (int k = 0; k < 3; ++k) if (k < nv && dep[k]) keep[nk++] = k;
+    unsigned nl = 0;
+    for (int idx = 0; idx < 8; ++idx) {
+        int m = 0;
+        for (int j = 0; j < nk; ++j) if ((idx >> (2 - j)) & 1) m |= 1 << (2 - keep[j]);
+        nl |= ((lut >> m) & 1u) << idx;
+    }
+    ScbNodeFn f;
+    f.arity = nk; f.flags = flags; f.lut = nl;
+    const int fill = nk ? vars[keep[0]] : 0;
+    for (int j = 0; j < 3; ++j) f.in[j] = j < nk ? vars[keep[j]] : fill;
+    return f;
+}
+
 /* The AND-term tables of one node from its (at most three) upstream nodes, as the reference builds them:
  * every non-empty subset of the inputs in itertools.product order over ((a, empty), (b, empty), (c, empty)),
  * i.e. [abc, ab, ac, a, bc, b, c] (ruleMaker.py:188-200, :300-335), each term padded with -1 and the table
@@ -160,23 +182,24 @@ SCB_HD inline ScbNodeFn scb_compile_node(int i, int N, int indLen, const int32_t
         }
         lut |= (unsigned)v << m;
     }
-    /* drop inputs the table does not depend on */
-    const bool dep[3] = { (((lut >> 4) ^ lut) & 0x0Fu) != 0,
-                          (((lut >> 2) ^ lut) & 0x33u) != 0,
-                          (((lut >> 1) ^ lut) & 0x55u) != 0 };
-    int keep[3] = {0, 0, 0}, nk = 0;
-    for (int k = 0; k < 3; ++k) if (k < nv && dep[k]) keep[nk++] = k;
-    unsigned nl = 0;
-    for (int idx = 0; idx < 8; ++idx) {
-        int m = 0;
-        for (int j = 0; j < nk; ++j) if ((idx >> (2 - j)) & 1) m |= 1 << (2 - keep[j]);
-        nl |= ((lut >> m) & 1u) << idx;
+    return scb_finish_fn(vars, nv, lut, flags);
+}
+
+/* Constant propagation (the steady program of K2): `f` with every input whose value is known (cst[node] = 0 or 1,
+ * anything else = unknown) fixed to that value, dead inputs dropped again.  Exact wherever the inputs really hold
+ * those values. */
+SCB_HD inline ScbNodeFn scb_restrict_fn(const ScbNodeFn &f, const unsigned char *cst)
+{
+    unsigned lut = f.lut;
+    for (int j = 0; j < f.arity; ++j) {
+        const unsigned v = cst[f.in[j]];
+        if (v > 1u) continue;
+        const unsigned bit = 1u << (2 - j);
+        unsigned nl = 0;
+        for (unsigned idx = 0; idx < 8; ++idx) nl |= ((lut >> ((idx & ~bit) | (v ? bit : 0u))) & 1u) << idx;
+        lut = nl;
     }
-    ScbNodeFn f;
-    f.arity = nk; f.flags = flags; f.lut = nl;
-    const int fill = nk ? vars[keep[0]] : 0;
-    for (int j = 0; j < 3; ++j) f.in[j] = j < nk ? vars[keep[j]] : fill;
-    return f;
+    return scb_finish_fn(f.in, f.arity, lut, 0);
 }
 
 /* generic table lookup on 32 cells at once (host tests and the emulator; the device path uses

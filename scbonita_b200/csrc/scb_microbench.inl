@@ -55,9 +55,10 @@ __global__ void __launch_bounds__(1024) scb_k_mb_lds(uint32_t *out)
     uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
     for (int it = 0; it < SCB_MB_ITERS; ++it) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {    /* 8 rows of 16 KB: a warp reads 512 consecutive bytes per instruction */
+        for (int i = 0; i < 8; ++i) {    /* 8 rows of 16 KB: a warp reads 512 consecutive bytes per instruction; volatile, or ptxas
+                                            hoists the loop-invariant loads out of the loop */
             uint32_t v0, v1, v2, v3;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
                          : "r"(base + (uint32_t)i * 16384u));
             acc0 ^= v0; acc1 ^= v1; acc2 ^= v2; acc3 ^= v3;
         }

@@ -47,6 +47,9 @@
  * attractor window (simulator.c:641-648) */
 #define SCB_MODE_IMPORTANCE 3
 
+/* constant propagation depth cap of the steady program (K0): must stay below the first snapshot step */
+#define SCB_STEADY_MAX_DEPTH 24
+
 /* kernel behaviour flags (ScbSimArgs.flags) */
 #define SCB_KF_EARLY  1u
 #define SCB_KF_SNAP   2u
@@ -62,6 +65,7 @@ struct ScbDiag {                      /* device-side counters, zeroed per evalua
     unsigned long long resolver_chunks;
     unsigned long long steps_executed;
     unsigned long long tiles;
+    unsigned long long rows_moved;      /* state rows K2 loaded + stored in its steps (x 128*K bytes = shared-memory traffic) */
     unsigned long long cyc_prologue, cyc_steps, cyc_epilogue;   /* SM clocks of thread 0 of every K2 CTA, per phase */
 };
 
@@ -81,6 +85,9 @@ struct ScbCompileArgs {
     int koStride;                 /* 0: one shared `ko`; N: program p reads ko + p * N (batched importance scores) */
     uint4 *descs;                 /* [P][Npad] */
     int4 *counts;                 /* [P] */
+    uint4 *descs2;                /* [P][Npad] the steady program: descs after constant propagation */
+    int4 *counts2;                /* [P] */
+    int *depth;                   /* [P] D: the constants of the steady program hold in S_t for every t >= D */
     ScbDiag *diag;
 };
 
@@ -99,6 +106,11 @@ struct ScbSimArgs {
     int wordBase;                 /* first word of this launch's tile range (tail tiles use a narrower K) */
     const uint4 *descs;
     const int4 *counts;
+    const uint4 *descs2;          /* steady programs (constant-propagated), used for steps >= depth + 2 */
+    const int4 *counts2;
+    const int *depth;
+    int useSteady;
+    int firstSnap;                /* first step that takes a snapshot (1000: none): the steady program must be in use by then */
     unsigned long long *fitness;  /* [P] */
     int32_t *nodewise;            /* [P][N] or null */
     int32_t *cellwise;            /* [P][C] or null */

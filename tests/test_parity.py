@@ -43,7 +43,9 @@ def test_synthetic_matches_oracle(backend, n, cells, pop):
 @pytest.mark.parametrize("opts", [dict(early_exit=0, snapshots=0), dict(early_exit=1, snapshots=0),
                                   dict(early_exit=0, snapshots=1), dict(words=1), dict(words=2, check_every=3),
                                   dict(warps=4), dict(period_search=24), dict(check_every=1), dict(snap_min_gap=1, check_every=4),
-                                  dict(snap_min_gap=20, snap_lo=1 << 20, snap_hi=0), dict(fuse=0), dict(fuse=0, early_exit=0, snapshots=0)])
+                                  dict(snap_min_gap=20, snap_lo=1 << 20, snap_hi=0), dict(fuse=0), dict(fuse=0, early_exit=0, snapshots=0),
+                                  dict(steady=0), dict(steady=1, snap_lo=(1 << 4) | (1 << 30), snap_hi=0, snap_min_gap=2),
+                                  dict(steady=1, tmem=0), dict(steady=1, early_exit=0, snapshots=0)])
 def test_every_schedule_gives_identical_integers(backend, opts):
     """Early exit, snapshot resolution and tile geometry are optimisations: results must not move."""
     pr = Problem.synthetic(60, big(backend, 2100, 21000), big(backend, 5, 24))
@@ -459,3 +461,72 @@ def test_compact_population_rejects_inconsistent_triples(backend):
         with pytest.raises(simulator.ScbError) as e:
             sim.fetch(0)
         assert e.value.code == _lib.ERR_INVALID
+
+
+# ---- steady program (constant propagation in K0) ---------------------------------------------------
+@pytest.mark.parametrize("chain", [3, 23, 24, 25, 40])
+@pytest.mark.parametrize("opts", [dict(), dict(steady=0)])
+def test_constants_spreading_along_chains(backend, chain, opts):
+    """A knocked node feeding a chain of copies: node j of the chain is constant from step j + 1 on, so the
+    constant-propagation depth is the chain length -- below, at and above the cap (SCB_STEADY_MAX_DEPTH = 24).
+    The steady program may only be used once both state buffers hold the constants."""
+    pr = ring_problem([5, 9], chain, big(backend, 700, 9000))
+    with pr.simulator(backend[1], **opts) as sim:
+        pr.check(sim)
+
+
+def test_steady_program_moves_fewer_rows(backend):
+    """The always-knocked node 0 and its zero-input copies erase AND-terms: the steady program must move clearly
+    fewer state rows through shared memory for the same, identical, result."""
+    pr = Problem.synthetic(120, big(backend, 1500, 20000), 6)
+    rows = {}
+    for steady in (0, 1):
+        with pr.simulator(backend[1], steady=steady) as sim:
+            st = pr.check(sim, modes=(0,))
+            rows[steady] = st["state_rows_moved"]
+    assert 0 < rows[1] < 0.8 * rows[0], rows
+
+
+def test_every_truth_table(backend):
+    """Every Boolean function of three inputs as a rule (a DNF of up to seven minterms, each a 3-literal AND-term
+    with inversion flags), so that every entry of the LOP3 jump table -- and, through the functions that ignore an
+    input, of the two-input and one-input paths -- is compared with the oracle's term-by-term evaluation."""
+    luts = list(range(1, 255))                       # 0 and 255 are constants (8 minterms do not fit 7 terms)
+    luts = [l for l in luts if bin(l).count("1") <= 7]
+    n = 3 + len(luts)
+    cells = big(backend, 300, 5000)
+    net = type("Net", (), {})()
+    net.n = n
+    net.and_len = np.zeros(n, np.int32)
+    net.parse = np.zeros(n + 1, np.int32)
+    net.and_nodes = np.zeros((n, 7, 3), np.int32)
+    net.and_inv = np.zeros((n, 7, 3), np.int32)
+    bits = []
+    for i in range(3):                               # free inputs: x <- x
+        net.and_len[i] = 1
+        net.and_nodes[i, 0] = [i, -1, -1]
+        net.and_inv[i, 0] = [0, -1, -1]
+        net.parse[i] = len(bits)
+        bits.append(1)
+    for k, lut in enumerate(luts):
+        i = 3 + k
+        net.and_len[i] = 7
+        net.parse[i] = len(bits)
+        terms = [m for m in range(8) if (lut >> m) & 1]
+        for a in range(7):
+            if a < len(terms):
+                m = terms[a]
+                net.and_nodes[i, a] = [0, 1, 2]
+                net.and_inv[i, a] = [1 - ((m >> 2) & 1), 1 - ((m >> 1) & 1), 1 - (m & 1)]   # literal true <=> x == bit
+                bits.append(1)
+            else:
+                net.and_nodes[i, a] = [0, 1, 2]
+                net.and_inv[i, a] = [0, 0, 0]
+                bits.append(0)
+    net.parse[n] = len(bits)
+    net.ind_len = len(bits)
+    rng = np.random.default_rng(11)
+    rows = (rng.random((n, cells)) < 0.5).astype(np.uint8)
+    pr = Problem(net, rows, rng.permutation(n).astype(np.int32), np.asarray(bits, np.int32).reshape(1, -1))
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim)
