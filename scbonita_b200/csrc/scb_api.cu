@@ -90,9 +90,9 @@ struct scb_ctx {
     /* device data */
     DevBuf<uint32_t> dX;
     DevBuf<int32_t> dInd, dAndLen, dParse, dAn, dAi, dKo, dKi;
-    DevBuf<uint4> dDescs, dDescs2;
-    DevBuf<int4> dCounts, dCounts2;
-    DevBuf<int> dDepth;
+    DevBuf<uint4> dDescs, dProgs;
+    DevBuf<int4> dCounts;
+    DevBuf<unsigned char> dProgFrom;
     DevBuf<unsigned long long> dFitness;
     DevBuf<int32_t> dNodewise, dCellwise;
     DevBuf<unsigned int> dCounters;      /* [0] K2 work head, [1] resolve count, [2] K3 work head */
@@ -233,7 +233,7 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock)
     ca.individuals = c->dInd.p; ca.andLen = c->dAndLen.p; ca.parse = c->dParse.p;
     ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p; ca.koStride = c->koStride; ca.compact = c->compact;
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
-    ca.descs2 = c->dDescs2.p; ca.counts2 = c->dCounts2.p; ca.depth = c->dDepth.p;
+    ca.progs = c->dProgs.p; ca.progFrom = c->dProgFrom.p;
     const int cthr = std::min(256, ((N + 31) / 32) * 32);
     SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
     CK(cudaGetLastError());
@@ -428,7 +428,7 @@ int scb_ctx_destroy(scb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
-    c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dDescs2.release(); c->dCounts2.release(); c->dDepth.release();
+    c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dProgFrom.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
@@ -517,7 +517,7 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
     if ((rc = c->dAndLen.ensure(N)) || (rc = c->dParse.ensure(N)) || (rc = c->dKo.ensure((size_t)koRows * N)) || (rc = c->dKi.ensure(N))) return rc;
     if ((rc = c->dAn.ensure(ntab * tbl)) || (rc = c->dAi.ensure(ntab * tbl))) return rc;
     if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
-    if ((rc = c->dDescs2.ensure((size_t)P * N)) || (rc = c->dCounts2.ensure(P)) || (rc = c->dDepth.ensure(P))) return rc;
+    if ((rc = c->dProgs.ensure((size_t)P * SCB_NPROG * (N + 1))) || (rc = c->dProgFrom.ensure((size_t)P * 8))) return rc;
     if ((rc = c->dFitness.ensure(P))) return rc;
     const size_t chunks = (size_t)c->Wpad / 32;
     if ((rc = c->dReady.ensure((size_t)P * chunks))) return rc;
@@ -599,7 +599,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.X = c->dX.p; sa.N = N; sa.C = c->C; sa.Wpad = c->Wpad;
     sa.P = P; sa.Npad = N; sa.mode = mode;
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
-    sa.descs2 = c->dDescs2.p; sa.counts2 = c->dCounts2.p; sa.depth = c->dDepth.p; sa.useSteady = c->optSteady;
+    sa.progs = c->dProgs.p; sa.progFrom = c->dProgFrom.p; sa.useSteady = c->optSteady;
     sa.firstSnap = 1000;
     for (int t = SCB_LAST - 1; t >= 1; --t)
         if (t < 64 ? ((c->snapLo >> t) & 1ull) : ((c->snapHi >> (t - 64)) & 1ull)) sa.firstSnap = t;
@@ -706,20 +706,24 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
 }
 
 /* test / diagnostics hook: the compiled programs of individual p of the last run (uint32[N][4] each: three input
- * nodes, node | table << 24; counts = nodes of arity 3, 2, 1, 0) and the constant-propagation depth */
-int scb_debug_programs(scb_ctx *c, int p, uint32_t *descs, int32_t *counts, uint32_t *descs2, int32_t *counts2, int32_t *depth)
+ * nodes, node | table << 24; counts = nodes of arity 3, 2, 1, 0): the full program and the reduced program `k`
+ * (0 .. SCB_NPROG-1, the last one is the fixed point) with the first step it may compute (0: not emitted) */
+int scb_debug_programs(scb_ctx *c, int p, int k, uint32_t *descs, int32_t *counts, uint32_t *descsK, int32_t *countsK, int32_t *fromK)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->ran || p < 0 || p >= c->P) return fail(SCB_ERR_INVALID, "no such individual in the last run");
+    if (!c->ran || p < 0 || p >= c->P || k < 0 || k >= SCB_NPROG) return fail(SCB_ERR_INVALID, "no such program in the last run");
     const size_t n = (size_t)c->N;
     CK(cudaStreamSynchronize(c->stream));
+    const uint4 *pk = c->dProgs.p + ((size_t)p * SCB_NPROG + k) * (n + 1);
+    unsigned char from[8];
     if (descs) CK(cudaMemcpy(descs, c->dDescs.p + p * n, n * 16, cudaMemcpyDeviceToHost));
     if (counts) CK(cudaMemcpy(counts, c->dCounts.p + p, 16, cudaMemcpyDeviceToHost));
-    if (descs2) CK(cudaMemcpy(descs2, c->dDescs2.p + p * n, n * 16, cudaMemcpyDeviceToHost));
-    if (counts2) CK(cudaMemcpy(counts2, c->dCounts2.p + p, 16, cudaMemcpyDeviceToHost));
-    if (depth) CK(cudaMemcpy(depth, c->dDepth.p + p, 4, cudaMemcpyDeviceToHost));
+    if (descsK) CK(cudaMemcpy(descsK, pk, n * 16, cudaMemcpyDeviceToHost));
+    if (countsK) CK(cudaMemcpy(countsK, pk + n, 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(from, c->dProgFrom.p + (size_t)p * 8, 8, cudaMemcpyDeviceToHost));
+    if (fromK) *fromK = from[k];
     return SCB_OK;
 }
 

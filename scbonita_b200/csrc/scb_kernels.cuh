@@ -117,6 +117,29 @@ SCB_DEV void scb_mbar_wait(uint32_t mbar, uint32_t parity)
 SCB_DEV void scb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+/* ---- 16-byte asynchronous global -> shared copies (LDGSTS): the next reduced program is fetched into its staging
+ * buffer while the steps of the current one run ---- */
+SCB_DEV void scb_cp_async16(void *smemDst, const void *gsrc)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
+#else
+    *reinterpret_cast<uint4 *>(smemDst) = *reinterpret_cast<const uint4 *>(gsrc);
+#endif
+}
+SCB_DEV void scb_cp_async_commit()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+SCB_DEV void scb_cp_async_wait()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 /* ---- tensor memory as a scratchpad --------------------------------------------------------------------
  * The simulator uses no tensor cores, so the SM's 256 KB of TMEM (128 lanes x 512 columns x 32 bit) is free.
  * K2 keeps its snapshot S_s there instead of in global memory: a warp owns the 32 lanes of its quarter
@@ -359,68 +382,89 @@ __global__ void scb_k_compile(ScbCompileArgs A)
         const int off = ar == 3 ? 0 : ar == 2 ? c3 : ar == 1 ? c3 + c2 : c3 + c2 + c1;
         out[off + before] = sd[i];
     }
-    /* ---- the steady program.  c(t) = nodes whose value in S_t is the same constant for every cell: c(1) = the
-     * constant rules (knock-outs, knock-ins, constant-TRUE literals), c(t+1) = rules that are constant once the
-     * inputs in c(t) are fixed.  Knowledge only grows, so c(D) stays valid for every t >= D; D = the fixed point
-     * or the cap.  K2 runs this program from step D + 2 on (both state buffers then hold the constant rows): the
-     * always-knocked node 0 and its zero-input copies (Q2) erase most AND-terms of a typical network.
+    /* ---- reduced programs by constant propagation.  c(t) = nodes whose value in S_t is the same constant for every
+     * cell: c(1) = the constant rules (knock-outs, knock-ins, constant-TRUE literals), c(t+1) = rules that are
+     * constant once the inputs in c(t) are fixed.  Knowledge only grows, so c(D) stays valid for every t >= D.  A
+     * program restricted by c(D) (constant inputs folded into the tables, constant nodes no longer computed) is
+     * exact for every step from D + 2 on: then both state buffers of K2 hold the constant rows.  The always-knocked
+     * node 0 and its zero-input copies (Q2) erase most AND-terms of a typical network, a few more with
+     * every round.  Programs are emitted at the fixed depths SCB_STAGE_DEPTHS and at the fixed point (or the cap).
      * The dead term tables' shared memory is reused. */
     unsigned char *cst = reinterpret_cast<unsigned char *>(an);
     unsigned char *pend = cst + ((N + 15) / 16) * 16;
     unsigned char *sar2 = pend + ((N + 15) / 16) * 16;
     uint4 *sd2 = reinterpret_cast<uint4 *>(sar2 + ((N + 15) / 16) * 16);
-    int *chg = reinterpret_cast<int *>(sd2 + N);                           /* [0] changed, [1..4] class counts, [5] late constants */
+    int *chg = reinterpret_cast<int *>(sd2 + N);                 /* [0] changed, [1..4] class counts */
+    const int stageDepth[SCB_NPROG - 1] = SCB_STAGE_DEPTHS;
+    uint4 *progs = A.progs + (long long)p * SCB_NPROG * (N + 1);
+    unsigned char *progFrom = A.progFrom + (long long)p * 8;
     for (int i = tid; i < N; i += nthr) cst[i] = sar[i] == 0 ? ((sd[i].w >> 24) ? 1 : 0) : 2;
-    if (tid < 8) chg[tid] = 0;
+    if (tid < 8) { chg[tid] = 0; progFrom[tid] = 0; }
     __syncthreads();
-    int D = 1;
-    for (; D < SCB_STEADY_MAX_DEPTH; ++D) {                                /* c(D + 1) from c(D) */
-        for (int i = tid; i < N; i += nthr) {
-            unsigned char v = 2;
-            if (cst[i] == 2) {
-                ScbNodeFn f;
-                f.arity = sar[i]; f.in[0] = (int)sd[i].x; f.in[1] = (int)sd[i].y; f.in[2] = (int)sd[i].z;
-                f.lut = sd[i].w >> 24; f.flags = 0;
-                const ScbNodeFn r = scb_restrict_fn(f, cst);
-                if (r.arity == 0) v = r.lut ? 1 : 0;
+    int D = 1, stage = 0;
+    for (;;) {
+        /* knowledge here is c(D) */
+        bool last = D >= SCB_STEADY_MAX_DEPTH;
+        if (!last) {                                                       /* c(D + 1) from c(D) */
+            for (int i = tid; i < N; i += nthr) {
+                unsigned char v = 2;
+                if (cst[i] == 2) {
+                    ScbNodeFn f;
+                    f.arity = sar[i]; f.in[0] = (int)sd[i].x; f.in[1] = (int)sd[i].y; f.in[2] = (int)sd[i].z;
+                    f.lut = sd[i].w >> 24; f.flags = 0;
+                    const ScbNodeFn r = scb_restrict_fn(f, cst);
+                    if (r.arity == 0) v = r.lut ? 1 : 0;
+                }
+                pend[i] = v;
+                if (v != 2) atomicOr(reinterpret_cast<unsigned int *>(&chg[0]), 1u);
             }
-            pend[i] = v;
+            __syncthreads();
+            last = chg[0] == 0;                                            /* fixed point: c(D + 1) == c(D) */
         }
+        const bool emitStage = !last && stage < SCB_NPROG - 1 && D == stageDepth[stage];
+        if (last || emitStage) {
+            /* the program restricted by c(D) */
+            for (int i = tid; i < N; i += nthr) {
+                ScbNodeFn r;
+                if (cst[i] != 2) r = scb_const_fn(cst[i], 0);
+                else {
+                    ScbNodeFn f;
+                    f.arity = sar[i]; f.in[0] = (int)sd[i].x; f.in[1] = (int)sd[i].y; f.in[2] = (int)sd[i].z;
+                    f.lut = sd[i].w >> 24; f.flags = 0;
+                    r = scb_restrict_fn(f, cst);
+                    /* constant under c(D) but not in c(D): constant only from S_(D+1) on -- such a node keeps its
+                     * full rule in this program (there are none at the fixed point) */
+                    if (r.arity == 0) r = f;
+                }
+                sd2[i] = make_uint4((unsigned)r.in[0], (unsigned)r.in[1], (unsigned)r.in[2], (unsigned)i | (r.lut << 24));
+                sar2[i] = (unsigned char)r.arity;
+                atomicAdd(reinterpret_cast<unsigned int *>(&chg[1 + 3 - r.arity]), 1u);
+            }
+            __syncthreads();
+            const int s3 = chg[1], s2 = chg[2], s1 = chg[3], s0 = chg[4];
+            const int slot = last ? SCB_NPROG - 1 : stage;
+            uint4 *out2 = progs + (long long)slot * (N + 1);
+            for (int i = tid; i < N; i += nthr) {
+                const int ar = sar2[i];
+                int before = 0;
+                for (int j = 0; j < i; ++j) before += (sar2[j] == ar);
+                const int off = ar == 3 ? 0 : ar == 2 ? s3 : ar == 1 ? s3 + s2 : s3 + s2 + s1;
+                out2[off + before] = sd2[i];
+            }
+            if (tid == 0) {
+                out2[N] = make_uint4((unsigned)s3, (unsigned)s2, (unsigned)s1, (unsigned)s0);   /* the counts travel with the program */
+                progFrom[slot] = (unsigned char)(D + 2);
+            }
+            __syncthreads();
+            if (tid < 8) chg[tid] = tid == 0 ? chg[0] : 0;
+            if (emitStage) ++stage;
+        }
+        if (last) break;
+        for (int i = tid; i < N; i += nthr) if (pend[i] != 2) cst[i] = pend[i];
         __syncthreads();
-        for (int i = tid; i < N; i += nthr) if (pend[i] != 2) { cst[i] = pend[i]; atomicOr(reinterpret_cast<unsigned int *>(&chg[0]), 1u); }
-        __syncthreads();
-        const int changed = chg[0];
-        __syncthreads();
-        if (!changed) break;
         if (tid == 0) chg[0] = 0;
-    }
-    for (int i = tid; i < N; i += nthr) {
-        ScbNodeFn r;
-        if (cst[i] != 2) r = scb_const_fn(cst[i], 0);
-        else {
-            ScbNodeFn f;
-            f.arity = sar[i]; f.in[0] = (int)sd[i].x; f.in[1] = (int)sd[i].y; f.in[2] = (int)sd[i].z;
-            f.lut = sd[i].w >> 24; f.flags = 0;
-            r = scb_restrict_fn(f, cst);
-            /* only possible when the cap stopped the propagation: constant under c(D) means constant from S_(D+1) on */
-            if (r.arity == 0) atomicOr(reinterpret_cast<unsigned int *>(&chg[5]), 1u);
-        }
-        sd2[i] = make_uint4((unsigned)r.in[0], (unsigned)r.in[1], (unsigned)r.in[2], (unsigned)i | (r.lut << 24));
-        sar2[i] = (unsigned char)r.arity;
-        atomicAdd(reinterpret_cast<unsigned int *>(&chg[1 + 3 - r.arity]), 1u);
-    }
-    __syncthreads();
-    {
-        const int s3 = chg[1], s2 = chg[2], s1 = chg[3], s0 = chg[4];
-        uint4 *out2 = A.descs2 + (long long)p * A.Npad;
-        for (int i = tid; i < N; i += nthr) {
-            const int ar = sar2[i];
-            int before = 0;
-            for (int j = 0; j < i; ++j) before += (sar2[j] == ar);
-            const int off = ar == 3 ? 0 : ar == 2 ? s3 : ar == 1 ? s3 + s2 : s3 + s2 + s1;
-            out2[off + before] = sd2[i];
-        }
-        if (tid == 0) { A.counts2[p] = make_int4(s3, s2, s1, s0); A.depth[p] = D + (chg[5] ? 1 : 0); }
+        ++D;
+        __syncthreads();
     }
     if (tid == 0) {
         A.counts[p] = make_int4(c3, c2, c1, c0);
@@ -488,7 +532,7 @@ __global__ void scb_k_pack_csr(ScbPackCsrArgs A)
 /* shared-memory carve-up, identical formula on host and device */
 SCB_HD inline size_t scb_smem_bytes(int N, int K, int nbuf)
 {
-    return (size_t)nbuf * N * 128 * K + (size_t)N * 32 + (size_t)6 * 32 * K * 4 + 4096 + 256;   /* two programs */
+    return (size_t)nbuf * N * 128 * K + (size_t)N * 32 + 16 + (size_t)6 * 32 * K * 4 + 4096 + 256;   /* program + staged program */
 }
 
 /* load individual p's program into shared memory, scaling node indices to row byte offsets */
@@ -646,8 +690,8 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
     const int WT = 32 * K;                              /* words per tile */
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + 2u * BUFB);
-    uint4 *desc2 = desc + N;                            /* the steady program (constants propagated), staged */
-    uint32_t *dm2 = reinterpret_cast<uint32_t *>(desc2 + N);
+    uint4 *desc2 = desc + N;                            /* staging buffer of the next reduced program: N nodes + its counts */
+    uint32_t *dm2 = reinterpret_cast<uint32_t *>(desc2 + N + 1);
     uint32_t *dmz = dm2 + WT;
     uint32_t *Rm = dmz + WT;
     uint32_t *vm = Rm + WT;
@@ -706,9 +750,29 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         const int w0 = A.wordBase + tile * WT;
         int4 cnt = A.counts[p];
         scb_load_program<K>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
-        int steadyFrom = A.useSteady ? A.depth[p] + 2 : 1000;           /* first step computed with the steady program */
-        if (steadyFrom > A.firstSnap) steadyFrom = 1000;
-        if (steadyFrom < 1000) scb_load_program<K>(desc2, A.descs2 + (long long)p * A.Npad, A.counts2[p], N, tid, nthr);
+        /* reduced programs (K0): program k may compute steps >= from[k]; the next one is staged in desc2 by
+         * asynchronous copies while the current one runs.  All switches happen before the first snapshot, whose
+         * tensor-memory slots follow the program's node order. */
+        const uint4 *progBase = A.progs + (long long)p * SCB_NPROG * (N + 1);
+        unsigned long long fromBytes = A.useSteady ? *reinterpret_cast<const unsigned long long *>(A.progFrom + (long long)p * 8) : 0ull;
+        int switchAt = 1000, nextProg = 0;
+        unsigned rowsPerStep = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
+        int segStart = 0;
+#define SCB_NEXT_PROGRAM(after)                                                                           \
+        do {                                                                                              \
+            switchAt = 1000;                                                                              \
+            for (; nextProg < SCB_NPROG; ++nextProg) {                                                    \
+                const int from = (int)((fromBytes >> (8 * nextProg)) & 0xffull);                          \
+                if (from > (after) && from <= A.firstSnap) { switchAt = from; break; }                    \
+            }                                                                                             \
+            if (switchAt < 1000) {                                                                        \
+                const uint4 *src = progBase + (long long)nextProg * (N + 1);                              \
+                for (int j = tid; j <= N; j += nthr) scb_cp_async16(&desc2[j], &src[j]);                  \
+                scb_cp_async_commit();                                                                    \
+                ++nextProg;                                                                               \
+            }                                                                                             \
+        } while (0)
+        SCB_NEXT_PROGRAM(0);
         bool tileByTma = false;
 #if defined(__CUDA_ARCH__)
         if (A.useTma) {
@@ -756,12 +820,19 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         bool allres = false, allfound = false, plainOnly = false, haveFin = false;
         while (t < target) {
             const int tn = t + 1;                       /* this iteration computes S_tn */
-            if (tn == steadyFrom) {
-                /* from here on the steady program: it replaces the full one in place (every warp is past the barrier
-                 * of the previous step), so the step code keeps one program address */
-                for (int j = tid; j < N; j += nthr) desc[j] = desc2[j];
-                cnt = A.counts2[p];
+            if (tn == switchAt) {
+                /* the staged program replaces the current one in place (every warp is past the barrier of the
+                 * previous step), so the step code keeps one program address */
+                scb_cp_async_wait();
                 __syncthreads();
+                rowsMoved += (unsigned)(t - segStart) * rowsPerStep;
+                segStart = t;
+                const uint4 c4 = desc2[N];
+                cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
+                rowsPerStep = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
+                scb_load_program<K>(desc, desc2, cnt, N, tid, nthr);
+                __syncthreads();
+                SCB_NEXT_PROGRAM(tn);
             }
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
             if (!plainOnly) {
@@ -832,14 +903,9 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         if (!haveFin) finOff = (t == SCB_LAST) ? dstOff : srcOff;
         if (allres) allfound = true;
         stepsDone += (unsigned)t; ++tilesDone;
-#ifndef SCB_DBG_NO_ROWS
-        {   /* state rows moved through shared memory by the steps of this tile (loads + stores) */
-            const int nFull = t < steadyFrom - 1 ? t : steadyFrom - 1;
-            const int4 cf = A.counts[p], cs = A.counts2[p];     /* re-read: nothing extra stays live across the step loop */
-            rowsMoved += (unsigned)nFull * (unsigned)(4 * cf.x + 3 * cf.y + 2 * cf.z)
-                         + (unsigned)(t - nFull) * (unsigned)(4 * cs.x + 3 * cs.y + 2 * cs.z);
-        }
-#endif
+        rowsMoved += (unsigned)(t - segStart) * rowsPerStep;   /* state rows moved through shared memory (loads + stores) */
+        scb_cp_async_wait();                                   /* a staged program this tile never reached */
+#undef SCB_NEXT_PROGRAM
         const long long c2 = scb_clock();
 
         if (A.mode == SCB_MODE_IMPORTANCE) {

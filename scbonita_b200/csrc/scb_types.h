@@ -49,6 +49,9 @@
 
 /* constant propagation depth cap of the steady program (K0): must stay below the first snapshot step */
 #define SCB_STEADY_MAX_DEPTH 24
+/* reduced programs per individual: at these propagation depths, plus the fixed point (or the cap) */
+#define SCB_NPROG 5
+#define SCB_STAGE_DEPTHS {2, 5, 8, 12}
 
 /* kernel behaviour flags (ScbSimArgs.flags) */
 #define SCB_KF_EARLY  1u
@@ -85,9 +88,9 @@ struct ScbCompileArgs {
     int koStride;                 /* 0: one shared `ko`; N: program p reads ko + p * N (batched importance scores) */
     uint4 *descs;                 /* [P][Npad] */
     int4 *counts;                 /* [P] */
-    uint4 *descs2;                /* [P][Npad] the steady program: descs after constant propagation */
-    int4 *counts2;                /* [P] */
-    int *depth;                   /* [P] D: the constants of the steady program hold in S_t for every t >= D */
+    uint4 *progs;                 /* [P][SCB_NPROG][N + 1] reduced programs (constants propagated to a fixed depth; the
+                                     last one to the fixed point); entry N of each holds its arity counts */
+    unsigned char *progFrom;      /* [P][8] first step each reduced program may compute (0: not emitted) */
     ScbDiag *diag;
 };
 
@@ -106,9 +109,8 @@ struct ScbSimArgs {
     int wordBase;                 /* first word of this launch's tile range (tail tiles use a narrower K) */
     const uint4 *descs;
     const int4 *counts;
-    const uint4 *descs2;          /* steady programs (constant-propagated), used for steps >= depth + 2 */
-    const int4 *counts2;
-    const int *depth;
+    const uint4 *progs;           /* reduced programs of K0, [P][SCB_NPROG][N + 1] */
+    const unsigned char *progFrom;/* [P][8] */
     int useSteady;
     int firstSnap;                /* first step that takes a snapshot (1000: none): the steady program must be in use by then */
     unsigned long long *fitness;  /* [P] */

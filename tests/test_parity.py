@@ -464,12 +464,13 @@ def test_compact_population_rejects_inconsistent_triples(backend):
 
 
 # ---- steady program (constant propagation in K0) ---------------------------------------------------
-@pytest.mark.parametrize("chain", [3, 23, 24, 25, 40])
+@pytest.mark.parametrize("chain", [1, 2, 3, 4, 5, 6, 8, 9, 12, 13, 23, 24, 25, 40])
 @pytest.mark.parametrize("opts", [dict(), dict(steady=0)])
 def test_constants_spreading_along_chains(backend, chain, opts):
     """A knocked node feeding a chain of copies: node j of the chain is constant from step j + 1 on, so the
-    constant-propagation depth is the chain length -- below, at and above the cap (SCB_STEADY_MAX_DEPTH = 24).
-    The steady program may only be used once both state buffers hold the constants."""
+    constant-propagation depth is the chain length -- around every depth at which K0 emits a reduced program
+    (2, 5, 8, 12, the fixed point) and below, at and above the cap (SCB_STEADY_MAX_DEPTH = 24).  A reduced program
+    may only compute a step once both state buffers hold its constants."""
     pr = ring_problem([5, 9], chain, big(backend, 700, 9000))
     with pr.simulator(backend[1], **opts) as sim:
         pr.check(sim)
