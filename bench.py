@@ -320,8 +320,9 @@ def run_ours(args, wl, rank, world, local_rank):
         info = sim.info()
         k2_ms = sim_ms / sim_steps
         per_gpu_units = float(P) * C * N * STEPS_PER_CELL
-        # algorithmic HBM bytes of one K2 launch: packed matrix N*C/8, rule programs 16 B/node, fitness 8 B
-        alg_bytes = N * C / 8.0 + P * N * 16.0 + P * 8.0
+        # algorithmic HBM bytes of one K2 launch: packed matrix N*C/8, the full rule program (16 B/node) and the five
+        # reduced programs K0 emits per individual ((N + 1) x 16 B each), fitness 8 B
+        alg_bytes = N * C / 8.0 + P * N * 16.0 + P * 5 * (N + 1) * 16.0 + P * 8.0
         hbm_ach = alg_bytes / (k2_ms * 1e-3) / 1e9
         traffic = None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed `ncu --set full` capture

@@ -1,0 +1,10 @@
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+timeout 300 $CMD > gpurun_out/f2_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/f2_launches.csv $CMD > gpurun_out/f2_ncu_launches.log 2>&1
+echo "launch list rc=$?"
+CMD2="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --opt fuse=0"
+timeout 300 $CMD2 > gpurun_out/f2_plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:scb_k_sim -s 1 -c 1 -f -o gpurun_out/f2_prof_sim $CMD2 > gpurun_out/f2_ncu_full.log 2>&1
+echo "full rc=$?"
+ls -la gpurun_out/f2_*

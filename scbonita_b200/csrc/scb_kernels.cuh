@@ -333,7 +333,44 @@ template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, c
  * ---------------------------------------------------------------------------------------- */
 SCB_HD inline size_t scb_compile_smem_bytes(int N)
 {
-    return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4;
+    return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4 + 256;
+}
+
+/* stable counting sort of a program by arity class (3, 2, 1, 0): out[classOffset + number of earlier nodes of the
+ * same class] = sdv[i].  Warp ballots + per-warp counts in `wc` ([warps][4], shared) instead of an O(N) look-back
+ * per thread.  All threads of the CTA call it (blockDim.x is a multiple of 32, at most 8 warps). */
+SCB_DEV void scb_scatter_by_arity(const uint4 *sdv, const unsigned char *sarv, int N, int n3, int n2, int n1,
+                                  uint4 *out, unsigned int *wc, int tid, int nthr)
+{
+    const int lane = tid & 31, warp = tid >> 5, W = nthr >> 5;
+    int run3 = 0, run2 = 0, run1 = 0, run0 = 0;
+    for (int base = 0; base < N; base += nthr) {
+        const int i = base + tid;
+        const int ar = i < N ? (int)sarv[i] : -1;
+        const unsigned m3 = __ballot_sync(0xffffffffu, ar == 3), m2 = __ballot_sync(0xffffffffu, ar == 2);
+        const unsigned m1 = __ballot_sync(0xffffffffu, ar == 1), m0 = __ballot_sync(0xffffffffu, ar == 0);
+        if (lane == 0) {
+            wc[warp * 4 + 0] = (unsigned)__popc(m3); wc[warp * 4 + 1] = (unsigned)__popc(m2);
+            wc[warp * 4 + 2] = (unsigned)__popc(m1); wc[warp * 4 + 3] = (unsigned)__popc(m0);
+        }
+        __syncthreads();
+        int p3 = 0, p2 = 0, p1 = 0, p0 = 0, t3 = 0, t2 = 0, t1 = 0, t0 = 0;
+        for (int w = 0; w < W; ++w) {
+            const int c3 = (int)wc[w * 4 + 0], c2 = (int)wc[w * 4 + 1], c1 = (int)wc[w * 4 + 2], c0 = (int)wc[w * 4 + 3];
+            t3 += c3; t2 += c2; t1 += c1; t0 += c0;
+            if (w < warp) { p3 += c3; p2 += c2; p1 += c1; p0 += c0; }
+        }
+        if (i < N) {
+            const unsigned lt = (1u << lane) - 1u;
+            const int pos = ar == 3 ? run3 + p3 + __popc(m3 & lt)
+                          : ar == 2 ? n3 + run2 + p2 + __popc(m2 & lt)
+                          : ar == 1 ? n3 + n2 + run1 + p1 + __popc(m1 & lt)
+                                    : n3 + n2 + n1 + run0 + p0 + __popc(m0 & lt);
+            out[pos] = sdv[i];
+        }
+        run3 += t3; run2 += t2; run1 += t1; run0 += t0;
+        __syncthreads();
+    }
 }
 
 __global__ void scb_k_compile(ScbCompileArgs A)
@@ -374,14 +411,8 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     }
     __syncthreads();
     const int c3 = (int)cn[0], c2 = (int)cn[1], c1 = (int)cn[2], c0 = (int)cn[3];
-    uint4 *out = A.descs + (long long)p * A.Npad;
-    for (int i = tid; i < N; i += nthr) {
-        const int ar = sar[i];
-        int before = 0;
-        for (int j = 0; j < i; ++j) before += (sar[j] == ar);
-        const int off = ar == 3 ? 0 : ar == 2 ? c3 : ar == 1 ? c3 + c2 : c3 + c2 + c1;
-        out[off + before] = sd[i];
-    }
+    unsigned int *wc = reinterpret_cast<unsigned int *>(smraw + scb_compile_smem_bytes(N) - 256);
+    scb_scatter_by_arity(sd, sar, N, c3, c2, c1, A.descs + (long long)p * A.Npad, wc, tid, nthr);
     /* ---- reduced programs by constant propagation.  c(t) = nodes whose value in S_t is the same constant for every
      * cell: c(1) = the constant rules (knock-outs, knock-ins, constant-TRUE literals), c(t+1) = rules that are
      * constant once the inputs in c(t) are fixed.  Knowledge only grows, so c(D) stays valid for every t >= D.  A
@@ -444,13 +475,7 @@ __global__ void scb_k_compile(ScbCompileArgs A)
             const int s3 = chg[1], s2 = chg[2], s1 = chg[3], s0 = chg[4];
             const int slot = last ? SCB_NPROG - 1 : stage;
             uint4 *out2 = progs + (long long)slot * (N + 1);
-            for (int i = tid; i < N; i += nthr) {
-                const int ar = sar2[i];
-                int before = 0;
-                for (int j = 0; j < i; ++j) before += (sar2[j] == ar);
-                const int off = ar == 3 ? 0 : ar == 2 ? s3 : ar == 1 ? s3 + s2 : s3 + s2 + s1;
-                out2[off + before] = sd2[i];
-            }
+            scb_scatter_by_arity(sd2, sar2, N, s3, s2, s1, out2, wc, tid, nthr);
             if (tid == 0) {
                 out2[N] = make_uint4((unsigned)s3, (unsigned)s2, (unsigned)s1, (unsigned)s0);   /* the counts travel with the program */
                 progFrom[slot] = (unsigned char)(D + 2);
@@ -1462,12 +1487,22 @@ __global__ void scb_k_fill(ScbResolveArgs R)
         const int word = qq * 32 + (cell >> 5), sb = cell & 31;
         const int4 cnt = A.counts[p];
         const uint4 *gdesc = A.descs + (long long)p * A.Npad;
-        const int e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
+        int e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
         uint32_t *cur = st, *nxt = st + N;
         for (int i = lane; i < N; i += 32) { cur[i] = A.X[(long long)i * A.Wpad + word]; sdesc[i] = gdesc[i]; }
         const uint4 *desc = sdesc;
+        /* from this step on the fixed-point program of K0 (constants propagated) does the same with fewer nodes:
+         * both state vectors hold its constants by then */
+        const uint4 *gfinal = A.progs + ((long long)p * SCB_NPROG + (SCB_NPROG - 1)) * (N + 1);
+        const int from = A.useSteady ? (int)A.progFrom[(long long)p * 8 + (SCB_NPROG - 1)] : 0;
         __syncwarp();
         for (int t = 1; t <= SCB_LAST - 1; ++t) {
+            if (t == from) {
+                for (int i = lane; i < N; i += 32) sdesc[i] = gfinal[i];
+                const uint4 c4 = gfinal[N];
+                e1 = (int)(c4.x + c4.y + c4.z); e0 = e1 + (int)c4.w;
+                __syncwarp();
+            }
             for (int j = lane; j < e1; j += 32) {
                 const uint4 d = desc[j];
                 nxt[d.w & 0xFFFFFFu] = scb_lut_apply_mux(d.w >> 24, cur[d.x], cur[d.y], cur[d.z]);
