@@ -1156,11 +1156,20 @@ struct ScbResolveArgs {
  * On return: buffer A rows hold S_98, buffer B rows hold e = (S_98 xor S_0) & valid for every node,
  * Fm[32*KR] = found & valid per word (how != 2), vm[32*KR] = valid masks.  All threads call it. */
 template <int KR, bool TTM = false>
-SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uint4 *desc, int4 cnt,
+SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *desc, int4 cnt, int p,
                                uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
                                const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr, int onlyLane = -1,
                                uint32_t tm = SCB_TMEM_OFF)
 {
+    /* Like the simulator, the passes switch to K0's reduced programs as soon as each one is exact (program k from step
+     * from[k] on: the constants it no longer computes are then in both state buffers, and they equal T's -- T = S_99
+     * lies beyond every from[k] -- so leaving them out of the compare with T is exact too).  With T in tensor memory
+     * its slots follow the program's node order and are re-laid out from Tglob at every switch (how == 1 only). */
+    const int4 cntFull = cnt;
+    const uint4 *progBase = A.progs + (long long)p * SCB_NPROG * (A.N + 1);
+    const unsigned long long fromBytes = (A.useSteady && !(TTM && how == 0))
+        ? *reinterpret_cast<const unsigned long long *>(A.progFrom + (long long)p * 8) : 0ull;
+    bool replaced = false;
     /* TTM: the target state T = S_99 is kept in tensor memory (this warp's slots start at tm, one slot of KR
      * columns per non-constant node in the order scb_step visits them) instead of a third shared-memory buffer,
      * so that a whole 4-chunk tile fits; the per-step fold then goes through dmz with one extra barrier. */
@@ -1179,6 +1188,16 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
 
     for (int pass = (how == 0 ? 0 : 1); pass < 2; ++pass) {
         const bool cmp = pass == 1 && how != 2;
+        if (replaced) {                       /* the previous pass ended on a reduced program: start again with the full one */
+            cnt = cntFull;
+            scb_load_program<KR>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+            replaced = false;
+        }
+        int nextProg = 0, switchAt = 1000;
+        for (; nextProg < SCB_NPROG; ++nextProg) {
+            const int from = (int)((fromBytes >> (8 * nextProg)) & 0xffull);
+            if (from > 0) { switchAt = from; break; }
+        }
         for (int row = warp; row < N; row += S) {
             const ScbVec<KR> v = scb_ldg<KR>(A.X + (long long)row * A.Wpad + w0 + lane * KR);
             scb_st<KR>(bufA + (uint32_t)row * ROWB + laneOff, v);
@@ -1235,6 +1254,31 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, const uin
         const int last = pass == 0 ? SCB_LAST : SCB_LAST - 1;
         uint32_t srcOff = 0u, dstOff = BUFB;
         for (int tn = 1; tn <= last; ++tn) {
+            if (tn == switchAt) {
+                /* every warp is past the barrier that ended step tn - 1: the program can be replaced in place */
+                const uint4 *src = progBase + (long long)nextProg * (N + 1);
+                const uint4 c4 = src[N];
+                cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
+                scb_load_program<KR>(desc, src, cnt, N, tid, nthr);
+                replaced = true;
+                __syncthreads();
+                if (TTM && cmp) {
+                    /* T into this warp's tensor-memory slots in the new program's node order */
+                    const int e1 = cnt.x + cnt.y + cnt.z;
+                    uint32_t tmc = tm;
+                    for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR) {
+                        const int node = (int)((desc[j].w & 0xFFFFFFu) / ROWB);
+                        scb_tmem_st<KR>(tmc, scb_ld<KR>(reinterpret_cast<const unsigned char *>(Tglob + (long long)node * GW + lane * KR)));
+                    }
+                    scb_tmem_wait_st();
+                }
+                const int prev = switchAt;
+                switchAt = 1000;
+                for (++nextProg; nextProg < SCB_NPROG; ++nextProg) {
+                    const int from = (int)((fromBytes >> (8 * nextProg)) & 0xffull);
+                    if (from > prev) { switchAt = from; break; }
+                }
+            }
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
             if (cmp) f |= TTM ? SCB_SF_ZCMP : SCB_SF_TCMP;
 #pragma unroll
@@ -1334,7 +1378,7 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
         if (tid == 0) { sh[2] = 0; sh[3] = 0; }
         __syncthreads();
         const bool haveT = it < A.resolveTCap;
-        scb_resolve_chunk<KR, TTM>(A, sm, desc, cnt, dmz, Fm, vm, q, haveT ? 1 : 0,
+        scb_resolve_chunk<KR, TTM>(A, sm, desc, cnt, p, dmz, Fm, vm, q, haveT ? 1 : 0,
                                    A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf, -1, tm);
 
         /* source cell of every cell: itself when found, else the nearest earlier found cell of the group
