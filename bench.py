@@ -406,7 +406,8 @@ def run_ours(args, wl, rank, world, local_rank):
                              "achieved_executed": lop_exec, "frac_executed": lop_exec / mb["lop3"] if mb.get("lop3") else None,
                              "popc_peak": mb.get("popc"),
                              "note": "algorithmic = CRE/s x 7/32 (SURVEY 8d mux-tree figure); executed = one LOP3 per "
-                                     "node-word-step actually simulated; POPC is used once per (node, word, tile)"},
+                                     "node-word-step actually simulated (upper bound: counts all N nodes, the reduced "
+                                     "programs compute fewer); POPC is used once per (node, word, tile)"},
             "stats": stats, "clocks": clocks, "cpu_baseline": cpu,
             "fitness_checksum": int(fit.sum()),
         }
