@@ -600,6 +600,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.P = P; sa.Npad = N; sa.mode = mode;
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
     sa.progs = c->dProgs.p; sa.progFrom = c->dProgFrom.p; sa.useSteady = c->optSteady;
+    sa.firstChk = c->optChk * ((3 + c->optChk - 1) / c->optChk);
     sa.firstSnap = 1000;
     for (int t = SCB_LAST - 1; t >= 1; --t)
         if (t < 64 ? ((c->snapLo >> t) & 1ull) : ((c->snapHi >> (t - 64)) & 1ull)) sa.firstSnap = t;

@@ -838,13 +838,28 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
 #endif
         __syncthreads();
 
-        const bool laneActive = ((long long)w0 + lane * K) * 32 < A.C;       /* the lane holds a valid cell */
+        int laneActiveI = ((long long)w0 + lane * K) * 32 < A.C ? 1 : 0;      /* the lane holds a valid cell */
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+r"(laneActiveI));             /* kept in a register: otherwise the 64-bit test is redone in every step */
+#endif
+        const bool laneActive = laneActiveI != 0;
         const long long c1 = scb_clock();
         uint32_t srcOff = 0u, dstOff = BUFB, finOff = 0u;
         int t = 0, target = SCB_LAST, zs = -1, ncmp = 0, searchLeft = 0;
         bool allres = false, allfound = false, plainOnly = false, haveFin = false;
+        /* the schedule as two counters (next period-<=2 check, next snapshot) instead of a modulo and two 64-bit
+         * mask tests per step */
+        int nextChk = A.firstChk, nextSnap = A.firstSnap;
         while (t < target) {
             const int tn = t + 1;                       /* this iteration computes S_tn */
+            bool chkNow = false, snapNow = false;
+            if (tn == nextChk) { chkNow = true; nextChk += A.chkEvery; }
+            if (tn == nextSnap) {
+                snapNow = true;
+                nextSnap = 1000;
+                for (int u = tn + 1; u < SCB_LAST; ++u)
+                    if (u < 64 ? ((A.snapLo >> u) & 1ull) != 0ull : ((A.snapHi >> (u - 64)) & 1ull) != 0ull) { nextSnap = u; break; }
+            }
             if (tn == switchAt) {
                 /* the staged program replaces the current one in place (every warp is past the barrier of the
                  * previous step), so the step code keeps one program address */
@@ -862,22 +877,22 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
             if (!plainOnly) {
                 if (!allres) {
-                    if (tn == SCB_LAST || (early && tn >= 3 && (tn % A.chkEvery) == 0)) f |= SCB_SF_CMP2;
+                    if (tn == SCB_LAST || (early && chkNow)) f |= SCB_SF_CMP2;
                     /* a cell of period L matches the snapshot at every multiple of L, so the first compares after a
                      * snapshot can be skipped without losing any cell: only the proof comes a little later */
                     if (useZ && zs >= 0 && (tn - zs >= A.snapMinGap || tn == SCB_LAST)) f |= SCB_SF_ZCMP;
-                    const bool snapNow = tn < 64 ? ((A.snapLo >> tn) & 1ull) != 0ull
-                                                 : ((A.snapHi >> (tn - 64)) & 1ull) != 0ull;
                     if (useZ && snapNow && tn < SCB_LAST) f |= SCB_SF_ZSNAP;
                 } else if (useZ && zs >= 0 && searchLeft > 0) {
                     f |= SCB_SF_ZCMP; --searchLeft;   /* all cells proven: look for a tile-wide period */
                 }
             }
             ScbVec<K> d2, dz;
-#pragma unroll
-            for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
             if (f == 0u) scb_step<K, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, zg, sa, d2, dz, laneActive);
-            else scb_step<K, false, TM>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, zg, sa, d2, dz, laneActive, tm);
+            else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
+                scb_step<K, false, TM>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, zg, sa, d2, dz, laneActive, tm);
+            }
             if (f & SCB_SF_CMP2) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
