@@ -77,7 +77,7 @@ struct scb_ctx {
     size_t smemLimit = 0;
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
-    int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 6, optSearch = 0, optMinGap = 8;
+    int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 8, optSearch = 0, optMinGap = 8;
     int optTmem = 1, optFuse = 1, optTma = 1, optSteady = 1;
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */

@@ -554,10 +554,13 @@ __global__ void scb_k_pack_csr(ScbPackCsrArgs A)
 /* ------------------------------------------------------------------------------------------
  * shared pieces of K2 / K3
  * ---------------------------------------------------------------------------------------- */
+/* A program in shared memory is followed by SCB_DESC_PAD unused entries: a warp fetches the descriptor of its next
+ * node (index + warps, at most 24 ahead) before it knows whether there is one, without a bounds test */
+#define SCB_DESC_PAD 24
 /* shared-memory carve-up, identical formula on host and device */
 SCB_HD inline size_t scb_smem_bytes(int N, int K, int nbuf)
 {
-    return (size_t)nbuf * N * 128 * K + (size_t)N * 32 + 16 + (size_t)6 * 32 * K * 4 + 4096 + 256;   /* program + staged program */
+    return (size_t)nbuf * N * 128 * K + (size_t)N * 32 + 16 + SCB_DESC_PAD * 16 + (size_t)6 * 32 * K * 4 + 4096 + 256;   /* program + pad + staged program */
 }
 
 /* load individual p's program into shared memory, scaling node indices to row byte offsets */
@@ -630,14 +633,13 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
     /* the next node's descriptor is fetched while the current node is processed */
     const uint32_t dstep = 16u * (uint32_t)S;
     scb_saddr dp = desc + 16u * (uint32_t)j;
-    const scb_saddr dlast = desc + 16u * (uint32_t)(e0 - 1);
     uint4 d = scb_lds_desc(dp);
     ScbVec<K> zn;
 #pragma unroll
     for (int k = 0; k < K; ++k) zn.v[k] = 0u;
     if ((flags & SCB_SF_ZCMP) && !TM && j < e1) zn = scb_ldcg<K>(zg + (d.w & 0xFFFFFFu));
     for (; j < e3; j += S) {
-        dp = (dp + dstep <= dlast) ? dp + dstep : dp;
+        dp += dstep;                 /* may run into the pad behind the program: that descriptor is never used */
         const uint4 dn = scb_lds_desc(dp);
         SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
         const ScbVec<K> a = scb_lds<K>(src + d.x), b = scb_lds<K>(src + d.y), c = scb_lds<K>(src + d.z);
@@ -646,7 +648,7 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
         d = dn;
     }
     for (; j < e2; j += S) {
-        dp = (dp + dstep <= dlast) ? dp + dstep : dp;
+        dp += dstep;                 /* may run into the pad behind the program: that descriptor is never used */
         const uint4 dn = scb_lds_desc(dp);
         SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
         const ScbVec<K> a = scb_lds<K>(src + d.x), b = scb_lds<K>(src + d.y);
@@ -655,7 +657,7 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
         d = dn;
     }
     for (; j < e1; j += S) {
-        dp = (dp + dstep <= dlast) ? dp + dstep : dp;
+        dp += dstep;                 /* may run into the pad behind the program: that descriptor is never used */
         const uint4 dn = scb_lds_desc(dp);
         SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
         ScbVec<K> r = scb_lds<K>(src + d.x);
@@ -715,7 +717,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
     const int WT = 32 * K;                              /* words per tile */
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + 2u * BUFB);
-    uint4 *desc2 = desc + N;                            /* staging buffer of the next reduced program: N nodes + its counts */
+    uint4 *desc2 = desc + N + SCB_DESC_PAD;             /* staging buffer of the next reduced program: N nodes + its counts */
     uint32_t *dm2 = reinterpret_cast<uint32_t *>(desc2 + N + 1);
     uint32_t *dmz = dm2 + WT;
     uint32_t *Rm = dmz + WT;
@@ -1361,7 +1363,7 @@ SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR, bool ttm = false)
 {
     /* state buffers (three, or two when T lives in tensor memory) + program + dmz/Fm/vm + scalars +
      * srcc[1024*KR] int16 + (shared-memory T only) D[2][<=24 warps][32*KR] + slack */
-    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + (size_t)N * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 2
+    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + (size_t)(N + SCB_DESC_PAD) * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 2
            + (ttm ? 0 : (size_t)2 * 24 * 32 * KR * 4) + 256;
 }
 
@@ -1375,7 +1377,7 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
     const int GW = 32 * KR, GC = 1024 * KR;
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + (TTM ? 2u : 3u) * BUFB);
-    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N);
+    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N + SCB_DESC_PAD);
     uint32_t *Fm = dmz + GW;
     uint32_t *vm = Fm + GW;
     int *sh = reinterpret_cast<int *>(vm + GW);            /* [2] pending cells, [3] not-found cells */
