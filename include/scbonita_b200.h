@@ -220,6 +220,13 @@ int scb_importance_scores(scb_ctx *ctx, const int32_t *individual, int indLen,
                           const int32_t *andNodes, const int32_t *andNodeInvertList,
                           int nItems, const int32_t *knockouts, const int32_t *knockins, double *scores);
 
+/* ---- diagnostics / tests: the compiled programs of individual p of the last scb_pop_run.  descs / descsK are
+ * uint32[N][4] (three input nodes, node | truth table << 24, sorted by arity), counts / countsK the number of nodes of
+ * arity 3, 2, 1, 0.  The full program, and reduced program k (0 .. 4: constants propagated to depth 2, 5, 8, 12 and to
+ * the fixed point) with fromK = the first step it may compute (0: not emitted).  Any pointer may be NULL. */
+int scb_debug_programs(scb_ctx *ctx, int p, int k, uint32_t *descs, int32_t *counts,
+                       uint32_t *descsK, int32_t *countsK, int32_t *fromK);
+
 /* ---- measured on-box peaks for the roofline report (bench.py): kind 0 = 32-bit LOP3 ops/s, 1 = POPC ops/s,
  * 2 = bytes/s of conflict-free 128-bit shared-memory loads, all SMs busy.  Not part of the reference's interface. */
 int scb_microbench(scb_ctx *ctx, int kind, double *perSecond);

@@ -26,7 +26,7 @@ SYMBOLS = (
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
     "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
     "scb_eval_local_search", "scb_eval_local_search_all", "scb_hamming_argmin", "scb_attractors", "scb_importance_score",
-    "scb_importance_scores", "scb_microbench",
+    "scb_importance_scores", "scb_microbench", "scb_debug_programs",
     "scb_set_legacy_geometry", "scSyncBool", "importanceScore", "cluster",
 )
 
@@ -103,6 +103,8 @@ def load(path=None):
     lib.scb_importance_score.restype = ctypes.c_int
     lib.scb_importance_scores.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, ctypes.c_int, i32p, i32p, vp]
     lib.scb_importance_scores.restype = ctypes.c_int
+    lib.scb_debug_programs.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.scb_debug_programs.restype = ctypes.c_int
     lib.scb_microbench.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     lib.scb_microbench.restype = ctypes.c_int
     lib.scb_set_legacy_geometry.argtypes = [ctypes.c_int, ctypes.c_int]

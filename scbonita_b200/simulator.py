@@ -216,6 +216,17 @@ class Simulator:
         _lib.check(self.lib, self.lib.scb_ctx_stream(self._ctx, ctypes.byref(p)))
         return p.value or 0
 
+    def programs(self, p=0, k=4):
+        """Diagnostics: the compiled full program of individual ``p`` of the last run and its reduced program ``k``
+        (0..4; 4 = constants propagated to the fixed point).  Returns a dict with ``descs`` / ``descs_k``
+        (uint32[N][4]), ``counts`` / ``counts_k`` (nodes of arity 3, 2, 1, 0) and ``from_k`` (first step the reduced
+        program may compute, 0 if it was not emitted)."""
+        n = self.model.n
+        d1, dk = np.zeros((n, 4), np.uint32), np.zeros((n, 4), np.uint32)
+        c1, ck, fk = np.zeros(4, np.int32), np.zeros(4, np.int32), np.zeros(1, np.int32)
+        _lib.check(self.lib, self.lib.scb_debug_programs(self._ctx, int(p), int(k), _ptr(d1), _ptr(c1), _ptr(dk), _ptr(ck), _ptr(fk)))
+        return {"descs": d1, "counts": c1, "descs_k": dk, "counts_k": ck, "from_k": int(fk[0])}
+
     def microbench(self, kind):
         """Measured peak of one on-chip resource with every SM busy: "lop3" / "popc" in thread-level ops per
         second, "lds" in bytes per second of conflict-free 128-bit shared-memory loads (roofline denominators)."""

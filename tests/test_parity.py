@@ -531,3 +531,24 @@ def test_every_truth_table(backend):
     pr = Problem(net, rows, rng.permutation(n).astype(np.int32), np.asarray(bits, np.int32).reshape(1, -1))
     with pr.simulator(backend[1]) as sim:
         pr.check(sim)
+
+
+@pytest.mark.parametrize("chain,want_from", [(7, [4, 7, 0, 0, 9]), (1, [0, 0, 0, 0, 3]), (14, [4, 7, 10, 14, 16]), (40, [4, 7, 10, 14, 26])])
+def test_reduced_program_schedule(backend, chain, want_from):
+    """K0's reduced programs on a chain fed by a knocked node: chain node j is constant from S_(j+1) on, so c(t) is the
+    first t chain nodes.  Programs are emitted at depths 2, 5, 8, 12 (while the propagation still runs) and at the
+    fixed point (or the cap of 24); program of depth D may compute steps >= D + 2; the fixed-point program has lost
+    exactly the constant chain nodes."""
+    pr = ring_problem([5], chain, 300)
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim, modes=(0,))
+        got = [sim.programs(0, k) for k in range(5)]
+    assert [g["from_k"] for g in got] == want_from
+    full = got[0]["counts"]
+    assert int(full.sum()) == pr.n and int(full[3]) == 1                       # the knocked chain head is the only constant rule
+    depth = want_from[4] - 2
+    assert int(got[4]["counts_k"][3]) == min(chain, depth)                     # constants of the last program = c(depth)
+    for k, g in enumerate(got):
+        if g["from_k"]:
+            assert int(g["counts_k"].sum()) == pr.n
+            assert int(g["counts_k"][3]) == min(chain, g["from_k"] - 2)
