@@ -68,6 +68,7 @@ extern "C" {
 #define SCB_OPT_TMEM         11 /* 1 (default): keep the snapshot in tensor memory, 0: in global scratch    */
 #define SCB_OPT_TMA          13 /* 1 (default): load the S_0 tile with TMA bulk copies (cp.async.bulk + mbarrier)   */
 #define SCB_OPT_STEADY       14 /* 1 (default): steps after the constants have spread run the constant-propagated program */
+#define SCB_OPT_CHECK_FROM   15 /* k (default 3): no period-<=2 check before reduced program k may run; -1: check from step 3 */
 #define SCB_OPT_FUSE         12 /* 1 (default): CTAs that run out of tiles resolve queued groups in the same launch */
 
 typedef struct scb_ctx scb_ctx;

@@ -78,7 +78,7 @@ struct scb_ctx {
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
     int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 8, optSearch = 0, optMinGap = 8;
-    int optTmem = 1, optFuse = 1, optTma = 1, optSteady = 1;
+    int optTmem = 1, optFuse = 1, optTma = 1, optSteady = 1, optChkFrom = SCB_NPROG - 2;
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
@@ -462,6 +462,9 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
             c->optMinGap = (int)value; return SCB_OK;
         case SCB_OPT_TMA: c->optTma = value != 0; return SCB_OK;
         case SCB_OPT_STEADY: c->optSteady = value != 0; return SCB_OK;
+        case SCB_OPT_CHECK_FROM:
+            if (value < -1 || value >= SCB_NPROG) return fail(SCB_ERR_INVALID, "check-from program must be in [-1,%d]", SCB_NPROG - 1);
+            c->optChkFrom = (int)value; return SCB_OK;
         case SCB_OPT_TMEM: c->optTmem = value != 0; break;
         case SCB_OPT_FUSE: c->optFuse = value != 0; break;
         case SCB_OPT_SNAP_LO: c->snapLo = (unsigned long long)value; return SCB_OK;
@@ -601,6 +604,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
     sa.progs = c->dProgs.p; sa.progFrom = c->dProgFrom.p; sa.useSteady = c->optSteady;
     sa.firstChk = c->optChk * ((3 + c->optChk - 1) / c->optChk);
+    sa.chkFromProg = c->optChkFrom;
     sa.firstSnap = 1000;
     for (int t = SCB_LAST - 1; t >= 1; --t)
         if (t < 64 ? ((c->snapLo >> t) & 1ull) : ((c->snapHi >> (t - 64)) & 1ull)) sa.firstSnap = t;

@@ -852,6 +852,13 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         /* the schedule as two counters (next period-<=2 check, next snapshot) instead of a modulo and two 64-bit
          * mask tests per step */
         int nextChk = A.firstChk, nextSnap = A.firstSnap;
+        {   /* no period-<=2 check before the constants have spread: until then the nodes they will reach still carry
+             * shifting cell data, so the tile cannot have settled (the checks are an optimisation, results never depend
+             * on when they run) */
+            int fromK = A.chkFromProg >= 0 ? (int)((fromBytes >> (8 * A.chkFromProg)) & 0xffull) : 0;
+            if (fromK == 0 && A.chkFromProg >= 0) fromK = (int)((fromBytes >> (8 * (SCB_NPROG - 1))) & 0xffull);   /* that depth was not reached */
+            while (nextChk < fromK) nextChk += A.chkEvery;
+        }
         while (t < target) {
             const int tn = t + 1;                       /* this iteration computes S_tn */
             bool chkNow = false, snapNow = false;

@@ -112,6 +112,7 @@ struct ScbSimArgs {
     const uint4 *progs;           /* reduced programs of K0, [P][SCB_NPROG][N + 1] */
     const unsigned char *progFrom;/* [P][8] */
     int useSteady;
+    int chkFromProg;              /* >= 0: no period-<=2 check before reduced program `chkFromProg` may run; -1: no such delay */
     int firstChk;                 /* first step >= 3 that is a multiple of chkEvery */
     int firstSnap;                /* first step that takes a snapshot (1000: none): the steady program must be in use by then */
     unsigned long long *fitness;  /* [P] */

@@ -21,6 +21,10 @@ def test_bench_line_has_contract_keys(emu_lib, monkeypatch, capsys):
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
     assert line["value"] > 0 and line["e2e"]["value"] > 0
     assert line["gpu_launches"] == 3 * 2
+    # extra evidence next to the contract keys: compact hand-over, binding (shared-memory) and integer-logic rooflines
+    assert line["e2e_compact"]["h2d_bytes_per_step"] < line["e2e"]["h2d_bytes_per_step"]
+    assert set(("bound", "achieved", "peak", "frac")) <= set(line["roofline_binding"])
+    assert "achieved_algorithmic" in line["roofline_lop"] and line["stats"]["state_rows_moved"] > 0
 
 
 def test_reference_arm_line(capsys):

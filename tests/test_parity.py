@@ -45,7 +45,8 @@ def test_synthetic_matches_oracle(backend, n, cells, pop):
                                   dict(warps=4), dict(period_search=24), dict(check_every=1), dict(snap_min_gap=1, check_every=4),
                                   dict(snap_min_gap=20, snap_lo=1 << 20, snap_hi=0), dict(fuse=0), dict(fuse=0, early_exit=0, snapshots=0),
                                   dict(steady=0), dict(steady=1, snap_lo=(1 << 4) | (1 << 30), snap_hi=0, snap_min_gap=2),
-                                  dict(steady=1, tmem=0), dict(steady=1, early_exit=0, snapshots=0)])
+                                  dict(steady=1, tmem=0), dict(steady=1, early_exit=0, snapshots=0),
+                                  dict(check_from=-1), dict(check_from=0, check_every=3), dict(check_from=4)])
 def test_every_schedule_gives_identical_integers(backend, opts):
     """Early exit, snapshot resolution and tile geometry are optimisations: results must not move."""
     pr = Problem.synthetic(60, big(backend, 2100, 21000), big(backend, 5, 24))
