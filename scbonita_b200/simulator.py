@@ -346,11 +346,7 @@ class Simulator:
         return out
 
     # -- attractor companion ------------------------------------------------------------------
-    def attractors(self, individual, knockouts=None, knockins=None, semantics="python", max_states=10):
-        """Per-cell attractor window and its states (singleCell.py:1162-1192 runs this one cell at a time in
-        pure Python).  ``semantics``: "python" = singleCell.__cluster with simSteps 10 (rows res[0]..res[1]
-        inclusive; [-1,-1] yields the last row), "c" = simulator.c cluster with simSteps 100 (rows
-        [res[0], res[1])).  Returns (res[C][2], n_states[C], states[C][max_states][N] as 0/1 uint8)."""
+    def _attractors_packed(self, individual, knockouts, knockins, semantics, max_states):
         m = self.model
         sem = {"c": 0, "python": 1}[semantics]
         ind = _i32(individual)
@@ -364,23 +360,34 @@ class Simulator:
                                      _ptr(m.and_nodes), _ptr(m.and_node_invert_list), _ptr(ko), _ptr(ki), sem,
                                      int(max_states), _ptr(res), _ptr(nst), _ptr(packed))
         _lib.check(self.lib, rc)
-        bits = np.unpackbits(packed.view(np.uint8), axis=-1, bitorder="little")[..., :m.n]
+        return res, nst, packed
+
+    def attractors(self, individual, knockouts=None, knockins=None, semantics="python", max_states=10):
+        """Per-cell attractor window and its states (singleCell.py:1162-1192 runs this one cell at a time in
+        pure Python).  ``semantics``: "python" = singleCell.__cluster with simSteps 10 (rows res[0]..res[1]
+        inclusive; [-1,-1] yields the last row), "c" = simulator.c cluster with simSteps 100 (rows
+        [res[0], res[1])).  Returns (res[C][2], n_states[C], states[C][max_states][N] as 0/1 uint8)."""
+        res, nst, packed = self._attractors_packed(individual, knockouts, knockins, semantics, max_states)
+        bits = np.unpackbits(packed.view(np.uint8), axis=-1, bitorder="little")[..., :self.model.n]
         return res, nst, bits
 
     def attractor_set(self, individual, knockouts=None, knockins=None, remove_zero=True):
         """The unique attractor states of all cells, as assignAttractors collects them
-        (singleCell.py:1189-1207), in first-seen order (the reference's order is Python set order)."""
-        _, nst, bits = self.attractors(individual, knockouts, knockins, "python", 10)
-        seen, out = set(), []
-        for c in range(self.n_cells):
-            for s in range(min(int(nst[c]), 10)):
-                key = bits[c, s].tobytes()
-                if key not in seen:
-                    seen.add(key)
-                    out.append(bits[c, s].astype(np.int32))
+        (singleCell.py:1189-1207), in first-seen order (the reference's order is Python set order).  The states
+        are deduplicated as packed words (one sort of the [cells x states] rows), only the unique ones are unpacked."""
+        n = self.model.n
+        _, nst, packed = self._attractors_packed(individual, knockouts, knockins, "python", 10)
+        nw = packed.shape[2]
+        rows = packed[np.arange(packed.shape[1])[None, :] < np.minimum(nst, 10)[:, None]]       # cell-major, then state order
+        if rows.shape[0] == 0:
+            return np.zeros((0, n), dtype=np.int32)
+        keys = np.ascontiguousarray(rows).view(np.dtype((np.void, nw * 4))).ravel()
+        _, first = np.unique(keys, return_index=True)
+        uniq = rows[np.sort(first)]
+        out = np.unpackbits(uniq.view(np.uint8), axis=-1, bitorder="little")[:, :n].astype(np.int32)
         if remove_zero:
-            out = [a for a in out if a.sum() > 0]
-        return np.array(out, dtype=np.int32).reshape(-1, self.model.n)
+            out = out[out.sum(axis=1) > 0]
+        return np.ascontiguousarray(out).reshape(-1, n)
 
     def hamming_argmin(self, attractors, want_dist=True):
         """singleCell.py:1211-1238: returns (dist[C][A] or None, decider[C], deciderDistance[C])."""
