@@ -1,5 +1,6 @@
 """Population sharding across GPUs: one process per GPU, the packed cell matrix replicated, individuals
-split in contiguous blocks, one all-gather of the int64 fitness vector per generation.
+split in contiguous blocks, one all-gather of the int64 fitness vector per generation;
+and independent pathways spread over the GPUs with no communication until the end (config C4).
 
 The reference has no distributed layer at all (one SLURM job per network, pipeline.py:24-61); the GA itself
 is sequential Python.  After the all-gather every rank holds the complete fitness vector, so the unchanged,
@@ -18,6 +19,44 @@ def shard_bounds(n_items, rank, world):
     base, extra = divmod(int(n_items), int(world))
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def pathway_cost(n_nodes, n_cells, evaluations=1):
+    """Work of one pathway in cell-rule evaluations: nodes x cells x 99 steps x scored rule sets."""
+    return float(n_nodes) * float(n_cells) * 99.0 * float(evaluations)
+
+
+def assign_pathways(costs, world):
+    """Independent KEGG pathways over the GPUs of a box (BASELINE config C4, SURVEY 8e ii): longest-processing-time
+    first, every pathway to the currently least loaded rank, ties to the lower rank.  The reference runs one SLURM
+    job per network (pipeline.py:24-61); here a pathway is one context on one GPU and nothing is exchanged until the
+    results are collected.  Returns ``world`` lists of pathway indices; deterministic, so every rank can compute it."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * int(world)
+    out = [[] for _ in range(int(world))]
+    for i in order:
+        r = min(range(int(world)), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += float(costs[i])
+    return out
+
+
+def run_pathways(pathways, evaluate, costs=None, group=None):
+    """Every rank evaluates the pathways :func:`assign_pathways` gives it (``evaluate(index, pathway)`` builds the
+    context on this rank's GPU and returns a picklable result) and all ranks collect all results at the end with ONE
+    ``all_gather_object`` -- the only communication of config C4.  Returns the results in pathway order."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if costs is None:
+        costs = [1.0] * len(pathways)
+    mine = assign_pathways(costs, world)[rank]
+    local = {i: evaluate(i, pathways[i]) for i in mine}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local, group=group)
+    merged = {}
+    for part in gathered:
+        merged.update(part)
+    return [merged[i] for i in range(len(pathways))]
 
 
 class _DevicePointer:
