@@ -859,16 +859,24 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
             if (fromK == 0 && A.chkFromProg >= 0) fromK = (int)((fromBytes >> (8 * (SCB_NPROG - 1))) & 0xffull);   /* that depth was not reached */
             while (nextChk < fromK) nextChk += A.chkEvery;
         }
+        /* most steps are plain: nextEvent is the first step at which a check, snapshot or compare can be due, so the
+         * schedule logic below runs only from there on (and is re-armed after every non-plain step) */
+#define SCB_NEXT_EVENT(now)                                                                           \
+        do {                                                                                          \
+            if (plainOnly) nextEvent = 1000;                                                          \
+            else if (allres) nextEvent = (useZ && zs >= 0 && searchLeft > 0) ? (now) + 1 : 1000;      \
+            else {                                                                                    \
+                nextEvent = SCB_LAST;                                                                 \
+                if (early && nextChk < nextEvent) nextEvent = nextChk;                                \
+                if (useZ && nextSnap < nextEvent) nextEvent = nextSnap;                               \
+                if (useZ && zs >= 0 && zs + A.snapMinGap < nextEvent) nextEvent = zs + A.snapMinGap;  \
+                if (nextEvent <= (now)) nextEvent = (now) + 1;                                        \
+            }                                                                                         \
+        } while (0)
+        int nextEvent;
+        SCB_NEXT_EVENT(0);
         while (t < target) {
             const int tn = t + 1;                       /* this iteration computes S_tn */
-            bool chkNow = false, snapNow = false;
-            if (tn == nextChk) { chkNow = true; nextChk += A.chkEvery; }
-            if (tn == nextSnap) {
-                snapNow = true;
-                nextSnap = 1000;
-                for (int u = tn + 1; u < SCB_LAST; ++u)
-                    if (u < 64 ? ((A.snapLo >> u) & 1ull) != 0ull : ((A.snapHi >> (u - 64)) & 1ull) != 0ull) { nextSnap = u; break; }
-            }
             if (tn == switchAt) {
                 /* the staged program replaces the current one in place (every warp is past the barrier of the
                  * previous step), so the step code keeps one program address */
@@ -884,7 +892,16 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 SCB_NEXT_PROGRAM(tn);
             }
             unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
-            if (!plainOnly) {
+            if (tn >= nextEvent) {
+                bool chkNow = false, snapNow = false;
+                while (nextChk < tn) nextChk += A.chkEvery;
+                if (tn == nextChk) { chkNow = true; nextChk += A.chkEvery; }
+                if (tn >= nextSnap) {
+                    snapNow = tn == nextSnap;
+                    nextSnap = 1000;
+                    for (int u = tn + 1; u < SCB_LAST; ++u)
+                        if (u < 64 ? ((A.snapLo >> u) & 1ull) != 0ull : ((A.snapHi >> (u - 64)) & 1ull) != 0ull) { nextSnap = u; break; }
+                }
                 if (!allres) {
                     if (tn == SCB_LAST || (early && chkNow)) f |= SCB_SF_CMP2;
                     /* a cell of period L matches the snapshot at every multiple of L, so the first compares after a
@@ -946,7 +963,9 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 }
             }
             if (f & SCB_SF_ZSNAP) zs = tn;
+            if (tn >= nextEvent) SCB_NEXT_EVENT(tn);
         }
+#undef SCB_NEXT_EVENT
         /* loop ran out at t == target (98: src = S_98; 99: dst = S_98; E3: src = S_target == S_98),
          * or stopped early at t > target when the last cell resolved at t == 99 */
         if (!haveFin) finOff = (t == SCB_LAST) ? dstOff : srcOff;
