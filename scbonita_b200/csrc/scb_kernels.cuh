@@ -1,14 +1,17 @@
 /*
  * scb_kernels.cuh -- sm_100a kernels of the rule-inference fitness hot path.
  *
- *   K0  scb_k_compile    reference-format rule tables -> per-individual programs of 3-input truth tables
- *                        (scb_compile.h), sorted by arity; one CTA per individual
+ *   K0  scb_k_compile    reference-format rule tables (or upstream triples) -> per-individual programs of 3-input
+ *                        truth tables (scb_compile.h), sorted by arity; one CTA per individual.  Also the REDUCED
+ *                        programs: constants (knocked nodes, their copies, the AND-terms they erase) propagated to
+ *                        depths 2, 5, 8, 12 and to the fixed point, each exact from step depth + 2 on
  *   K1  scb_k_pack       int32 / uint8 binarized matrix -> node-major 32-cells-per-word S_0
  *   K1b scb_k_pack_csr   the same straight from a CSR matrix
  *   K2  scb_k_sim<K,TM>  the simulator: persistent CTAs, one (individual, cell tile) per work item, state
  *                        ping-pong in shared memory, one LOP3 per node per 32 cells reached through a brx.idx
- *                        jump table, snapshot in tensor memory (TM); CTAs that run out of tiles resolve queued
- *                        groups in the same launch
+ *                        jump table, snapshot in tensor memory (TM); the next reduced program is staged with
+ *                        cp.async and replaces the current one at its first legal step; CTAs that run out of tiles
+ *                        resolve queued groups in the same launch
  *   K3  scb_resolve_item / scb_k_resolve   exact second pass for the 1024-cell chunks K2 could not prove
  *                        "attractor found" for (literally getAttractCycle2 on packed words);
  *       scb_k_fill       the reference's fill-forward across chunks, one warp per item
