@@ -60,7 +60,7 @@ def liboracle():
         if not os.path.exists(path):
             build(ref=False)
         _lib = ctypes.CDLL(path)
-        for name in ("scbo_sync_bool", "scbo_cluster", "scbo_py_cluster", "scbo_hamming_argmin",
+        for name in ("scbo_sync_bool", "scbo_cluster", "scbo_cluster_literal", "scbo_py_cluster", "scbo_hamming_argmin",
                      "scbo_importance_score", "scbo_packed_population"):
             getattr(_lib, name).restype = ctypes.c_int
     return _lib
@@ -172,6 +172,29 @@ def c_cluster(model, individual, bin_mat, cell, sim_steps=100):
     return traj, res
 
 
+def c_cluster_literal(model, individual, bin_mat, cell, sim_data=None, sim_stride=None, sim_steps=100):
+    """C `cluster` restated LITERALLY on a scratch like the caller's ``simData`` (incl. the knock-out branch's
+    column slip, simulator.c:518).  ``sim_data``: int32[100][sim_stride] scratch (zeros when None; the reference's
+    Python passes zeros).  Returns (sim_data after the call, res[2])."""
+    lib = liboracle()
+    bm = _i32(bin_mat)
+    ind = _i32(individual)
+    if sim_stride is None:
+        sim_stride = max(int(model.node_positions.max()) + 1, model.n)
+    sd = np.zeros((REF_STEP, sim_stride), dtype=np.int32) if sim_data is None else np.array(sim_data, dtype=np.int32, order="C")
+    assert sd.shape == (REF_STEP, sim_stride)
+    res = np.zeros(2, dtype=np.int32)
+    d = Diag()
+    rc = lib.scbo_cluster_literal(ctypes.c_int(cell), _p(ind), ctypes.c_int(len(ind)), ctypes.c_int(model.n),
+                                  _p(model.and_len), _p(model.parse), _p(model.and_nodes), _p(model.and_inv),
+                                  ctypes.c_int(sim_steps), _p(model.knockouts), _p(model.knockins), _p(bm),
+                                  ctypes.c_int64(bm.shape[1]), _p(model.node_positions), _p(sd),
+                                  ctypes.c_int64(sim_stride), _p(res), ctypes.byref(d))
+    if rc:
+        raise ValueError("scbo_cluster_literal: rc=%d" % rc)
+    return sd, res
+
+
 def hamming_argmin(attractors, bin_mat, node_positions, n_cells, want_dist=True):
     lib = liboracle()
     at = _i32(attractors)
@@ -266,9 +289,12 @@ class RefSimulator:
                                  V(model.node_positions.ctypes.data), V(score.ctypes.data))
         return float(score[0])
 
-    def cluster(self, model, individual, bin_mat, cell, sim_steps=100):
+    def cluster(self, model, individual, bin_mat, cell, sim_steps=100, sim_data=None):
+        """sim_data: optional int32[100][k] initial scratch contents (copied into the first k columns)."""
         ind = _i32(individual)
         vals = np.zeros((REF_STEP, REF_NODE), dtype=np.int32)
+        if sim_data is not None:
+            vals[:, :np.shape(sim_data)[1]] = sim_data
         res = np.full(2, 2, dtype=np.int32)
         V = ctypes.c_void_p
         self.lib.cluster(V(vals.ctypes.data), V(res.ctypes.data), V(cell), V(ind.ctypes.data),

@@ -185,6 +185,44 @@ int scbo_cluster(int sampleIndex, const int32_t *individual, int indLen, int nod
     return rc;
 }
 
+/* simulator.c:487-552 `cluster`, LITERALLY, on the caller's scratch: simData[SCBO_STEP][simStride] is read and
+ * written exactly like the reference does, including the knock-out branch that records the knocked node in
+ * column i instead of column nodePositions[i] (:518) -- so a knocked node's own column keeps whatever the scratch
+ * held (or what another node wrote there) and column i may clobber the node recorded there.  The window search
+ * (getAttract, :551) then runs over the nodePositions columns of that scratch.  simStride must exceed both
+ * max(nodePositions) and nodeNum - 1. */
+int scbo_cluster_literal(int sampleIndex, const int32_t *individual, int indLen, int nodeNum,
+                         const int32_t *andLenList, const int32_t *individualParse,
+                         const int32_t *andNodes, const int32_t *andNodeInvertList,
+                         int simSteps, const int32_t *knockouts, const int32_t *knockins,
+                         const int32_t *binMat, int64_t binMatStride, const int32_t *nodePositions,
+                         int32_t *simData, int64_t simStride, int32_t res[2], scbo_diag *diag)
+{
+    if (nodeNum <= 0 || simSteps > SCBO_STEP || simStride < nodeNum) return -1;
+    if (simStride <= max_pos(nodePositions, nodeNum)) return -1;
+    net_t m = { nodeNum, indLen, individual, andLenList, individualParse,
+                andNodes, andNodeInvertList, knockouts, knockins };
+    if (diag) memset(diag, 0, sizeof(*diag));
+    int32_t *old = (int32_t *)malloc(sizeof(int32_t) * nodeNum);
+    int32_t *nw = (int32_t *)malloc(sizeof(int32_t) * nodeNum);
+    int rc = 0;
+    for (int i = 0; i < nodeNum; ++i) {                                       /* :499-504 */
+        nw[i] = binMat[(int64_t)nodePositions[i] * binMatStride + sampleIndex];
+        simData[nodePositions[i]] = nw[i];
+    }
+    for (int s = 1; s < simSteps && !rc; ++s) {                               /* :506 */
+        memcpy(old, nw, sizeof(int32_t) * nodeNum);
+        if (sync_step(&m, old, nw, diag)) { rc = -1; break; }
+        for (int i = 0; i < nodeNum; ++i) {                                   /* writes in the loop order of :512 */
+            if (knockouts[i] == 1) simData[s * simStride + i] = nw[i];        /* :518, column i (sic) */
+            else simData[s * simStride + nodePositions[i]] = nw[i];
+        }
+    }
+    if (!rc) attract_window(simData, simStride, nodePositions, nodeNum, res); /* :551 */
+    free(old); free(nw);
+    return rc;
+}
+
 /* ---- Python attractor path ------------------------------------------------------------ */
 
 /* singleCell.py:924-959 __updateBool: like rule_value; the inner loop starts at input 0 and

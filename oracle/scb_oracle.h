@@ -77,6 +77,15 @@ int scbo_hamming_argmin(const int32_t *attractors, int nAttr, int nodeNum, int l
 
 /* simulator.c:555-755 (importanceScore), literal incl. its quirks.
  * returns -2 instead of dividing by zero when a cell's attractor is not found. */
+/* `cluster` restated literally on the caller's scratch, incl. the column slip of its knock-out branch
+ * (simulator.c:518); see scb_oracle.c */
+int scbo_cluster_literal(int sampleIndex, const int32_t *individual, int indLen, int nodeNum,
+                         const int32_t *andLenList, const int32_t *individualParse,
+                         const int32_t *andNodes, const int32_t *andNodeInvertList,
+                         int simSteps, const int32_t *knockouts, const int32_t *knockins,
+                         const int32_t *binMat, int64_t binMatStride, const int32_t *nodePositions,
+                         int32_t *simData, int64_t simStride, int32_t res[2], scbo_diag *diag);
+
 int scbo_importance_score(const int32_t *individual, int indLen, int nodeNum,
                           const int32_t *andLenList, const int32_t *individualParse,
                           const int32_t *andNodes, const int32_t *andNodeInvertList,

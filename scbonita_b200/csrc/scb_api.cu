@@ -9,6 +9,7 @@
  * (ruleMaker.py:1077-1221) onto simulator.c's scSyncBool / importanceScore / cluster.
  */
 #include "../../include/scbonita_b200.h"
+#include "scb_sim_tu.h"
 #include "scb_kernels.cuh"
 
 #include <algorithm>
@@ -21,11 +22,6 @@
 #include <new>
 #include <vector>
 
-#ifdef SCB_EMU
-#define SCB_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch(kernel, grid, block, smem, __VA_ARGS__)
-#else
-#define SCB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
-#endif
 
 namespace {
 
@@ -107,7 +103,8 @@ struct scb_ctx {
     DevBuf<uint32_t> dAttr;
     DevBuf<int32_t> dDist, dDecider, dDeciderDist;
     DevBuf<unsigned char> dFlush;
-    DevBuf<uint32_t> dTraj, dStates;
+    DevBuf<uint32_t> dTraj, dStates, dRecBits;
+    DevBuf<unsigned char> dRecOn;
     DevBuf<int32_t> dRes, dNStates;
     /* current population */
     int P = 0, indLen = 0, tpi = 0;
@@ -116,7 +113,7 @@ struct scb_ctx {
     int lastMode = -1;
     bool ran = false;
     ScbDiag hDiag = {};
-    std::mutex mu;
+    std::recursive_mutex mu;             /* one lock per public call; composite calls hold it across upload + run + fetch */
 };
 
 namespace {
@@ -139,14 +136,16 @@ int sim_geometry(scb_ctx *c, int K, int optWarps, SimGeom *g)
     S = std::min(S, SCB_SIM_MAX_WARPS); /* __launch_bounds__ of scb_k_sim */
     g->warps = S;
     int occ = 1;
-    if (K == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (scb_k_sim<4, false>), S * 32, g->smem));
-    else if (K == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (scb_k_sim<2, false>), S * 32, g->smem));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (scb_k_sim<1, false>), S * 32, g->smem));
+    if (K == 4) CK((cudaError_t)scb_sim_occupancy_k4_tm0(S * 32, g->smem, &occ));
+    else if (K == 2) CK((cudaError_t)scb_sim_occupancy_k2_tm0(S * 32, g->smem, &occ));
+    else CK((cudaError_t)scb_sim_occupancy_k1_tm0(S * 32, g->smem, &occ));
     if (occ < 1) return fail(SCB_ERR_UNSUPPORTED, "simulator kernel does not fit on an SM (N=%d, K=%d, warps=%d)", N, K, S);
     g->ctas = c->numSM * occ;
     if (c->optMaxCtas > 0) g->ctas = std::min(g->ctas, c->optMaxCtas);
     {   /* snapshot in tensor memory when the columns of all co-resident CTAs fit into the SM's 512 */
-        const int npw = (N + S - 1) / S;
+        /* a warp's piece of the table-sorted program is cut by rows moved, not by nodes: at most 4N/S + 4 rows,
+         * i.e. 2 ceil(N/S) + 2 one-input nodes (scb_load_program) */
+        const int npw = 2 * ((N + S - 1) / S) + 2;
         const int need = K * ((S + 3) / 4) * npw;
         int cols = 32;
         while (cols < need) cols <<= 1;
@@ -172,12 +171,12 @@ int pick_geometry(scb_ctx *c)
     if (scb_resolve_smem_bytes(N, 1) > c->smemLimit)
         return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the resolver's three state buffers", N);
 #ifndef SCB_EMU
-    CK(cudaFuncSetAttribute((scb_k_sim<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute((scb_k_sim<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute((scb_k_sim<4, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute((scb_k_sim<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute((scb_k_sim<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute((scb_k_sim<4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    CK((cudaError_t)scb_sim_set_smem_k1_tm0((int)c->smemLimit));
+    CK((cudaError_t)scb_sim_set_smem_k2_tm0((int)c->smemLimit));
+    CK((cudaError_t)scb_sim_set_smem_k4_tm0((int)c->smemLimit));
+    CK((cudaError_t)scb_sim_set_smem_k1_tm1((int)c->smemLimit));
+    CK((cudaError_t)scb_sim_set_smem_k2_tm1((int)c->smemLimit));
+    CK((cudaError_t)scb_sim_set_smem_k4_tm1((int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
@@ -280,6 +279,13 @@ int scb_ctx_create(scb_ctx **out, int device, int nodeNum, int lenSamples, const
     if (rowStride < lenSamples) return fail(SCB_ERR_INVALID, "rowStride %lld < lenSamples %d", (long long)rowStride, lenSamples);
     for (int i = 0; i < nodeNum; ++i)
         if (nodePositions[i] < 0) return fail(SCB_ERR_INVALID, "nodePositions[%d] is negative", i);
+    {   /* two nodes on one gene row alias one simData column in the reference (the later node overwrites the earlier
+         * one in the attractor search and in the error); the packed kernels keep nodes independent, so refuse */
+        std::vector<int32_t> sorted(nodePositions, nodePositions + nodeNum);
+        std::sort(sorted.begin(), sorted.end());
+        for (int i = 1; i < nodeNum; ++i)
+            if (sorted[i] == sorted[i - 1]) return fail(SCB_ERR_UNSUPPORTED, "nodePositions holds gene row %d twice", sorted[i]);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(SCB_ERR_CUDA, "no CUDA device available");
     if (device < 0 || device >= ndev) return fail(SCB_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
@@ -352,6 +358,12 @@ int scb_ctx_create_csr(scb_ctx **out, int device, int nodeNum, int lenSamples, c
     if (nodeNum > 65535) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > 65535", nodeNum);
     if (!indptr || !indices || !nodePositions) return fail(SCB_ERR_INVALID, "null CSR / nodePositions pointer");
     long long nnz = 0;
+    {
+        std::vector<int32_t> sorted(nodePositions, nodePositions + nodeNum);
+        std::sort(sorted.begin(), sorted.end());
+        for (int i = 1; i < nodeNum; ++i)
+            if (sorted[i] == sorted[i - 1]) return fail(SCB_ERR_UNSUPPORTED, "nodePositions holds gene row %d twice", sorted[i]);
+    }
     for (int i = 0; i < nodeNum; ++i) {
         const int r = nodePositions[i];
         if (r < 0 || r >= nRows) return fail(SCB_ERR_INVALID, "nodePositions[%d] = %d outside the %d CSR rows", i, r, nRows);
@@ -432,7 +444,7 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
-    c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release();
+    c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dRecBits.release(); c->dRecOn.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
     if (c->evSim1) cudaEventDestroy(c->evSim1);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -447,7 +459,7 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     switch (key) {
         case SCB_OPT_EARLY_EXIT: c->optEarly = value != 0; return SCB_OK;
         case SCB_OPT_SNAPSHOTS: c->optSnap = value != 0; break;
@@ -512,7 +524,7 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
     if (indLen < 0) return fail(SCB_ERR_INVALID, "indLen must be >= 0");
     if (!andLenList || !individualParse || !andNodes || !andNodeInvertList || !knockouts || !knockins || (!individuals && indLen > 0))
         return fail(SCB_ERR_INVALID, "null table pointer");
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     const int N = c->N;
     const size_t tbl = compact ? (size_t)N * SCB_MAX_IN : (size_t)N * SCB_MAX_TERMS * SCB_MAX_IN;
     const size_t ntab = tablesPerIndividual ? (size_t)P : 1;
@@ -581,7 +593,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (c->P <= 0) return fail(SCB_ERR_INVALID, "no population uploaded");
     if (!c->geomValid && (rc = pick_geometry(c))) return rc;
     const int N = c->N, P = c->P;
@@ -641,16 +653,17 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
         const dim3 block((unsigned)g.warps * 32);
         const size_t smemLaunch = fuse ? std::max(g.smem, c->smemRes) : g.smem;
         sa.smemBytes = (unsigned)smemLaunch;
+        int le;
         if (sa.tmemCols > 0) {
-            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, true>), dim3(grid), block, smemLaunch, st, sa);
-            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, true>), dim3(grid), block, smemLaunch, st, sa);
-            else SCB_LAUNCH((scb_k_sim<1, true>), dim3(grid), block, smemLaunch, st, sa);
+            if (g.K == 4) le = scb_sim_launch_k4_tm1(dim3(grid), block, smemLaunch, st, sa);
+            else if (g.K == 2) le = scb_sim_launch_k2_tm1(dim3(grid), block, smemLaunch, st, sa);
+            else le = scb_sim_launch_k1_tm1(dim3(grid), block, smemLaunch, st, sa);
         } else {
-            if (g.K == 4) SCB_LAUNCH((scb_k_sim<4, false>), dim3(grid), block, smemLaunch, st, sa);
-            else if (g.K == 2) SCB_LAUNCH((scb_k_sim<2, false>), dim3(grid), block, smemLaunch, st, sa);
-            else SCB_LAUNCH((scb_k_sim<1, false>), dim3(grid), block, smemLaunch, st, sa);
+            if (g.K == 4) le = scb_sim_launch_k4_tm0(dim3(grid), block, smemLaunch, st, sa);
+            else if (g.K == 2) le = scb_sim_launch_k2_tm0(dim3(grid), block, smemLaunch, st, sa);
+            else le = scb_sim_launch_k1_tm0(dim3(grid), block, smemLaunch, st, sa);
         }
-        CK(cudaGetLastError());
+        CK((cudaError_t)le);
     }
     CK(cudaEventRecord(c->evSim1, st));
 
@@ -673,7 +686,7 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!c->ran) return fail(SCB_ERR_INVALID, "scb_pop_run has not been called for this population");
     if (mode != c->lastMode && mode != SCB_MODE_SUM) return fail(SCB_ERR_INVALID, "mode %d was not computed by the last run (mode %d)", mode, c->lastMode);
     cudaStream_t st = c->stream;
@@ -717,7 +730,7 @@ int scb_debug_programs(scb_ctx *c, int p, int k, uint32_t *descs, int32_t *count
 {
     int rc = check_ctx(c);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!c->ran || p < 0 || p >= c->P || k < 0 || k >= SCB_NPROG) return fail(SCB_ERR_INVALID, "no such program in the last run");
     const size_t n = (size_t)c->N;
     CK(cudaStreamSynchronize(c->stream));
@@ -736,6 +749,9 @@ int scb_pop_result_dev(scb_ctx *c, int mode, void **devPtr, int64_t *bytes)
 {
     if (!c || !devPtr) return fail(SCB_ERR_INVALID, "null argument");
     if (mode < 0 || mode > 2) return fail(SCB_ERR_INVALID, "unknown mode %d", mode);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (!c->ran) return fail(SCB_ERR_INVALID, "scb_pop_run has not been called for this population");
+    if (mode != c->lastMode && mode != SCB_MODE_SUM) return fail(SCB_ERR_INVALID, "mode %d was not computed by the last run (mode %d)", mode, c->lastMode);
     *devPtr = mode == SCB_MODE_SUM ? (void *)c->dFitness.p : mode == SCB_MODE_NODEWISE ? (void *)c->dNodewise.p : (void *)c->dCellwise.p;
     if (bytes) *bytes = (int64_t)result_bytes(c, mode);
     return SCB_OK;
@@ -746,6 +762,10 @@ int scb_eval_population(scb_ctx *c, int P, const int32_t *individuals, int indLe
                         int tablesPerIndividual, const int32_t *knockouts, const int32_t *knockins, int mode,
                         void *out, scb_stats *stats)
 {
+    if (!c) return fail(SCB_ERR_INVALID, "null context");
+    /* upload + run + fetch under ONE lock: concurrent callers of a shared context (the reference drives local
+     * search from a ThreadPool, singleCell.py:490-492) must not interleave their populations */
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     int rc = scb_pop_upload(c, P, individuals, indLen, andLenList, individualParse, andNodes, andNodeInvertList,
                             tablesPerIndividual, knockouts, knockins);
     if (rc) return rc;
@@ -893,7 +913,7 @@ int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t
     if (!attractors || nAttr <= 0 || !decider || !deciderDistance) return fail(SCB_ERR_INVALID, "bad argument");
     const int N = c->N, C = c->C, NW = (N + 31) / 32;
     if (NW > SCB_HAM_MAXW) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > %d for the Hamming kernel", N, SCB_HAM_MAXW * 32);
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     std::vector<uint32_t> packed((size_t)nAttr * NW, 0u);
     for (int a = 0; a < nAttr; ++a)
         for (int i = 0; i < N; ++i) {

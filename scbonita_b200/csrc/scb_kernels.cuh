@@ -327,6 +327,7 @@ template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, c
     return r;
 }
 
+#ifndef SCB_SIM_ONLY   /* the simulator's own translation units (scb_sim_tu.cu) leave the other kernels out */
 /* ------------------------------------------------------------------------------------------
  * K0: rule compiler.  One CTA per individual, one thread per node; the program is written sorted
  * by arity (stable in node order, so the layout is deterministic).
@@ -334,46 +335,87 @@ template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, c
  * own 2 x 84 bytes would otherwise be fetched as scattered 4-byte reads).
  * dynamic shared memory: N * 16 (descriptors) + N (arity) + 64 + 2 * N * 21 * 4 (tables)
  * ---------------------------------------------------------------------------------------- */
+/* scratch of the table sort at the end of K0's shared memory: bins[SCB_SORT_BINS] counts -> starts,
+ * cost[SCB_SORT_BINS] rows before each bin, run[SCB_SORT_BINS] non-empty bins before each bin, rank[N] (uint16) */
+#define SCB_SORT_BINS 258          /* 256 tables, then the two constants */
+SCB_HD inline size_t scb_sort_smem_bytes(int N) { return (size_t)3 * SCB_SORT_BINS * 4 + (size_t)((N + 7) / 8) * 16 + 32; }
 SCB_HD inline size_t scb_compile_smem_bytes(int N)
 {
-    return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4 + 256;
+    return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4 + scb_sort_smem_bytes(N);
 }
 
-/* stable counting sort of a program by arity class (3, 2, 1, 0): out[classOffset + number of earlier nodes of the
- * same class] = sdv[i].  Warp ballots + per-warp counts in `wc` ([warps][4], shared) instead of an O(N) look-back
- * per thread.  All threads of the CTA call it (blockDim.x is a multiple of 32, at most 8 warps). */
-SCB_DEV void scb_scatter_by_arity(const uint4 *sdv, const unsigned char *sarv, int N, int n3, int n2, int n1,
-                                  uint4 *out, unsigned int *wc, int tid, int nthr)
+/* number of inputs a table in lop3 convention depends on */
+SCB_HD inline int scb_lut_arity(unsigned lut)
 {
+    return ((((lut >> 4) ^ lut) & 0x0Fu) != 0) + ((((lut >> 2) ^ lut) & 0x33u) != 0) + ((((lut >> 1) ^ lut) & 0x55u) != 0);
+}
+
+/* The program as K2 wants it: the non-constant nodes sorted by truth table (stable in node order, so the layout is
+ * deterministic), the constants behind them.  Nodes with the same table form a RUN that K2 executes in a loop
+ * specialised for that table; a warp is given a contiguous, cost-balanced piece of the sorted list, so the spare
+ * upper halves of the descriptor words carry what scb_load_program needs to cut the list without a scan of its own:
+ *   x >> 16  state rows (loads + store) moved by all earlier nodes of the list
+ *   y >> 16  arity
+ *   z >> 16  number of runs that start before this node's run
+ * Stable counting sort: within a warp __match_any_sync ranks equal keys, the warps add their counts to the bins one
+ * after the other.  All threads of the CTA call it (blockDim.x a multiple of 32). */
+SCB_DEV void scb_scatter_by_table(const uint4 *sdv, const unsigned char *sarv, int N, uint4 *out, unsigned int *scr,
+                                  int tid, int nthr)
+{
+    unsigned int *bins = scr, *cost = scr + SCB_SORT_BINS, *run = scr + 2 * SCB_SORT_BINS;
+    unsigned short *rank = reinterpret_cast<unsigned short *>(scr + 3 * SCB_SORT_BINS);
     const int lane = tid & 31, warp = tid >> 5, W = nthr >> 5;
-    int run3 = 0, run2 = 0, run1 = 0, run0 = 0;
+    for (int k = tid; k < SCB_SORT_BINS; k += nthr) bins[k] = 0u;
+    __syncthreads();
     for (int base = 0; base < N; base += nthr) {
         const int i = base + tid;
-        const int ar = i < N ? (int)sarv[i] : -1;
-        const unsigned m3 = __ballot_sync(0xffffffffu, ar == 3), m2 = __ballot_sync(0xffffffffu, ar == 2);
-        const unsigned m1 = __ballot_sync(0xffffffffu, ar == 1), m0 = __ballot_sync(0xffffffffu, ar == 0);
-        if (lane == 0) {
-            wc[warp * 4 + 0] = (unsigned)__popc(m3); wc[warp * 4 + 1] = (unsigned)__popc(m2);
-            wc[warp * 4 + 2] = (unsigned)__popc(m1); wc[warp * 4 + 3] = (unsigned)__popc(m0);
-        }
-        __syncthreads();
-        int p3 = 0, p2 = 0, p1 = 0, p0 = 0, t3 = 0, t2 = 0, t1 = 0, t0 = 0;
+        unsigned key = 0xFFFFu;                                   /* lanes beyond N: a key no node has */
+        if (i < N) key = sarv[i] == 0 ? 256u + ((sdv[i].w >> 24) ? 1u : 0u) : (sdv[i].w >> 24);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs((int)peers) - 1;
+        const unsigned before = (unsigned)__popc(peers & ((1u << lane) - 1u));
         for (int w = 0; w < W; ++w) {
-            const int c3 = (int)wc[w * 4 + 0], c2 = (int)wc[w * 4 + 1], c1 = (int)wc[w * 4 + 2], c0 = (int)wc[w * 4 + 3];
-            t3 += c3; t2 += c2; t1 += c1; t0 += c0;
-            if (w < warp) { p3 += c3; p2 += c2; p1 += c1; p0 += c0; }
+            if (w == warp) {
+                unsigned b = 0;
+                if (lane == leader && i < N) { b = bins[key]; bins[key] = b + (unsigned)__popc(peers); }
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (i < N) rank[i] = (unsigned short)(b + before);
+            }
+            __syncthreads();
         }
-        if (i < N) {
-            const unsigned lt = (1u << lane) - 1u;
-            const int pos = ar == 3 ? run3 + p3 + __popc(m3 & lt)
-                          : ar == 2 ? n3 + run2 + p2 + __popc(m2 & lt)
-                          : ar == 1 ? n3 + n2 + run1 + p1 + __popc(m1 & lt)
-                                    : n3 + n2 + n1 + run0 + p0 + __popc(m0 & lt);
-            out[pos] = sdv[i];
-        }
-        run3 += t3; run2 += t2; run1 += t1; run0 += t0;
-        __syncthreads();
     }
+    if (warp == 0) {
+        /* exclusive prefixes over the bins: node position, rows moved, runs */
+        unsigned cN = 0, cC = 0, cR = 0;
+        for (int k0 = 0; k0 < SCB_SORT_BINS; k0 += 32) {
+            const int k = k0 + lane;
+            const unsigned n = k < SCB_SORT_BINS ? bins[k] : 0u;
+            const unsigned rows = k < 256 ? n * (unsigned)(scb_lut_arity((unsigned)k) + 1) : 0u;
+            const unsigned isrun = (n != 0u && k < 256) ? 1u : 0u;
+            unsigned pn = n, pc = rows, pr = isrun;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned tn = __shfl_sync(0xffffffffu, pn, (lane - o) & 31), tc = __shfl_sync(0xffffffffu, pc, (lane - o) & 31);
+                const unsigned tr = __shfl_sync(0xffffffffu, pr, (lane - o) & 31);
+                if (lane >= o) { pn += tn; pc += tc; pr += tr; }
+            }
+            if (k < SCB_SORT_BINS) { bins[k] = cN + pn - n; cost[k] = cC + pc - rows; run[k] = cR + pr - isrun; }
+            cN += __shfl_sync(0xffffffffu, pn, 31); cC += __shfl_sync(0xffffffffu, pc, 31); cR += __shfl_sync(0xffffffffu, pr, 31);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += nthr) {
+        uint4 d = sdv[i];
+        const unsigned ar = sarv[i];
+        const unsigned key = ar == 0 ? 256u + ((d.w >> 24) ? 1u : 0u) : (d.w >> 24);
+        const unsigned r = rank[i];
+        if (ar) {
+            d.x |= (cost[key] + r * (ar + 1u)) << 16;
+            d.y |= ar << 16;
+            d.z |= run[key] << 16;
+        }
+        out[bins[key] + r] = d;
+    }
+    __syncthreads();
 }
 
 __global__ void scb_k_compile(ScbCompileArgs A)
@@ -414,8 +456,8 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     }
     __syncthreads();
     const int c3 = (int)cn[0], c2 = (int)cn[1], c1 = (int)cn[2], c0 = (int)cn[3];
-    unsigned int *wc = reinterpret_cast<unsigned int *>(smraw + scb_compile_smem_bytes(N) - 256);
-    scb_scatter_by_arity(sd, sar, N, c3, c2, c1, A.descs + (long long)p * A.Npad, wc, tid, nthr);
+    unsigned int *wc = reinterpret_cast<unsigned int *>(smraw + scb_compile_smem_bytes(N) - scb_sort_smem_bytes(N));
+    scb_scatter_by_table(sd, sar, N, A.descs + (long long)p * A.Npad, wc, tid, nthr);
     /* ---- reduced programs by constant propagation.  c(t) = nodes whose value in S_t is the same constant for every
      * cell: c(1) = the constant rules (knock-outs, knock-ins, constant-TRUE literals), c(t+1) = rules that are
      * constant once the inputs in c(t) are fixed.  Knowledge only grows, so c(D) stays valid for every t >= D.  A
@@ -478,7 +520,7 @@ __global__ void scb_k_compile(ScbCompileArgs A)
             const int s3 = chg[1], s2 = chg[2], s1 = chg[3], s0 = chg[4];
             const int slot = last ? SCB_NPROG - 1 : stage;
             uint4 *out2 = progs + (long long)slot * (N + 1);
-            scb_scatter_by_arity(sd2, sar2, N, s3, s2, s1, out2, wc, tid, nthr);
+            scb_scatter_by_table(sd2, sar2, N, out2, wc, tid, nthr);
             if (tid == 0) {
                 out2[N] = make_uint4((unsigned)s3, (unsigned)s2, (unsigned)s1, (unsigned)s0);   /* the counts travel with the program */
                 progFrom[slot] = (unsigned char)(D + 2);
@@ -554,136 +596,260 @@ __global__ void scb_k_pack_csr(ScbPackCsrArgs A)
     if (v == 1.0) atomicOr(&A.X[(long long)A.rowOfNnz[e] * A.Wpad + (c >> 5)], 1u << (c & 31));
 }
 
+#endif  /* SCB_SIM_ONLY */
+
 /* ------------------------------------------------------------------------------------------
  * shared pieces of K2 / K3
  * ---------------------------------------------------------------------------------------- */
-/* A program in shared memory is followed by SCB_DESC_PAD unused entries: a warp fetches the descriptor of its next
- * node (index + warps, at most 24 ahead) before it knows whether there is one, without a bounds test */
-#define SCB_DESC_PAD 24
+/* ---- the program in shared memory ------------------------------------------------------------------------
+ * K0 hands over the non-constant nodes sorted by truth table.  Warp w of S owns a contiguous piece of that list,
+ * cut so that every warp moves about the same number of state rows per step (a node costs arity + 1 rows), laid
+ * out in ITS part of the program area (PW entries of 16 bytes per warp) as RUNS of nodes with the same table:
+ *     header {SCB_NOIN | table, SCB_NOIN | n, SCB_NOIN, 0}   then n node entries   ...   header {SCB_NOIN | SCB_CLS_END, ..}
+ * Node entry: x, y, z = byte offsets of the input rows within a state buffer, SCB_NOIN (sign bit) for an input the
+ * table does not depend on; w = byte offset of the node's own row | table << 24.
+ * Plain steps run the list through scb_step_runs: one jump per RUN into a loop specialised for that table (no
+ * dispatch, no loads for unused inputs, no LOP3 for copies).  Flagged steps (compares, snapshots) walk the same list
+ * entry by entry (scb_step), skipping the headers.  Constant nodes are not in the list: their rows are written at
+ * steps 1 and 2 straight from the global program (scb_const_rows). */
+#define SCB_NOIN 0x80000000u
+#define SCB_DST_MASK 0xFFFFFu
+#define SCB_CLS_END 256u
+#define SCB_PROG_MAX_WARPS 24
+/* entries per warp: nodes + run headers of a piece whose rows do not exceed 4N/S + 4, plus the end header and two
+ * entries of slack for the descriptor prefetch of scb_step.  Worst cases: 2N/S + 2 one-input nodes (2 tables),
+ * (4N/S + 4) / 3 two-input nodes of distinct tables, N/S + 1 three-input nodes of distinct tables. */
+SCB_HD inline int scb_prog_stride(int N, int S) { const int q = (N + S - 1) / S; return (8 * q) / 3 + 10; }
+/* entries reserved for a program (any S <= SCB_PROG_MAX_WARPS: S * PW <= 8N/3 + 8S/3 + 10 S) */
+SCB_HD inline size_t scb_prog_entries(int N) { return (size_t)(8 * N) / 3 + (size_t)SCB_PROG_MAX_WARPS * 13; }
 /* shared-memory carve-up, identical formula on host and device */
 SCB_HD inline size_t scb_smem_bytes(int N, int K, int nbuf)
 {
-    return (size_t)nbuf * N * 128 * K + (size_t)N * 32 + 16 + SCB_DESC_PAD * 16 + (size_t)6 * 32 * K * 4 + 4096 + 256;   /* program + pad + staged program */
+    return (size_t)nbuf * N * 128 * K + scb_prog_entries(N) * 16 + (size_t)(N + 1) * 16 + (size_t)6 * 32 * K * 4 + 4096 + 256;   /* program + staged program */
 }
 
-/* load individual p's program into shared memory, scaling node indices to row byte offsets */
+/* individual p's program (global or staged layout: table-sorted, fields of scb_scatter_by_table) -> the per-warp
+ * run lists.  winfo[w] = entries of warp w's list without the end header; winfo[32 + w], winfo[64 + w]: scratch
+ * (first node / end of the warp's piece).  Contains barriers: all threads of the CTA call it. */
 template <int K>
-SCB_DEV void scb_load_program(uint4 *desc, const uint4 *g, int4 cnt, int N, int tid, int nthr)
+SCB_DEV void scb_load_program(uint4 *wl, int *winfo, const uint4 *g, int4 cnt, int N, int S, int tid, int nthr)
 {
     const uint32_t ROWB = 128u * K;
-    for (int j = tid; j < N; j += nthr) {
-        uint4 d = g[j];
-        unsigned lut = d.w >> 24;
-        if (j >= cnt.x && j < cnt.x + cnt.y) lut = scb_compress2(lut);
-        else if (j >= cnt.x + cnt.y && j < cnt.x + cnt.y + cnt.z) lut = (lut == 0x0Fu) ? 1u : 0u;   /* NOT : copy */
-        else if (j >= cnt.x + cnt.y + cnt.z) lut = lut ? 1u : 0u;
-        d.x *= ROWB; d.y *= ROWB; d.z *= ROWB;
-        d.w = ((d.w & 0xFFFFFFu) * ROWB) | (lut << 24);
-        desc[j] = d;
+    const int e1 = cnt.x + cnt.y + cnt.z;
+    const unsigned total = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
+    const int PW = scb_prog_stride(N, S);
+    int *first = winfo + 32, *last = winfo + 64;
+    if (tid <= S) first[tid] = e1;
+    __syncthreads();
+#define SCB_WARP_OF(d) ((int)((((d).x >> 16) * (unsigned)S) / total))
+    for (int j = tid; j < e1; j += nthr) {
+        const int w = SCB_WARP_OF(g[j]);
+        if (j == 0 || SCB_WARP_OF(g[j - 1]) != w) first[w] = j;
+    }
+    __syncthreads();
+    if (tid < S) {
+        int e = e1;                                       /* the piece ends where the next non-empty one starts */
+        for (int w = tid + 1; w < S; ++w) if (first[w] < e1) { e = first[w]; break; }
+        last[tid] = e;
+        if (first[tid] >= e1) {                           /* no nodes: an empty list */
+            wl[tid * PW] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+            winfo[tid] = 0;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < e1; j += nthr) {
+        const uint4 d = g[j];
+        const int w = SCB_WARP_OF(d);
+        const int s0 = first[w], end = last[w];
+        const unsigned lut = d.w >> 24, ar = (d.y >> 16) & 3u;
+        const bool runStart = j == s0 || (g[j - 1].w >> 24) != lut;
+        const int idx = (j - s0) + (int)((d.z >> 16) - (g[s0].z >> 16)) + 1;
+        uint4 o;
+        o.x = (d.x & 0xFFFFu) * ROWB;
+        o.y = ar >= 2u ? (d.y & 0xFFFFu) * ROWB : SCB_NOIN;
+        o.z = ar >= 3u ? (d.z & 0xFFFFu) * ROWB : SCB_NOIN;
+        o.w = ((d.w & 0xFFFFu) * ROWB) | (lut << 24);
+        uint4 *mine = wl + w * PW;
+#ifdef SCB_EMU
+        if (idx + 3 > PW) abort();                        /* the bound of scb_prog_stride is rigorous; checked under the emulator */
+#endif
+        mine[idx] = o;
+        if (runStart) {
+            int len = 1;
+            while (j + len < end && (g[j + len].w >> 24) == lut) ++len;
+            mine[idx - 1] = make_uint4(SCB_NOIN | lut, SCB_NOIN | (unsigned)len, SCB_NOIN, 0u);
+        }
+        if (j == end - 1) {
+            mine[idx + 1] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+            winfo[w] = idx + 1;
+        }
+    }
+#undef SCB_WARP_OF
+    __syncthreads();
+}
+
+/* the constant rows of a program (entries e1 .. e1 + n0 of the GLOBAL program) into `dst` (lane-adjusted), and
+ * into the global snapshot when zg != null */
+template <int K>
+SCB_DEV void scb_const_rows(scb_saddr dst, const uint4 *gconst, int n0, int warp, int S, unsigned char *zg)
+{
+    const uint32_t ROWB = 128u * K;
+    for (int j = warp; j < n0; j += S) {
+        const uint4 dc = gconst[j];
+        ScbVec<K> r;
+        const uint32_t val = (dc.w >> 24) ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.v[k] = val;
+        const uint32_t off = (dc.w & 0xFFFFFFu) * ROWB;
+        scb_sts<K>(dst + off, r);
+        if (zg) scb_stcg<K>(zg + off, r);
     }
 }
 
-/* one synchronous update S_t -> S_{t+1} for the warp's share of the nodes.
- *   src, dst : lane-adjusted pointers into the two state buffers
- *   zg       : lane-adjusted pointer into the global snapshot (ZCMP / ZSNAP)
- *   tsm      : lane-adjusted pointer into the shared-memory target state (TCMP)
- * d2 / dz accumulate, per word, the cells whose new state differs from S_{t-1} ... */
+/* load a state row unless the descriptor marks the input unused (sign bit of `off`) */
+template <int K> SCB_DEV void scb_lds_if(ScbVec<K> &r, scb_saddr base, uint32_t off)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t a = base + off;
+    if (K == 4) asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %5, 0;\n@p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
+                             : "+r"(r.v[0]), "+r"(r.v[1 % K]), "+r"(r.v[2 % K]), "+r"(r.v[3 % K]) : "r"(a), "r"(off));
+    else if (K == 2) asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %3, 0;\n@p ld.shared.v2.u32 {%0,%1}, [%2];\n}"
+                                  : "+r"(r.v[0]), "+r"(r.v[1 % K]) : "r"(a), "r"(off));
+    else asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %2, 0;\n@p ld.shared.u32 %0, [%1];\n}" : "+r"(r.v[0]) : "r"(a), "r"(off));
+#else
+    if ((int32_t)off >= 0) r = scb_ld<K>(base + off);
+#endif
+}
+
+/* one synchronous update S_t -> S_{t+1} for the warp's share of the nodes (its list `wl` of `nw` entries, run
+ * headers included), entry by entry with a table dispatch per node: the form the flagged steps use.
+ *   src, dst : lane-adjusted addresses of the two state buffers
+ *   zg       : lane-adjusted pointer into the global snapshot (ZCMP / ZSNAP without tensor memory)
+ *   tsm      : lane-adjusted address of the shared-memory target state (TCMP)
+ * d2 / dz accumulate, per word, the cells whose new state differs from S_{t-1} ...
+ *
+ * Software pipeline, two register sets: while node k is computed (table dispatch, LOP3, store), the rows of node
+ * k + 1 are already in flight and the descriptor of node k + 3 is being fetched, so that a warp never waits for a
+ * full shared-memory round trip per node (the first version issued descriptor -> rows -> table serially: 9 warp
+ * cycles per instruction with 5 warps per scheduler). */
 template <int K, bool PLAIN, bool TM = false, unsigned FIXED = 0u>
-SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr desc, int4 cnt,
-                      int warp, int S, unsigned flagsRt, unsigned char *zg, scb_saddr tsm,
+SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr wl, int nw, unsigned flagsRt, unsigned char *zg, scb_saddr tsm,
                       ScbVec<K> &d2, ScbVec<K> &dz, bool active = true, uint32_t tm = SCB_TMEM_OFF)
 {
-    /* TM: the snapshot lives in tensor memory; tm is the address of this warp's first slot and the warp's n-th
-     * node (in the order of this loop) uses columns tm + K*n.  Otherwise it lives in global scratch (zg). */
+    /* TM: the snapshot lives in tensor memory; tm is the address of this warp's first slot and the warp's k-th
+     * list entry uses columns tm + K*k.  Otherwise it lives in global scratch (zg). */
     /* `active` is false for lanes whose words lie entirely beyond the last cell (the padding of the last
      * tile): they skip the step, which cuts the shared-memory wavefronts of a mostly empty tile.
-     * PLAIN steps (no compare, no snapshot, no constant rows: the majority) are a separate
-     * instantiation so that their loop carries no flag tests */
+     * PLAIN steps (no compare, no snapshot: the majority) are a separate instantiation so that their loop
+     * carries no flag tests */
     /* FIXED != 0: the flags are a compile-time constant (the resolver's compare-with-target steps) */
     const unsigned flags = PLAIN ? 0u : (FIXED ? FIXED : flagsRt);
-    /* SCB_PRE issues the loads a compare needs before the node's own work (the old S_{t-2} row from
-     * shared memory) and, one node ahead, the snapshot row from global memory, so that the L2 latency
-     * of the snapshot is covered by a whole node's processing. */
-#define SCB_PRE(dsto, dstoNext)                                                                   \
-        ScbVec<K> o2, zc = zn;                                                                    \
-        if (flags & SCB_SF_CMP2) o2 = scb_lds<K>(dst + (dsto));                                   \
-        if (flags & SCB_SF_TCMP) zc = scb_lds<K>(tsm + (dsto));                                   \
-        if (flags & SCB_SF_ZCMP) {                                                                \
-            if (TM) scb_tmem_ld<K>(tmc, zc);                                                      \
-            else zn = scb_ldcg<K>(zg + (dstoNext));                                               \
-        }
-#define SCB_POST(r, dsto)                                                                         \
-    do {                                                                                          \
-        if (flags & SCB_SF_CMP2) {                                                                \
-            _Pragma("unroll") for (int k = 0; k < K; ++k) d2.v[k] |= (r).v[k] ^ o2.v[k]; }        \
-        if (flags & (SCB_SF_ZCMP | SCB_SF_TCMP)) {                                                \
-            if (TM && (flags & SCB_SF_ZCMP)) scb_tmem_wait_ld<K>(zc);                             \
-            _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= (r).v[k] ^ zc.v[k]; }        \
-        scb_sts<K>(dst + (dsto), (r));                                                            \
-        if (flags & SCB_SF_ZSNAP) {                                                               \
-            if (TM) scb_tmem_st<K>(tmc, (r));                                                     \
-            else scb_stcg<K>(zg + (dsto), (r));                                                   \
-        }                                                                                         \
-        if (TM) tmc += (uint32_t)K;                                                               \
-    } while (0)
-
-    int j = warp;
-    const int e3 = cnt.x, e2 = cnt.x + cnt.y, e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
     /* lanes without valid cells sit out the plain steps; compare / snapshot steps keep the warp converged
      * because the tensor-memory instructions are warp-collective (their garbage is masked by the valid mask) */
-    if (j >= e0 || ((PLAIN || !TM) && !active)) return;
+    if (nw <= 0 || ((PLAIN || !TM) && !active)) return;
     uint32_t tmc = tm;
-    /* the next node's descriptor is fetched while the current node is processed */
-    const uint32_t dstep = 16u * (uint32_t)S;
-    scb_saddr dp = desc + 16u * (uint32_t)j;
-    uint4 d = scb_lds_desc(dp);
-    ScbVec<K> zn;
+    ScbVec<K> A0, B0, C0, A1, B1, C1, Z0, Z1;
 #pragma unroll
-    for (int k = 0; k < K; ++k) zn.v[k] = 0u;
-    if ((flags & SCB_SF_ZCMP) && !TM && j < e1) zn = scb_ldcg<K>(zg + (d.w & 0xFFFFFFu));
-    for (; j < e3; j += S) {
-        dp += dstep;                 /* may run into the pad behind the program: that descriptor is never used */
-        const uint4 dn = scb_lds_desc(dp);
-        SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
-        const ScbVec<K> a = scb_lds<K>(src + d.x), b = scb_lds<K>(src + d.y), c = scb_lds<K>(src + d.z);
-        ScbVec<K> r = scb_apply3<K>(d.w >> 24, a, b, c);
-        SCB_POST(r, d.w & 0xFFFFFFu);
-        d = dn;
+    for (int k = 0; k < K; ++k) { A0.v[k] = B0.v[k] = C0.v[k] = A1.v[k] = B1.v[k] = C1.v[k] = Z0.v[k] = Z1.v[k] = 0u; }
+    uint32_t W0, W1 = 0u, X0, X1 = SCB_NOIN;
+    const bool zglob = !TM && (flags & SCB_SF_ZCMP);
+    /* rows (and the global snapshot row) of the node described by D into register set s */
+#define SCB_ISSUE(s, D)                                                                           \
+    do {                                                                                          \
+        scb_lds_if<K>(A##s, src, (D).x); scb_lds_if<K>(B##s, src, (D).y); scb_lds_if<K>(C##s, src, (D).z); \
+        W##s = (D).w; X##s = (D).x;                                                               \
+        if (zglob && (int32_t)(D).x >= 0) Z##s = scb_ldcg<K>(zg + ((D).w & SCB_DST_MASK));        \
+    } while (0)
+    /* run headers (sign bit in x) are skipped: they take no tensor-memory slot either */
+#define SCB_COMPUTE(s)                                                                            \
+    if ((int32_t)X##s >= 0) {                                                                     \
+        const uint32_t dsto = W##s & SCB_DST_MASK;                                                \
+        ScbVec<K> o2, zc = Z##s;                                                                  \
+        if (flags & SCB_SF_CMP2) o2 = scb_lds<K>(dst + dsto);                                     \
+        if (flags & SCB_SF_TCMP) zc = scb_lds<K>(tsm + dsto);                                     \
+        if (TM && (flags & SCB_SF_ZCMP)) scb_tmem_ld<K>(tmc, zc);                                 \
+        const ScbVec<K> r = scb_apply3<K>(W##s >> 24, A##s, B##s, C##s);                          \
+        if (flags & SCB_SF_CMP2) {                                                                \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) d2.v[k] |= r.v[k] ^ o2.v[k]; }          \
+        if (flags & (SCB_SF_ZCMP | SCB_SF_TCMP)) {                                                \
+            if (TM && (flags & SCB_SF_ZCMP)) scb_tmem_wait_ld<K>(zc);                             \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) dz.v[k] |= r.v[k] ^ zc.v[k]; }          \
+        scb_sts<K>(dst + dsto, r);                                                                \
+        if (flags & SCB_SF_ZSNAP) {                                                               \
+            if (TM) scb_tmem_st<K>(tmc, r);                                                       \
+            else scb_stcg<K>(zg + dsto, r);                                                       \
+        }                                                                                         \
+        if (TM) tmc += (uint32_t)K;                                                               \
     }
-    for (; j < e2; j += S) {
-        dp += dstep;                 /* may run into the pad behind the program: that descriptor is never used */
-        const uint4 dn = scb_lds_desc(dp);
-        SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
-        const ScbVec<K> a = scb_lds<K>(src + d.x), b = scb_lds<K>(src + d.y);
-        ScbVec<K> r = scb_apply2<K>(d.w >> 24, a, b);
-        SCB_POST(r, d.w & 0xFFFFFFu);
-        d = dn;
-    }
-    for (; j < e1; j += S) {
-        dp += dstep;                 /* may run into the pad behind the program: that descriptor is never used */
-        const uint4 dn = scb_lds_desc(dp);
-        SCB_PRE(d.w & 0xFFFFFFu, dn.w & 0xFFFFFFu)
-        ScbVec<K> r = scb_lds<K>(src + d.x);
-        const uint32_t inv = (d.w >> 24) ? 0xffffffffu : 0u;
-#pragma unroll
-        for (int k = 0; k < K; ++k) r.v[k] ^= inv;
-        SCB_POST(r, d.w & 0xFFFFFFu);
-        d = dn;
-    }
-    if (flags & SCB_SF_CONST) {
-        for (; j < e0; j += S) {
-            const uint4 dc = scb_lds_desc(desc + 16u * (uint32_t)j);
-            ScbVec<K> r;
-            const uint32_t val = (dc.w >> 24) ? 0xffffffffu : 0u;
-#pragma unroll
-            for (int k = 0; k < K; ++k) r.v[k] = val;
-            scb_sts<K>(dst + (dc.w & 0xFFFFFFu), r);
-            if ((flags & SCB_SF_ZSNAP) && !TM) scb_stcg<K>(zg + (dc.w & 0xFFFFFFu), r);
-        }
+
+    uint4 D0 = scb_lds_desc(wl), D1 = scb_lds_desc(wl + 16);
+    SCB_ISSUE(0, D0);
+    D0 = scb_lds_desc(wl + 32);
+    scb_saddr dp = wl;
+    for (int k = 0;;) {
+        SCB_ISSUE(1, D1);
+        D1 = scb_lds_desc(dp + 48);
+        SCB_COMPUTE(0);
+        if (++k >= nw) break;
+        SCB_ISSUE(0, D0);
+        D0 = scb_lds_desc(dp + 64);
+        SCB_COMPUTE(1);
+        if (++k >= nw) break;
+        dp += 32;
     }
     if (TM && (flags & SCB_SF_ZSNAP)) scb_tmem_wait_st();
-#undef SCB_POST
-#undef SCB_PRE
+#undef SCB_COMPUTE
+#undef SCB_ISSUE
+}
+
+/* One step for the warp's list through the RUN interpreter (generated PTX, scb_lut_ptx.inc / gen_lut_ptx.py): one
+ * table dispatch per run into a loop specialised for that table.  FLAGS = 0 (plain: most steps), SCB_SF_CMP2,
+ * SCB_SF_ZCMP (snapshot in tensor memory) or both; the compare accumulators d2 / dz stay in registers.  Lanes without
+ * valid cells sit out the plain steps; compare steps keep the warp converged (tcgen05.ld is warp-collective, the
+ * garbage of those lanes is masked by the valid mask). */
+template <int K, unsigned FLAGS>
+SCB_DEV void scb_step_runs(scb_saddr src, scb_saddr dst, scb_saddr wl, bool active, ScbVec<K> &d2, ScbVec<K> &dz, uint32_t tm)
+{
+    if (!(FLAGS & SCB_SF_ZCMP) && !active) return;
+#if defined(__CUDA_ARCH__)
+#define SCB_RUNS_ASM(NAME)                                                                                             \
+    do {                                                                                                               \
+        if (K == 4) asm volatile(NAME##_K4 : "+r"(d2.v[0]), "+r"(d2.v[1 % K]), "+r"(d2.v[2 % K]), "+r"(d2.v[3 % K]),   \
+                                 "+r"(dz.v[0]), "+r"(dz.v[1 % K]), "+r"(dz.v[2 % K]), "+r"(dz.v[3 % K])                \
+                                 : "r"(wl), "r"(src), "r"(dst), "r"(tm) : "memory");                                   \
+        else if (K == 2) asm volatile(NAME##_K2 : "+r"(d2.v[0]), "+r"(d2.v[1 % K]), "+r"(dz.v[0]), "+r"(dz.v[1 % K])   \
+                                      : "r"(wl), "r"(src), "r"(dst), "r"(tm) : "memory");                              \
+        else asm volatile(NAME##_K1 : "+r"(d2.v[0]), "+r"(dz.v[0]) : "r"(wl), "r"(src), "r"(dst), "r"(tm) : "memory"); \
+    } while (0)
+    if (FLAGS == 0u) SCB_RUNS_ASM(SCB_RUNS_PTX);
+    else if (FLAGS == SCB_SF_CMP2) SCB_RUNS_ASM(SCB_RUNS_CMP2_PTX);
+    else if (FLAGS == SCB_SF_ZCMP) SCB_RUNS_ASM(SCB_RUNS_ZCMP_PTX);
+    else SCB_RUNS_ASM(SCB_RUNS_CMP2_ZCMP_PTX);
+#undef SCB_RUNS_ASM
+#else
+    const uint4 *e = reinterpret_cast<const uint4 *>(wl);
+    uint32_t tmc = tm;
+    for (;;) {
+        const uint4 h = *e++;
+        const unsigned cls = h.x & 0x1ffu, cnt = h.y & 0xffffu;
+        if (cls == SCB_CLS_END) break;
+        for (unsigned i = 0; i < cnt; ++i) {
+            const uint4 d = *e++;
+            if ((d.w >> 24) != cls) abort();                       /* a node in a run of another table */
+            const ScbVec<K> a = scb_ld<K>(src + d.x);
+            const ScbVec<K> b = (int32_t)d.y >= 0 ? scb_ld<K>(src + d.y) : a, c = (int32_t)d.z >= 0 ? scb_ld<K>(src + d.z) : a;
+            ScbVec<K> r, o, t;
+            if (FLAGS & SCB_SF_CMP2) o = scb_ld<K>(dst + (d.w & SCB_DST_MASK));
+            if (FLAGS & SCB_SF_ZCMP) { scb_tmem_ld<K>(tmc, t); tmc += (uint32_t)K; }
+            for (int k = 0; k < K; ++k) {
+                r.v[k] = scb_lut_apply(cls, a.v[k], b.v[k], c.v[k]);
+                if (FLAGS & SCB_SF_CMP2) d2.v[k] |= r.v[k] ^ o.v[k];
+                if (FLAGS & SCB_SF_ZCMP) dz.v[k] |= r.v[k] ^ t.v[k];
+            }
+            scb_st<K>(dst + (d.w & SCB_DST_MASK), r);
+        }
+    }
+#endif
 }
 
 /* valid-cell mask of word w (cells w*32 .. w*32+31 below C) */
@@ -720,12 +886,13 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
     const int WT = 32 * K;                              /* words per tile */
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + 2u * BUFB);
-    uint4 *desc2 = desc + N + SCB_DESC_PAD;             /* staging buffer of the next reduced program: N nodes + its counts */
+    uint4 *desc2 = desc + scb_prog_entries(N);          /* staging buffer of the next reduced program: N nodes + its counts */
     uint32_t *dm2 = reinterpret_cast<uint32_t *>(desc2 + N + 1);
     uint32_t *dmz = dm2 + WT;
     uint32_t *Rm = dmz + WT;
     uint32_t *vm = Rm + WT;
     int *sh = reinterpret_cast<int *>(vm + WT);          /* [0] item, [1],[2] flag words, [4..4+K) chunk flags */
+    int *winfo = sh + 32;                                /* [96] per-warp list lengths + scratch of scb_load_program */
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31;
     int warp = tid >> 5, S = nthr >> 5;
@@ -779,7 +946,11 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         const long long c0 = scb_clock();
         const int w0 = A.wordBase + tile * WT;
         int4 cnt = A.counts[p];
-        scb_load_program<K>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+        const uint4 *gfull = A.descs + (long long)p * A.Npad;
+        const int e1full = cnt.x + cnt.y + cnt.z, n0full = cnt.w;      /* the constants of the FULL program are written at steps 1, 2 */
+        scb_load_program<K>(desc, winfo, gfull, cnt, N, S, tid, nthr);
+        int nw = winfo[warp];
+        scb_saddr wl = sdesc + 16u * (uint32_t)(warp * scb_prog_stride(N, S));
         /* reduced programs (K0): program k may compute steps >= from[k]; the next one is staged in desc2 by
          * asynchronous copies while the current one runs.  All switches happen before the first snapshot, whose
          * tensor-memory slots follow the program's node order. */
@@ -879,7 +1050,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         int nextEvent;
         SCB_NEXT_EVENT(0);
         while (t < target) {
-            const int tn = t + 1;                       /* this iteration computes S_tn */
+            int tn = t + 1;                             /* this iteration computes S_tn */
             if (tn == switchAt) {
                 /* the staged program replaces the current one in place (every warp is past the barrier of the
                  * previous step), so the step code keeps one program address */
@@ -890,12 +1061,31 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 const uint4 c4 = desc2[N];
                 cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
                 rowsPerStep = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
-                scb_load_program<K>(desc, desc2, cnt, N, tid, nthr);
-                __syncthreads();
+                scb_load_program<K>(desc, winfo, desc2, cnt, N, S, tid, nthr);
+                nw = winfo[warp];
                 SCB_NEXT_PROGRAM(tn);
             }
-            unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
-            if (tn >= nextEvent) {
+            ScbVec<K> d2, dz;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
+            if (tn <= 2) scb_const_rows<K>(sa + dstOff + laneOff, gfull + e1full, n0full, warp, S, nullptr);
+            if (tn < nextEvent) {
+                /* a run of plain steps: nothing but update, barrier, swap until the next event, program switch or
+                 * the target (most of a tile's steps) */
+                int until = nextEvent < switchAt ? nextEvent : switchAt;
+                if (until > target + 1) until = target + 1;
+                if (tn <= 2) until = tn + 1;            /* the constant rows go into both buffers */
+#pragma unroll 1
+                for (; tn < until; ++tn) {
+                    scb_step_runs<K, 0u>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
+                    __syncthreads();
+                    const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
+                }
+                t = until - 1;
+                continue;
+            }
+            unsigned f = 0u;
+            {
                 bool chkNow = false, snapNow = false;
                 while (nextChk < tn) nextChk += A.chkEvery;
                 if (tn == nextChk) { chkNow = true; nextChk += A.chkEvery; }
@@ -915,13 +1105,12 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                     f |= SCB_SF_ZCMP; --searchLeft;   /* all cells proven: look for a tile-wide period */
                 }
             }
-            ScbVec<K> d2, dz;
-            if (f == 0u) scb_step<K, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, zg, sa, d2, dz, laneActive);
-            else {
-#pragma unroll
-                for (int k = 0; k < K; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
-                scb_step<K, false, TM>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, zg, sa, d2, dz, laneActive, tm);
-            }
+            /* compare steps run through the interpreter too (snapshot in tensor memory); snapshot steps, the global
+             * snapshot fallback and the odd step without a flag take the entry-by-entry form */
+            if (f == SCB_SF_CMP2) scb_step_runs<K, SCB_SF_CMP2>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
+            else if (TM && f == SCB_SF_ZCMP) scb_step_runs<K, SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
+            else if (TM && f == (SCB_SF_CMP2 | SCB_SF_ZCMP)) scb_step_runs<K, SCB_SF_CMP2 | SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
+            else scb_step<K, false, TM>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, nw, f, zg, sa, d2, dz, laneActive, tm);
             if (f & SCB_SF_CMP2) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
@@ -1093,8 +1282,8 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
             /* two nodes in flight per warp: the S_0 rows come from L2 */
             const int j1 = j0 + S;
             const bool two = j1 < N;
-            const uint32_t dsto0 = desc[j0].w & 0xFFFFFFu, dsto1 = desc[two ? j1 : j0].w & 0xFFFFFFu;
-            const int node0 = (int)(dsto0 / ROWB), node1 = (int)(dsto1 / ROWB);
+            const int node0 = j0, node1 = two ? j1 : j0;
+            const uint32_t dsto0 = (uint32_t)node0 * ROWB, dsto1 = (uint32_t)node1 * ROWB;
             const ScbVec<K> x0 = scb_ldg<K>(A.X + (long long)node0 * A.Wpad + w0 + lane * K);
             const ScbVec<K> x1 = scb_ldg<K>(A.X + (long long)node1 * A.Wpad + w0 + lane * K);
             const ScbVec<K> s0 = scb_ld<K>(fin + dsto0), s1 = scb_ld<K>(fin + dsto1);
@@ -1202,7 +1391,7 @@ struct ScbResolveArgs {
  * On return: buffer A rows hold S_98, buffer B rows hold e = (S_98 xor S_0) & valid for every node,
  * Fm[32*KR] = found & valid per word (how != 2), vm[32*KR] = valid masks.  All threads call it. */
 template <int KR, bool TTM = false>
-SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *desc, int4 cnt, int p,
+SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *desc, int *winfo, int4 cnt, int p,
                                uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
                                const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr, int onlyLane = -1,
                                uint32_t tm = SCB_TMEM_OFF)
@@ -1231,12 +1420,18 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
     unsigned char *bufA = sm, *bufB = sm + BUFB, *bufT = sm + 2u * BUFB;
     const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
     ScbVec<KR> d2, dz;
+    const uint4 *gfull = A.descs + (long long)p * A.Npad;
+    const int e1full = cntFull.x + cntFull.y + cntFull.z, n0full = cntFull.w;
+    const uint4 *wlp = desc + warp * scb_prog_stride(N, S);       /* this warp's list (generic pointer) */
+    const scb_saddr wl = sdesc + 16u * (uint32_t)(warp * scb_prog_stride(N, S));
+    int nw = winfo[warp];                                         /* list entries, run headers included */
 
     for (int pass = (how == 0 ? 0 : 1); pass < 2; ++pass) {
         const bool cmp = pass == 1 && how != 2;
         if (replaced) {                       /* the previous pass ended on a reduced program: start again with the full one */
             cnt = cntFull;
-            scb_load_program<KR>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+            scb_load_program<KR>(desc, winfo, gfull, cnt, N, S, tid, nthr);
+            nw = winfo[warp];
             replaced = false;
         }
         int nextProg = 0, switchAt = 1000;
@@ -1254,11 +1449,12 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
         if (tid < GW) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; Fm[tid] = 0u; }
         if (TTM && pass == 1 && how == 1) {
             /* T from the simulator's hand-over buffer into this warp's tensor-memory slots */
-            const int e1 = cnt.x + cnt.y + cnt.z;
             uint32_t tmc = tm;
-            for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR) {
-                const int node = (int)((desc[j].w & 0xFFFFFFu) / ROWB);
+            for (int k = 0; k < nw; ++k) {
+                if ((int32_t)wlp[k].x < 0) continue;               /* run header */
+                const int node = (int)((wlp[k].w & SCB_DST_MASK) / ROWB);
                 scb_tmem_st<KR>(tmc, scb_ld<KR>(reinterpret_cast<const unsigned char *>(Tglob + (long long)node * GW + lane * KR)));
+                tmc += (uint32_t)KR;
             }
             scb_tmem_wait_st();
         }
@@ -1269,19 +1465,21 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
 #pragma unroll
             for (int k = 0; k < KR; ++k) d.v[k] = 0u;
             if (TTM) {
-                const int e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
                 uint32_t tmc = tm;
-                for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR) {
+                for (int i = 0; i < nw; ++i) {
+                    if ((int32_t)wlp[i].x < 0) continue;           /* run header */
                     ScbVec<KR> y;
                     scb_tmem_ld<KR>(tmc, y);
-                    const ScbVec<KR> x = scb_ld<KR>(bufA + (desc[j].w & 0xFFFFFFu) + laneOff);
+                    tmc += (uint32_t)KR;
+                    const ScbVec<KR> x = scb_ld<KR>(bufA + (wlp[i].w & SCB_DST_MASK) + laneOff);
                     scb_tmem_wait_ld<KR>(y);
 #pragma unroll
                     for (int k = 0; k < KR; ++k) d.v[k] |= x.v[k] ^ y.v[k];
                 }
-                for (int j = e1 + warp; j < e0; j += S) {           /* constant rows: T holds the constant */
-                    const ScbVec<KR> x = scb_ld<KR>(bufA + (desc[j].w & 0xFFFFFFu) + laneOff);
-                    const uint32_t cv = (desc[j].w >> 24) ? 0xffffffffu : 0u;
+                for (int j = warp; j < n0full; j += S) {            /* constant rows (the full program is loaded): T holds the constant */
+                    const uint4 dc = gfull[e1full + j];
+                    const ScbVec<KR> x = scb_ld<KR>(bufA + (dc.w & 0xFFFFFFu) * ROWB + laneOff);
+                    const uint32_t cv = (dc.w >> 24) ? 0xffffffffu : 0u;
 #pragma unroll
                     for (int k = 0; k < KR; ++k) d.v[k] |= x.v[k] ^ cv;
                 }
@@ -1305,16 +1503,17 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
                 const uint4 *src = progBase + (long long)nextProg * (N + 1);
                 const uint4 c4 = src[N];
                 cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
-                scb_load_program<KR>(desc, src, cnt, N, tid, nthr);
+                scb_load_program<KR>(desc, winfo, src, cnt, N, S, tid, nthr);
+                nw = winfo[warp];
                 replaced = true;
-                __syncthreads();
                 if (TTM && cmp) {
                     /* T into this warp's tensor-memory slots in the new program's node order */
-                    const int e1 = cnt.x + cnt.y + cnt.z;
                     uint32_t tmc = tm;
-                    for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR) {
-                        const int node = (int)((desc[j].w & 0xFFFFFFu) / ROWB);
+                    for (int k = 0; k < nw; ++k) {
+                        if ((int32_t)wlp[k].x < 0) continue;       /* run header */
+                        const int node = (int)((wlp[k].w & SCB_DST_MASK) / ROWB);
                         scb_tmem_st<KR>(tmc, scb_ld<KR>(reinterpret_cast<const unsigned char *>(Tglob + (long long)node * GW + lane * KR)));
+                        tmc += (uint32_t)KR;
                     }
                     scb_tmem_wait_st();
                 }
@@ -1325,14 +1524,17 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
                     if (from > prev) { switchAt = from; break; }
                 }
             }
-            unsigned f = (tn <= 2) ? SCB_SF_CONST : 0u;
+            unsigned f = 0u;
             if (cmp) f |= TTM ? SCB_SF_ZCMP : SCB_SF_TCMP;
 #pragma unroll
             for (int k = 0; k < KR; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
             const bool act = onlyLane < 0 || lane == onlyLane;
+            /* the constant rows of the full program (it is the one in use at steps 1, 2): they equal T's, so the
+             * compare leaves them out */
+            if (tn <= 2) scb_const_rows<KR>(sa + dstOff + laneOff, gfull + e1full, n0full, warp, S, nullptr);
             if (TTM && cmp) {
                 /* compare with T in tensor memory, fold through dmz */
-                scb_step<KR, false, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa, d2, dz, true, tm);
+                scb_step_runs<KR, SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, true, d2, dz, tm);
 #pragma unroll
                 for (int k = 0; k < KR; ++k) if (dz.v[k]) atomicOr(&dmz[lane * KR + k], dz.v[k]);
                 __syncthreads();
@@ -1341,9 +1543,9 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
                 const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
                 continue;
             }
-            if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
-            else if (f == SCB_SF_TCMP) scb_step<KR, false, false, SCB_SF_TCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
-            else scb_step<KR, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
+            if (f == 0u && TTM) scb_step_runs<KR, 0u>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, act, d2, dz, tm);
+            else if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, nw, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
+            else scb_step<KR, false, false, SCB_SF_TCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, nw, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             if (cmp) {
                 uint32_t *Dw = D + ((size_t)(tn & 1) * S + warp) * GW + lane * KR;
 #pragma unroll
@@ -1363,10 +1565,12 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
         if (pass == 0) {
             /* S_99 sits in buffer B (99 is odd): T = B */
             if (TTM) {
-                const int e1 = cnt.x + cnt.y + cnt.z;
                 uint32_t tmc = tm;
-                for (int j = warp; j < e1; j += S, tmc += (uint32_t)KR)
-                    scb_tmem_st<KR>(tmc, scb_ld<KR>(bufB + (desc[j].w & 0xFFFFFFu) + laneOff));
+                for (int k = 0; k < nw; ++k) {
+                    if ((int32_t)wlp[k].x < 0) continue;           /* run header */
+                    scb_tmem_st<KR>(tmc, scb_ld<KR>(bufB + (wlp[k].w & SCB_DST_MASK) + laneOff));
+                    tmc += (uint32_t)KR;
+                }
                 scb_tmem_wait_st();
             } else
             for (int row = warp; row < N; row += S)
@@ -1392,7 +1596,7 @@ SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR, bool ttm = false)
 {
     /* state buffers (three, or two when T lives in tensor memory) + program + dmz/Fm/vm + scalars +
      * srcc[1024*KR] int16 + (shared-memory T only) D[2][<=24 warps][32*KR] + slack */
-    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + (size_t)(N + SCB_DESC_PAD) * 16 + (size_t)3 * 32 * KR * 4 + 64 + (size_t)1024 * KR * 2
+    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + scb_prog_entries(N) * 16 + (size_t)3 * 32 * KR * 4 + 64 + 384 + (size_t)1024 * KR * 2
            + (ttm ? 0 : (size_t)2 * 24 * 32 * KR * 4) + 256;
 }
 
@@ -1406,11 +1610,12 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
     const int GW = 32 * KR, GC = 1024 * KR;
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + (TTM ? 2u : 3u) * BUFB);
-    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + N + SCB_DESC_PAD);
+    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + scb_prog_entries(N));
     uint32_t *Fm = dmz + GW;
     uint32_t *vm = Fm + GW;
     int *sh = reinterpret_cast<int *>(vm + GW);            /* [2] pending cells, [3] not-found cells */
-    short *srcc = reinterpret_cast<short *>(sh + 16);      /* [GC] source cell of each cell */
+    int *winfo = sh + 16;                                  /* [96] per-warp list lengths + scratch of scb_load_program */
+    short *srcc = reinterpret_cast<short *>(winfo + 96);   /* [GC] source cell of each cell */
     uint32_t *Dbuf = reinterpret_cast<uint32_t *>(srcc + GC);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
@@ -1420,11 +1625,11 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
         const int q = (int)(A.resolveItems[it].y & 0xFFFFFFu);
         const unsigned flagged = A.resolveItems[it].y >> 24;       /* bit j: chunk q + j was left out by K2 */
         const int4 cnt = A.counts[p];
-        scb_load_program<KR>(desc, A.descs + (long long)p * A.Npad, cnt, N, tid, nthr);
+        scb_load_program<KR>(desc, winfo, A.descs + (long long)p * A.Npad, cnt, N, S, tid, nthr);
         if (tid == 0) { sh[2] = 0; sh[3] = 0; }
         __syncthreads();
         const bool haveT = it < A.resolveTCap;
-        scb_resolve_chunk<KR, TTM>(A, sm, desc, cnt, p, dmz, Fm, vm, q, haveT ? 1 : 0,
+        scb_resolve_chunk<KR, TTM>(A, sm, desc, winfo, cnt, p, dmz, Fm, vm, q, haveT ? 1 : 0,
                                    A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf, -1, tm);
 
         /* source cell of every cell: itself when found, else the nearest earlier found cell of the group
@@ -1466,8 +1671,8 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
         /* per-node sums over the flagged chunks: found cells plus the copies made by not-found cells */
         unsigned tot = 0;
         for (int j = warp; j < N; j += S) {
-            const uint32_t dsto = desc[j].w & 0xFFFFFFu;
-            const int node = (int)(dsto / ROWB);
+            const int node = j;
+            const uint32_t dsto = (uint32_t)node * ROWB;
             unsigned c = 0;
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
@@ -1519,6 +1724,7 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
     }
 }
 
+#ifndef SCB_SIM_ONLY
 /* K3 phase 1 as a kernel of its own (used when the simulator does not resolve in its own tail) */
 template <int KR>
 __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
@@ -1595,7 +1801,7 @@ __global__ void scb_k_fill(ScbResolveArgs R)
             }
             for (int j = lane; j < e1; j += 32) {
                 const uint4 d = desc[j];
-                nxt[d.w & 0xFFFFFFu] = scb_lut_apply_mux(d.w >> 24, cur[d.x], cur[d.y], cur[d.z]);
+                nxt[d.w & 0xFFFFu] = scb_lut_apply_mux(d.w >> 24, cur[d.x & 0xFFFFu], cur[d.y & 0xFFFFu], cur[d.z & 0xFFFFu]);
             }
             if (t <= 2)
                 for (int j = e1 + lane; j < e0; j += 32) {
@@ -1642,7 +1848,11 @@ __global__ void scb_k_traj(ScbTrajArgs A)
     const uint32_t laneOff = (uint32_t)lane * 4u;
     const int4 cnt = A.counts[0];
     const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
-    scb_load_program<1>(desc, A.descs, cnt, N, tid, nthr);
+    int *winfo = reinterpret_cast<int *>(desc + scb_prog_entries(N));
+    scb_load_program<1>(desc, winfo, A.descs, cnt, N, S, tid, nthr);
+    const int e1 = cnt.x + cnt.y + cnt.z;
+    const int nw = winfo[warp];
+    const scb_saddr wl = sdesc + 16u * (uint32_t)(warp * scb_prog_stride(N, S));
     for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
         const int w0 = tile * 32;
         uint32_t *tbase = A.traj + (unsigned long long)tile * A.steps * N * 32;
@@ -1658,14 +1868,19 @@ __global__ void scb_k_traj(ScbTrajArgs A)
         d2.v[0] = 0u; dz.v[0] = 0u;
         for (int t = 1; t < A.steps; ++t) {
             unsigned char *zg = reinterpret_cast<unsigned char *>(tbase + (unsigned long long)t * N * 32) + laneOff;
-            scb_step<1, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, sdesc, cnt, warp, S,
-                               SCB_SF_ZSNAP | SCB_SF_CONST, zg, sa, d2, dz);
+            scb_step<1, false>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, nw, SCB_SF_ZSNAP, zg, sa, d2, dz);
+            scb_const_rows<1>(sa + dstOff + laneOff, A.descs + e1, cnt.w, warp, S, zg);
             __syncthreads();
             const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
         }
-        if (A.zeroNode >= 0)
-            for (int i = tid; i < (A.steps - 1) * 32; i += nthr)
-                tbase[((unsigned long long)(1 + i / 32) * N + A.zeroNode) * 32 + (i & 31)] = 0u;
+        if (A.recOn) {
+            __syncthreads();
+            for (int node = warp; node < N; node += S) {
+                if (!A.recOn[node]) continue;
+                for (int t = 1; t < A.steps; ++t)
+                    tbase[((unsigned long long)t * N + node) * 32 + lane] = ((A.recBits[node * 4 + (t >> 5)] >> (t & 31)) & 1u) ? 0xffffffffu : 0u;
+            }
+        }
     }
 }
 
@@ -1781,5 +1996,7 @@ __global__ void scb_k_hamming(ScbHammingArgs A)
         A.deciderDistance[c] = bestD;
     }
 }
+
+#endif  /* SCB_SIM_ONLY */
 
 #endif

@@ -16,6 +16,118 @@ void legacy_env()
         if (const char *e = getenv("SCB_LEGACY_NODE")) { int v = atoi(e); if (v > 0) g_legacyNode = v; }
     });
 }
+/* The reference's symbols return void and have no error convention; its own failure mode is a crash.  A failed
+ * evaluation must never look like a result: the unmodified Python scores `sum(errors)` and a GA that minimises
+ * error would read untouched zeros as a perfect individual.  Default: message + abort().  With
+ * SCB_LEGACY_ON_ERROR=sentinel the outputs are filled with values no evaluation can produce and the call returns. */
+bool legacy_sentinel_mode()
+{
+    const char *e = getenv("SCB_LEGACY_ON_ERROR");
+    return e && strcmp(e, "sentinel") == 0;
+}
+
+[[noreturn]] void legacy_die(const char *fn, const char *msg)
+{
+    fprintf(stderr, "scbonita_b200: %s failed: %s\n", fn, msg);
+    fflush(stderr);
+    abort();
+}
+
+void legacy_fatal(const char *fn, const char *msg)
+{
+    if (!legacy_sentinel_mode()) legacy_die(fn, msg);
+    fprintf(stderr, "scbonita_b200: %s failed: %s (outputs set to sentinels)\n", fn, msg);
+}
+
+/* ---- packed contexts of the legacy symbols, cached by content -------------------------------------------------
+ * The reference's Python passes the same dense matrix on every call (2 538 local-search calls per network,
+ * ruleMaker.py:1247-1259); packing it again and again (cudaMalloc + H2D + K1) dominated a level-0 drop-in call.
+ * Key: two independent 64-bit hashes of the N used rows (lenSamples ints each) and of nodePositions, plus the sizes
+ * and the device.  A few entries, least recently used out first; an entry in use is never evicted. */
+struct LegacyEntry {
+    uint64_t h1 = 0, h2 = 0;
+    int N = 0, C = 0, device = 0;
+    scb_ctx *ctx = nullptr;
+    int inUse = 0;
+    unsigned long long stamp = 0;
+};
+std::mutex g_legacyMu;
+LegacyEntry g_legacyCache[4];
+unsigned long long g_legacyClock = 0;
+
+int legacy_device()
+{
+    const char *e = getenv("SCB_DEVICE");
+    return e ? atoi(e) : 0;
+}
+
+void legacy_hash(const int32_t *binMat, long long rowStride, const int32_t *pos, int N, int C, uint64_t *h1, uint64_t *h2)
+{
+    uint64_t a = 0x9E3779B97F4A7C15ull ^ (uint64_t)N, b = 0xC2B2AE3D27D4EB4Full ^ (uint64_t)C;
+    for (int i = 0; i < N; ++i) {
+        const int32_t *row = binMat + (long long)pos[i] * rowStride;
+        a = (a ^ (uint64_t)(uint32_t)pos[i]) * 0x100000001B3ull;
+        b = (b + (uint64_t)(uint32_t)pos[i]) * 0xFF51AFD7ED558CCDull; b ^= b >> 29;
+        int c = 0;
+        for (; c + 1 < C; c += 2) {
+            const uint64_t v = (uint64_t)(uint32_t)row[c] | ((uint64_t)(uint32_t)row[c + 1] << 32);
+            a = (a ^ v) * 0x100000001B3ull; a ^= a >> 31;
+            b = (b + v) * 0xFF51AFD7ED558CCDull; b ^= b >> 29;
+        }
+        if (c < C) { a = (a ^ (uint64_t)(uint32_t)row[c]) * 0x100000001B3ull; b = (b + (uint64_t)(uint32_t)row[c]) * 0xFF51AFD7ED558CCDull; }
+    }
+    *h1 = a; *h2 = b;
+}
+
+/* a context for (binMat rows nodePositions, lenSamples), from the cache or new; release with legacy_release */
+int legacy_ctx(scb_ctx **out, int N, int C, const int32_t *binMat, const int32_t *nodePositions)
+{
+    *out = nullptr;
+    if (!binMat || !nodePositions) return fail(SCB_ERR_INVALID, "null binMat / nodePositions");
+    for (int i = 0; i < N; ++i) if (nodePositions[i] < 0) return fail(SCB_ERR_INVALID, "nodePositions[%d] is negative", i);
+    const int device = legacy_device();
+    uint64_t h1, h2;
+    legacy_hash(binMat, g_legacyCell, nodePositions, N, C, &h1, &h2);
+    {
+        std::lock_guard<std::mutex> lk(g_legacyMu);
+        for (auto &e : g_legacyCache)
+            if (e.ctx && e.h1 == h1 && e.h2 == h2 && e.N == N && e.C == C && e.device == device) {
+                ++e.inUse; e.stamp = ++g_legacyClock;
+                *out = e.ctx;
+                return SCB_OK;
+            }
+    }
+    scb_ctx *ctx = nullptr;
+    int rc = scb_ctx_create(&ctx, device, N, C, binMat, 4, g_legacyCell, nodePositions);
+    if (rc) return rc;
+    scb_ctx *evict = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_legacyMu);
+        LegacyEntry *slot = nullptr;
+        for (auto &e : g_legacyCache) if (!e.ctx) { slot = &e; break; }
+        if (!slot)
+            for (auto &e : g_legacyCache) if (e.inUse == 0 && (!slot || e.stamp < slot->stamp)) slot = &e;
+        if (slot) {
+            evict = slot->ctx;
+            slot->h1 = h1; slot->h2 = h2; slot->N = N; slot->C = C; slot->device = device; slot->ctx = ctx;
+            slot->inUse = 1; slot->stamp = ++g_legacyClock;
+        }
+        /* every slot busy: the context stays private to this call and is destroyed on release */
+    }
+    if (evict) scb_ctx_destroy(evict);
+    *out = ctx;
+    return SCB_OK;
+}
+
+void legacy_release(scb_ctx *ctx)
+{
+    if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lk(g_legacyMu);
+        for (auto &e : g_legacyCache) if (e.ctx == ctx) { --e.inUse; return; }
+    }
+    scb_ctx_destroy(ctx);
+}
 }  // namespace
 
 extern "C" {
@@ -39,13 +151,14 @@ void scSyncBool(void *simData, const int32_t *individual, intptr_t indLen, intpt
     (void)simData; (void)importanceScores;
     legacy_env();
     const int N = (int)nodeNum, C = (int)lenSamples, L = (int)indLen;
-    if ((int)simSteps != SCB_STEPS) {
-        fprintf(stderr, "scbonita_b200: scSyncBool supports simSteps == 100 only (got %d); errors left untouched\n", (int)simSteps);
-        return;
-    }
-    if (C <= 0 || N <= 0) return;
+    if (C <= 0 || N <= 0) return;                       /* the reference's loops do not run either */
+    int rc = SCB_OK;
     scb_ctx *ctx = nullptr;
-    int rc = scb_ctx_create(&ctx, 0, N, C, binMat, 4, g_legacyCell, nodePositions);
+    if ((int)simSteps != SCB_STEPS)
+        rc = fail(SCB_ERR_UNSUPPORTED, "simSteps must be 100 (getAttractCycle2 always scans 100 rows, simulator.c:306-331), got %d", (int)simSteps);
+    else if (C > g_legacyCell)
+        rc = fail(SCB_ERR_INVALID, "lenSamples %d exceeds the binMat row stride %d (SCB_LEGACY_CELL / scb_set_legacy_geometry)", C, g_legacyCell);
+    else rc = legacy_ctx(&ctx, N, C, binMat, nodePositions);
     if (rc == SCB_OK) {
         const int mode = localSearch ? SCB_MODE_NODEWISE : SCB_MODE_CELLWISE;
         std::vector<int32_t> out((size_t)(localSearch ? N : C));
@@ -56,12 +169,20 @@ void scSyncBool(void *simData, const int32_t *individual, intptr_t indLen, intpt
             else for (int c = 0; c < C; ++c) errors[c] = out[c];
         }
     }
-    if (rc != SCB_OK) fprintf(stderr, "scbonita_b200: scSyncBool failed (%d): %s\n", rc, scb_last_error());
-    scb_ctx_destroy(ctx);
+    legacy_release(ctx);
+    if (rc != SCB_OK) {
+        legacy_fatal("scSyncBool", scb_last_error());
+        /* sentinel mode: no evaluation can reach these (an error is at most nodeNum per cell, lenSamples per node);
+         * the sum over the array still fits an int64 */
+        const int n = localSearch ? N : C;
+        for (int i = 0; i < n; ++i) errors[i] = 0x7fffffff / (n > 0 ? n : 1);
+    }
 }
 
-/* trajectories + attractor windows of the uploaded single individual (P == 1 already on the device) */
-static int run_trajectories(scb_ctx *c, int sem, int steps, int maxStates, int zeroNode)
+/* trajectories + attractor windows of the uploaded single individual (P == 1 already on the device).
+ * recOn / recBits (host, may be null): nodes whose RECORDED rows of steps >= 1 are overridden, see ScbTrajArgs */
+static int run_trajectories(scb_ctx *c, int sem, int steps, int maxStates, const unsigned char *recOn = nullptr,
+                            const uint32_t *recBits = nullptr)
 {
     const int N = c->N, tiles = (c->W + 31) / 32, NW = (N + 31) / 32;
     int rc;
@@ -74,7 +195,14 @@ static int run_trajectories(scb_ctx *c, int sem, int steps, int maxStates, int z
     if ((rc = launch_compile(c, sem, c->dKo.p))) return rc;
     ScbTrajArgs ta;
     ta.X = c->dX.p; ta.N = N; ta.C = c->C; ta.Wpad = c->Wpad; ta.tiles = tiles; ta.steps = steps;
-    ta.descs = c->dDescs.p; ta.counts = c->dCounts.p; ta.traj = c->dTraj.p; ta.zeroNode = zeroNode;
+    ta.descs = c->dDescs.p; ta.counts = c->dCounts.p; ta.traj = c->dTraj.p; ta.recOn = nullptr; ta.recBits = nullptr;
+    if (recOn) {
+        if ((rc = c->dRecOn.ensure(N)) || (rc = c->dRecBits.ensure((size_t)N * 4))) return rc;
+        CK(cudaMemcpyAsync(c->dRecOn.p, recOn, (size_t)N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->dRecBits.p, recBits, (size_t)N * 16, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                /* the host arrays are the caller's temporaries */
+        ta.recOn = c->dRecOn.p; ta.recBits = c->dRecBits.p;
+    }
     const int warps = std::min(16, std::max(1, (N + 3) / 4));
     const unsigned grid = (unsigned)std::max(1, std::min(tiles, c->numSM * 2));
     SCB_LAUNCH(scb_k_traj, dim3(grid), dim3((unsigned)warps * 32), scb_smem_bytes(N, 1, 2), st, ta);
@@ -108,17 +236,22 @@ int scb_attractors(scb_ctx *c, const int32_t *individual, int indLen, const int3
     if (rc) return rc;
     if (semantics != 0 && semantics != 1) return fail(SCB_ERR_INVALID, "semantics must be 0 (C cluster) or 1 (Python __cluster)");
     if (maxStates < 0 || !res || !nStates || (maxStates > 0 && !states)) return fail(SCB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);        /* upload + kernels + copies under one lock */
     rc = scb_pop_upload(c, 1, individual, indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0, knockouts, knockins);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
     const int N = c->N, NW = (N + 31) / 32;
-    int zeroNode = -1;
+    std::vector<unsigned char> recOn;
+    std::vector<uint32_t> recBits;
     if (semantics == 1) {
-        /* singleCell.py:1037-1038: the last node falls through without being updated or recorded */
+        /* singleCell.py:1037-1038: the last node falls through without being updated or recorded: its rows stay 0 */
         const int al = andLenList[N - 1];
-        if (knockouts[N - 1] != 1 && knockins[N - 1] != 1 && al != 1 && al != 0) zeroNode = N - 1;
+        if (knockouts[N - 1] != 1 && knockins[N - 1] != 1 && al != 1 && al != 0) {
+            recOn.assign((size_t)N, 0); recBits.assign((size_t)N * 4, 0u);
+            recOn[N - 1] = 1;
+        }
     }
-    rc = run_trajectories(c, semantics == 1 ? SCB_SEM_PY : SCB_SEM_C, semantics == 1 ? 10 : SCB_STEPS, maxStates, zeroNode);
+    rc = run_trajectories(c, semantics == 1 ? SCB_SEM_PY : SCB_SEM_C, semantics == 1 ? 10 : SCB_STEPS, maxStates,
+                          recOn.empty() ? nullptr : recOn.data(), recOn.empty() ? nullptr : recBits.data());
     if (rc) return rc;
     cudaStream_t st = c->stream;
     CK(cudaMemcpyAsync(res, c->dRes.p, (size_t)c->C * 2 * 4, cudaMemcpyDeviceToHost, st));
@@ -127,11 +260,13 @@ int scb_attractors(scb_ctx *c, const int32_t *individual, int indLen, const int3
     return check_compile_diag(c);
 }
 
-/* simulator.c:487-552.  One cell (`sampleIndex`); resSubmit = attractor window; the trajectory is left in
- * simData[step][nodePositions[i]] (row stride = legacy NODE) like the reference does.  The reference's
- * knock-out branch writes column i instead of nodePositions[i] (simulator.c:518); this shim writes the true
- * trajectory at nodePositions[i] for every node, which is identical whenever no node is knocked out or
- * nodePositions is the identity. */
+/* simulator.c:487-552.  One cell (`sampleIndex`); resSubmit = attractor window; the scratch `simData[step][column]`
+ * (row stride = legacy NODE) is left exactly as the reference leaves it.  That includes the slip of its knock-out
+ * branch, which records a knocked node i in column i instead of column nodePositions[i] (simulator.c:518): the
+ * knocked node's own column keeps what the caller's scratch held (or the 0 another knocked node wrote there), and
+ * column i may overwrite the node recorded there when i comes later in the loop.  The window search runs over the
+ * columns as recorded, so the kernel is told which nodes' recorded rows differ from their true rows (the dynamics
+ * never do).  The caller's scratch must hold 0/1 where it shows through (the reference's Python passes zeros). */
 void cluster(void *simData, int32_t *resSubmit, intptr_t sampleIndex, const int32_t *individual, intptr_t indLen,
              intptr_t nodeNum, const int32_t *andLenList, const int32_t *individualParse, const int32_t *andNodes,
              const int32_t *andNodeInvertList, intptr_t simSteps, const int32_t *knockouts, const int32_t *knockins,
@@ -139,34 +274,56 @@ void cluster(void *simData, int32_t *resSubmit, intptr_t sampleIndex, const int3
 {
     legacy_env();
     const int N = (int)nodeNum;
-    if ((int)simSteps != SCB_STEPS) {
-        fprintf(stderr, "scbonita_b200: cluster supports simSteps == 100 only (got %d)\n", (int)simSteps);
-        return;
+    if (!resSubmit) legacy_die("cluster", "null resSubmit");
+    /* sentinel mode: a window no trajectory has */
+#define SCB_CLUSTER_FAIL(msg) do { legacy_fatal("cluster", msg); resSubmit[0] = resSubmit[1] = -0x7fffffff; return; } while (0)
+    if ((int)simSteps != SCB_STEPS) SCB_CLUSTER_FAIL("simSteps must be 100 (simulator.c:306-331 always scans 100 rows)");
+    if (N <= 0) SCB_CLUSTER_FAIL("nodeNum must be positive");
+    int32_t *sd = static_cast<int32_t *>(simData);
+    std::vector<unsigned char> recOn((size_t)N, 0);
+    std::vector<uint32_t> recBits((size_t)N * 4, 0u);
+    bool anyRec = false;
+    for (int k = 0; k < N; ++k) {
+        const int col = nodePositions[k];
+        const bool koK = knockouts[k] == 1, koCol = col < N && knockouts[col] == 1;
+        if (!koK && !(koCol && col > k)) continue;            /* the true trajectory is what the column shows */
+        recOn[k] = 1; anyRec = true;
+        if (koCol) continue;                                  /* a knocked node's 0 is the last write: bits stay 0 */
+        for (int t = 1; t < SCB_STEPS && sd; ++t) {           /* nobody writes the column: the caller's scratch shows through */
+            const int32_t v = sd[(long long)t * g_legacyNode + col];
+            if (v != 0 && v != 1) SCB_CLUSTER_FAIL("the scratch holds a value other than 0/1 in a column the knock-out branch leaves unwritten");
+            if (v) recBits[(size_t)k * 4 + (t >> 5)] |= 1u << (t & 31);
+        }
     }
     scb_ctx *ctx = nullptr;
-    int rc = scb_ctx_create(&ctx, 0, N, 1, binMat + (long long)sampleIndex, 4, g_legacyCell, nodePositions);
-    if (rc == SCB_OK) {
+    int rc = legacy_ctx(&ctx, N, 1, binMat + (long long)sampleIndex, nodePositions);
+    std::vector<uint32_t> traj((size_t)SCB_STEPS * N * 32);
+    int32_t r2[2] = {0, 0};
+    if (rc == SCB_OK)
         rc = scb_pop_upload(ctx, 1, individual, (int)indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0,
                             knockouts, knockins);
-        if (rc == SCB_OK) rc = run_trajectories(ctx, SCB_SEM_C, SCB_STEPS, 0, -1);
-        std::vector<uint32_t> traj((size_t)SCB_STEPS * N * 32);
-        int32_t r2[2] = {0, 0};
+    if (rc == SCB_OK) {
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        rc = run_trajectories(ctx, SCB_SEM_C, SCB_STEPS, 0, anyRec ? recOn.data() : nullptr, anyRec ? recBits.data() : nullptr);
         if (rc == SCB_OK) {
             cudaMemcpyAsync(traj.data(), ctx->dTraj.p, traj.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
             cudaMemcpyAsync(r2, ctx->dRes.p, 8, cudaMemcpyDeviceToHost, ctx->stream);
             rc = check_compile_diag(ctx);
         }
-        if (rc == SCB_OK) {
-            int32_t *sd = static_cast<int32_t *>(simData);
-            if (sd)
-                for (int t = 0; t < SCB_STEPS; ++t)
-                    for (int i = 0; i < N; ++i)
-                        sd[(long long)t * g_legacyNode + nodePositions[i]] = (int32_t)(traj[((size_t)t * N + i) * 32] & 1u);
-            resSubmit[0] = r2[0]; resSubmit[1] = r2[1];
+    }
+    legacy_release(ctx);
+    if (rc != SCB_OK) SCB_CLUSTER_FAIL(scb_last_error());
+#undef SCB_CLUSTER_FAIL
+    if (sd) {
+        for (int t = 0; t < SCB_STEPS; ++t) {
+            if (t > 0)
+                for (int i = 0; i < N; ++i)
+                    if (knockouts[i] == 1) sd[(long long)t * g_legacyNode + i] = 0;              /* :518 */
+            for (int i = 0; i < N; ++i)                                                         /* the columns as recorded */
+                sd[(long long)t * g_legacyNode + nodePositions[i]] = (int32_t)(traj[((size_t)t * N + i) * 32] & 1u);
         }
     }
-    if (rc != SCB_OK) fprintf(stderr, "scbonita_b200: cluster failed (%d): %s\n", rc, scb_last_error());
-    scb_ctx_destroy(ctx);
+    resSubmit[0] = r2[0]; resSubmit[1] = r2[1];
 }
 
 /* simulator.c:555-755, incl. its quirks: both passes force knocked nodes to 0 and accumulate into
@@ -203,6 +360,7 @@ int scb_importance_scores(scb_ctx *ctx, const int32_t *individual, int indLen, c
         else { passOf[2 * k + 1] = (int)(knock.size() / N); knock.insert(knock.end(), ki, ki + N); }
     }
     const int P = (int)(knock.size() / N);
+    std::lock_guard<std::recursive_mutex> lkAll(ctx->mu);   /* upload + run + fetch under one lock */
     rc = pop_upload_impl(ctx, P, 1, individual, indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0,
                          P, knock.data(), knockins);
     if (rc) return rc;
@@ -210,7 +368,7 @@ int scb_importance_scores(scb_ctx *ctx, const int32_t *individual, int indLen, c
     std::vector<int32_t> cnt((size_t)P * N);
     std::vector<unsigned long long> noWindow((size_t)P);
     {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         CK(cudaMemcpyAsync(cnt.data(), ctx->dNodewise.p, cnt.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(noWindow.data(), ctx->dFitness.p, noWindow.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
         if ((rc = check_compile_diag(ctx))) return rc;
@@ -257,18 +415,22 @@ void importanceScore(void *simData, const int32_t *individual, intptr_t indLen, 
     const int N = (int)nodeNum, C = (int)lenSamples;
     if (!importanceScores) return;
     importanceScores[0] = 0.0;
-    if ((int)simSteps != SCB_STEPS) {
-        fprintf(stderr, "scbonita_b200: importanceScore supports simSteps == 100 only (got %d)\n", (int)simSteps);
-        return;
-    }
     if (N <= 0 || C <= 0) return;
     scb_ctx *ctx = nullptr;
-    int rc = scb_ctx_create(&ctx, 0, N, C, binMat, 4, g_legacyCell, nodePositions);
+    int rc;
+    if ((int)simSteps != SCB_STEPS) rc = fail(SCB_ERR_UNSUPPORTED, "simSteps must be 100, got %d", (int)simSteps);
+    else if (C > g_legacyCell) rc = fail(SCB_ERR_INVALID, "lenSamples %d exceeds the binMat row stride %d", C, g_legacyCell);
+    else rc = legacy_ctx(&ctx, N, C, binMat, nodePositions);
     if (rc == SCB_OK)
         rc = scb_importance_score(ctx, individual, (int)indLen, andLenList, individualParse, andNodes, andNodeInvertList,
                                   knockouts, knockins, importanceScores);
-    if (rc != SCB_OK) fprintf(stderr, "scbonita_b200: importanceScore failed (%d): %s\n", rc, scb_last_error());
-    scb_ctx_destroy(ctx);
+    legacy_release(ctx);
+    /* a cell without an attractor window: the reference divides by zero (SIGFPE); here the score is NaN, which no
+     * caller can mistake for a result */
+    if (rc != SCB_OK && !(rc == SCB_ERR_INVALID && importanceScores[0] != importanceScores[0])) {
+        legacy_fatal("importanceScore", scb_last_error());
+        importanceScores[0] = nan("");
+    }
 }
 
 }  /* extern "C" */

@@ -74,7 +74,7 @@ extern "C" int scb_microbench(scb_ctx *c, int kind, double *perSecond)
     if (rc) return rc;
     if (!perSecond) return fail(SCB_ERR_INVALID, "null argument");
     if (kind < 0 || kind > 2) return fail(SCB_ERR_INVALID, "unknown microbenchmark %d", kind);
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if ((rc = c->dFlush.ensure(4096))) return rc;
     uint32_t *out = reinterpret_cast<uint32_t *>(c->dFlush.p);
     cudaStream_t st = c->stream;

@@ -154,7 +154,8 @@ struct ScbTrajArgs {
     const uint4 *descs;           /* one compiled program */
     const int4 *counts;
     uint32_t *traj;
-    int zeroNode;                 /* >= 0: rows of this node are recorded as 0 for steps >= 1 */
+    const unsigned char *recOn;   /* [N] or null: != 0 -> the node's RECORDED rows of steps >= 1 are overridden (the dynamics are not) */
+    const uint32_t *recBits;      /* [N][4]: bit t = recorded value at step t of an overridden node (simulator.c:518) */
 };
 
 struct ScbWindowArgs {

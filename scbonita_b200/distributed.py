@@ -59,13 +59,6 @@ def run_pathways(pathways, evaluate, costs=None, group=None):
     return [merged[i] for i in range(len(pathways))]
 
 
-class _DevicePointer:
-    """Minimal __cuda_array_interface__ view so that torch can wrap the library's device buffer."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-
-
 class ShardedEvaluator:
     """Scores a population with every rank of ``group`` working on its block of individuals."""
 
@@ -90,24 +83,16 @@ class ShardedEvaluator:
             ai = and_inv[lo:hi] if per_ind else and_inv
             self.sim.upload(inds[lo:hi], knockouts, knockins, an, ai)
             self.sim.run(MODE_SUM)
-        if self.backend == "nccl" and hi - lo == width:
-            # all-gather straight from the library's device buffer, on the library's stream
-            self.sim.sync()
-            ptr, _ = self.sim.result_device_pointer(MODE_SUM)
-            dev = torch.device("cuda", torch.cuda.current_device())
-            src = torch.as_tensor(_DevicePointer(ptr, width), device=dev)
-            out = torch.empty(self.world * width, dtype=torch.int64, device=dev)
-            self.dist.all_gather_into_tensor(out, src, group=self.group)
-            gathered = out.cpu().numpy()
-        else:
-            if hi > lo:
-                local[:hi - lo] = self.sim.fetch(MODE_SUM)
-            src = torch.from_numpy(local)
-            if self.backend == "nccl":
-                src = src.cuda()
-            outs = [torch.empty_like(src) for _ in range(self.world)]
-            self.dist.all_gather(outs, src, group=self.group)
-            gathered = torch.cat(outs).cpu().numpy()
+            # fetch() also reads the compile diagnostics (bad index, > 7 terms, ...) and raises on them: garbage
+            # fitness must not be gathered
+            local[:hi - lo] = self.sim.fetch(MODE_SUM)
+        # the collective is chosen from (P, world, backend) only, so every rank issues the same one
+        src = torch.from_numpy(local)
+        if self.backend == "nccl":
+            src = src.cuda()
+        out = torch.empty(self.world * width, dtype=torch.int64, device=src.device)
+        self.dist.all_gather_into_tensor(out, src, group=self.group)
+        gathered = out.cpu().numpy()
         full = np.zeros(P, dtype=np.int64)
         for r in range(self.world):
             a, b = shard_bounds(P, r, self.world)

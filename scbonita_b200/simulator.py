@@ -239,9 +239,22 @@ class Simulator:
         """Score P individuals in one launch.  Returns int64[P] (SUM), int32[P][N] (NODEWISE) or
         int32[P][C] (CELLWISE).  ``and_nodes`` / ``and_inv`` may be [P][N][7][3] (every GA individual owns
         a model copy, ruleMaker.py:650) or None for the context's shared model."""
-        self.upload(individuals, knockouts, knockins, and_nodes, and_inv)
-        self.run(mode)
-        return self.fetch(mode)
+        m = self.model
+        inds, an, ai, per_ind = self._tables(individuals, and_nodes, and_inv)
+        ko = _i32(knockouts if knockouts is not None else np.zeros(m.n))
+        ki = _i32(knockins if knockins is not None else np.zeros(m.n))
+        out = self._out_array(mode, inds.shape[0])
+        st = Stats()
+        # ONE library call (upload + run + fetch under the context's lock): safe from a ThreadPool, which is how the
+        # reference drives its parallel local search (singleCell.py:490-492); upload()/run()/fetch() used separately
+        # are for a single driving thread (bench.py's timed loops)
+        rc = self.lib.scb_eval_population(self._ctx, inds.shape[0], _ptr(inds), m.ind_len, _ptr(m.and_len_list),
+                                          _ptr(m.individual_parse), _ptr(an), _ptr(ai), per_ind, _ptr(ko), _ptr(ki),
+                                          int(mode), _ptr(out), ctypes.byref(st))
+        self.last_stats = st.as_dict()
+        self._P = inds.shape[0]
+        _lib.check(self.lib, rc)
+        return out
 
     # -- the reference's per-individual entry point ------------------------------------------
     def evaluate_by_node(self, individual, KOlist, KIlist, cFunction=None, localSearch=False,

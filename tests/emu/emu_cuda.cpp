@@ -67,6 +67,18 @@ uint32_t emu_shfl(uint32_t v, int srcLane)
     return r;
 }
 
+unsigned __match_any_sync(unsigned, unsigned v)
+{
+    WarpCtx *w = tl_warp;
+    const int lane = threadIdx.x & 31;
+    w->slot[lane] = v;
+    w->bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if (w->slot[i] == v) r |= 1u << i;
+    w->bar.arrive_and_wait();
+    return r;
+}
+
 void emu_launch_impl(const std::function<void()> &body, dim3 grid, dim3 block, size_t smem)
 {
     /* one launch at a time, process-wide: host threads that launch concurrently (the re-entrancy tests) would

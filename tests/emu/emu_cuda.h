@@ -41,6 +41,7 @@ static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exc
 void __syncthreads();
 void __syncwarp(unsigned mask = 0xffffffffu);
 unsigned __ballot_sync(unsigned mask, int pred);
+unsigned __match_any_sync(unsigned mask, unsigned value);   /* all 32 lanes must call it */
 uint32_t emu_shfl(uint32_t v, int srcLane);
 static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int laneMask) { return emu_shfl(v, (int)(threadIdx.x & 31) ^ laneMask); }
 static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu_shfl(v, src & 31); }

@@ -4,6 +4,9 @@ oracle/_ref exist):   python tests/golden/make_golden.py
 * sim_*.npz -- seeded inputs in the reference's int32 layouts plus the outputs of the UNMODIFIED reference
   C (oracle/_ref/simulator.so driven with the reference's own ctypes convention): errors[] of scSyncBool
   for localSearch = 0 (cellwise) and 1 (nodewise), for every individual.
+* imp_*.npz / cluster_*.npz -- the same for the reference's importanceScore (one double per knock-out / knock-in
+  pair) and `cluster` (attractor window + the scratch the call leaves behind, incl. knock-outs on permuted
+  nodePositions, simulator.c:518).
 * hamming_kat.npz -- the reference's own packaged known answer for the distance / decider stage:
   src/scBONITA/data/hsa00010.graphml_processed.graphml_attractorDistance.csv (100 cells x 51 attractors +
   deciderDistance + decider) together with the pickled binarized matrix it was computed from.  The script
@@ -90,6 +93,68 @@ def hamming_kat():
 
 
 # ---------------------------------------------------------------------------------------------
+# importanceScore (simulator.c:555-755) and cluster (simulator.c:487-552) from the unmodified reference build
+# ---------------------------------------------------------------------------------------------
+def _knock_rows(n, lists):
+    out = np.zeros((len(lists), n), np.int32)
+    for k, nodes in enumerate(lists):
+        out[k, list(nodes)] = 1
+    return out
+
+
+def save_importance(name, pr, knock_lists):
+    """One reference importanceScore call per (knock-out list, knock-in list).  Items for which a cell has no
+    attractor window are left out: the reference divides by zero there (SIGFPE, simulator.c:647)."""
+    ref = oracle.RefSimulator(pr.n_cells)
+    bm = ref.dense(pr.bin_rows.astype(np.int32), pr.node_positions)
+    an = pr.net.and_nodes if pr.pop_an is None else pr.pop_an[0]
+    ai = pr.net.and_inv if pr.pop_ai is None else pr.pop_ai[0]
+    kos, kis, scores = [], [], []
+    for ko_nodes, ki_nodes in knock_lists:
+        ko, ki = _knock_rows(pr.n, [ko_nodes])[0], _knock_rows(pr.n, [ki_nodes])[0]
+        m = oracle.Model(pr.net.and_len, pr.net.parse, an, ai, pr.node_positions, pr.net.ind_len, ko, ki)
+        try:
+            oracle.importance_score(m, pr.individuals[0], pr.bm, pr.n_cells)
+        except ValueError:
+            continue
+        kos.append(ko); kis.append(ki)
+        scores.append(ref.importance_score(m, pr.individuals[0], bm, pr.n_cells))
+    np.savez_compressed(os.path.join(HERE, name), and_len=pr.net.and_len, parse=pr.net.parse, and_nodes=an, and_inv=ai,
+                        node_positions=pr.node_positions, ind_len=pr.net.ind_len, n_cells=pr.n_cells,
+                        bin_rows=np.packbits(pr.bin_rows, axis=1), individual=pr.individuals[0],
+                        knockouts=np.array(kos, np.int32), knockins=np.array(kis, np.int32),
+                        ref_scores=np.array(scores, np.float64))
+    print(name, "%d items" % len(scores), scores[:4])
+
+
+def save_cluster(name, pr, knock_lists, cells):
+    """The reference's `cluster` for a few cells per knock list, on a zeroed scratch like the reference's Python
+    passes: the attractor window and the first `stride` columns of the scratch it leaves behind."""
+    ref = oracle.RefSimulator(pr.n_cells)
+    bm = ref.dense(pr.bin_rows.astype(np.int32), pr.node_positions)
+    an = pr.net.and_nodes if pr.pop_an is None else pr.pop_an[0]
+    ai = pr.net.and_inv if pr.pop_ai is None else pr.pop_ai[0]
+    stride = max(int(pr.node_positions.max()) + 1, pr.n)
+    kos = _knock_rows(pr.n, [k for k, _ in knock_lists])
+    kis = _knock_rows(pr.n, [k for _, k in knock_lists])
+    sims = np.zeros((len(knock_lists), len(cells), 100, stride), np.int8)
+    ress = np.zeros((len(knock_lists), len(cells), 2), np.int32)
+    for k in range(len(knock_lists)):
+        m = oracle.Model(pr.net.and_len, pr.net.parse, an, ai, pr.node_positions, pr.net.ind_len, kos[k], kis[k])
+        for ci, cell in enumerate(cells):
+            vals, res = ref.cluster(m, pr.individuals[0], bm, int(cell))
+            assert not vals[:, stride:].any()
+            sims[k, ci] = vals[:, :stride]
+            ress[k, ci] = res
+    np.savez_compressed(os.path.join(HERE, name), and_len=pr.net.and_len, parse=pr.net.parse, and_nodes=an, and_inv=ai,
+                        node_positions=pr.node_positions, ind_len=pr.net.ind_len, n_cells=pr.n_cells,
+                        bin_rows=np.packbits(pr.bin_rows, axis=1), individual=pr.individuals[0],
+                        knockouts=kos, knockins=kis, cells=np.asarray(cells, np.int32), stride=stride,
+                        ref_sim=sims, ref_res=ress)
+    print(name, "windows", sorted({tuple(r) for r in ress.reshape(-1, 2)})[:8])
+
+
+# ---------------------------------------------------------------------------------------------
 # Python attractor path (singleCell.__cluster, singleCell.py:990-1059) run from the reference itself
 # ---------------------------------------------------------------------------------------------
 def import_reference_single_cell():
@@ -157,5 +222,10 @@ if __name__ == "__main__":
     save_sim("sim_ring45_chain12.npz", ring_problem([45], 12, 1500))
     save_sim("sim_ring60_undefined_lead.npz", ring_problem([60], 0, 200, lead_found=True))
     hamming_kat()
+    pr = Problem.synthetic(33, 400, 1, knock=False, net_seed=31)
+    save_importance("imp_n33.npz", pr, [([i], [i]) for i in range(33)] + [([1], [32]), ([], []), ([3, 9], [4, 5, 6])])
+    save_importance("imp_ring.npz", ring_problem([40, 5], 3, 300), [([i], [i]) for i in range(0, 49, 3)])
+    save_cluster("cluster_n33.npz", pr, [([], []), ([], [16]), ([2], []), ([0, 32], [1]), ([11, 22], [])], [0, 7, 200, 399])
+    save_cluster("cluster_ring.npz", ring_problem([7, 4], 3, 50), [([], []), ([12], []), ([1, 9], [3])], [0, 7, 21, 49])
     save_py_cluster("pycluster_n24.npz", 24, 70, 501)
     save_py_cluster("pycluster_n40.npz", 40, 50, 777)

@@ -136,8 +136,10 @@ def test_attractor_set_then_decider(backend):
 
 @pytest.mark.parametrize("n,cells,seed", [(12, 30, None), (20, 200, 4242), (9, 64, 99)])
 def test_legacy_importanceScore_symbol(backend, n, cells, seed):
-    """importanceScore (simulator.c:555-755): double result bit-identical to the oracle restatement, which is
-    itself checked against the unmodified reference in tests/test_oracle.py."""
+    """importanceScore (simulator.c:555-755): double result bit-identical to the oracle restatement.  The
+    restatement is pinned against the unmodified reference build in tests/test_oracle.py
+    (test_importance_restatement_matches_reference_build) and the reference's own numbers travel to the GPU box
+    as tests/golden/imp_*.npz (test_importance_golden_from_reference_build below)."""
     pr = Problem.synthetic(n, cells, 1, knock=False, net_seed=seed)
     lib = _lib.load(backend[1])
     stride = 256
@@ -253,3 +255,122 @@ def test_importance_scores_long_cycles(backend, rings, cells):
                 sim.importance_scores(pr.individuals[0], [[i] for i in range(n)])
     assert _same_doubles(got, want), (got, want)
     assert (~np.isnan(np.asarray(want))).any()
+
+
+# ---- golden vectors produced by the UNMODIFIED reference build (tests/golden/make_golden.py) -------------------
+def _golden_problem(g):
+    C = int(g["n_cells"]); pos = g["node_positions"]
+    bm = np.zeros((int(pos.max()) + 1, C), np.int32)
+    bm[pos] = np.unpackbits(g["bin_rows"], axis=1)[:, :C]
+    model = simulator.ModelTables(g["and_len"], g["parse"], g["and_nodes"], g["and_inv"], pos, int(g["ind_len"]))
+    return C, bm, model
+
+
+@pytest.mark.parametrize("name", ["imp_n33.npz", "imp_ring.npz"])
+def test_importance_golden_from_reference_build(backend, name):
+    """importanceScore of the reference itself (oracle/_ref, simulator.c:555-755): every double bit-identical,
+    through the batched entry point and, for a few items, through the legacy 15-argument symbol."""
+    g = np.load(os.path.join(GOLDEN, name))
+    C, bm, model = _golden_problem(g)
+    kos, kis, want = g["knockouts"], g["knockins"], g["ref_scores"]
+    lib = _lib.load(backend[1])
+    with simulator.Simulator(bm, model, lib_path=backend[1]) as sim:
+        if backend[0] == "emu":
+            sim.set_option(_lib.OPT_MAX_CTAS, 3)
+        ind = np.ascontiguousarray(g["individual"], np.int32)
+        got = np.zeros(len(want), np.float64)
+        P = lambda a: ctypes.c_void_p(a.ctypes.data)
+        m = sim.model
+        kos_c, kis_c = np.ascontiguousarray(kos, np.int32), np.ascontiguousarray(kis, np.int32)
+        rc = lib.scb_importance_scores(sim._ctx, P(ind), m.ind_len, P(m.and_len_list), P(m.individual_parse), P(m.and_nodes),
+                                       P(m.and_node_invert_list), len(want), P(kos_c), P(kis_c), P(got))
+    assert rc == _lib.OK
+    assert got.tobytes() == want.tobytes(), (got, want)
+    # the drop-in symbol, reference argument list
+    stride = 512
+    lib.scb_set_legacy_geometry(64, stride)
+    wide = np.zeros((bm.shape[0], stride), np.int32)
+    wide[:, :C] = bm
+    V = ctypes.c_void_p
+    fn = lib.importanceScore
+    fn.restype = None
+    fn.argtypes = None
+    al, parse, an, ai, pos = [np.ascontiguousarray(a, np.int32) for a in (g["and_len"], g["parse"], g["and_nodes"], g["and_inv"], g["node_positions"])]
+    for k in (0, len(want) // 2, len(want) - 1):
+        score = np.zeros(1, np.float64)
+        ko, ki = np.ascontiguousarray(kos[k]), np.ascontiguousarray(kis[k])
+        fn(V(0), V(ind.ctypes.data), V(len(ind)), V(model.n), V(al.ctypes.data), V(parse.ctypes.data), V(an.ctypes.data),
+           V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data), V(C), V(wide.ctypes.data), V(pos.ctypes.data),
+           V(score.ctypes.data))
+        assert score.tobytes() == want[k:k + 1].tobytes(), (k, score, want[k])
+    lib.scb_set_legacy_geometry(20000, 15000)
+
+
+@pytest.mark.parametrize("name", ["cluster_n33.npz", "cluster_ring.npz"])
+def test_cluster_golden_from_reference_build(backend, name):
+    """The reference's own `cluster` (oracle/_ref, simulator.c:487-552): attractor window and the scratch the call
+    leaves behind, including knock-outs on permuted nodePositions, where the reference records the knocked node in
+    column i instead of column nodePositions[i] (:518)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    C, bm, model = _golden_problem(g)
+    stride, cstride = int(g["stride"]), 512
+    lib = _lib.load(backend[1])
+    lib.scb_set_legacy_geometry(stride, cstride)
+    wide = np.zeros((bm.shape[0], cstride), np.int32)
+    wide[:, :C] = bm
+    V = ctypes.c_void_p
+    fn = lib.cluster
+    fn.restype = None
+    fn.argtypes = None
+    ind, al, parse, an, ai, pos = [np.ascontiguousarray(a, np.int32) for a in (g["individual"], g["and_len"], g["parse"], g["and_nodes"],
+                                                                              g["and_inv"], g["node_positions"])]
+    try:
+        for k in range(len(g["knockouts"])):
+            ko, ki = np.ascontiguousarray(g["knockouts"][k]), np.ascontiguousarray(g["knockins"][k])
+            for ci, cell in enumerate(g["cells"]):
+                vals = np.zeros((100, stride), np.int32)
+                res = np.full(2, 2, np.int32)
+                fn(V(vals.ctypes.data), V(res.ctypes.data), V(int(cell)), V(ind.ctypes.data), V(len(ind)), V(model.n), V(al.ctypes.data),
+                   V(parse.ctypes.data), V(an.ctypes.data), V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data),
+                   V(wide.ctypes.data), V(pos.ctypes.data))
+                assert tuple(res) == tuple(g["ref_res"][k, ci]), (k, cell, res, g["ref_res"][k, ci])
+                assert np.array_equal(vals.astype(np.int8), g["ref_sim"][k, ci]), (k, cell)
+    finally:
+        lib.scb_set_legacy_geometry(20000, 15000)
+
+
+def test_cluster_symbol_with_dirty_scratch(backend):
+    """A knocked node on permuted positions leaves its own column unwritten (simulator.c:518): what the caller's
+    scratch held there shows through, in the window search too.  Against the literal restatement, which
+    tests/test_oracle.py pins against the reference build for exactly this case."""
+    pr = Problem.synthetic(20, 40, 1, knock=False)
+    n = pr.n
+    stride = max(int(pr.node_positions.max()) + 1, n)
+    ko = np.zeros(n, np.int32); ko[[2, 11]] = 1
+    ki = np.zeros(n, np.int32); ki[5] = 1
+    m = oracle_model(pr.net, pr.node_positions, ko, ki)
+    m.and_nodes, m.and_inv = pr.pop_an[0], pr.pop_ai[0]
+    rng = np.random.default_rng(17)
+    dirty = rng.integers(0, 2, (100, stride)).astype(np.int32)
+    lib = _lib.load(backend[1])
+    lib.scb_set_legacy_geometry(stride, 64)
+    wide = np.zeros((pr.bm.shape[0], 64), np.int32)
+    wide[:, :40] = pr.bm
+    V = ctypes.c_void_p
+    fn = lib.cluster
+    fn.restype = None
+    fn.argtypes = None
+    ind, al, parse, an, ai, pos = [np.ascontiguousarray(a, np.int32) for a in (pr.individuals[0], pr.net.and_len, pr.net.parse, pr.pop_an[0],
+                                                                              pr.pop_ai[0], pr.node_positions)]
+    try:
+        for cell in (0, 13, 39):
+            vals = dirty.copy()
+            res = np.full(2, 2, np.int32)
+            fn(V(vals.ctypes.data), V(res.ctypes.data), V(cell), V(ind.ctypes.data), V(len(ind)), V(n), V(al.ctypes.data),
+               V(parse.ctypes.data), V(an.ctypes.data), V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data),
+               V(wide.ctypes.data), V(pos.ctypes.data))
+            sd, wres = oracle.c_cluster_literal(m, pr.individuals[0], pr.bm, cell, sim_data=dirty, sim_stride=stride)
+            assert tuple(res) == tuple(wres), (cell, res, wres)
+            assert np.array_equal(vals, sd), cell
+    finally:
+        lib.scb_set_legacy_geometry(20000, 15000)

@@ -45,7 +45,7 @@ def test_synthetic_matches_oracle(backend, n, cells, pop):
                                   dict(warps=4), dict(period_search=24), dict(check_every=1), dict(snap_min_gap=1, check_every=4),
                                   dict(snap_min_gap=20, snap_lo=1 << 20, snap_hi=0), dict(fuse=0), dict(fuse=0, early_exit=0, snapshots=0),
                                   dict(steady=0), dict(steady=1, snap_lo=(1 << 4) | (1 << 30), snap_hi=0, snap_min_gap=2),
-                                  dict(steady=1, tmem=0), dict(steady=1, early_exit=0, snapshots=0),
+                                  dict(steady=1, tmem=0), dict(steady=0, tmem=0), dict(steady=1, early_exit=0, snapshots=0),
                                   dict(check_from=-1), dict(check_from=0, check_every=3), dict(check_from=4)])
 def test_every_schedule_gives_identical_integers(backend, opts):
     """Early exit, snapshot resolution and tile geometry are optimisations: results must not move."""
@@ -553,3 +553,94 @@ def test_reduced_program_schedule(backend, chain, want_from):
         if g["from_k"]:
             assert int(g["counts_k"].sum()) == pr.n
             assert int(g["counts_k"][3]) == min(chain, g["from_k"] - 2)
+
+
+# ---- advisor findings of round 1 ---------------------------------------------------------------------------
+def test_shared_context_from_many_threads(backend):
+    """One context driven from a ThreadPool (what replacing __checkNodePossibilities inside the reference's parallel
+    local search does, singleCell.py:490-492; ctypes releases the GIL): every composite call holds the context's lock
+    across upload + run + fetch, so concurrent populations cannot interleave."""
+    from multiprocessing.pool import ThreadPool
+    pr = Problem.synthetic(24, big(backend, 300, 3000), 8)
+    o = pr.oracle()
+    with pr.simulator(backend[1]) as sim:
+        def one(k):
+            p = k % 8
+            got = sim.evaluate_population(pr.individuals[p:p + 1], pr.ko, pr.ki, pr.pop_an[p:p + 1], pr.pop_ai[p:p + 1],
+                                          mode=1 + (k % 2))
+            want = o["nodewise"][p] if k % 2 == 0 else o["cellwise"][p]
+            return np.array_equal(got[0], want)
+        with ThreadPool(6) as pool:
+            ok = pool.map(one, range(32))
+    assert all(ok), ok
+
+
+def test_duplicate_node_positions_are_refused(backend):
+    """Two nodes on one gene row alias one simData column in the reference (the later node overwrites the earlier one
+    in the attractor search and the error); the packed kernels keep nodes independent, so such input is refused."""
+    pr = Problem.synthetic(12, 64, 1)
+    pos = pr.node_positions.copy()
+    pos[3] = pos[7]
+    with pytest.raises(simulator.ScbError) as ei:
+        simulator.Simulator(pr.bm, tables(pr.net, pos), lib_path=backend[1])
+    assert ei.value.code == _lib.ERR_UNSUPPORTED and "twice" in str(ei.value)
+
+
+def test_result_pointer_needs_a_matching_run(backend):
+    pr = Problem.synthetic(12, 64, 2)
+    with pr.simulator(backend[1]) as sim:
+        sim.upload(pr.individuals, pr.ko, pr.ki, pr.pop_an, pr.pop_ai)
+        with pytest.raises(simulator.ScbError):
+            sim.result_device_pointer(simulator.MODE_SUM)                 # nothing has run yet
+        sim.run(simulator.MODE_SUM)
+        sim.result_device_pointer(simulator.MODE_SUM)
+        with pytest.raises(simulator.ScbError):
+            sim.result_device_pointer(simulator.MODE_NODEWISE)            # not what the last run produced
+
+
+_LEGACY_FAIL_SCRIPT = r"""
+import ctypes, sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+from common import Problem
+from scbonita_b200 import _lib
+pr = Problem.synthetic(12, 40, 1)
+lib = _lib.load(%(lib)r)
+lib.scb_set_legacy_geometry(64, 64)
+bm = np.zeros((pr.bm.shape[0], 64), np.int32); bm[:, :40] = pr.bm
+V = ctypes.c_void_p
+ind, al, parse, an, ai, ko, ki, pos = [np.ascontiguousarray(a, np.int32) for a in (pr.individuals[0], pr.net.and_len, pr.net.parse,
+                                       pr.pop_an[0], pr.pop_ai[0], pr.ko, pr.ki, pr.node_positions)]
+fn = lib.scSyncBool; fn.restype = None; fn.argtypes = None
+for local in (0, 1):
+    errors = np.zeros(64, np.int32)
+    fn(V(0), V(ind.ctypes.data), V(len(ind)), V(pr.n), V(al.ctypes.data), V(parse.ctypes.data), V(an.ctypes.data), V(ai.ctypes.data),
+       V(50), V(ko.ctypes.data), V(ki.ctypes.data), V(40), V(bm.ctypes.data), V(pos.ctypes.data), V(errors.ctypes.data), V(local), V(0))
+    n = pr.n if local else 40
+    print("SUM", int(errors[:n].astype(np.int64).sum()), int(errors[:n].min()))
+"""
+
+
+@pytest.mark.parametrize("how", ["abort", "sentinel"])
+def test_legacy_symbol_failure_cannot_look_like_a_result(backend, how):
+    """A failed drop-in scSyncBool (here: simSteps != 100) must never leave `errors` as the caller's zeros -- the
+    unmodified Python would score sum(errors) == 0 as a perfect individual.  Default: message + abort();
+    SCB_LEGACY_ON_ERROR=sentinel: every entry a value no evaluation can reach."""
+    import subprocess
+    import sys as _sys
+    env = dict(os.environ)
+    if how == "sentinel":
+        env["SCB_LEGACY_ON_ERROR"] = "sentinel"
+    else:
+        env.pop("SCB_LEGACY_ON_ERROR", None)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, "-c", _LEGACY_FAIL_SCRIPT % dict(root=root, lib=backend[1])], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert "scSyncBool failed" in r.stderr and "simSteps" in r.stderr, r.stderr
+    if how == "abort":
+        assert r.returncode != 0 and "SUM" not in r.stdout
+    else:
+        assert r.returncode == 0, r.stderr
+        sums = [line.split() for line in r.stdout.splitlines() if line.startswith("SUM")]
+        assert len(sums) == 2
+        for _, total, smallest in sums:
+            assert int(total) > 10 ** 9 and int(smallest) > 12 * 40         # far beyond any reachable error
