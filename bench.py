@@ -35,6 +35,7 @@ WORKLOADS = {
     "C2": dict(nodes=60, cells=10_000, population=100, name="C2: synthetic 10k cells x 60-node network, population 100"),
     "C3": dict(nodes=200, cells=50_000, population=500, name="C3: synthetic 50k cells x 200-node network, population 500"),
     "T0": dict(nodes=24, cells=2_500, population=6, name="T0: tiny self-test shape (not a benchmark)"),
+    "N90": dict(nodes=90, cells=50_000, population=500, name="N90: 50k cells x 90-node network, population 500 (occupancy experiment, not a benchmark)"),
 }
 STEPS_PER_CELL = 99            # simulator.c:375 with simSteps = 100
 METRIC = "cell_rule_evals_per_sec"

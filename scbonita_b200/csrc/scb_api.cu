@@ -86,7 +86,7 @@ struct scb_ctx {
     /* device data */
     DevBuf<uint32_t> dX;
     DevBuf<int32_t> dInd, dAndLen, dParse, dAn, dAi, dKo, dKi;
-    DevBuf<uint4> dDescs, dProgs;
+    DevBuf<uint4> dDescs, dProgs, dImgs;
     DevBuf<int4> dCounts;
     DevBuf<unsigned char> dProgFrom;
     DevBuf<unsigned long long> dFitness;
@@ -118,56 +118,49 @@ struct scb_ctx {
 
 namespace {
 
-/* launch geometry of the simulator kernel for one tile width (K words per lane) */
-int sim_geometry(scb_ctx *c, int K, int optWarps, SimGeom *g)
+/* launch geometry of the simulator kernel for tiles of K words per lane and S warps per CTA: shared memory of the
+ * launch (the in-kernel resolver shares the CTA), CTAs per SM, tensor-memory columns */
+int sim_geometry(scb_ctx *c, int K, int S, SimGeom *g, int *occOut)
 {
     const int N = c->N;
     g->K = K;
-    g->smem = scb_smem_bytes(N, K, 2);
-    const int occGuess = (int)std::max<size_t>(1, (c->smemLimit + 1024) / (g->smem + 1024));
-    int S = optWarps;
-    if (S == 0) {
-        S = 32 / occGuess;
-        S = std::min(SCB_SIM_MAX_WARPS, std::max(2, S));
-        S = std::min(S, std::max(1, (N + 3) / 4));
-        if (occGuess == 1) S = std::min(S, std::max(8, N / 10));       /* ~10 nodes per warp measured best */
-    }
     S = std::max(S, K);                 /* the mask arrays need 32*K threads */
     S = std::min(S, SCB_SIM_MAX_WARPS); /* __launch_bounds__ of scb_k_sim */
     g->warps = S;
-    int occ = 1;
-    if (K == 4) CK((cudaError_t)scb_sim_occupancy_k4_tm0(S * 32, g->smem, &occ));
-    else if (K == 2) CK((cudaError_t)scb_sim_occupancy_k2_tm0(S * 32, g->smem, &occ));
-    else CK((cudaError_t)scb_sim_occupancy_k1_tm0(S * 32, g->smem, &occ));
-    if (occ < 1) return fail(SCB_ERR_UNSUPPORTED, "simulator kernel does not fit on an SM (N=%d, K=%d, warps=%d)", N, K, S);
-    g->ctas = c->numSM * occ;
-    if (c->optMaxCtas > 0) g->ctas = std::min(g->ctas, c->optMaxCtas);
-    {   /* snapshot in tensor memory when the columns of all co-resident CTAs fit into the SM's 512 */
-        /* a warp's piece of the table-sorted program is cut by rows moved, not by nodes: at most 4N/S + 4 rows,
-         * i.e. 2 ceil(N/S) + 2 one-input nodes (scb_load_program) */
-        const int npw = 2 * ((N + S - 1) / S) + 2;
-        const int need = K * ((S + 3) / 4) * npw;
-        int cols = 32;
-        while (cols < need) cols <<= 1;
-        g->tmemCols = (c->optTmem && c->optSnap && cols <= 512 && cols * occ <= 512) ? cols : 0;
-        g->tmemSlotsPerWarp = npw;
+    g->smem = scb_smem_bytes(N, K, 2, S);
+    /* a warp's piece of the table-sorted program is cut by rows moved, not by nodes: at most 4N/S + 4 rows, i.e.
+     * 2 ceil(N/S) + 2 one-input nodes (scb_layout_program): slots of the snapshot / the resolver's target state */
+    const int npw = 2 * ((N + S - 1) / S) + 2;
+    const int need = K * ((S + 3) / 4) * npw;
+    int cols = 32;
+    while (cols < need) cols <<= 1;
+    const bool tmemFits = c->optTmem && c->optSnap && cols <= 512;
+    /* inside the simulator launch the resolver keeps its target state in tensor memory and works on whole tiles with
+     * the simulator's own two-buffer layout; without tensor memory it needs three buffers of one or two chunks */
+    size_t smemLaunch = g->smem;
+    if (c->optFuse) {
+        if (tmemFits) smemLaunch = std::max(smemLaunch, scb_resolve_smem_bytes(N, K, true, S));
+        else smemLaunch = std::max(smemLaunch, scb_resolve_smem_bytes(N, (K >= 2 && scb_resolve_smem_bytes(N, 2) <= c->smemLimit) ? 2 : 1));
     }
+    if (smemLaunch > c->smemLimit) { *occOut = 0; return SCB_OK; }
+    int occ = 0;
+    if (K == 4) CK((cudaError_t)scb_sim_occupancy_k4_tm0(S * 32, smemLaunch, &occ));
+    else if (K == 2) CK((cudaError_t)scb_sim_occupancy_k2_tm0(S * 32, smemLaunch, &occ));
+    else CK((cudaError_t)scb_sim_occupancy_k1_tm0(S * 32, smemLaunch, &occ));
+    if (occ > 4) occ = 4;
+    g->ctas = c->numSM * std::max(occ, 1);
+    if (c->optMaxCtas > 0) g->ctas = std::min(g->ctas, c->optMaxCtas);
+    /* snapshot in tensor memory when the columns of all co-resident CTAs fit into the SM's 512 */
+    g->tmemCols = (tmemFits && cols * std::max(occ, 1) <= 512) ? cols : 0;
+    g->tmemSlotsPerWarp = npw;
+    *occOut = occ;
     return SCB_OK;
 }
 
 int pick_geometry(scb_ctx *c)
 {
     const int N = c->N;
-    int K = c->optWords;
-    if (K != 0 && K != 1 && K != 2 && K != 4) return fail(SCB_ERR_INVALID, "SCB_OPT_WORDS must be 0, 1, 2 or 4");
-    if (K == 0) {
-        K = 4;
-        while (K >= 1 && scb_smem_bytes(N, K, 2) > c->smemLimit) K >>= 1;
-        if (K < 1)
-            return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the %zu-byte shared-memory state buffers", N, c->smemLimit);
-    } else if (scb_smem_bytes(N, K, 2) > c->smemLimit) {
-        return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d with %d words per lane exceeds shared memory", N, K);
-    }
+    if (c->optWords != 0 && c->optWords != 1 && c->optWords != 2 && c->optWords != 4) return fail(SCB_ERR_INVALID, "SCB_OPT_WORDS must be 0, 1, 2 or 4");
     if (scb_resolve_smem_bytes(N, 1) > c->smemLimit)
         return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the resolver's three state buffers", N);
 #ifndef SCB_EMU
@@ -184,8 +177,36 @@ int pick_geometry(scb_ctx *c)
     CK(cudaFuncSetAttribute(scb_k_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
 #endif
-    int rc = sim_geometry(c, K, c->optWarps, &c->main);
-    if (rc) return rc;
+    /* Candidates: tile width K (words per lane) x warps per CTA.  The widest tile that fits wins: a narrower tile
+     * doubles the instructions and the per-warp chain of shared-memory round trips per cell (measured on C3: two CTAs
+     * of K = 2 tiles per SM 3.87 ms against one CTA of K = 4 tiles 3.03 ms).  At that width, a second CTA on the SM
+     * fills the phases in which the first one has nothing in flight (barrier, table dispatch): measured at 90 nodes,
+     * 2 CTAs x 8 warps 1.15 ms against 1 CTA x 16 warps 1.53 ms.  Then the most resident warps. */
+    SimGeom best; int bestOcc = 0, bestScore = -1;
+    int rc;
+    const int kList[3] = {4, 2, 1}, sList[4] = {16, 8, 5, 4};
+    int widest = 0;
+    for (int ki = 0; ki < 3; ++ki) {
+        const int K = kList[ki];
+        if (c->optWords && K != c->optWords) continue;
+        if (widest && K < widest) break;
+        for (int si = 0; si < 4; ++si) {
+            int S = c->optWarps ? c->optWarps : sList[si];
+            if (!c->optWarps) S = std::min(S, std::max(1, (N + 3) / 4));
+            SimGeom g; int occ = 0;
+            if ((rc = sim_geometry(c, K, S, &g, &occ))) return rc;
+            if (occ < 1) continue;
+            if (!widest) widest = K;
+            const int resident = std::min(occ * g.warps, SCB_SIM_MAX_WARPS);
+            const int score = (std::min(occ, 2) >= 2 ? 1000 : 0) + resident * 10 + (K == 4 ? 2 : K == 2 ? 1 : 0);
+            if (score > bestScore) { bestScore = score; best = g; bestOcc = occ; }
+            if (c->optWarps) break;
+        }
+    }
+    if (bestScore < 0)
+        return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the %zu-byte shared-memory state buffers", N, c->smemLimit);
+    c->main = best; c->occ = bestOcc;
+    const int K = best.K;
     /* One launch covers all tiles; the last, partly filled tile is made cheap inside the kernel by
      * idling the lanes that hold no valid word (a separate narrow-tile launch was measured slower:
      * its few long-running tiles leave most SMs idle).  The tail geometry stays available. */
@@ -193,21 +214,20 @@ int pick_geometry(scb_ctx *c)
     c->mainTiles = (c->W + WT - 1) / WT;
     c->tailTiles = 0;
     c->K = K; c->warps = c->main.warps; c->ctas = c->main.ctas; c->smemSim = c->main.smem;
-    /* resolver: two adjacent chunks per item when the simulator tile holds >= 2 chunks and three 64-word
-     * state buffers fit; the fill-forward kernel always works on single chunks */
+    /* resolver items: whole tiles with the target state in tensor memory inside the simulator launch; else two
+     * adjacent chunks (one for K = 1 or when three 64-word buffers do not fit) with three shared-memory buffers */
     c->resGroup = (K >= 2 && scb_resolve_smem_bytes(N, 2) <= c->smemLimit) ? 2 : 1;
     c->smemRes = scb_resolve_smem_bytes(N, c->resGroup);
-    /* inside the simulator launch the resolver can keep its target state in tensor memory and work on whole
-     * 4-chunk tiles with the simulator's own two-buffer layout */
-    if (c->optFuse && K == 4 && c->main.tmemCols > 0 && scb_resolve_smem_bytes(N, 4, true) <= c->smemLimit) {
-        c->resGroup = 4;
-        c->smemRes = scb_resolve_smem_bytes(N, 4, true);
+    if (c->optFuse && c->main.tmemCols > 0) {
+        c->resGroup = K;
+        c->smemRes = scb_resolve_smem_bytes(N, K, true, c->main.warps);
     }
-    c->smemFill = scb_resolve_smem_bytes(N, 1);
     int occR = 1;
     c->resWarps = std::min(c->resGroup == 2 ? 24 : 16, std::max(c->resGroup, (N + 3) / 4));
-    if (c->resGroup == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<2>, c->resWarps * 32, c->smemRes));
-    else if (c->resGroup == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<1>, c->resWarps * 32, c->smemRes));
+    if (!(c->optFuse && c->main.tmemCols > 0)) {
+        if (c->resGroup == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<2>, c->resWarps * 32, c->smemRes));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, scb_k_resolve<1>, c->resWarps * 32, c->smemRes));
+    }
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
     /* fill-forward: one warp per item, two N-word state vectors per warp */
@@ -216,7 +236,6 @@ int pick_geometry(scb_ctx *c)
     c->fillCtas = c->numSM * 4;
     if (c->optMaxCtas > 0) c->fillCtas = std::min(c->fillCtas, c->optMaxCtas);
     size_t zwords = (size_t)c->main.ctas * N * 32 * K;
-    if (c->tailTiles) zwords = std::max(zwords, (size_t)c->tail.ctas * N * 32 * c->tail.K);
     if ((rc = c->dZ.ensure(zwords))) return rc;
     c->geomValid = true;
     return SCB_OK;
@@ -224,7 +243,7 @@ int pick_geometry(scb_ctx *c)
 
 /* K0 on the uploaded population; `knock` is the array the rules read as knock-outs (the importance score
  * passes its knock-in list through the same slot, simulator.c:674) */
-int launch_compile(scb_ctx *c, int sem, const int32_t *knock)
+int launch_compile(scb_ctx *c, int sem, const int32_t *knock, bool wantImages = false)
 {
     const int N = c->N, P = c->P;
     ScbCompileArgs ca;
@@ -233,6 +252,15 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock)
     ca.an = c->dAn.p; ca.ai = c->dAi.p; ca.ko = knock; ca.ki = c->dKi.p; ca.koStride = c->koStride; ca.compact = c->compact;
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
     ca.progs = c->dProgs.p; ca.progFrom = c->dProgFrom.p;
+    ca.imgs = nullptr; ca.imgStride = 0; ca.imgWarps = 0; ca.imgRowBytes = 0;
+    if (wantImages) {
+        /* the program images are cut for the simulator launch that follows: its warps, its row width */
+        ca.imgStride = (int)scb_img_entries(N, c->main.warps);
+        ca.imgWarps = c->main.warps; ca.imgRowBytes = 128u * (unsigned)c->main.K;
+        int rc = c->dImgs.ensure((size_t)P * (SCB_NPROG + 1) * ca.imgStride);
+        if (rc) return rc;
+        ca.imgs = c->dImgs.p;
+    }
     const int cthr = std::min(256, ((N + 31) / 32) * 32);
     SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
     CK(cudaGetLastError());
@@ -440,7 +468,7 @@ int scb_ctx_destroy(scb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
-    c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dProgFrom.release();
+    c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dImgs.release(); c->dProgFrom.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
@@ -607,7 +635,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     CK(cudaMemsetAsync(c->dCounters.p, 0, 8 * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
 
-    if ((rc = launch_compile(c, sem, c->dKo.p))) return rc;
+    if ((rc = launch_compile(c, sem, c->dKo.p, true))) return rc;
 
     ScbSimArgs sa;
     memset(&sa, 0, sizeof(sa));
@@ -615,7 +643,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.P = P; sa.Npad = N; sa.mode = mode;
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
     sa.progs = c->dProgs.p; sa.progFrom = c->dProgFrom.p; sa.useSteady = c->optSteady;
-    sa.firstChk = c->optChk * ((3 + c->optChk - 1) / c->optChk);
+    sa.imgs = c->dImgs.p; sa.imgStride = (int)scb_img_entries(N, c->main.warps);
     sa.chkFromProg = c->optChkFrom;
     sa.firstSnap = 1000;
     for (int t = SCB_LAST - 1; t >= 1; --t)
@@ -629,8 +657,22 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.fillCount = c->dCounters.p + 3; sa.fillItems = c->dFillItems.p;
     sa.zscratch = c->dZ.p;
     sa.flags = (c->optEarly ? SCB_KF_EARLY : 0u) | (c->optSnap ? SCB_KF_SNAP : 0u);
-    sa.chkEvery = c->optChk; sa.snapLo = c->snapLo; sa.snapHi = c->snapHi; sa.periodSearch = c->optSearch;
+    sa.periodSearch = c->optSnap ? c->optSearch : 0;
     sa.snapMinGap = c->optMinGap;
+    {   /* the static schedule of the flagged steps as 128-bit masks over the steps 1 .. 99 */
+        unsigned long long chk[2] = {0ull, 0ull}, snp[2] = {0ull, 0ull}, zc[2] = {0ull, 0ull};
+        auto setb = [](unsigned long long *m, int t) { m[t >> 6] |= 1ull << (t & 63); };
+        auto getb = [](const unsigned long long *m, int t) { return (m[t >> 6] >> (t & 63)) & 1ull; };
+        const unsigned long long given[2] = {c->snapLo, c->snapHi};
+        if (c->optEarly) for (int t = 3; t < SCB_LAST; ++t) if (t % c->optChk == 0) setb(chk, t);
+        setb(chk, SCB_LAST);                                       /* the last state is always compared: E2 or the resolver */
+        int last = -1;
+        for (int t = 1; t <= SCB_LAST; ++t) {
+            if (c->optSnap && last >= 0 && (t - last >= c->optMinGap || t == SCB_LAST)) setb(zc, t);
+            if (c->optSnap && t < SCB_LAST && getb(given, t)) { setb(snp, t); last = t; }
+        }
+        sa.chkLo = chk[0]; sa.chkHi = chk[1]; sa.snapLo = snp[0]; sa.snapHi = snp[1]; sa.zcmpLo = zc[0]; sa.zcmpHi = zc[1];
+    }
     sa.diag = c->dDiag.p;
     /* the simulator resolves queued groups in its own tail when a single launch covers all tiles */
     const bool fuse = c->optFuse && c->tailTiles == 0;
@@ -652,6 +694,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, g.ctas));
         const dim3 block((unsigned)g.warps * 32);
         const size_t smemLaunch = fuse ? std::max(g.smem, c->smemRes) : g.smem;
+        if (smemLaunch > c->smemLimit) return fail(SCB_ERR_UNSUPPORTED, "simulator launch needs %zu bytes of shared memory", smemLaunch);
         sa.smemBytes = (unsigned)smemLaunch;
         int le;
         if (sa.tmemCols > 0) {
@@ -744,6 +787,18 @@ int scb_debug_programs(scb_ctx *c, int p, int k, uint32_t *descs, int32_t *count
     if (fromK) *fromK = from[k];
     return SCB_OK;
 }
+
+#ifdef SCB_TRACE
+/* measurement build only: the step trace of the last fetched run (see ScbDiag::trace) */
+extern "C" int scb_debug_trace(scb_ctx *c, unsigned int *trace, unsigned int *flags)
+{
+    if (!c || !trace || !flags) return fail(SCB_ERR_INVALID, "null argument");
+    memcpy(trace, c->hDiag.trace, sizeof(c->hDiag.trace));
+    memcpy(flags, c->hDiag.traceFlags, sizeof(c->hDiag.traceFlags));
+    memcpy(flags + 100, c->hDiag.exitHist, sizeof(c->hDiag.exitHist));
+    return SCB_OK;
+}
+#endif
 
 int scb_pop_result_dev(scb_ctx *c, int mode, void **devPtr, int64_t *bytes)
 {

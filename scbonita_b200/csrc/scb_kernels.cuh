@@ -327,6 +327,113 @@ template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, c
     return r;
 }
 
+/* ---- the program image --------------------------------------------------------------------------------------
+ * K0 sorts the non-constant nodes of a program by truth table and lays the result out the way the simulator's
+ * warps consume it (scb_layout_program), once per individual and program, so that K2 only has to copy the image
+ * into shared memory (cp.async, while the previous program still runs) and can switch programs by swapping two
+ * buffers.  Warp w of S owns a contiguous piece of the sorted list, cut so that every warp moves about the same
+ * number of state rows per step (a node costs arity + 1 rows), as RUNS of nodes with the same table:
+ *     header {SCB_NOIN | table, SCB_NOIN | n, SCB_NOIN, 0}   then n node entries   ...   header {SCB_NOIN | SCB_CLS_END, ..}
+ * Image:  [0] = {n3, n2, n1, n0} (nodes by arity; n0 = constants, which are NOT in the lists)
+ *         [1 + w/2] = {offset, entries} of warp w (x, y for even w; z, w for odd w), offset in 16-byte entries from
+ *                     the image start, entries without the end header
+ *         then the lists, each followed by its end header and two entries of slack (the descriptor prefetch of the
+ *         step code reads that far).
+ * Node entry: x, y, z = byte offsets of the input rows within a state buffer, SCB_NOIN (sign bit) for an input the
+ * table does not depend on; w = byte offset of the node's own row | table << 24.
+ * Plain and compare steps run a list through scb_step_runs: one jump per RUN into a loop specialised for that table
+ * (no per-node dispatch, no loads for unused inputs, no LOP3 for copies).  Snapshot steps walk the same list entry by
+ * entry (scb_step), skipping the headers.  Constant rows are written at steps 1 and 2 straight from the global
+ * program (scb_const_rows). */
+#define SCB_NOIN 0x80000000u
+#define SCB_DST_MASK 0xFFFFFu
+#define SCB_CLS_END 256u
+#define SCB_PROG_MAX_WARPS 24
+#define SCB_LIST_TAIL 3           /* end header + two entries of slack per warp */
+SCB_HD inline int scb_img_hdr(int S) { return 1 + (S + 1) / 2; }
+/* entries of an image for S warps: header, every node, every run (at most one per distinct table, plus one more
+ * for every piece boundary that cuts a run), the tails */
+SCB_HD inline size_t scb_img_entries(int N, int S) { return (size_t)scb_img_hdr(S) + (size_t)N + (size_t)(N < 255 ? N : 255) + (size_t)S * (1 + SCB_LIST_TAIL); }
+SCB_HD inline size_t scb_img_entries_max(int N) { return scb_img_entries(N, SCB_PROG_MAX_WARPS); }
+/* shared-memory carve-up of the simulator for S warps, identical formula on host and device: state buffers, ONE
+ * program image (the next one waits in registers, SCB_STAGE_REGS uint4 per thread), masks, scalars.  Kept tight:
+ * two CTAs of K = 2 tiles share an SM for a 200-node network (see pick_geometry). */
+#define SCB_STAGE_REGS 3
+SCB_HD inline size_t scb_smem_bytes(int N, int K, int nbuf, int S)
+{
+    return (size_t)nbuf * N * 128 * K + scb_img_entries(N, S) * 16 + (size_t)8 * 32 * K * 4 + 512;
+}
+
+/* {offset, entries} of `warp` in an image */
+SCB_DEV void scb_img_warp(const uint4 *img, int warp, int &off, int &nw)
+{
+    const uint4 h = img[1 + (warp >> 1)];
+    off = (int)((warp & 1) ? h.z : h.x);
+    nw = (int)((warp & 1) ? h.w : h.y);
+}
+
+/* table-sorted program g (fields of scb_scatter_by_table) -> image for S warps and rows of ROWB bytes, in global or
+ * shared memory.  scr: 3 x 32 ints of shared scratch.  Contains barriers: all threads of the CTA call it. */
+SCB_DEV void scb_layout_program(uint4 *img, int *scr, const uint4 *g, int4 cnt, int N, int S, uint32_t ROWB, int tid, int nthr)
+{
+    const int e1 = cnt.x + cnt.y + cnt.z;
+    const unsigned total = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
+    int *first = scr, *last = scr + 32, *offs = scr + 64;
+    if (tid <= S) first[tid] = e1;
+    __syncthreads();
+#define SCB_WARP_OF(d) ((int)((((d).x >> 16) * (unsigned)S) / total))
+    for (int j = tid; j < e1; j += nthr) {
+        const int w = SCB_WARP_OF(g[j]);
+        if (j == 0 || SCB_WARP_OF(g[j - 1]) != w) first[w] = j;
+    }
+    __syncthreads();
+    if (tid < S) {
+        int e = e1;                                       /* the piece ends where the next non-empty one starts */
+        for (int w = tid + 1; w < S; ++w) if (first[w] < e1) { e = first[w]; break; }
+        last[tid] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        img[0] = make_uint4((unsigned)cnt.x, (unsigned)cnt.y, (unsigned)cnt.z, (unsigned)cnt.w);
+        int o = scb_img_hdr(S);
+        for (int w = 0; w < S; ++w) {
+            const int f = first[w], l = last[w];
+            /* entries of the piece: its nodes + its runs (the piece's first node always starts one) */
+            const int n = f < e1 ? (l - f) + (int)((g[l - 1].z >> 16) - (g[f].z >> 16)) + 1 : 0;
+            offs[w] = o;
+            uint4 *h = img + 1 + (w >> 1);
+            if (w & 1) { h->z = (unsigned)o; h->w = (unsigned)n; } else { h->x = (unsigned)o; h->y = (unsigned)n; }
+            img[o + n] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+            img[o + n + 1] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+            img[o + n + 2] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+            o += n + SCB_LIST_TAIL;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < e1; j += nthr) {
+        const uint4 d = g[j];
+        const int w = SCB_WARP_OF(d);
+        const int s0 = first[w], end = last[w];
+        const unsigned lut = d.w >> 24, ar = (d.y >> 16) & 3u;
+        const bool runStart = j == s0 || (g[j - 1].w >> 24) != lut;
+        const int idx = (j - s0) + (int)((d.z >> 16) - (g[s0].z >> 16)) + 1;
+        uint4 o;
+        o.x = (d.x & 0xFFFFu) * ROWB;
+        o.y = ar >= 2u ? (d.y & 0xFFFFu) * ROWB : SCB_NOIN;
+        o.z = ar >= 3u ? (d.z & 0xFFFFu) * ROWB : SCB_NOIN;
+        o.w = ((d.w & 0xFFFFu) * ROWB) | (lut << 24);
+        uint4 *mine = img + offs[w];
+        mine[idx] = o;
+        if (runStart) {
+            int len = 1;
+            while (j + len < end && (g[j + len].w >> 24) == lut) ++len;
+            mine[idx - 1] = make_uint4(SCB_NOIN | lut, SCB_NOIN | (unsigned)len, SCB_NOIN, 0u);
+        }
+    }
+#undef SCB_WARP_OF
+    __syncthreads();
+}
+
 #ifndef SCB_SIM_ONLY   /* the simulator's own translation units (scb_sim_tu.cu) leave the other kernels out */
 /* ------------------------------------------------------------------------------------------
  * K0: rule compiler.  One CTA per individual, one thread per node; the program is written sorted
@@ -338,7 +445,7 @@ template <int K> SCB_DEV ScbVec<K> scb_apply2(unsigned l4, const ScbVec<K> &a, c
 /* scratch of the table sort at the end of K0's shared memory: bins[SCB_SORT_BINS] counts -> starts,
  * cost[SCB_SORT_BINS] rows before each bin, run[SCB_SORT_BINS] non-empty bins before each bin, rank[N] (uint16) */
 #define SCB_SORT_BINS 258          /* 256 tables, then the two constants */
-SCB_HD inline size_t scb_sort_smem_bytes(int N) { return (size_t)3 * SCB_SORT_BINS * 4 + (size_t)((N + 7) / 8) * 16 + 32; }
+SCB_HD inline size_t scb_sort_smem_bytes(int N) { return (size_t)3 * SCB_SORT_BINS * 4 + (size_t)((N + 7) / 8) * 16 + 32 + 96 * 4; }
 SCB_HD inline size_t scb_compile_smem_bytes(int N)
 {
     return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4 + scb_sort_smem_bytes(N);
@@ -458,6 +565,10 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     const int c3 = (int)cn[0], c2 = (int)cn[1], c1 = (int)cn[2], c0 = (int)cn[3];
     unsigned int *wc = reinterpret_cast<unsigned int *>(smraw + scb_compile_smem_bytes(N) - scb_sort_smem_bytes(N));
     scb_scatter_by_table(sd, sar, N, A.descs + (long long)p * A.Npad, wc, tid, nthr);
+    /* the images the simulator copies into its shared memory: image 0 = the full program, 1 + k = reduced program k */
+    int *lscr = reinterpret_cast<int *>(smraw + scb_compile_smem_bytes(N) - 96 * 4);
+    uint4 *imgs = A.imgs ? A.imgs + (long long)p * (SCB_NPROG + 1) * A.imgStride : nullptr;
+    if (imgs) scb_layout_program(imgs, lscr, A.descs + (long long)p * A.Npad, make_int4(c3, c2, c1, c0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
     /* ---- reduced programs by constant propagation.  c(t) = nodes whose value in S_t is the same constant for every
      * cell: c(1) = the constant rules (knock-outs, knock-ins, constant-TRUE literals), c(t+1) = rules that are
      * constant once the inputs in c(t) are fixed.  Knowledge only grows, so c(D) stays valid for every t >= D.  A
@@ -521,6 +632,7 @@ __global__ void scb_k_compile(ScbCompileArgs A)
             const int slot = last ? SCB_NPROG - 1 : stage;
             uint4 *out2 = progs + (long long)slot * (N + 1);
             scb_scatter_by_table(sd2, sar2, N, out2, wc, tid, nthr);
+            if (imgs) scb_layout_program(imgs + (long long)(1 + slot) * A.imgStride, lscr, out2, make_int4(s3, s2, s1, s0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
             if (tid == 0) {
                 out2[N] = make_uint4((unsigned)s3, (unsigned)s2, (unsigned)s1, (unsigned)s0);   /* the counts travel with the program */
                 progFrom[slot] = (unsigned char)(D + 2);
@@ -601,93 +713,6 @@ __global__ void scb_k_pack_csr(ScbPackCsrArgs A)
 /* ------------------------------------------------------------------------------------------
  * shared pieces of K2 / K3
  * ---------------------------------------------------------------------------------------- */
-/* ---- the program in shared memory ------------------------------------------------------------------------
- * K0 hands over the non-constant nodes sorted by truth table.  Warp w of S owns a contiguous piece of that list,
- * cut so that every warp moves about the same number of state rows per step (a node costs arity + 1 rows), laid
- * out in ITS part of the program area (PW entries of 16 bytes per warp) as RUNS of nodes with the same table:
- *     header {SCB_NOIN | table, SCB_NOIN | n, SCB_NOIN, 0}   then n node entries   ...   header {SCB_NOIN | SCB_CLS_END, ..}
- * Node entry: x, y, z = byte offsets of the input rows within a state buffer, SCB_NOIN (sign bit) for an input the
- * table does not depend on; w = byte offset of the node's own row | table << 24.
- * Plain steps run the list through scb_step_runs: one jump per RUN into a loop specialised for that table (no
- * dispatch, no loads for unused inputs, no LOP3 for copies).  Flagged steps (compares, snapshots) walk the same list
- * entry by entry (scb_step), skipping the headers.  Constant nodes are not in the list: their rows are written at
- * steps 1 and 2 straight from the global program (scb_const_rows). */
-#define SCB_NOIN 0x80000000u
-#define SCB_DST_MASK 0xFFFFFu
-#define SCB_CLS_END 256u
-#define SCB_PROG_MAX_WARPS 24
-/* entries per warp: nodes + run headers of a piece whose rows do not exceed 4N/S + 4, plus the end header and two
- * entries of slack for the descriptor prefetch of scb_step.  Worst cases: 2N/S + 2 one-input nodes (2 tables),
- * (4N/S + 4) / 3 two-input nodes of distinct tables, N/S + 1 three-input nodes of distinct tables. */
-SCB_HD inline int scb_prog_stride(int N, int S) { const int q = (N + S - 1) / S; return (8 * q) / 3 + 10; }
-/* entries reserved for a program (any S <= SCB_PROG_MAX_WARPS: S * PW <= 8N/3 + 8S/3 + 10 S) */
-SCB_HD inline size_t scb_prog_entries(int N) { return (size_t)(8 * N) / 3 + (size_t)SCB_PROG_MAX_WARPS * 13; }
-/* shared-memory carve-up, identical formula on host and device */
-SCB_HD inline size_t scb_smem_bytes(int N, int K, int nbuf)
-{
-    return (size_t)nbuf * N * 128 * K + scb_prog_entries(N) * 16 + (size_t)(N + 1) * 16 + (size_t)6 * 32 * K * 4 + 4096 + 256;   /* program + staged program */
-}
-
-/* individual p's program (global or staged layout: table-sorted, fields of scb_scatter_by_table) -> the per-warp
- * run lists.  winfo[w] = entries of warp w's list without the end header; winfo[32 + w], winfo[64 + w]: scratch
- * (first node / end of the warp's piece).  Contains barriers: all threads of the CTA call it. */
-template <int K>
-SCB_DEV void scb_load_program(uint4 *wl, int *winfo, const uint4 *g, int4 cnt, int N, int S, int tid, int nthr)
-{
-    const uint32_t ROWB = 128u * K;
-    const int e1 = cnt.x + cnt.y + cnt.z;
-    const unsigned total = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
-    const int PW = scb_prog_stride(N, S);
-    int *first = winfo + 32, *last = winfo + 64;
-    if (tid <= S) first[tid] = e1;
-    __syncthreads();
-#define SCB_WARP_OF(d) ((int)((((d).x >> 16) * (unsigned)S) / total))
-    for (int j = tid; j < e1; j += nthr) {
-        const int w = SCB_WARP_OF(g[j]);
-        if (j == 0 || SCB_WARP_OF(g[j - 1]) != w) first[w] = j;
-    }
-    __syncthreads();
-    if (tid < S) {
-        int e = e1;                                       /* the piece ends where the next non-empty one starts */
-        for (int w = tid + 1; w < S; ++w) if (first[w] < e1) { e = first[w]; break; }
-        last[tid] = e;
-        if (first[tid] >= e1) {                           /* no nodes: an empty list */
-            wl[tid * PW] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
-            winfo[tid] = 0;
-        }
-    }
-    __syncthreads();
-    for (int j = tid; j < e1; j += nthr) {
-        const uint4 d = g[j];
-        const int w = SCB_WARP_OF(d);
-        const int s0 = first[w], end = last[w];
-        const unsigned lut = d.w >> 24, ar = (d.y >> 16) & 3u;
-        const bool runStart = j == s0 || (g[j - 1].w >> 24) != lut;
-        const int idx = (j - s0) + (int)((d.z >> 16) - (g[s0].z >> 16)) + 1;
-        uint4 o;
-        o.x = (d.x & 0xFFFFu) * ROWB;
-        o.y = ar >= 2u ? (d.y & 0xFFFFu) * ROWB : SCB_NOIN;
-        o.z = ar >= 3u ? (d.z & 0xFFFFu) * ROWB : SCB_NOIN;
-        o.w = ((d.w & 0xFFFFu) * ROWB) | (lut << 24);
-        uint4 *mine = wl + w * PW;
-#ifdef SCB_EMU
-        if (idx + 3 > PW) abort();                        /* the bound of scb_prog_stride is rigorous; checked under the emulator */
-#endif
-        mine[idx] = o;
-        if (runStart) {
-            int len = 1;
-            while (j + len < end && (g[j + len].w >> 24) == lut) ++len;
-            mine[idx - 1] = make_uint4(SCB_NOIN | lut, SCB_NOIN | (unsigned)len, SCB_NOIN, 0u);
-        }
-        if (j == end - 1) {
-            mine[idx + 1] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
-            winfo[w] = idx + 1;
-        }
-    }
-#undef SCB_WARP_OF
-    __syncthreads();
-}
-
 /* the constant rows of a program (entries e1 .. e1 + n0 of the GLOBAL program) into `dst` (lane-adjusted), and
  * into the global snapshot when zg != null */
 template <int K>
@@ -804,28 +829,40 @@ SCB_DEV void scb_step(scb_saddr src, scb_saddr dst, scb_saddr wl, int nw, unsign
 
 /* One step for the warp's list through the RUN interpreter (generated PTX, scb_lut_ptx.inc / gen_lut_ptx.py): one
  * table dispatch per run into a loop specialised for that table.  FLAGS = 0 (plain: most steps), SCB_SF_CMP2,
- * SCB_SF_ZCMP (snapshot in tensor memory) or both; the compare accumulators d2 / dz stay in registers.  Lanes without
- * valid cells sit out the plain steps; compare steps keep the warp converged (tcgen05.ld is warp-collective, the
- * garbage of those lanes is masked by the valid mask). */
+ * SCB_SF_ZCMP (snapshot / resolver target in tensor memory, list order) or both; the compare accumulators d2 / dz stay
+ * in registers.  Lanes without valid cells sit out the steps without a tensor-memory compare; those keep the warp
+ * converged (tcgen05.ld is warp-collective, the garbage of those lanes is masked by the valid mask). */
+/* the head of a warp's list (first run header, first node entry): constant over the steps of a program, so the step
+ * code gets it in registers instead of waiting for a shared-memory round trip at the start of every step */
+struct ScbListHead { uint32_t h0, h1; uint4 d; };
+SCB_DEV ScbListHead scb_list_head(const uint4 *list)
+{
+    ScbListHead r;
+    r.h0 = list[0].x; r.h1 = list[0].y; r.d = list[1];
+    return r;
+}
+
 template <int K, unsigned FLAGS>
-SCB_DEV void scb_step_runs(scb_saddr src, scb_saddr dst, scb_saddr wl, bool active, ScbVec<K> &d2, ScbVec<K> &dz, uint32_t tm)
+SCB_DEV void scb_step_runs(scb_saddr src, scb_saddr dst, scb_saddr wl, const ScbListHead &hd, bool active, ScbVec<K> &d2, ScbVec<K> &dz, uint32_t tm)
 {
     if (!(FLAGS & SCB_SF_ZCMP) && !active) return;
 #if defined(__CUDA_ARCH__)
+#define SCB_RUNS_IN "r"(wl), "r"(src), "r"(dst), "r"(tm), "r"(hd.h0), "r"(hd.h1), "r"(hd.d.x), "r"(hd.d.y), "r"(hd.d.z), "r"(hd.d.w)
 #define SCB_RUNS_ASM(NAME)                                                                                             \
     do {                                                                                                               \
         if (K == 4) asm volatile(NAME##_K4 : "+r"(d2.v[0]), "+r"(d2.v[1 % K]), "+r"(d2.v[2 % K]), "+r"(d2.v[3 % K]),   \
                                  "+r"(dz.v[0]), "+r"(dz.v[1 % K]), "+r"(dz.v[2 % K]), "+r"(dz.v[3 % K])                \
-                                 : "r"(wl), "r"(src), "r"(dst), "r"(tm) : "memory");                                   \
+                                 : SCB_RUNS_IN : "memory");                                                            \
         else if (K == 2) asm volatile(NAME##_K2 : "+r"(d2.v[0]), "+r"(d2.v[1 % K]), "+r"(dz.v[0]), "+r"(dz.v[1 % K])   \
-                                      : "r"(wl), "r"(src), "r"(dst), "r"(tm) : "memory");                              \
-        else asm volatile(NAME##_K1 : "+r"(d2.v[0]), "+r"(dz.v[0]) : "r"(wl), "r"(src), "r"(dst), "r"(tm) : "memory"); \
+                                      : SCB_RUNS_IN : "memory");                                                       \
+        else asm volatile(NAME##_K1 : "+r"(d2.v[0]), "+r"(dz.v[0]) : SCB_RUNS_IN : "memory");                          \
     } while (0)
     if (FLAGS == 0u) SCB_RUNS_ASM(SCB_RUNS_PTX);
     else if (FLAGS == SCB_SF_CMP2) SCB_RUNS_ASM(SCB_RUNS_CMP2_PTX);
     else if (FLAGS == SCB_SF_ZCMP) SCB_RUNS_ASM(SCB_RUNS_ZCMP_PTX);
     else SCB_RUNS_ASM(SCB_RUNS_CMP2_ZCMP_PTX);
 #undef SCB_RUNS_ASM
+#undef SCB_RUNS_IN
 #else
     const uint4 *e = reinterpret_cast<const uint4 *>(wl);
     uint32_t tmc = tm;
@@ -852,6 +889,22 @@ SCB_DEV void scb_step_runs(scb_saddr src, scb_saddr dst, scb_saddr wl, bool acti
 #endif
 }
 
+/* index of the first set bit above `after` in the 128-bit mask (lo, hi); 1000 if there is none */
+SCB_DEV int scb_next_bit(unsigned long long lo, unsigned long long hi, int after)
+{
+    int s = after + 1;
+    if (s < 64) {
+        const unsigned long long m = lo >> s;
+        if (m) return s + __ffsll((long long)m) - 1;
+        s = 64;
+    }
+    if (s < 128) {
+        const unsigned long long m = hi >> (s - 64);
+        if (m) return s + __ffsll((long long)m) - 1;
+    }
+    return 1000;
+}
+
 /* valid-cell mask of word w (cells w*32 .. w*32+31 below C) */
 SCB_DEV uint32_t scb_valid_mask(long long w, int C)
 {
@@ -874,9 +927,24 @@ SCB_DEV uint32_t scb_valid_mask(long long w, int C)
  *       are, the tile runs plain steps to S_98.  Cells still unproven after the last compare
  *       at t = 99 are queued, as 1024-cell chunks, for K3, and K2 leaves them out of its sums.
  * ---------------------------------------------------------------------------------------- */
-template <int KR, bool TTM = false> SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it, uint32_t tm = SCB_TMEM_OFF);
+template <int KR, bool TTM = false> SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it, uint32_t tm = SCB_TMEM_OFF, bool useImg = false);
 
-#define SCB_SIM_MAX_WARPS 20     /* 640 threads: 96 registers per thread, enough to keep every address of the step loop live */
+#ifndef SCB_SIM_MAX_WARPS
+#define SCB_SIM_MAX_WARPS 16     /* 512 threads: 128 registers per thread.  At 640 threads (96 registers) the control code between
+                                   * the steps spills, and with 229 KB of the SM's L1 given to shared memory a spill reload is
+                                   * an L2 round trip (measured: 2.94 ms against 3.19 ms per C3 generation) */
+#endif
+#if defined(SCB_TRACE) && defined(__CUDA_ARCH__)
+#define SCB_TRACE_MARK(step, which, fl)                                                                          \
+    do {                                                                                                         \
+        if (blockIdx.x == 0 && tilesDone == 0 && lane == 0 && (step) < 100) {                                    \
+            A.diag->trace[((step) * 24 + warp) * 4 + (which)] = (unsigned)clock64();                             \
+            if (warp == 0 && (which) == 0) A.diag->traceFlags[(step)] = (fl);                                    \
+        }                                                                                                        \
+    } while (0)
+#else
+#define SCB_TRACE_MARK(step, which, fl) do { } while (0)
+#endif
 template <int K, bool TM>
 __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArgs A)
 {
@@ -886,18 +954,20 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
     const int WT = 32 * K;                              /* words per tile */
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + 2u * BUFB);
-    uint4 *desc2 = desc + scb_prog_entries(N);          /* staging buffer of the next reduced program: N nodes + its counts */
-    uint32_t *dm2 = reinterpret_cast<uint32_t *>(desc2 + N + 1);
-    uint32_t *dmz = dm2 + WT;
-    uint32_t *Rm = dmz + WT;
-    uint32_t *vm = Rm + WT;
-    int *sh = reinterpret_cast<int *>(vm + WT);          /* [0] item, [1],[2] flag words, [4..4+K) chunk flags */
-    int *winfo = sh + 32;                                /* [96] per-warp list lengths + scratch of scb_load_program */
+    /* one program image; the next program waits in registers (fetched right after a switch, stored at the next one) */
+    const uint32_t IMGB = (uint32_t)scb_img_entries(N, (int)(blockDim.x >> 5)) * 16u;
+    /* compare accumulators: three buffers of {d2[WT], dz[WT]} used in turn, so that a compare step needs no barrier of
+     * its own (the buffer of compare n is cleared after the barrier of compare n + 1 and reused by compare n + 3);
+     * word lane * K + k of the tile sits at [k * 32 + lane]: a warp's atomics hit 32 different banks */
+    uint32_t *cm = reinterpret_cast<uint32_t *>(smraw + 2u * BUFB + IMGB);
+    uint32_t *vm = cm + 6 * WT;
+    uint32_t *Rm = vm + WT;                              /* cells a repeat has been seen for (found) */
+    int *sh = reinterpret_cast<int *>(Rm + WT);          /* [0] item, [4..4+K) chunk flags, [20..28) compare flags of the folding warps */
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31;
     int warp = tid >> 5, S = nthr >> 5;
     uint32_t laneOff = (uint32_t)lane * 4u * K;
-    const bool early = (A.flags & SCB_KF_EARLY) != 0, useZ = (A.flags & SCB_KF_SNAP) != 0;
+
     unsigned char *zg = reinterpret_cast<unsigned char *>(A.zscratch + (unsigned long long)blockIdx.x * A.zstride) + laneOff;
     scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
 #if defined(__CUDA_ARCH__)
@@ -948,13 +1018,20 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         int4 cnt = A.counts[p];
         const uint4 *gfull = A.descs + (long long)p * A.Npad;
         const int e1full = cnt.x + cnt.y + cnt.z, n0full = cnt.w;      /* the constants of the FULL program are written at steps 1, 2 */
-        scb_load_program<K>(desc, winfo, gfull, cnt, N, S, tid, nthr);
-        int nw = winfo[warp];
-        scb_saddr wl = sdesc + 16u * (uint32_t)(warp * scb_prog_stride(N, S));
-        /* reduced programs (K0): program k may compute steps >= from[k]; the next one is staged in desc2 by
-         * asynchronous copies while the current one runs.  All switches happen before the first snapshot, whose
-         * tensor-memory slots follow the program's node order. */
-        const uint4 *progBase = A.progs + (long long)p * SCB_NPROG * (N + 1);
+        /* K0 laid every program out as the image this CTA's warps consume: the full program is copied into one
+         * image buffer now, the next reduced program (program k may compute steps >= from[k]) is staged into the other
+         * one by asynchronous copies while the current one runs, and a switch just swaps the two.  All switches happen
+         * before the first snapshot, whose tensor-memory slots follow the program's node order. */
+        const uint4 *imgBase = A.imgs + (long long)p * (SCB_NPROG + 1) * A.imgStride;
+        uint4 stage[SCB_STAGE_REGS];                        /* this thread's entries of the next program image */
+        for (int j = tid; j < A.imgStride; j += nthr) scb_cp_async16(&desc[j], &imgBase[j]);
+        scb_cp_async_commit();
+        scb_cp_async_wait();
+        __syncthreads();
+        int nw, woff;
+        scb_img_warp(desc, warp, woff, nw);
+        scb_saddr wl = sdesc + 16u * (uint32_t)woff;
+        ScbListHead hd = scb_list_head(desc + woff);
         unsigned long long fromBytes = A.useSteady ? *reinterpret_cast<const unsigned long long *>(A.progFrom + (long long)p * 8) : 0ull;
         int switchAt = 1000, nextProg = 0;
         unsigned rowsPerStep = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
@@ -967,9 +1044,11 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 if (from > (after) && from <= A.firstSnap) { switchAt = from; break; }                    \
             }                                                                                             \
             if (switchAt < 1000) {                                                                        \
-                const uint4 *src = progBase + (long long)nextProg * (N + 1);                              \
-                for (int j = tid; j <= N; j += nthr) scb_cp_async16(&desc2[j], &src[j]);                  \
-                scb_cp_async_commit();                                                                    \
+                const uint4 *src = imgBase + (long long)(1 + nextProg) * A.imgStride;                     \
+                _Pragma("unroll") for (int r = 0; r < SCB_STAGE_REGS; ++r) {                              \
+                    const int j = tid + r * nthr;                                                         \
+                    if (j < A.imgStride) stage[r] = src[j];                                               \
+                }                                                                                         \
                 ++nextProg;                                                                               \
             }                                                                                             \
         } while (0)
@@ -1007,8 +1086,8 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
             for (; row < N; row += S)
                 scb_st<K>(sm + (uint32_t)row * ROWB + laneOff, scb_ldg<K>(xs + (long long)row * A.Wpad));
         }
-        if (tid < WT) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); Rm[tid] = 0u; dm2[tid] = 0u; dmz[tid] = 0u; }
-        if (tid == 0) { sh[1] = 0; sh[2] = 0; }
+        if (tid < WT) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); Rm[tid] = 0u; }
+        for (int i = tid; i < 6 * WT; i += nthr) cm[i] = 0u;
 #if defined(__CUDA_ARCH__)
         if (tileByTma) { scb_mbar_wait(mbarAddr, tmaParity); tmaParity ^= 1u; }
 #endif
@@ -1023,46 +1102,40 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         uint32_t srcOff = 0u, dstOff = BUFB, finOff = 0u;
         int t = 0, target = SCB_LAST, zs = -1, ncmp = 0, searchLeft = 0;
         bool allres = false, allfound = false, plainOnly = false, haveFin = false;
-        /* the schedule as two counters (next period-<=2 check, next snapshot) instead of a modulo and two 64-bit
-         * mask tests per step */
-        int nextChk = A.firstChk, nextSnap = A.firstSnap;
+        /* The schedule of the flagged steps is static (host-built 128-bit masks: period-<=2 checks, snapshots, snapshot
+         * compares); the tile only delays its first check.  Every warp runs this control code, so it is kept short. */
+        unsigned long long chkLo = A.chkLo, chkHi = A.chkHi;
         {   /* no period-<=2 check before the constants have spread: until then the nodes they will reach still carry
              * shifting cell data, so the tile cannot have settled (the checks are an optimisation, results never depend
              * on when they run) */
             int fromK = A.chkFromProg >= 0 ? (int)((fromBytes >> (8 * A.chkFromProg)) & 0xffull) : 0;
             if (fromK == 0 && A.chkFromProg >= 0) fromK = (int)((fromBytes >> (8 * (SCB_NPROG - 1))) & 0xffull);   /* that depth was not reached */
-            while (nextChk < fromK) nextChk += A.chkEvery;
+            if (fromK > 0) {
+                if (fromK >= 64) { chkLo = 0ull; chkHi &= ~((1ull << (fromK >= 99 ? 35 : fromK - 64)) - 1ull); }
+                else chkLo &= ~((1ull << fromK) - 1ull);
+            }
         }
-        /* most steps are plain: nextEvent is the first step at which a check, snapshot or compare can be due, so the
-         * schedule logic below runs only from there on (and is re-armed after every non-plain step) */
-#define SCB_NEXT_EVENT(now)                                                                           \
-        do {                                                                                          \
-            if (plainOnly) nextEvent = 1000;                                                          \
-            else if (allres) nextEvent = (useZ && zs >= 0 && searchLeft > 0) ? (now) + 1 : 1000;      \
-            else {                                                                                    \
-                nextEvent = SCB_LAST;                                                                 \
-                if (early && nextChk < nextEvent) nextEvent = nextChk;                                \
-                if (useZ && nextSnap < nextEvent) nextEvent = nextSnap;                               \
-                if (useZ && zs >= 0 && zs + A.snapMinGap < nextEvent) nextEvent = zs + A.snapMinGap;  \
-                if (nextEvent <= (now)) nextEvent = (now) + 1;                                        \
-            }                                                                                         \
-        } while (0)
-        int nextEvent;
-        SCB_NEXT_EVENT(0);
+        const unsigned long long evLo = chkLo | A.snapLo | A.zcmpLo, evHi = chkHi | A.snapHi | A.zcmpHi;
+        int nextEvent = scb_next_bit(evLo, evHi, 0);        /* most steps are plain: the first step with a flag */
         while (t < target) {
             int tn = t + 1;                             /* this iteration computes S_tn */
             if (tn == switchAt) {
-                /* the staged program replaces the current one in place (every warp is past the barrier of the
-                 * previous step), so the step code keeps one program address */
-                scb_cp_async_wait();
+                /* the image waiting in registers replaces the program in use (every warp is past the barrier of the
+                 * previous step, so nobody reads the old one any more) */
+#pragma unroll
+                for (int r = 0; r < SCB_STAGE_REGS; ++r) {
+                    const int j = tid + r * nthr;
+                    if (j < A.imgStride) desc[j] = stage[r];
+                }
                 __syncthreads();
                 rowsMoved += (unsigned)(t - segStart) * rowsPerStep;
                 segStart = t;
-                const uint4 c4 = desc2[N];
+                const uint4 c4 = desc[0];
                 cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
                 rowsPerStep = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
-                scb_load_program<K>(desc, winfo, desc2, cnt, N, S, tid, nthr);
-                nw = winfo[warp];
+                scb_img_warp(desc, warp, woff, nw);
+                wl = sdesc + 16u * (uint32_t)woff;
+                hd = scb_list_head(desc + woff);
                 SCB_NEXT_PROGRAM(tn);
             }
             ScbVec<K> d2, dz;
@@ -1077,7 +1150,9 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 if (tn <= 2) until = tn + 1;            /* the constant rows go into both buffers */
 #pragma unroll 1
                 for (; tn < until; ++tn) {
-                    scb_step_runs<K, 0u>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
+                    SCB_TRACE_MARK(tn, 0, rowsPerStep << 16);
+                    scb_step_runs<K, 0u>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, hd, laneActive, d2, dz, tm);
+                    SCB_TRACE_MARK(tn, 1, 0u);
                     __syncthreads();
                     const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
                 }
@@ -1085,57 +1160,57 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 continue;
             }
             unsigned f = 0u;
-            {
-                bool chkNow = false, snapNow = false;
-                while (nextChk < tn) nextChk += A.chkEvery;
-                if (tn == nextChk) { chkNow = true; nextChk += A.chkEvery; }
-                if (tn >= nextSnap) {
-                    snapNow = tn == nextSnap;
-                    nextSnap = 1000;
-                    for (int u = tn + 1; u < SCB_LAST; ++u)
-                        if (u < 64 ? ((A.snapLo >> u) & 1ull) != 0ull : ((A.snapHi >> (u - 64)) & 1ull) != 0ull) { nextSnap = u; break; }
-                }
-                if (!allres) {
-                    if (tn == SCB_LAST || (early && chkNow)) f |= SCB_SF_CMP2;
-                    /* a cell of period L matches the snapshot at every multiple of L, so the first compares after a
-                     * snapshot can be skipped without losing any cell: only the proof comes a little later */
-                    if (useZ && zs >= 0 && (tn - zs >= A.snapMinGap || tn == SCB_LAST)) f |= SCB_SF_ZCMP;
-                    if (useZ && snapNow && tn < SCB_LAST) f |= SCB_SF_ZSNAP;
-                } else if (useZ && zs >= 0 && searchLeft > 0) {
-                    f |= SCB_SF_ZCMP; --searchLeft;   /* all cells proven: look for a tile-wide period */
-                }
+            if (!allres) {
+                /* a cell of period L matches the snapshot at every multiple of L, so the first compares after a
+                 * snapshot can be skipped without losing any cell (the gap is part of the static mask) */
+                const unsigned sh6 = (unsigned)tn & 63u;
+                const unsigned long long c = tn < 64 ? chkLo : chkHi, z = tn < 64 ? A.zcmpLo : A.zcmpHi, sn = tn < 64 ? A.snapLo : A.snapHi;
+                f = (((c >> sh6) & 1ull) ? SCB_SF_CMP2 : 0u) | (((z >> sh6) & 1ull) ? SCB_SF_ZCMP : 0u) | (((sn >> sh6) & 1ull) ? SCB_SF_ZSNAP : 0u);
+            } else if (zs >= 0 && searchLeft > 0) {
+                f = SCB_SF_ZCMP; --searchLeft;        /* all cells proven: look for a tile-wide period */
             }
             /* compare steps run through the interpreter too (snapshot in tensor memory); snapshot steps, the global
              * snapshot fallback and the odd step without a flag take the entry-by-entry form */
-            if (f == SCB_SF_CMP2) scb_step_runs<K, SCB_SF_CMP2>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
-            else if (TM && f == SCB_SF_ZCMP) scb_step_runs<K, SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
-            else if (TM && f == (SCB_SF_CMP2 | SCB_SF_ZCMP)) scb_step_runs<K, SCB_SF_CMP2 | SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, laneActive, d2, dz, tm);
+            SCB_TRACE_MARK(tn, 0, f | 0x100u | (rowsPerStep << 16));
+            if (f == SCB_SF_CMP2) scb_step_runs<K, SCB_SF_CMP2>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, hd, laneActive, d2, dz, tm);
+            else if (TM && f == SCB_SF_ZCMP) scb_step_runs<K, SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, hd, laneActive, d2, dz, tm);
+            else if (TM && f == (SCB_SF_CMP2 | SCB_SF_ZCMP)) scb_step_runs<K, SCB_SF_CMP2 | SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, hd, laneActive, d2, dz, tm);
             else scb_step<K, false, TM>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, nw, f, zg, sa, d2, dz, laneActive, tm);
+            SCB_TRACE_MARK(tn, 1, 0u);
+            /* word lane * K + k of the tile is kept at [k * 32 + lane]: a warp's atomics hit 32 different banks */
             if (f & SCB_SF_CMP2) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&dm2[lane * K + k], d2.v[k]);
+                for (int k = 0; k < K; ++k) if (d2.v[k]) atomicOr(&cm[k * 32 + lane], d2.v[k]);
             }
             if (f & SCB_SF_ZCMP) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) if (dz.v[k]) atomicOr(&dmz[lane * K + k], dz.v[k]);
+                for (int k = 0; k < K; ++k) if (dz.v[k]) atomicOr(&cm[WT + k * 32 + lane], dz.v[k]);
             }
             __syncthreads();
+            SCB_TRACE_MARK(tn, 2, 0u);
             t = tn;
             { const uint32_t x = srcOff; srcOff = dstOff; dstOff = x; }   /* src = S_t, dst = S_{t-1} */
             if (f & (SCB_SF_CMP2 | SCB_SF_ZCMP)) {
-                unsigned int *flagw = reinterpret_cast<unsigned int *>(&sh[1 + (ncmp & 1)]);
+                /* the first K warps fold one word per thread and vote; their flags go to a slot per warp and compare
+                 * (double buffered by compare parity), so no atomics on one address */
+                int *fslot = sh + 20 + 4 * (ncmp & 1);
                 if (tid < WT) {
                     const uint32_t v = vm[tid];
-                    const uint32_t m2 = (f & SCB_SF_CMP2) ? dm2[tid] : 0xffffffffu;
-                    const uint32_t mz = (f & SCB_SF_ZCMP) ? dmz[tid] : 0xffffffffu;
-                    const uint32_t r = Rm[tid] | ~m2 | ~mz;   /* a repeat was seen for these cells */
-                    Rm[tid] = r; dm2[tid] = 0u; dmz[tid] = 0u;
-                    const unsigned bits = ((m2 & v) ? 1u : 0u) | ((mz & v) ? 2u : 0u) | ((~r & v) ? 4u : 0u);
-                    if (bits) atomicOr(flagw, bits);
+                    const int slot = (tid % K) * 32 + tid / K;
+                    const uint32_t m2 = (f & SCB_SF_CMP2) ? cm[slot] : 0xffffffffu;
+                    const uint32_t mz = (f & SCB_SF_ZCMP) ? cm[WT + slot] : 0xffffffffu;
+                    const uint32_t r = Rm[tid] | ~m2 | ~mz;    /* a repeat was seen for these cells */
+                    Rm[tid] = r;
+                    cm[slot] = 0u; cm[WT + slot] = 0u;
+                    const unsigned b1 = __ballot_sync(0xffffffffu, (m2 & v) != 0u), b2 = __ballot_sync(0xffffffffu, (mz & v) != 0u);
+                    const unsigned b4 = __ballot_sync(0xffffffffu, (~r & v) != 0u);
+                    if (lane == 0) fslot[warp] = (int)((b1 ? 1u : 0u) | (b2 ? 2u : 0u) | (b4 ? 4u : 0u));
                 }
                 __syncthreads();
-                const unsigned fl = *flagw;
-                if (tid == 0) sh[1 + ((ncmp + 1) & 1)] = 0;    /* the other word serves the next compare */
+                unsigned fl = 0u;
+#pragma unroll
+                for (int k = 0; k < K; ++k) fl |= (unsigned)fslot[k];
+                SCB_TRACE_MARK(tn, 3, 0u);
                 ++ncmp;
                 allres = (fl & 4u) == 0u;
                 if ((f & SCB_SF_CMP2) && !(fl & 1u)) {
@@ -1155,16 +1230,22 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 }
             }
             if (f & SCB_SF_ZSNAP) zs = tn;
-            if (tn >= nextEvent) SCB_NEXT_EVENT(tn);
+            if (plainOnly) nextEvent = 1000;
+            else if (allres) nextEvent = (zs >= 0 && searchLeft > 0) ? tn + 1 : 1000;
+            else nextEvent = scb_next_bit(evLo, evHi, tn);
         }
-#undef SCB_NEXT_EVENT
         /* loop ran out at t == target (98: src = S_98; 99: dst = S_98; E3: src = S_target == S_98),
          * or stopped early at t > target when the last cell resolved at t == 99 */
         if (!haveFin) finOff = (t == SCB_LAST) ? dstOff : srcOff;
         if (allres) allfound = true;
+#if defined(SCB_TRACE) && defined(__CUDA_ARCH__)
+        if (tid == 0) {
+            atomicAdd(&A.diag->exitHist[t < 100 ? t : 99], 1u);
+            atomicAdd(&A.diag->exitHist[haveFin ? 100 : plainOnly ? 101 : allfound ? 102 : 103], 1u);
+        }
+#endif
         stepsDone += (unsigned)t; ++tilesDone;
         rowsMoved += (unsigned)(t - segStart) * rowsPerStep;   /* state rows moved through shared memory (loads + stores) */
-        scb_cp_async_wait();                                   /* a staged program this tile never reached */
 #undef SCB_NEXT_PROGRAM
         const long long c2 = scb_clock();
 
@@ -1182,12 +1263,16 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
 #pragma unroll
                 for (int k = 0; k < K; ++k) df.v[k] |= a.v[k] ^ b.v[k];
             }
+            uint32_t *dm2 = cm, *dmz = cm + WT;               /* word-indexed here; the compare buffers are no longer needed */
+            __syncthreads();
+            for (int i = tid; i < 2 * WT; i += nthr) cm[i] = 0u;
+            __syncthreads();
 #pragma unroll
             for (int k = 0; k < K; ++k) if (df.v[k]) atomicOr(&dm2[lane * K + k], df.v[k]);
             __syncthreads();
             if (tid < WT) {
                 const uint32_t fp = ~dm2[tid] & vm[tid];
-                dmz[tid] = fp; dm2[tid] = 0u; Rm[tid] |= fp;
+                dmz[tid] = fp; Rm[tid] |= fp;
             }
             __syncthreads();
         }
@@ -1258,7 +1343,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
             const unsigned char *fin = sm + finOff + laneOff;
             ScbVec<K> fpm;
 #pragma unroll
-            for (int k = 0; k < K; ++k) fpm.v[k] = dmz[lane * K + k];
+            for (int k = 0; k < K; ++k) fpm.v[k] = cm[WT + lane * K + k];
             for (int j = warp; j < N; j += S) {
                 const ScbVec<K> s = scb_ld<K>(fin + (uint32_t)j * ROWB);
                 unsigned c = 0;
@@ -1348,9 +1433,10 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
             __syncthreads();
             const int it = slot[0];
             if (it < 0) break;
-            if (TM && K == 4 && A.resolveGroup == 4) scb_resolve_item<4, true>(A, smraw, (unsigned)it, tm);
-            else if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it);
-            else scb_resolve_item<1>(A, smraw, (unsigned)it);
+            /* K0's images are cut for this launch (K words per lane, this CTA's warps): usable where KR == K */
+            if (TM && A.resolveGroup == K) scb_resolve_item<K, true>(A, smraw, (unsigned)it, tm, true);
+            else if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
+            else scb_resolve_item<1>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
         }
     }
 #if defined(__CUDA_ARCH__)
@@ -1390,8 +1476,30 @@ struct ScbResolveArgs {
  *   how = 2: 98 plain steps only (Fm is not computed)
  * On return: buffer A rows hold S_98, buffer B rows hold e = (S_98 xor S_0) & valid for every node,
  * Fm[32*KR] = found & valid per word (how != 2), vm[32*KR] = valid masks.  All threads call it. */
+/* program `which` (0 = full, 1 + k = reduced k) of individual p into the image buffer `desc`: K0's image when it was
+ * cut for this CTA's geometry (the simulator's own launch), else laid out here from the table-sorted program.
+ * All threads call it (barriers inside); returns the program's arity counts. */
+template <int KR>
+SCB_DEV int4 scb_fetch_program(const ScbSimArgs &A, uint4 *desc, int *scr, int p, int which, bool useImg, int S, int tid, int nthr)
+{
+    const int N = A.N;
+    if (useImg) {
+        const uint4 *src = A.imgs + ((long long)p * (SCB_NPROG + 1) + which) * A.imgStride;
+        for (int j = tid; j < A.imgStride; j += nthr) desc[j] = src[j];
+        __syncthreads();
+        const uint4 c4 = desc[0];
+        return make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
+    }
+    const uint4 *g = which == 0 ? A.descs + (long long)p * A.Npad : A.progs + ((long long)p * SCB_NPROG + (which - 1)) * (N + 1);
+    int4 cnt;
+    if (which == 0) cnt = A.counts[p];
+    else { const uint4 c4 = g[N]; cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w); }
+    scb_layout_program(desc, scr, g, cnt, N, S, 128u * KR, tid, nthr);
+    return cnt;
+}
+
 template <int KR, bool TTM = false>
-SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *desc, int *winfo, int4 cnt, int p,
+SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *desc, int *winfo, bool useImg, int4 cnt, int p,
                                uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
                                const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr, int onlyLane = -1,
                                uint32_t tm = SCB_TMEM_OFF)
@@ -1401,7 +1509,6 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
      * lies beyond every from[k] -- so leaving them out of the compare with T is exact too).  With T in tensor memory
      * its slots follow the program's node order and are re-laid out from Tglob at every switch (how == 1 only). */
     const int4 cntFull = cnt;
-    const uint4 *progBase = A.progs + (long long)p * SCB_NPROG * (A.N + 1);
     const unsigned long long fromBytes = (A.useSteady && !(TTM && how == 0))
         ? *reinterpret_cast<const unsigned long long *>(A.progFrom + (long long)p * 8) : 0ull;
     bool replaced = false;
@@ -1422,16 +1529,17 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
     ScbVec<KR> d2, dz;
     const uint4 *gfull = A.descs + (long long)p * A.Npad;
     const int e1full = cntFull.x + cntFull.y + cntFull.z, n0full = cntFull.w;
-    const uint4 *wlp = desc + warp * scb_prog_stride(N, S);       /* this warp's list (generic pointer) */
-    const scb_saddr wl = sdesc + 16u * (uint32_t)(warp * scb_prog_stride(N, S));
-    int nw = winfo[warp];                                         /* list entries, run headers included */
+    int woff, nw;                                                 /* this warp's list: offset, entries (run headers included) */
+    scb_img_warp(desc, warp, woff, nw);
+    const uint4 *wlp = desc + woff;
+    scb_saddr wl = sdesc + 16u * (uint32_t)woff;
 
     for (int pass = (how == 0 ? 0 : 1); pass < 2; ++pass) {
         const bool cmp = pass == 1 && how != 2;
         if (replaced) {                       /* the previous pass ended on a reduced program: start again with the full one */
-            cnt = cntFull;
-            scb_load_program<KR>(desc, winfo, gfull, cnt, N, S, tid, nthr);
-            nw = winfo[warp];
+            cnt = scb_fetch_program<KR>(A, desc, winfo, p, 0, useImg, S, tid, nthr);
+            scb_img_warp(desc, warp, woff, nw);
+            wlp = desc + woff; wl = sdesc + 16u * (uint32_t)woff;
             replaced = false;
         }
         int nextProg = 0, switchAt = 1000;
@@ -1500,11 +1608,9 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
         for (int tn = 1; tn <= last; ++tn) {
             if (tn == switchAt) {
                 /* every warp is past the barrier that ended step tn - 1: the program can be replaced in place */
-                const uint4 *src = progBase + (long long)nextProg * (N + 1);
-                const uint4 c4 = src[N];
-                cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
-                scb_load_program<KR>(desc, winfo, src, cnt, N, S, tid, nthr);
-                nw = winfo[warp];
+                cnt = scb_fetch_program<KR>(A, desc, winfo, p, 1 + nextProg, useImg, S, tid, nthr);
+                scb_img_warp(desc, warp, woff, nw);
+                wlp = desc + woff; wl = sdesc + 16u * (uint32_t)woff;
                 replaced = true;
                 if (TTM && cmp) {
                     /* T into this warp's tensor-memory slots in the new program's node order */
@@ -1534,7 +1640,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
             if (tn <= 2) scb_const_rows<KR>(sa + dstOff + laneOff, gfull + e1full, n0full, warp, S, nullptr);
             if (TTM && cmp) {
                 /* compare with T in tensor memory, fold through dmz */
-                scb_step_runs<KR, SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, true, d2, dz, tm);
+                scb_step_runs<KR, SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, scb_list_head(wlp), true, d2, dz, tm);
 #pragma unroll
                 for (int k = 0; k < KR; ++k) if (dz.v[k]) atomicOr(&dmz[lane * KR + k], dz.v[k]);
                 __syncthreads();
@@ -1543,7 +1649,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
                 const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
                 continue;
             }
-            if (f == 0u && TTM) scb_step_runs<KR, 0u>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, act, d2, dz, tm);
+            if (f == 0u && TTM) scb_step_runs<KR, 0u>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, scb_list_head(wlp), act, d2, dz, tm);
             else if (f == 0u) scb_step<KR, true>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, nw, 0u, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             else scb_step<KR, false, false, SCB_SF_TCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, nw, f, nullptr, sa + 2u * BUFB + laneOff, d2, dz, act);
             if (cmp) {
@@ -1592,29 +1698,29 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
 }
 
 /* shared-memory carve-up of the resolver kernels (after the three state buffers) */
-SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR, bool ttm = false)
+SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR, bool ttm = false, int S = SCB_PROG_MAX_WARPS)
 {
     /* state buffers (three, or two when T lives in tensor memory) + program + dmz/Fm/vm + scalars +
      * srcc[1024*KR] int16 + (shared-memory T only) D[2][<=24 warps][32*KR] + slack */
-    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + scb_prog_entries(N) * 16 + (size_t)3 * 32 * KR * 4 + 64 + 384 + (size_t)1024 * KR * 2
+    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + scb_img_entries(N, S) * 16 + (size_t)3 * 32 * KR * 4 + 64 + 384 + (size_t)1024 * KR * 2
            + (ttm ? 0 : (size_t)2 * 24 * 32 * KR * 4) + 256;
 }
 
 /* K3 phase 1: exact found mask and error sums of every queued group of KR chunks; leading not-found cells that
  * must copy a cell of an earlier chunk are queued for phase 2.  Only the chunks K2 flagged are summed here. */
 template <int KR, bool TTM>
-SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it, uint32_t tm)
+SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigned it, uint32_t tm, bool useImg)
 {
     const int N = A.N;
     const uint32_t ROWB = 128u * KR, BUFB = (uint32_t)N * ROWB;
     const int GW = 32 * KR, GC = 1024 * KR;
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + (TTM ? 2u : 3u) * BUFB);
-    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + scb_prog_entries(N));
+    uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + scb_img_entries(N, TTM ? (int)(blockDim.x >> 5) : SCB_PROG_MAX_WARPS));
     uint32_t *Fm = dmz + GW;
     uint32_t *vm = Fm + GW;
     int *sh = reinterpret_cast<int *>(vm + GW);            /* [2] pending cells, [3] not-found cells */
-    int *winfo = sh + 16;                                  /* [96] per-warp list lengths + scratch of scb_load_program */
+    int *winfo = sh + 16;                                  /* [96] scratch of scb_layout_program */
     short *srcc = reinterpret_cast<short *>(winfo + 96);   /* [GC] source cell of each cell */
     uint32_t *Dbuf = reinterpret_cast<uint32_t *>(srcc + GC);
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -1624,12 +1730,11 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
         const int p = (int)A.resolveItems[it].x;
         const int q = (int)(A.resolveItems[it].y & 0xFFFFFFu);
         const unsigned flagged = A.resolveItems[it].y >> 24;       /* bit j: chunk q + j was left out by K2 */
-        const int4 cnt = A.counts[p];
-        scb_load_program<KR>(desc, winfo, A.descs + (long long)p * A.Npad, cnt, N, S, tid, nthr);
+        const int4 cnt = scb_fetch_program<KR>(A, desc, winfo, p, 0, useImg, S, tid, nthr);
         if (tid == 0) { sh[2] = 0; sh[3] = 0; }
         __syncthreads();
         const bool haveT = it < A.resolveTCap;
-        scb_resolve_chunk<KR, TTM>(A, sm, desc, winfo, cnt, p, dmz, Fm, vm, q, haveT ? 1 : 0,
+        scb_resolve_chunk<KR, TTM>(A, sm, desc, winfo, useImg, cnt, p, dmz, Fm, vm, q, haveT ? 1 : 0,
                                    A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf, -1, tm);
 
         /* source cell of every cell: itself when found, else the nearest earlier found cell of the group
@@ -1848,11 +1953,12 @@ __global__ void scb_k_traj(ScbTrajArgs A)
     const uint32_t laneOff = (uint32_t)lane * 4u;
     const int4 cnt = A.counts[0];
     const scb_saddr sa = scb_smem_addr(sm), sdesc = scb_smem_addr(desc);
-    int *winfo = reinterpret_cast<int *>(desc + scb_prog_entries(N));
-    scb_load_program<1>(desc, winfo, A.descs, cnt, N, S, tid, nthr);
+    int *winfo = reinterpret_cast<int *>(desc + scb_img_entries(N, S));
+    scb_layout_program(desc, winfo, A.descs, cnt, N, S, 128u, tid, nthr);
     const int e1 = cnt.x + cnt.y + cnt.z;
-    const int nw = winfo[warp];
-    const scb_saddr wl = sdesc + 16u * (uint32_t)(warp * scb_prog_stride(N, S));
+    int woff, nw;
+    scb_img_warp(desc, warp, woff, nw);
+    const scb_saddr wl = sdesc + 16u * (uint32_t)woff;
     for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
         const int w0 = tile * 32;
         uint32_t *tbase = A.traj + (unsigned long long)tile * A.steps * N * 32;

@@ -186,7 +186,8 @@ static int run_trajectories(scb_ctx *c, int sem, int steps, int maxStates, const
 {
     const int N = c->N, tiles = (c->W + 31) / 32, NW = (N + 31) / 32;
     int rc;
-    if (scb_smem_bytes(N, 1, 2) > c->smemLimit) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d too large for the trajectory kernel", N);
+    const int warps = std::min(16, std::max(1, (N + 3) / 4));
+    if (scb_smem_bytes(N, 1, 2, warps) > c->smemLimit) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d too large for the trajectory kernel", N);
     if ((rc = c->dTraj.ensure((size_t)tiles * steps * N * 32))) return rc;
     if ((rc = c->dRes.ensure((size_t)c->C * 2)) || (rc = c->dNStates.ensure(c->C))) return rc;
     if ((rc = c->dStates.ensure((size_t)c->C * std::max(maxStates, 1) * NW))) return rc;
@@ -203,9 +204,8 @@ static int run_trajectories(scb_ctx *c, int sem, int steps, int maxStates, const
         CK(cudaStreamSynchronize(st));                /* the host arrays are the caller's temporaries */
         ta.recOn = c->dRecOn.p; ta.recBits = c->dRecBits.p;
     }
-    const int warps = std::min(16, std::max(1, (N + 3) / 4));
     const unsigned grid = (unsigned)std::max(1, std::min(tiles, c->numSM * 2));
-    SCB_LAUNCH(scb_k_traj, dim3(grid), dim3((unsigned)warps * 32), scb_smem_bytes(N, 1, 2), st, ta);
+    SCB_LAUNCH(scb_k_traj, dim3(grid), dim3((unsigned)warps * 32), scb_smem_bytes(N, 1, 2, warps), st, ta);
     CK(cudaGetLastError());
     ScbWindowArgs wa;
     wa.traj = c->dTraj.p; wa.N = N; wa.C = c->C; wa.tiles = tiles; wa.steps = steps; wa.sem = sem == SCB_SEM_PY ? 1 : 0;

@@ -48,7 +48,9 @@
 #define SCB_MODE_IMPORTANCE 3
 
 /* constant propagation depth cap of the steady program (K0): must stay below the first snapshot step */
+#ifndef SCB_STEADY_MAX_DEPTH
 #define SCB_STEADY_MAX_DEPTH 24
+#endif
 /* reduced programs per individual: at these propagation depths, plus the fixed point (or the cap) */
 #define SCB_NPROG 5
 #define SCB_STAGE_DEPTHS {2, 5, 8, 12}
@@ -70,6 +72,13 @@ struct ScbDiag {                      /* device-side counters, zeroed per evalua
     unsigned long long tiles;
     unsigned long long rows_moved;      /* state rows K2 loaded + stored in its steps (x 128*K bytes = shared-memory traffic) */
     unsigned long long cyc_prologue, cyc_steps, cyc_epilogue;   /* SM clocks of thread 0 of every K2 CTA, per phase */
+#ifdef SCB_TRACE
+    /* measurement build only (-DSCB_TRACE): SM clock of every warp of CTA 0 at the start and the end of every step
+     * of its first tile, [step][warp][2]; step 0 holds the step's flags in [0][0][0] .. */
+    unsigned int trace[100 * 24 * 4];
+    unsigned int traceFlags[100];
+    unsigned int exitHist[104];   /* tiles by the step their loop ended at; [100] E2 exits, [101] E3, [102] all proven, [103] queued for K3 */
+#endif
 };
 
 /* One compiled node: d.x, d.y, d.z = input node indices, d.w = node index | lut8 << 24.
@@ -91,6 +100,11 @@ struct ScbCompileArgs {
     uint4 *progs;                 /* [P][SCB_NPROG][N + 1] reduced programs (constants propagated to a fixed depth; the
                                      last one to the fixed point); entry N of each holds its arity counts */
     unsigned char *progFrom;      /* [P][8] first step each reduced program may compute (0: not emitted) */
+    uint4 *imgs;                  /* [P][SCB_NPROG + 1][imgStride] program images for the simulator (scb_layout_program):
+                                     image 0 = the full program, 1 + k = reduced program k; null: not wanted */
+    int imgStride;                /* entries per image */
+    int imgWarps;                 /* warps of the simulator CTA the images are cut for */
+    unsigned int imgRowBytes;     /* bytes of a state row in the simulator's shared memory (128 * K) */
     ScbDiag *diag;
 };
 
@@ -110,10 +124,13 @@ struct ScbSimArgs {
     const uint4 *descs;
     const int4 *counts;
     const uint4 *progs;           /* reduced programs of K0, [P][SCB_NPROG][N + 1] */
+    const uint4 *imgs;            /* program images of K0 for this launch's geometry, [P][SCB_NPROG + 1][imgStride] */
+    int imgStride;
     const unsigned char *progFrom;/* [P][8] */
     int useSteady;
     int chkFromProg;              /* >= 0: no period-<=2 check before reduced program `chkFromProg` may run; -1: no such delay */
-    int firstChk;                 /* first step >= 3 that is a multiple of chkEvery */
+    unsigned long long chkLo, chkHi;    /* bit t set: S_t is compared with S_{t-2} (every chkEvery-th step, and step 99) */
+    unsigned long long zcmpLo, zcmpHi;  /* bit t set: S_t is compared with the latest snapshot (from snapMinGap steps after it on) */
     int firstSnap;                /* first step that takes a snapshot (1000: none): the steady program must be in use by then */
     unsigned long long *fitness;  /* [P] */
     int32_t *nodewise;            /* [P][N] or null */
@@ -132,8 +149,7 @@ struct ScbSimArgs {
     uint32_t *zscratch;           /* snapshot scratch, zstride words per CTA */
     unsigned long long zstride;
     unsigned int flags;           /* SCB_KF_* */
-    int chkEvery;                 /* cadence of the period<=2 check */
-    unsigned long long snapLo, snapHi;  /* bit t set: take a snapshot when computing S_t */
+    unsigned long long snapLo, snapHi;  /* bit t set: take a snapshot when computing S_t (0 when snapshots are off) */
     int periodSearch;             /* snapshot-compare steps kept after all cells resolved */
     int snapMinGap;               /* first snapshot compare this many steps after the snapshot */
     int fuseResolve;              /* != 0: CTAs that run out of tiles resolve queued groups in the same launch */
@@ -143,7 +159,7 @@ struct ScbSimArgs {
     unsigned int smemBytes;       /* dynamic shared memory of the launch (the item slot sits in its last 64 bytes) */
     int useTma;                   /* != 0: the S_0 tile is loaded with cp.async.bulk (TMA) row copies */
     int tmemCols;                 /* > 0: the snapshot lives in tensor memory, this many columns per CTA */
-    int tmemSlotsPerWarp;         /* node slots reserved per warp (ceil(N / warps)) */
+    int tmemSlotsPerWarp;         /* node slots reserved per warp for the resolver's target state (program order) */
     ScbDiag *diag;
 };
 
