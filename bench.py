@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -172,6 +172,151 @@ def run_reference(args, wl, rank):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+class Generation:
+    """One (dataset, network, population shard) on this rank's GPU with pinned host copies of what a GA generation
+    hands over, and the step functions the timed loops call."""
+
+    def __init__(self, pr, bm, device, opts):
+        from scbonita_b200 import _lib, simulator
+        self.simulator, self.pr = simulator, pr
+        model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.net.and_nodes, pr.net.and_inv,
+                                      pr.node_positions, pr.net.ind_len)
+        self.sim = simulator.Simulator(bm, model, device=device)
+        for kv in opts:
+            k, v = kv.split("=")
+            self.sim.set_option(getattr(_lib, "OPT_" + k.upper()), int(v))
+        self.pin = []
+        self.set_population(pr.individuals, pr.pop_and_nodes, pr.pop_and_inv)
+
+    def pinned(self, a):
+        h = self.simulator.PinnedArray(a.shape, a.dtype)
+        h.array[...] = a
+        self.pin.append(h)
+        return h.array
+
+    def set_population(self, inds, an, ai):
+        sim_mod = self.simulator
+        self.P = inds.shape[0]
+        self.h_ind = self.pinned(np.ascontiguousarray(inds, np.int32))
+        self.h_an = self.pinned(np.ascontiguousarray(an, np.int32))
+        self.h_ai = self.pinned(np.ascontiguousarray(ai, np.int32))
+        self.h_out = self.pinned(np.zeros(self.P, np.int64))
+        up, ui = sim_mod.upstream_from_tables(self.pr.net.and_len, an, ai)
+        self.h_up, self.h_ui = self.pinned(up), self.pinned(ui)
+        n = self.pr.net.n
+        self.h2d = self.h_ind.nbytes + self.h_an.nbytes + self.h_ai.nbytes + 4 * n * 4
+        self.h2d_compact = self.h_ind.nbytes + self.h_up.nbytes + self.h_ui.nbytes + 4 * n * 4
+        self.d2h = self.h_out.nbytes
+
+    def upload(self):
+        self.sim.upload(self.h_ind, self.pr.knockouts, self.pr.knockins, self.h_an, self.h_ai)
+
+    def step_resident(self):
+        self.sim.run(self.simulator.MODE_SUM)
+
+    def step_e2e(self):
+        self.upload()
+        self.sim.run(self.simulator.MODE_SUM)
+        self.sim.fetch(self.simulator.MODE_SUM, out=self.h_out)
+
+    def step_e2e_compact(self):
+        self.sim.upload_compact(self.h_ind, self.h_up, self.h_ui, self.pr.knockouts, self.pr.knockins)
+        self.sim.run(self.simulator.MODE_SUM)
+        self.sim.fetch(self.simulator.MODE_SUM, out=self.h_out)
+
+
+def timed_steps(gen, step, steps, warmup, barrier, after=None, stats_each=False):
+    """`steps` timed calls of `step` after `warmup` untimed ones; every step bracketed by CUDA events on the library's
+    stream, L2 flushed before it.  Returns (per-step ms list, stats of the last step, K2-only ms list)."""
+    sim = gen.sim
+    for _ in range(warmup):
+        step()
+        if after:
+            after()
+    barrier()
+    ms, k2, stats = [], [], None
+    for _ in range(steps):
+        sim.flush_l2()
+        sim.event_record(0)
+        step()
+        sim.event_record(1)
+        ms.append(sim.event_elapsed_ms(0, 1))
+        if after:
+            after()
+        if stats_each:
+            sim.fetch(gen.simulator.MODE_SUM, out=gen.h_out)       # untimed: reads the stats of this step
+            stats = sim.last_stats
+            k2.append(stats["sim_ms"])
+    barrier()
+    return ms, stats, k2
+
+
+def spread(ms):
+    a = np.asarray(ms, np.float64)
+    return {"min": float(a.min()), "median": float(np.median(a)), "max": float(a.max())}
+
+
+def lpt_shards(costs, world):
+    """Individuals over the ranks, longest processing time first (every individual to the least loaded rank, ties to
+    the lower rank): the shards of a strong-scaling generation are balanced by predicted cost, not by count.  Every
+    rank gets the same number of slots (the exchange buffer is rectangular)."""
+    P = len(costs)
+    width = -(-P // world)
+    order = sorted(range(P), key=lambda i: (-int(costs[i]), i))
+    load, out = [0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = min((k for k in range(world) if len(out[k]) < width), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += int(costs[i])
+    return out, width
+
+
+def robustness_cases(args, wl, device):
+    """The 10 ms target off the happy path: other network seeds, no knock-outs, a fresh population in
+    every step, an adversarial long-period network of the same size.  A few steps each."""
+    cases = []
+    P, N, C = wl["population"], wl["nodes"], wl["cells"]
+    units = float(P) * C * N * STEPS_PER_CELL
+
+    def run_case(name, pr, bm, fresh=None):
+        gen = Generation(pr, bm, device, args.opt)
+        gen.upload()
+        pops = fresh or [None]
+        ms_all, fracs = [], []
+        for k, pop in enumerate(pops):
+            if pop is not None:
+                gen.set_population(*pop)
+                gen.upload()
+            ms, stats, _ = timed_steps(gen, gen.step_resident, 3 if fresh is None else 1, 2 if k == 0 else 1, gen.sim.sync, stats_each=True)
+            ms_all += ms
+            fracs.append(stats["steps_executed"] / (stats["tiles"] * 99.0))
+        e2e, _, _ = timed_steps(gen, gen.step_e2e, 2, 1, gen.sim.sync)
+        cases.append({"case": name, "ms_per_generation": spread(ms_all), "e2e_ms": float(np.median(e2e)),
+                      "executed_step_fraction": float(np.mean(fracs)), "not_found_cells": int(stats["not_found_cells"]),
+                      "resolver_chunks": int(stats["resolver_chunks"]), "cre_per_sec": units / (np.median(ms_all) * 1e-3),
+                      "fitness_checksum": int(gen.h_out.sum())})
+        gen.sim.close()
+
+    for seed in (4321, 99, 2024, 7):
+        pr = synth.make_problem(N, C, P, net_seed=seed, cell_seed=5678 + seed, pop_seed=91011 + seed)
+        bm = np.zeros((N, C), np.uint8); bm[pr.node_positions] = pr.bin_rows
+        run_case("network seed %d" % seed, pr, bm)
+    pr, bm = build_problem(wl)
+    pr.knockouts = np.zeros(N, np.int32); pr.knockins = np.zeros(N, np.int32)
+    run_case("default network, KO/KI all zero", pr, bm)
+    pr, bm = build_problem(wl)
+    fresh = [synth.make_population(pr.net, P, seed=555 + k) for k in range(3)]
+    run_case("default network, fresh population every step", pr, bm, fresh=fresh)
+    rings = (45, 50, 57) if N >= 180 else (N // 4, N // 3)
+    chain = N - 1 - sum(rings) - 4
+    if chain >= 2:
+        pr = synth.make_gated_rings(N, C, P, ring_lens=rings, chain_len=chain)
+        bm = np.zeros((N, C), np.uint8); bm[pr.node_positions] = pr.bin_rows
+        run_case("adversarial: gated rings of period %s (every tile runs 99 steps and goes to the exact resolver)" %
+                 "/".join(str(2 * r) for r in rings), pr, bm)
+    return cases
+
+
 def run_ours(args, wl, rank, world, local_rank):
     from scbonita_b200 import _lib, simulator
     lib = _lib.load()
@@ -183,65 +328,33 @@ def run_ours(args, wl, rank, world, local_rank):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # weak scaling: every rank scores a population of the same size drawn with the same seeds, so that the
-    # per-rank work is identical and the measured efficiency reflects the collective, not sampling noise
     pr, bm = build_problem(wl)
-    if args.scaling == "strong" and world > 1:
-        # fixed global population: every rank scores its contiguous block (scbonita_b200.distributed.shard_bounds)
-        from scbonita_b200.distributed import shard_bounds
-        lo, hi = shard_bounds(wl["population"], rank, world)
-        width = -(-wl["population"] // world)
-        lo = min(lo, wl["population"] - width)          # equal block sizes for the all-gather
-        pr.individuals = pr.individuals[lo:lo + width]
-        pr.pop_and_nodes = pr.pop_and_nodes[lo:lo + width]
-        pr.pop_and_inv = pr.pop_and_inv[lo:lo + width]
-        wl = dict(wl, population=width)
-    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.net.and_nodes, pr.net.and_inv,
-                                  pr.node_positions, pr.net.ind_len)
-    sim = simulator.Simulator(bm, model, device=local_rank)
-    for kv in args.opt:
-        k, v = kv.split("=")
-        sim.set_option(getattr(_lib, "OPT_" + k.upper()), int(v))
-    P, N, C = wl["population"], wl["nodes"], wl["cells"]
-    units_per_step = float(P) * C * N * STEPS_PER_CELL * world
-
-    # pinned host copies of the reference-format tables (what a GA generation hands over)
-    pin = []
-
-    def pinned(a):
-        h = simulator.PinnedArray(a.shape, a.dtype)
-        h.array[...] = a
-        pin.append(h)
-        return h.array
-    h_ind = pinned(np.ascontiguousarray(pr.individuals, np.int32))
-    h_an = pinned(np.ascontiguousarray(pr.pop_and_nodes, np.int32))
-    h_ai = pinned(np.ascontiguousarray(pr.pop_and_inv, np.int32))
-    h_out = pinned(np.zeros(P, np.int64))
-    # the same population in the compact form a GA driver can keep: upstream triples, not term tables
-    up, ui = simulator.upstream_from_tables(pr.net.and_len, pr.pop_and_nodes, pr.pop_and_inv)
-    h_up, h_ui = pinned(up), pinned(ui)
-    h2d_compact = h_ind.nbytes + h_up.nbytes + h_ui.nbytes + 4 * N * 4
-    h2d = h_ind.nbytes + h_an.nbytes + h_ai.nbytes + 4 * N * 4
-    d2h = h_out.nbytes
-
-    gather = None
-    if world > 1:
+    Pglobal, N, C = wl["population"], wl["nodes"], wl["cells"]
+    full_inds, full_an, full_ai = pr.individuals, pr.pop_and_nodes, pr.pop_and_inv
+    strong = args.scaling == "strong"
+    shard, width, costs_note = None, Pglobal, None
+    if world > 1 and strong:
+        # fixed global population (BASELINE config 3: "population 500, GA sweep at 1/2/4/8"): the individuals are
+        # dealt to the ranks by the cost a first, untimed generation measured on rank 0 (a (mu + lambda) GA scored
+        # most of them in the previous generation; scb_pop_costs is that predictor)
         import torch
-        ptr, nbytes = None, None
-        sim.upload(h_ind, pr.knockouts, pr.knockins, h_an, h_ai)
-        sim.run(simulator.MODE_SUM)
-        sim.sync()
-        ptr, nbytes = sim.result_device_pointer(simulator.MODE_SUM)
-
-        class _Wrap:
-            __cuda_array_interface__ = {"shape": (P,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-        local = torch.as_tensor(_Wrap(), device=torch.device("cuda", local_rank))
-        allfit = torch.empty(world * P, dtype=torch.int64, device=local.device)
-        ext = torch.cuda.ExternalStream(sim.stream_pointer(), device=local.device)
-
-        def gather():
-            with torch.cuda.stream(ext):
-                dist.all_gather_into_tensor(allfit, local)
+        costs = np.zeros(Pglobal, np.int64)
+        if rank == 0:
+            g0 = Generation(pr, bm, local_rank, args.opt)
+            g0.upload(); g0.step_resident(); g0.sim.sync()
+            costs[:] = g0.sim.costs()
+            g0.sim.close()
+        t = torch.from_numpy(costs).cuda()
+        dist.broadcast(t, 0)
+        costs = t.cpu().numpy()
+        shards, width = lpt_shards(costs, world)
+        shard = np.asarray(shards[rank], np.int64)
+        loads = [int(costs[sh].sum()) for sh in shards]
+        costs_note = {"predicted_load_max_over_mean": max(loads) / (sum(loads) / world)}
+        pr.individuals, pr.pop_and_nodes, pr.pop_and_inv = full_inds[shard], full_an[shard], full_ai[shard]
+    gen = Generation(pr, bm, local_rank, args.opt)
+    sim, P = gen.sim, gen.P
+    units_per_step = float(P if not (world > 1 and strong) else Pglobal) * C * N * STEPS_PER_CELL * (world if not strong else 1)
 
     def barrier():
         sim.sync()
@@ -250,101 +363,150 @@ def run_ours(args, wl, rank, world, local_rank):
             torch.cuda.synchronize()
             dist.barrier()
 
+    # ---- the generation's exchange: fitness shards over peer memory (one kernel at the end of the graph), or NCCL
+    gather_after, gather_kind, allfit = None, "none", None
+    gen.upload()
+    if world > 1:
+        import torch
+        if args.gather == "peer":
+            handles = sim.gather_init(world, rank, width)
+            hs = [None] * world
+            dist.all_gather_object(hs, handles.tobytes())
+            sim.gather_connect(np.frombuffer(b"".join(hs), np.uint8))
+            gather_kind = "peer memory: scb_k_gather, last kernel of the generation's CUDA graph (P2P stores over NVLink + flags)"
+        else:
+            sim.run(simulator.MODE_SUM); sim.sync()
+            ptr, _ = sim.result_device_pointer(simulator.MODE_SUM)
+
+            class _Wrap:
+                __cuda_array_interface__ = {"shape": (P,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+            local = torch.as_tensor(_Wrap(), device=torch.device("cuda", local_rank))
+            pad = torch.zeros(width, dtype=torch.int64, device=local.device)
+            allfit = torch.empty(world * width, dtype=torch.int64, device=local.device)
+            ext = torch.cuda.ExternalStream(sim.stream_pointer(), device=local.device)
+
+            def gather_after():
+                with torch.cuda.stream(ext):
+                    pad[:P].copy_(local)
+                    dist.all_gather_into_tensor(allfit, pad)
+            gather_kind = "NCCL all_gather_into_tensor issued on the library's stream after the graph"
+
     def step_resident():
-        sim.run(simulator.MODE_SUM)
-        if gather:
-            gather()
+        gen.step_resident()
+        if gather_after:
+            gather_after()
 
     def step_e2e():
-        sim.upload(h_ind, pr.knockouts, pr.knockins, h_an, h_ai)
-        sim.run(simulator.MODE_SUM)
-        if gather:
-            gather()
-        sim.fetch(simulator.MODE_SUM, out=h_out)
+        gen.upload()
+        gen.sim.run(simulator.MODE_SUM)
+        if gather_after:
+            gather_after()
+        gen.sim.fetch(simulator.MODE_SUM, out=gen.h_out)
 
-    def step_e2e_compact():
-        sim.upload_compact(h_ind, h_up, h_ui, pr.knockouts, pr.knockins)
-        sim.run(simulator.MODE_SUM)
-        if gather:
-            gather()
-        sim.fetch(simulator.MODE_SUM, out=h_out)
-
-    def timed(step, steps, warmup):
-        for _ in range(warmup):
-            step()
-        barrier()
-        total_ms, sim_ms, stats = 0.0, 0.0, None
-        for _ in range(steps):
-            sim.flush_l2()
-            sim.event_record(0)
-            step()
-            sim.event_record(1)
-            total_ms += sim.event_elapsed_ms(0, 1)
-            if step is step_resident:
-                sim.fetch(simulator.MODE_SUM, out=h_out)          # untimed: reads the stats of this step
-                stats = sim.last_stats
-                sim_ms += stats["sim_ms"]
-        barrier()
+    def reduce_max(ms_list):
+        tot = float(np.sum(ms_list))
         if world > 1:
             import torch
-            t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms, sim_ms, stats
+            t = torch.tensor(ms_list + [tot], dtype=torch.float64, device="cuda")
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            return tmax.cpu().numpy(), tmin.cpu().numpy()
+        a = np.asarray(ms_list + [tot])
+        return a, a
 
-    sim.upload(h_ind, pr.knockouts, pr.knockins, h_an, h_ai)
+    # cost-ordered work list from the warm-up generation
+    gen.step_resident(); sim.sync()
+    if not args.no_order:
+        sim.set_order(np.argsort(-sim.costs().astype(np.int64), kind="stable"))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms, sim_ms, stats = timed(step_resident, args.steps, args.warmup)
+    res_ms, _, _ = timed_steps(gen, step_resident, args.steps, args.warmup, barrier)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
-    fit = h_out.copy()
-    e2e_compact_ms, _, _ = timed(step_e2e_compact, args.steps, max(args.warmup, 3))
-    if not np.array_equal(fit, h_out):
-        raise RuntimeError("compact and table uploads disagree")
-    sim.upload(h_ind, pr.knockouts, pr.knockins, h_an, h_ai)
-    # roofline pass: the simulator kernel K2 timed on its own.  In the default configuration the same launch also
-    # resolves queued groups in its tail (K3 work), so K2's own duration is taken with that fusion switched off.
+    res_max, res_min = reduce_max(res_ms)
+    total_ms = float(res_max[-1])                       # max over ranks of the timed region's device time
+    e2e_ms_list, _, _ = timed_steps(gen, step_e2e, args.steps, max(args.warmup, 3), barrier)
+    e2e_max, _ = reduce_max(e2e_ms_list)
+    e2e_ms = float(e2e_max[-1])
+    fit = gen.h_out.copy()
+    e2e_compact_ms = None
+    if world == 1:
+        c_ms, _, _ = timed_steps(gen, gen.step_e2e_compact, args.steps, max(args.warmup, 3), barrier)
+        e2e_compact_ms = float(np.sum(c_ms))
+        if not np.array_equal(fit, gen.h_out):
+            raise RuntimeError("compact and table uploads disagree")
+
+    # ---- N > 1: the gathered vector must be the single-GPU answer
+    verify = None
+    if world > 1:
+        import torch
+        gen.step_resident(); 
+        if gather_after:
+            gather_after()
+        sim.sync(); torch.cuda.synchronize()
+        gathered = sim.gather_result() if args.gather == "peer" else allfit.cpu().numpy()
+        local_fit = sim.fetch(simulator.MODE_SUM).astype(np.int64)
+        ok_local = bool(np.array_equal(gathered[rank * width:rank * width + P], local_fit))
+        full = np.zeros(Pglobal if strong else world * P, np.int64)
+        if strong:
+            for r, sh in enumerate(lpt_shards(costs, world)[0]):
+                full[np.asarray(sh, np.int64)] = gathered[r * width:r * width + len(sh)]
+        else:
+            full[:] = gathered[:world * P]
+        ok_single = None
+        if rank == 0:
+            # rank 0 scores the WHOLE population on its own GPU (untimed): the exchanged vector must be that answer
+            prf, bmf = build_problem(wl)
+            gf = Generation(prf, bmf, local_rank, args.opt)
+            ref = gf.sim.evaluate_population(prf.individuals, prf.knockouts, prf.knockins, prf.pop_and_nodes, prf.pop_and_inv)
+            gf.sim.close()
+            ok_single = bool(np.array_equal(full, ref if strong else np.tile(ref, world)))
+        flags = [None] * world
+        dist.all_gather_object(flags, ok_local)
+        verify = {"every_rank_finds_its_shard_in_the_gathered_vector": all(flags),
+                  "gathered_vector_equals_single_gpu_evaluation": ok_single,
+                  "global_fitness_checksum": int(full.sum())}
+        if rank == 0 and not (all(flags) and ok_single):
+            raise RuntimeError("multi-GPU fitness vector differs from the single-GPU evaluation: %s" % verify)
+
+    # ---- roofline pass: K2 on its own (plain launches, resolver not fused, so that the duration is K2's own)
+    gen.upload()
+    sim.set_option(_lib.OPT_GRAPH, 0)
     fused_default = "fuse=0" not in args.opt
     if fused_default:
         sim.set_option(_lib.OPT_FUSE, 0)
-    _, sim_ms, stats = timed(step_resident, min(args.steps, 5), 2)
-    sim_steps = min(args.steps, 5)
+    gsave, gather_after = gather_after, None
+    _, stats, k2_list = timed_steps(gen, gen.step_resident, min(args.steps, 5), 2, sim.sync, stats_each=True)
+    _, stats_fused, _ = (None, stats, None)
     if fused_default:
         sim.set_option(_lib.OPT_FUSE, 1)
+    sim.set_option(_lib.OPT_GRAPH, 1)
+    gather_after = gsave
 
     if rank == 0:
         hbm_peak, sm_max, peak_kind = load_peaks()
         ms_per_step = total_ms / args.steps
         value = units_per_step / (ms_per_step * 1e-3)
         info = sim.info()
-        k2_ms = sim_ms / sim_steps
+        k2_ms = float(np.mean(k2_list))
         per_gpu_units = float(P) * C * N * STEPS_PER_CELL
-        # algorithmic HBM bytes of one K2 launch: packed matrix N*C/8, the full rule program (16 B/node) and the five
-        # reduced programs K0 emits per individual ((N + 1) x 16 B each), fitness 8 B
-        alg_bytes = N * C / 8.0 + P * N * 16.0 + P * 5 * (N + 1) * 16.0 + P * 8.0
+        # algorithmic HBM bytes of one K2 launch: the packed matrix N*C/8, one compiled program per individual
+        # (16 B per node) and the fitness; the reduced programs / program images K0 also emits are this implementation's
+        # own traffic and show up in `traffic`, not here
+        alg_bytes = N * C / 8.0 + P * N * 16.0 + P * 8.0
         hbm_ach = alg_bytes / (k2_ms * 1e-3) / 1e9
         traffic = None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed `ncu --set full` capture
-            with open(os.path.join(ROOT, "profiles", "r1", "k2_dram_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2", "k2_dram_traffic.json")) as f:
                 t = json.load(f)
             if t.get("workload") == args.workload:
                 traffic = t["dram_bytes_per_launch"]
         except Exception:
             pass
-        # binding resource: shared-memory bandwidth, 128 B/clk/SM.  Executed traffic of one launch =
-        # executed (tile, step) pairs x nodes x 128*K bytes x (inputs + 1 store); inputs/node from the network
         sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-        # state loads per node-update: 1, 1, 2, 3 for 0, 1, 3, 7 AND-terms (upper bound: K0 drops dead inputs)
-        arity = float(np.mean([{0: 1, 1: 1, 3: 2, 7: 3}.get(int(a), 3) for a in pr.net.and_len]))
-        smem_bytes_exec = stats["steps_executed"] * N * 128.0 * info["words_per_lane"] * (arity + 1.0)
-        if stats.get("state_rows_moved"):
-            # exact: K2 counts the rows its steps load and store (the steady program moves far fewer than the bound above)
-            smem_bytes_exec = stats["state_rows_moved"] * 128.0 * info["words_per_lane"]
+        smem_bytes_exec = stats["state_rows_moved"] * 128.0 * info["words_per_lane"]
         smem_peak = 148 * 128.0 * sm_mhz * 1e6 / 1e9
         smem_ach = smem_bytes_exec / (k2_ms * 1e-3) / 1e9
-        # measured on-box peaks of the on-chip resources (scb_microbench: every SM busy, independent chains)
         try:
             mb = {k: sim.microbench(k) for k in ("lop3", "popc", "lds")}
         except Exception as exc:
@@ -352,48 +514,60 @@ def run_ours(args, wl, rank, world, local_rank):
         smem_peak_nominal = smem_peak
         if mb.get("lds"):
             smem_peak = mb["lds"] / 1e9
-        # integer-logic roofline: algorithmic 7 LOP3 per (node, 32-cell word, step) = 0.21875 LOP3 per
-        # CRE (a runtime 3-input truth table as a 7-mux tree); executed: K2 issues ONE LOP3 per node-word-step (the
-        # table is an immediate reached through a jump table) and only for the steps it does not skip
         lop_alg = per_gpu_units * 0.21875 / (k2_ms * 1e-3)
         lop_exec = stats["steps_executed"] * N * 32.0 * info["words_per_lane"] / (k2_ms * 1e-3)
-        cpu = None
+        cpu, cpu1 = None, None
         if not args.no_cpu_baseline:
             try:
+                prc, _ = build_problem(wl)
                 cores = min(len(os.sched_getaffinity(0)), 64)
                 cells = min(C, 12_500)
-                dt, u, kind = reference_sample(pr, cells, cores, cores)
+                dt, u, kind = reference_sample(prc, cells, cores, cores)
+                what = "the unmodified reference C (oracle/_ref)" if kind == "reference" else "the C restatement (oracle/scb_oracle.c)"
                 cpu = {"value": u / dt, "unit": UNIT, "cores": cores, "kind": kind,
                        "sample": "%d individuals x %d cells x %d nodes, %d concurrent scSyncBool calls of %s, %.1f s" % (
-                           cores, cells, N, cores, "the unmodified reference C (oracle/_ref)" if kind == "reference"
-                           else "the C restatement (oracle/scb_oracle.c)", dt)}
+                           cores, cells, N, cores, what, dt)}
+                # the reference as shipped is single-threaded (the OpenMP pragma is commented out, simulator.c:366-368)
+                c1 = min(C, 6_000)
+                dt1, u1, kind1 = reference_sample(prc, c1, 1, 1)
+                cpu1 = {"value": u1 / dt1, "unit": UNIT, "cores": 1, "kind": kind1,
+                        "sample": "1 individual x %d cells x %d nodes, one scSyncBool call of %s, %.1f s" % (c1, N, what, dt1)}
             except Exception as exc:           # oracle/_ref absent on this box
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % exc}
+        cases = None
+        if world == 1 and not args.no_cases and args.workload in ("C2", "C3"):
+            cases = robustness_cases(args, wl, local_rank)
+        kernels_per_step = (3 if fused_default else 4) + (1 if (world > 1 and args.gather == "peer") else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": wl["name"], "population_per_gpu": P, "cells": C, "nodes": N,
-                       "population_seeds": "identical on every rank",
-                       "sharding": "individuals sharded over %d rank(s), packed matrix replicated, all-gather of int64 fitness" % world,
+            "config": {"workload": wl["name"], "population_global": Pglobal if (strong or world == 1) else world * P,
+                       "population_per_gpu": P, "cells": C, "nodes": N,
+                       "sharding": ("one GPU" if world == 1 else
+                                    ("the %d individuals dealt to %d ranks by predicted cost (LPT), " % (Pglobal, world) if strong else
+                                     "%d individuals per rank (same seeds on every rank), " % P) +
+                                    "packed matrix replicated, fitness exchange: " + gather_kind),
+                       "launch": "one CUDA graph per generation and rank (clears, K0, K2 + in-kernel resolver, fill-forward%s)" % (
+                           ", peer exchange" if (world > 1 and args.gather == "peer") else ""),
+                       "work_order": "tiles handed out costliest individual first (costs of the previous generation)" if not args.no_order else "index order",
                        "l2": "flushed (256 MiB memset) between timed steps", "geometry": info,
+                       "clock_sampling": "nvidia-smi every 100 ms on rank 0 during the resident timed region",
                        "options": args.opt},
             "ga_generations_per_sec": 1e3 / ms_per_step,
+            "per_step_ms": {"max_over_ranks": spread(res_max[:-1]), "min_over_ranks": spread(res_min[:-1]),
+                            "note": "device time of every timed generation incl. the exchange; max - min over ranks at a step = wait for the slowest rank"},
             "e2e": {"value": units_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
-                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "e2e_compact": {"value": units_per_step / (e2e_compact_ms / args.steps * 1e-3), "unit": UNIT,
-                            "ms_per_step": e2e_compact_ms / args.steps, "h2d_bytes_per_step": int(h2d_compact),
-                            "d2h_bytes_per_step": int(d2h),
-                            "note": "same generation, population handed over as bit-strings + upstream triples "
-                                    "(scb_pop_upload_compact) instead of the reference's [N][7][3] tables"},
-            "gpu_launches": (3 if fused_default else 4) * args.steps,   # K0 compile, K2 simulate (+ in-kernel K3), K3 fill
+                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(gen.h2d), "d2h_bytes_per_step": int(gen.d2h)},
+            "gpu_launches": kernels_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                         "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
                          "peak_source": peak_kind,
                          "kernel": "scb_k_sim<%d>" % info["words_per_lane"], "kernel_ms": k2_ms,
-                         "kernel_timing": "CUDA events around K2 on the library's stream, K2 run without the in-kernel "
-                                          "resolver tail (option fuse=0) so that the duration is K2's own",
-                         "note": "the path is shared-memory/issue bound, not HBM bound (SURVEY 8d): see roofline_binding"},
+                         "kernel_timing": "CUDA events around K2 on the library's stream (plain launches, resolver not fused, so that the duration is K2's own)",
+                         "note": "the path is shared-memory / latency bound, not HBM bound (SURVEY 8d): see roofline_binding"},
             "roofline_binding": {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
                                  "frac": smem_ach / smem_peak, "sm_mhz": sm_mhz,
                                  "peak_source": "measured: scb_microbench LDS.128, all SMs" if mb.get("lds") else
@@ -409,10 +583,27 @@ def run_ours(args, wl, rank, world, local_rank):
                              "note": "algorithmic = CRE/s x 7/32 (SURVEY 8d mux-tree figure); executed = one LOP3 per "
                                      "node-word-step actually simulated (upper bound: counts all N nodes, the reduced "
                                      "programs compute fewer); POPC is used once per (node, word, tile)"},
-            "stats": stats, "clocks": clocks, "cpu_baseline": cpu,
+            "stats": stats, "clocks": clocks, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1,
             "fitness_checksum": int(fit.sum()),
         }
+        if e2e_compact_ms is not None:
+            line["e2e_compact"] = {"value": units_per_step / (e2e_compact_ms / args.steps * 1e-3), "unit": UNIT,
+                                   "ms_per_step": e2e_compact_ms / args.steps, "h2d_bytes_per_step": int(gen.h2d_compact),
+                                   "d2h_bytes_per_step": int(gen.d2h),
+                                   "note": "same generation, population handed over as bit-strings + upstream triples "
+                                           "(scb_pop_upload_compact) instead of the reference's [N][7][3] tables"}
+        if costs_note:
+            line["shard_balance"] = costs_note
+        if verify:
+            line["multi_gpu_check"] = verify
+        if cases:
+            worst = max(c["ms_per_generation"]["max"] for c in cases)
+            line["robustness"] = {"cases": cases, "worst_ms_per_generation": worst,
+                                  "target_ms": 10.0, "worst_case_meets_target": bool(worst < 10.0)}
         print(json.dumps(line), flush=True)
+    if world > 1 and args.gather == "peer":
+        barrier()
+        sim.gather_close()
     sim.close()
     if world > 1:
         dist.destroy_process_group()
@@ -432,8 +623,13 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--opt", action="append", default=[], help="library option, e.g. early_exit=0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default): 500 individuals per GPU; strong: the 500 individuals split over the GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = the workload's population split over the GPUs (BASELINE config 3: "
+                         "'population 500, GA sweep at 1/2/4/8'); weak = the whole population on every GPU")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: the generation's fitness exchange -- peer memory kernel (default) or NCCL all-gather")
+    ap.add_argument("--no-order", action="store_true", help="hand tiles out in index order instead of costliest first")
+    ap.add_argument("--no-cases", action="store_true", help="skip the robustness cases (other seeds, adversarial network)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

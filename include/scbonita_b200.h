@@ -69,6 +69,7 @@ extern "C" {
 #define SCB_OPT_TMA          13 /* 1 (default): load the S_0 tile with TMA bulk copies (cp.async.bulk + mbarrier)   */
 #define SCB_OPT_STEADY       14 /* 1 (default): steps after the constants have spread run the constant-propagated program */
 #define SCB_OPT_CHECK_FROM   15 /* k (default 3): no period-<=2 check before reduced program k may run; -1: check from step 3 */
+#define SCB_OPT_GRAPH        16 /* 1 (default): a generation is one CUDA graph launch; 0: plain launches (per-kernel timing in scb_stats) */
 #define SCB_OPT_FUSE         12 /* 1 (default): CTAs that run out of tiles resolve queued groups in the same launch */
 
 typedef struct scb_ctx scb_ctx;
@@ -150,6 +151,25 @@ int scb_pop_upload_compact(scb_ctx *ctx, int P, const int32_t *individuals, int 
                            const int32_t *upstream, const int32_t *upstreamInvert,
                            int perIndividual, const int32_t *knockouts, const int32_t *knockins);
 int scb_pop_run(scb_ctx *ctx, int mode);
+/* Work-list order.  scb_pop_costs returns, per individual of the last finished run, a cost in state-row units
+ * (rows its tiles moved plus a fixed share per step); scb_pop_set_order hands the next runs a permutation of the
+ * individuals, costliest first, so that the last tiles of a launch are short ones (most individuals of a (mu + lambda)
+ * generation were scored before: their last cost predicts the next).  order = NULL: back to index order. */
+int scb_pop_costs(scb_ctx *ctx, uint32_t *costs);
+int scb_pop_set_order(scb_ctx *ctx, const int32_t *order, int P);
+
+/* ---- the generation's fitness all-gather over peer memory (one process per GPU of a box) -----------------------
+ * Replaces the NCCL all-gather of the sharded population with one small kernel at the end of the
+ * generation's graph: every rank stores its shard of `width` int64 values into every rank's gather buffer over
+ * NVLink and raises a flag there.  scb_gather_init allocates this rank's buffers and returns two CUDA IPC handles
+ * (128 bytes); the caller exchanges them between the ranks (any transport; bench.py uses torch.distributed) and
+ * passes all of them, in rank order, to scb_gather_connect.  From then on every scb_pop_run(ctx, SCB_MODE_SUM) ends
+ * with the exchange; scb_gather_result waits and copies the gathered vector int64[world * width] (rank r's shard at
+ * r * width).  All ranks must run the same number of generations. */
+int scb_gather_init(scb_ctx *ctx, int world, int rank, int width, unsigned char *handles128);
+int scb_gather_connect(scb_ctx *ctx, const unsigned char *allHandles);
+int scb_gather_result(scb_ctx *ctx, int64_t *gathered);
+int scb_gather_close(scb_ctx *ctx);
 int scb_pop_fetch(scb_ctx *ctx, int mode, void *out, scb_stats *stats);
 int scb_pop_result_dev(scb_ctx *ctx, int mode, void **devPtr, int64_t *bytes);
 

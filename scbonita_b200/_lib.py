@@ -16,13 +16,14 @@ DEFAULT_PATH = os.environ.get("SCB_B200_LIB") or os.path.join(_HERE, "libscbonit
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4
 MODE_SUM, MODE_NODEWISE, MODE_CELLWISE = 0, 1, 2
 OPT_EARLY_EXIT, OPT_SNAPSHOTS, OPT_WARPS, OPT_MAX_CTAS, OPT_WORDS, OPT_CHECK_EVERY, OPT_PERIOD_SEARCH = 1, 2, 3, 4, 5, 6, 7
-OPT_SNAP_LO, OPT_SNAP_HI, OPT_SNAP_MIN_GAP, OPT_TMEM, OPT_FUSE, OPT_TMA, OPT_STEADY, OPT_CHECK_FROM = 8, 9, 10, 11, 12, 13, 14, 15
+OPT_SNAP_LO, OPT_SNAP_HI, OPT_SNAP_MIN_GAP, OPT_TMEM, OPT_FUSE, OPT_TMA, OPT_STEADY, OPT_CHECK_FROM, OPT_GRAPH = 8, 9, 10, 11, 12, 13, 14, 15, 16
 
 # every symbol include/scbonita_b200.h declares (tests check that the library exports them all)
 SYMBOLS = (
     "scb_last_error", "scb_version", "scb_device_count",
     "scb_ctx_create", "scb_ctx_create_csr", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info",
     "scb_eval_population", "scb_pop_upload", "scb_pop_upload_compact", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
+    "scb_pop_costs", "scb_pop_set_order", "scb_gather_init", "scb_gather_connect", "scb_gather_result", "scb_gather_close",
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
     "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
     "scb_eval_local_search", "scb_eval_local_search_all", "scb_hamming_argmin", "scb_attractors", "scb_importance_score",
@@ -84,6 +85,14 @@ def load(path=None):
     lib.scb_pop_run.argtypes = [vp, ctypes.c_int]
     lib.scb_pop_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Stats)]
     lib.scb_pop_result_dev.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
+    lib.scb_pop_costs.argtypes = [vp, vp]
+    lib.scb_pop_set_order.argtypes = [vp, vp, ctypes.c_int]
+    lib.scb_gather_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    lib.scb_gather_connect.argtypes = [vp, vp]
+    lib.scb_gather_result.argtypes = [vp, vp]
+    lib.scb_gather_close.argtypes = [vp]
+    for name in ("scb_pop_costs", "scb_pop_set_order", "scb_gather_init", "scb_gather_connect", "scb_gather_result", "scb_gather_close"):
+        getattr(lib, name).restype = ctypes.c_int
     lib.scb_ctx_stream.argtypes = [vp, ctypes.POINTER(vp)]
     lib.scb_ctx_sync.argtypes = [vp]
     lib.scb_ctx_event_record.argtypes = [vp, ctypes.c_int]

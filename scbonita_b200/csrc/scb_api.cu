@@ -43,12 +43,16 @@ int fail(int code, const char *fmt, ...)
             return fail(SCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+/* bumped by every (re)allocation of a device buffer: a captured generation graph holds raw pointers */
+unsigned long long g_allocEpoch = 0;
+
 template <class T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;            /* elements */
     int ensure(size_t n)
     {
         if (n <= cap && p) return SCB_OK;
+        ++g_allocEpoch;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         const size_t want = std::max<size_t>(n, 1);
@@ -74,7 +78,8 @@ struct scb_ctx {
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
     int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 8, optSearch = 0, optMinGap = 8;
-    int optTmem = 1, optFuse = 1, optTma = 1, optSteady = 1, optChkFrom = SCB_NPROG - 2;
+    int optTmem = 1, optFuse = 1, optTma = 1, optSteady = 1, optChkFrom = SCB_NPROG - 2, optGraph = 1;
+    unsigned long long optVersion = 0;   /* bumped by every scb_ctx_set_option */
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
     /* geometry (derived) */
     int K = 0, warps = 0, ctas = 0, occ = 1;
@@ -103,6 +108,21 @@ struct scb_ctx {
     DevBuf<uint32_t> dAttr;
     DevBuf<int32_t> dDist, dDecider, dDeciderDist;
     DevBuf<unsigned char> dFlush;
+    DevBuf<unsigned int> dCost;          /* [P] rows moved per individual in the last run */
+    DevBuf<int32_t> dOrder;              /* [P] individuals, costliest first (scb_pop_set_order) */
+    bool haveOrder = false;
+    /* the generation as a CUDA graph: clears + K0 + K2 + fill (+ peer gather), replayed while nothing it refers to moves */
+#ifndef SCB_EMU
+    cudaGraphExec_t graphExec = nullptr;
+#endif
+    unsigned long long graphKey = 0;
+    /* fitness exchange over peer memory (scb_gather_*) */
+    int gWorld = 0, gRank = 0, gWidth = 0;
+    bool gConnected = false;
+    unsigned long long *gBuf = nullptr;  /* own gather buffer [2][world * width] */
+    unsigned int *gFlags = nullptr;      /* own flag array [world], then generation counter, then timeout flag */
+    unsigned long long *gPeerBuf[SCB_MAX_PEERS] = {};
+    unsigned int *gPeerFlag[SCB_MAX_PEERS] = {};
     DevBuf<uint32_t> dTraj, dStates, dRecBits;
     DevBuf<unsigned char> dRecOn;
     DevBuf<int32_t> dRes, dNStates;
@@ -462,11 +482,20 @@ int scb_ctx_create_csr(scb_ctx **out, int device, int nodeNum, int lenSamples, c
     return SCB_OK;
 }
 
+#ifndef SCB_EMU
+static void gather_release(scb_ctx *c);
+#endif
+
 int scb_ctx_destroy(scb_ctx *c)
 {
     if (!c) return SCB_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+#ifndef SCB_EMU
+    gather_release(c);
+    if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
+#endif
+    c->dCost.release(); c->dOrder.release();
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dImgs.release(); c->dProgFrom.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
@@ -488,7 +517,9 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    ++c->optVersion;
     switch (key) {
+        case SCB_OPT_GRAPH: c->optGraph = value != 0; return SCB_OK;
         case SCB_OPT_EARLY_EXIT: c->optEarly = value != 0; return SCB_OK;
         case SCB_OPT_SNAPSHOTS: c->optSnap = value != 0; break;
         case SCB_OPT_CHECK_EVERY:
@@ -617,6 +648,8 @@ int scb_pop_run(scb_ctx *c, int mode)
 
 /* K0 + K2 + K3 on the uploaded population; mode may also be the internal SCB_MODE_IMPORTANCE (with
  * sem = SCB_SEM_IMPORTANCE), whose per-node counts land in the nodewise buffer */
+static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing);
+
 static int pop_run_impl(scb_ctx *c, int mode, int sem)
 {
     int rc = check_ctx(c);
@@ -627,10 +660,60 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     const int N = c->N, P = c->P;
     cudaStream_t st = c->stream;
     const bool wantNodewise = mode == SCB_MODE_NODEWISE || mode == SCB_MODE_IMPORTANCE;
+    /* every allocation happens here, before anything is enqueued (or captured) */
     if (wantNodewise && (rc = c->dNodewise.ensure((size_t)P * N))) return rc;
     if (mode == SCB_MODE_CELLWISE && (rc = c->dCellwise.ensure((size_t)P * c->C))) return rc;
+    if ((rc = c->dImgs.ensure((size_t)P * (SCB_NPROG + 1) * scb_img_entries(N, c->main.warps)))) return rc;
+    if ((rc = c->dCost.ensure(P))) return rc;
+#ifndef SCB_EMU
+    if (c->optGraph) {
+        /* One launch per generation: the clears, K0, K2 (+ resolver), the fill-forward kernel and the peer exchange are
+         * captured once and replayed for as long as nothing the graph refers to has moved (buffers, population shape,
+         * options, peers).  The generation's inputs change in place (uploads into the same buffers). */
+        unsigned long long key = 1469598103934665603ull;
+        auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+        mix(g_allocEpoch); mix(c->optVersion); mix((unsigned long long)P); mix((unsigned long long)mode); mix((unsigned long long)sem);
+        mix((unsigned long long)c->indLen); mix((unsigned long long)c->tpi); mix((unsigned long long)c->compact); mix((unsigned long long)c->koStride);
+        mix(c->haveOrder ? 1ull : 0ull); mix(c->gConnected ? (unsigned long long)(1 + c->gRank + 64 * c->gWorld + 4096ull * c->gWidth) : 0ull);
+        if (!c->graphExec || key != c->graphKey) {
+            if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = pop_enqueue(c, mode, sem, true);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(SCB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ci = cudaGraphInstantiate(&c->graphExec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ci != cudaSuccess) { c->graphExec = nullptr; return fail(SCB_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ci)); }
+            c->graphKey = key;
+        }
+        CK(cudaEventRecord(c->evRun0, st));
+        CK(cudaGraphLaunch(c->graphExec, st));
+        CK(cudaEventRecord(c->evRun1, st));
+        CK(cudaEventRecord(c->evSim0, st));          /* the per-kernel split needs SCB_OPT_GRAPH = 0 */
+        CK(cudaEventRecord(c->evSim1, st));
+        c->lastMode = mode; c->ran = true;
+        return SCB_OK;
+    }
+#endif
     CK(cudaEventRecord(c->evRun0, st));
+    if ((rc = pop_enqueue(c, mode, sem, false))) return rc;
+    CK(cudaEventRecord(c->evRun1, st));
+    c->lastMode = mode; c->ran = true;
+    return SCB_OK;
+}
+
+/* the generation on the context's stream: clears, K0, K2 (+ in-kernel resolver), resolver / fill-forward kernels and,
+ * when peers are connected, the fitness exchange */
+static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
+{
+    int rc;
+    const int N = c->N, P = c->P;
+    cudaStream_t st = c->stream;
+    const bool wantNodewise = mode == SCB_MODE_NODEWISE || mode == SCB_MODE_IMPORTANCE;
     CK(cudaMemsetAsync(c->dFitness.p, 0, (size_t)P * 8, st));
+    CK(cudaMemsetAsync(c->dCost.p, 0, (size_t)P * 4, st));
     if (wantNodewise) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
     CK(cudaMemsetAsync(c->dCounters.p, 0, 8 * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
@@ -644,6 +727,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
     sa.progs = c->dProgs.p; sa.progFrom = c->dProgFrom.p; sa.useSteady = c->optSteady;
     sa.imgs = c->dImgs.p; sa.imgStride = (int)scb_img_entries(N, c->main.warps);
+    sa.cost = c->dCost.p; sa.order = c->haveOrder ? c->dOrder.p : nullptr;
     sa.chkFromProg = c->optChkFrom;
     sa.firstSnap = 1000;
     for (int t = SCB_LAST - 1; t >= 1; --t)
@@ -680,7 +764,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     sa.useTma = c->optTma;
     sa.tilesDone = c->dCounters.p + 6; sa.readyFlags = c->dReady.p; sa.resolveCursor = c->dCounters.p + 2;
     if (fuse) CK(cudaMemsetAsync(c->dReady.p, 0, (size_t)sa.resolveCap * sizeof(unsigned int), st));
-    CK(cudaEventRecord(c->evSim0, st));
+    if (!capturing) CK(cudaEventRecord(c->evSim0, st));
     for (int part = 0; part < 2; ++part) {
         const SimGeom &g = part == 0 ? c->main : c->tail;
         const int tiles = part == 0 ? c->mainTiles : c->tailTiles;
@@ -708,7 +792,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
         }
         CK((cudaError_t)le);
     }
-    CK(cudaEventRecord(c->evSim1, st));
+    if (!capturing) CK(cudaEventRecord(c->evSim1, st));
 
     ScbResolveArgs ra;
     ra.s = sa; ra.itemCursor = c->dCounters.p + 2;
@@ -720,8 +804,157 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     ra.itemCursor = c->dCounters.p + 4;
     SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->fillCtas), dim3((unsigned)c->fillWarps * 32), c->smemFill, st, ra);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->evRun1, st));
-    c->lastMode = mode; c->ran = true;
+    if (c->gConnected && mode == SCB_MODE_SUM) {
+        /* the generation's all-gather: this rank's shard into every rank's buffer over peer memory */
+        ScbGatherArgs ga;
+        memset(&ga, 0, sizeof(ga));
+        ga.fitness = c->dFitness.p; ga.count = std::min(P, c->gWidth); ga.width = c->gWidth; ga.rank = c->gRank; ga.world = c->gWorld;
+        for (int r = 0; r < c->gWorld; ++r) { ga.peerBuf[r] = c->gPeerBuf[r]; ga.peerFlag[r] = c->gPeerFlag[r]; }
+        ga.generation = c->gFlags + SCB_MAX_PEERS; ga.timeout = c->gFlags + SCB_MAX_PEERS + 1;
+#ifndef SCB_EMU
+        SCB_LAUNCH(scb_k_gather, dim3(1), dim3(256), 0, st, ga);
+        CK(cudaGetLastError());
+#endif
+    }
+    return SCB_OK;
+}
+
+/* ---- cost-ordered work list ------------------------------------------------------------------------------------ */
+int scb_pop_costs(scb_ctx *c, uint32_t *costs)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (!c->ran || !costs) return fail(SCB_ERR_INVALID, "no finished run / null output");
+    CK(cudaMemcpyAsync(costs, c->dCost.p, (size_t)c->P * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SCB_OK;
+}
+
+int scb_pop_set_order(scb_ctx *c, const int32_t *order, int P)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (!order) { c->haveOrder = false; return SCB_OK; }
+    if (P <= 0) return fail(SCB_ERR_INVALID, "population size must be positive");
+    std::vector<char> seen((size_t)P, 0);
+    for (int i = 0; i < P; ++i) {
+        if (order[i] < 0 || order[i] >= P || seen[order[i]]) return fail(SCB_ERR_INVALID, "order is not a permutation of 0..%d", P - 1);
+        seen[order[i]] = 1;
+    }
+    if ((rc = c->dOrder.ensure(P))) return rc;
+    CK(cudaMemcpyAsync(c->dOrder.p, order, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));            /* `order` is the caller's temporary */
+    c->haveOrder = true;
+    return SCB_OK;
+}
+
+/* ---- fitness exchange over peer memory (one process per GPU of a box) ------------------------------------------ */
+#ifndef SCB_EMU
+static void gather_release(scb_ctx *c)
+{
+    for (int r = 0; r < c->gWorld; ++r) {
+        if (r == c->gRank) continue;
+        if (c->gPeerBuf[r]) cudaIpcCloseMemHandle(c->gPeerBuf[r]);
+        if (c->gPeerFlag[r]) cudaIpcCloseMemHandle(c->gPeerFlag[r]);
+    }
+    if (c->gBuf) cudaFree(c->gBuf);
+    if (c->gFlags) cudaFree(c->gFlags);
+    c->gBuf = nullptr; c->gFlags = nullptr; c->gConnected = false; c->gWorld = 0;
+    for (int r = 0; r < SCB_MAX_PEERS; ++r) { c->gPeerBuf[r] = nullptr; c->gPeerFlag[r] = nullptr; }
+    ++g_allocEpoch;
+}
+#endif
+
+int scb_gather_init(scb_ctx *c, int world, int rank, int width, unsigned char *handles)
+{
+#ifdef SCB_EMU
+    (void)c; (void)world; (void)rank; (void)width; (void)handles;
+    return fail(SCB_ERR_UNSUPPORTED, "peer-memory exchange needs CUDA devices");
+#else
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (world < 1 || world > SCB_MAX_PEERS || rank < 0 || rank >= world || width < 1 || !handles)
+        return fail(SCB_ERR_INVALID, "bad gather geometry (world %d, rank %d, width %d)", world, rank, width);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    CK(cudaStreamSynchronize(c->stream));
+    gather_release(c);
+    c->gWorld = world; c->gRank = rank; c->gWidth = width;
+    const size_t bufBytes = (size_t)2 * world * width * 8, flagBytes = (size_t)(SCB_MAX_PEERS + 2) * 4;
+    CK(cudaMalloc(reinterpret_cast<void **>(&c->gBuf), bufBytes));
+    CK(cudaMalloc(reinterpret_cast<void **>(&c->gFlags), flagBytes));
+    CK(cudaMemset(c->gBuf, 0, bufBytes));
+    CK(cudaMemset(c->gFlags, 0, flagBytes));
+    cudaIpcMemHandle_t hb, hf;
+    CK(cudaIpcGetMemHandle(&hb, c->gBuf));
+    CK(cudaIpcGetMemHandle(&hf, c->gFlags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    memcpy(handles, &hb, 64);
+    memcpy(handles + 64, &hf, 64);
+    return SCB_OK;
+#endif
+}
+
+int scb_gather_connect(scb_ctx *c, const unsigned char *allHandles)
+{
+#ifdef SCB_EMU
+    (void)c; (void)allHandles;
+    return fail(SCB_ERR_UNSUPPORTED, "peer-memory exchange needs CUDA devices");
+#else
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (!c->gBuf || !allHandles) return fail(SCB_ERR_INVALID, "scb_gather_init first");
+    for (int r = 0; r < c->gWorld; ++r) {
+        if (r == c->gRank) { c->gPeerBuf[r] = c->gBuf; c->gPeerFlag[r] = c->gFlags; continue; }
+        cudaIpcMemHandle_t hb, hf;
+        memcpy(&hb, allHandles + (size_t)r * 128, 64);
+        memcpy(&hf, allHandles + (size_t)r * 128 + 64, 64);
+        void *pb = nullptr, *pf = nullptr;
+        CK(cudaIpcOpenMemHandle(&pb, hb, cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+        c->gPeerBuf[r] = static_cast<unsigned long long *>(pb);
+        c->gPeerFlag[r] = static_cast<unsigned int *>(pf);
+    }
+    c->gConnected = true;
+    return SCB_OK;
+#endif
+}
+
+int scb_gather_result(scb_ctx *c, int64_t *out)
+{
+#ifdef SCB_EMU
+    (void)c; (void)out;
+    return fail(SCB_ERR_UNSUPPORTED, "peer-memory exchange needs CUDA devices");
+#else
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (!c->gConnected || !out) return fail(SCB_ERR_INVALID, "no connected gather / null output");
+    const size_t n = (size_t)c->gWorld * c->gWidth;
+    std::vector<unsigned long long> both(2 * n);
+    unsigned int tail[2] = {0u, 0u};
+    CK(cudaMemcpyAsync(both.data(), c->gBuf, 2 * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(tail, c->gFlags + SCB_MAX_PEERS, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (tail[1]) return fail(SCB_ERR_CUDA, "a peer did not take part in the fitness exchange (timeout)");
+    memcpy(out, both.data() + (size_t)(tail[0] & 1u) * n, n * 8);
+    return SCB_OK;
+#endif
+}
+
+int scb_gather_close(scb_ctx *c)
+{
+#ifndef SCB_EMU
+    if (!c) return SCB_OK;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    gather_release(c);
+#else
+    (void)c;
+#endif
     return SCB_OK;
 }
 

@@ -393,22 +393,27 @@ SCB_DEV void scb_layout_program(uint4 *img, int *scr, const uint4 *g, int4 cnt, 
         last[tid] = e;
     }
     __syncthreads();
-    if (tid == 0) {
-        img[0] = make_uint4((unsigned)cnt.x, (unsigned)cnt.y, (unsigned)cnt.z, (unsigned)cnt.w);
-        int o = scb_img_hdr(S);
-        for (int w = 0; w < S; ++w) {
-            const int f = first[w], l = last[w];
-            /* entries of the piece: its nodes + its runs (the piece's first node always starts one) */
-            const int n = f < e1 ? (l - f) + (int)((g[l - 1].z >> 16) - (g[f].z >> 16)) + 1 : 0;
-            offs[w] = o;
-            uint4 *h = img + 1 + (w >> 1);
-            if (w & 1) { h->z = (unsigned)o; h->w = (unsigned)n; } else { h->x = (unsigned)o; h->y = (unsigned)n; }
-            img[o + n] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
-            img[o + n + 1] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
-            img[o + n + 2] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
-            o += n + SCB_LIST_TAIL;
-        }
+    /* entries of every piece: its nodes + its runs (the piece's first node always starts one); one thread per piece
+     * (the two reads of g are L2 round trips: done side by side, not one piece after the other) */
+    int myN = 0;
+    if (tid < S) {
+        const int f = first[tid], l = last[tid];
+        myN = f < e1 ? (l - f) + (int)((g[l - 1].z >> 16) - (g[f].z >> 16)) + 1 : 0;
+        offs[tid] = myN;
     }
+    __syncthreads();
+    int myO = scb_img_hdr(S);
+    if (tid < S) for (int w = 0; w < tid; ++w) myO += offs[w] + SCB_LIST_TAIL;      /* S <= 24 additions from shared memory */
+    __syncthreads();
+    if (tid < S) {
+        offs[tid] = myO;
+        unsigned *h = reinterpret_cast<unsigned *>(img + 1 + (tid >> 1)) + ((tid & 1) ? 2 : 0);
+        h[0] = (unsigned)myO; h[1] = (unsigned)myN;
+        img[myO + myN] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+        img[myO + myN + 1] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+        img[myO + myN + 2] = make_uint4(SCB_NOIN | SCB_CLS_END, SCB_NOIN, SCB_NOIN, 0u);
+    }
+    if (tid == 0) img[0] = make_uint4((unsigned)cnt.x, (unsigned)cnt.y, (unsigned)cnt.z, (unsigned)cnt.w);
     __syncthreads();
     for (int j = tid; j < e1; j += nthr) {
         const uint4 d = g[j];
@@ -1012,7 +1017,8 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         if (tid == 0) sh[12 + ((iter + 1u) & 1u)] = (int)atomicAdd(A.workCounter, 1u);
         /* tile-major order: the long tiles of a hard individual are spread over the whole launch and the last
          * items to be handed out are the cheap, partly filled tail tiles, which keeps the end of the launch level */
-        const int p = (int)(item % (unsigned)A.P), tile = (int)(item / (unsigned)A.P);
+        const int pslot = (int)(item % (unsigned)A.P), tile = (int)(item / (unsigned)A.P);
+        const int p = A.order ? A.order[pslot] : pslot;      /* within a round of tiles: costliest individuals first */
         const long long c0 = scb_clock();
         const int w0 = A.wordBase + tile * WT;
         int4 cnt = A.counts[p];
@@ -1035,6 +1041,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         unsigned long long fromBytes = A.useSteady ? *reinterpret_cast<const unsigned long long *>(A.progFrom + (long long)p * 8) : 0ull;
         int switchAt = 1000, nextProg = 0;
         unsigned rowsPerStep = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
+        const unsigned rowsAtTileStart = rowsMoved;
         int segStart = 0;
 #define SCB_NEXT_PROGRAM(after)                                                                           \
         do {                                                                                              \
@@ -1246,6 +1253,8 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
 #endif
         stepsDone += (unsigned)t; ++tilesDone;
         rowsMoved += (unsigned)(t - segStart) * rowsPerStep;   /* state rows moved through shared memory (loads + stores) */
+        /* cost of the tile in row units: its rows plus ~128 rows' worth of fixed time per step (barrier, dispatch) */
+        if (A.cost && tid == 0) atomicAdd(&A.cost[p], rowsMoved - rowsAtTileStart + 128u * (unsigned)t);
 #undef SCB_NEXT_PROGRAM
         const long long c2 = scb_clock();
 
@@ -1930,6 +1939,50 @@ __global__ void scb_k_fill(ScbResolveArgs R)
         __syncwarp();
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Fitness exchange over peer memory: the all-gather of a GA generation as the last kernel of the
+ * generation's graph.  One CTA: the shard (a few hundred 8-byte values) is stored straight into every rank's gather
+ * buffer over NVLink, a system-scope fence orders the stores, then this rank's flag is raised in every rank's flag
+ * array; the CTA leaves when all ranks have raised theirs here.  No host round trip, no NCCL launch: the payload is
+ * 4 KB, the exchange is pure latency.  Buffers are double buffered by generation parity: a rank can run at most one
+ * generation ahead of the slowest one, whose host has consumed generation g before it launches g + 1.
+ * ---------------------------------------------------------------------------------------- */
+#ifndef SCB_EMU
+__global__ void scb_k_gather(ScbGatherArgs G)
+{
+    __shared__ unsigned int gen;
+    if (threadIdx.x == 0) gen = *G.generation + 1u;
+    __syncthreads();
+    const unsigned int g = gen;
+    const size_t half = (size_t)(g & 1u) * G.world * G.width;
+    for (int r = 0; r < G.world; ++r) {
+        unsigned long long *dst = G.peerBuf[r] + half + (size_t)G.rank * G.width;
+        for (int i = threadIdx.x; i < G.width; i += blockDim.x) dst[i] = i < G.count ? G.fitness[i] : 0ull;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < G.world) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(G.peerFlag[threadIdx.x] + G.rank), "r"(g) : "memory");
+        const unsigned int *mine = G.peerFlag[G.rank] + threadIdx.x;
+        unsigned int v = 0u;
+        long long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - g) >= 0) break;
+            if (++spins > 400000000ll) { atomicExch(G.timeout, 1u); break; }       /* seconds: a peer is gone */
+            __nanosleep(64);
+        }
+#else
+        G.peerFlag[threadIdx.x][G.rank] = g;
+#endif
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *G.generation = g;
+}
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * K4: trajectories for attractor extraction (the `cluster` companion, simulator.c:487-552, and

@@ -157,6 +157,8 @@ struct ScbSimArgs {
     unsigned int *readyFlags;     /* [resolveCap] item i is complete in memory */
     unsigned int *resolveCursor;  /* ticket counter of the in-kernel resolver */
     unsigned int smemBytes;       /* dynamic shared memory of the launch (the item slot sits in its last 64 bytes) */
+    unsigned int *cost;           /* [P] or null: state rows each individual's tiles moved (the cost predictor of the next generation) */
+    const int32_t *order;         /* [P] or null: individuals in the order their tiles are handed out (costliest first) */
     int useTma;                   /* != 0: the S_0 tile is loaded with cp.async.bulk (TMA) row copies */
     int tmemCols;                 /* > 0: the snapshot lives in tensor memory, this many columns per CTA */
     int tmemSlotsPerWarp;         /* node slots reserved per warp for the resolver's target state (program order) */
@@ -180,6 +182,18 @@ struct ScbWindowArgs {
     int32_t *res;                 /* [C][2] */
     int32_t *nStates;             /* [C] */
     uint32_t *states;             /* [C][maxStates][NW] */
+};
+
+/* fitness exchange between the GPUs of a box over peer memory (NVLink): every rank writes its shard into every
+ * rank's gather buffer and then raises its flag there; see scb_k_gather */
+#define SCB_MAX_PEERS 16
+struct ScbGatherArgs {
+    const unsigned long long *fitness;   /* this rank's shard, [count] */
+    int count, width, rank, world;       /* every rank owns `width` slots of the gathered vector */
+    unsigned long long *peerBuf[SCB_MAX_PEERS];   /* gather buffers [2][world * width] of every rank (own one included) */
+    unsigned int *peerFlag[SCB_MAX_PEERS];        /* flag arrays [world] of every rank */
+    unsigned int *generation;            /* this rank's generation counter (device) */
+    unsigned int *timeout;               /* set when a peer did not show up */
 };
 
 struct ScbHammingArgs {

@@ -192,6 +192,41 @@ class Simulator:
         _lib.check(self.lib, rc)
         return out
 
+    # -- cost-ordered work list, peer-memory fitness exchange --------------------------------
+    def costs(self):
+        """uint32[P]: cost of every individual of the last run in state-row units (scb_pop_costs)."""
+        out = np.zeros(self._P, dtype=np.uint32)
+        _lib.check(self.lib, self.lib.scb_pop_costs(self._ctx, _ptr(out)))
+        return out
+
+    def set_order(self, order):
+        """Hand the next runs their individuals costliest first (``np.argsort(-costs)``); None: index order."""
+        if order is None:
+            _lib.check(self.lib, self.lib.scb_pop_set_order(self._ctx, None, 0))
+            return
+        o = _i32(order)
+        _lib.check(self.lib, self.lib.scb_pop_set_order(self._ctx, _ptr(o), int(o.shape[0])))
+
+    def gather_init(self, world, rank, width):
+        """Allocates this rank's gather buffers; returns the 128 bytes of CUDA IPC handles the other ranks need."""
+        h = np.zeros(128, dtype=np.uint8)
+        _lib.check(self.lib, self.lib.scb_gather_init(self._ctx, int(world), int(rank), int(width), _ptr(h)))
+        self._gather = (int(world), int(width))
+        return h
+
+    def gather_connect(self, all_handles):
+        h = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        _lib.check(self.lib, self.lib.scb_gather_connect(self._ctx, _ptr(h)))
+
+    def gather_result(self, out=None):
+        world, width = self._gather
+        out = np.zeros(world * width, dtype=np.int64) if out is None else out
+        _lib.check(self.lib, self.lib.scb_gather_result(self._ctx, _ptr(out)))
+        return out
+
+    def gather_close(self):
+        _lib.check(self.lib, self.lib.scb_gather_close(self._ctx))
+
     def sync(self):
         _lib.check(self.lib, self.lib.scb_ctx_sync(self._ctx))
 

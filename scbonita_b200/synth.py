@@ -168,3 +168,55 @@ def make_problem(n, cells, pop, knock=True, net_seed=None, cell_seed=5678, pop_s
     inds, an, ai = make_population(net, pop, seed=pop_seed)
     ko, ki = default_knock(n) if knock else (np.zeros(n, np.int32), np.zeros(n, np.int32))
     return SynthProblem(net, bin_rows, pos, inds, an, ai, ko, ki)
+
+
+def make_gated_rings(n, cells, pop, ring_lens=(45, 50, 57), chain_len=24, seed=7, gate_density=0.5):
+    """An adversarial network for the early-exit machinery: rings of copy nodes with one inverter each, every ring
+    node ANDed with a gate node g (g <- g), a decaying chain fed by a knocked node, free copy nodes up to `n`.
+    A cell with g = 1 puts ring r on a cycle of period 2 * ring_lens[r] after a transient set by the chain; with
+    g = 0 everything dies to a fixed point.  Periods beyond 35 defeat the in-flight repeat proofs, periods beyond
+    99 make the cell "attractor not found" (SURVEY Q7): every tile runs all 99 steps and goes to the exact
+    resolver.  Returns a SynthProblem whose `pop` individuals are identical (one rule set per node)."""
+    nodes = [("copy", 0)]
+    for ln in ring_lens:
+        base = len(nodes)
+        for j in range(ln):
+            nodes.append(("and2", base + (j - 1) % ln, 0, 1 if j == 0 else 0))
+    chain_base = len(nodes)
+    for j in range(chain_len):
+        nodes.append(("ko",) if j == 0 else ("copy", chain_base + j - 1))
+    while len(nodes) < n:
+        nodes.append(("copy", len(nodes) - 1))
+    if len(nodes) != n:
+        raise ValueError("rings + chain need %d nodes, n = %d" % (len(nodes), n))
+    and_len = np.zeros(n, np.int32)
+    parse = np.zeros(n + 1, np.int32)
+    and_nodes = np.zeros((n, MAX_TERMS, MAX_IN), np.int32)
+    and_inv = np.zeros((n, MAX_TERMS, MAX_IN), np.int32)
+    bits, ko = [], np.zeros(n, np.int32)
+    for i, nd in enumerate(nodes):
+        parse[i] = len(bits)
+        if nd[0] in ("copy", "ko"):
+            and_len[i] = 1
+            and_nodes[i, 0] = [nd[1] if nd[0] == "copy" else i, -1, -1]
+            and_inv[i, 0] = [0, -1, -1]
+            ko[i] = 1 if nd[0] == "ko" else 0
+            bits.append(1)
+        else:
+            _, pred, gate, inv = nd
+            and_len[i] = 3                               # terms [pred & g, pred, g]; only the first is selected
+            and_nodes[i, 0] = [pred, gate, -1]; and_inv[i, 0] = [inv, 0, -1]
+            and_nodes[i, 1] = [pred, -1, -1]; and_inv[i, 1] = [inv, -1, -1]
+            and_nodes[i, 2] = [gate, -1, -1]; and_inv[i, 2] = [0, -1, -1]
+            bits.extend([1, 0, 0])
+    parse[n] = len(bits)
+    net = SynthNetwork(n, and_len, parse, len(bits), and_nodes, and_inv)
+    rng = np.random.default_rng(seed)
+    rows = (rng.random((n, cells)) < 0.5).astype(np.uint8)
+    rows[0] = (rng.random(cells) < gate_density).astype(np.uint8)
+    rows[0, 0] = 0                                       # the first cell reaches a fixed point: no undefined fill-forward
+    pos = rng.permutation(n).astype(np.int32)
+    inds = np.tile(np.asarray(bits, np.int32), (pop, 1))
+    an = np.broadcast_to(and_nodes, (pop,) + and_nodes.shape).copy()
+    ai = np.broadcast_to(and_inv, (pop,) + and_inv.shape).copy()
+    return SynthProblem(net, rows, pos, inds, an, ai, ko, np.zeros(n, np.int32))
