@@ -35,6 +35,7 @@ WORKLOADS = {
     "C2": dict(nodes=60, cells=10_000, population=100, name="C2: synthetic 10k cells x 60-node network, population 100"),
     "C3": dict(nodes=200, cells=50_000, population=500, name="C3: synthetic 50k cells x 200-node network, population 500"),
     "T0": dict(nodes=24, cells=2_500, population=6, name="T0: tiny self-test shape (not a benchmark)"),
+    "C3s8": dict(nodes=200, cells=50_000, population=63, name="C3s8: one rank's share of C3 at 8 GPUs (63 individuals; tuning aid, not a benchmark)"),
     "N90": dict(nodes=90, cells=50_000, population=500, name="N90: 50k cells x 90-node network, population 500 (occupancy experiment, not a benchmark)"),
 }
 STEPS_PER_CELL = 99            # simulator.c:375 with simSteps = 100
@@ -609,6 +610,197 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# C4: ~50 independent KEGG-sized pathways over the GPUs of a box, no collective until the end
+# ---------------------------------------------------------------------------------------------
+C4_SIZES = (47, 60, 100, 159, 200, 300)          # packaged hsa00010 (47), C2 (60), hsa04066 (159), C3 (200), hsa04010 cut to 300
+C4_PATHWAYS, C4_CELLS, C4_POP = 48, 60_000, 500
+
+
+def run_c4(args, rank, world, local_rank):
+    """BASELINE config 4 (GSE198339-shaped: ~60k cells, ~50 pathways): what the reference runs as one SLURM job per
+    network (pipeline.py:12-75).  Every pathway is its own context (own packed matrix, own stream) on the GPU the
+    longest-processing-time assignment gives it (scbonita_b200.distributed.assign_pathways); a step scores one GA
+    generation of 500 individuals for every pathway; nothing is exchanged until the fitness vectors are collected at
+    the end."""
+    from scbonita_b200 import _lib, simulator
+    from scbonita_b200.distributed import assign_pathways, pathway_cost
+    lib = _lib.load()
+    if lib.scb_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback exists)")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sizes = [C4_SIZES[i % len(C4_SIZES)] for i in range(C4_PATHWAYS)]
+    costs = [pathway_cost(n, C4_CELLS, C4_POP) for n in sizes]
+    mine = assign_pathways(costs, world)[rank]
+    base = {}                                        # one network + population per size, a different cell matrix per pathway
+    gens = []
+    for i in mine:
+        n = sizes[i]
+        if n not in base:
+            base[n] = synth.make_problem(n, 8, C4_POP)
+        b = base[n]
+        rows, pos = synth.make_cells(n, C4_CELLS, seed=5678 + i)
+        pr = synth.SynthProblem(b.net, rows, pos, b.individuals, b.pop_and_nodes, b.pop_and_inv, b.knockouts, b.knockins)
+        bm = np.zeros((n, C4_CELLS), np.uint8); bm[pos] = rows
+        g = Generation(pr, bm, local_rank, args.opt)
+        g.upload()
+        gens.append(g)
+    units = float(sum(costs))                        # cell-rule evaluations of one step (all pathways, all ranks)
+
+    def barrier():
+        for g in gens:
+            g.sim.sync()
+        if world > 1:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def step_resident():
+        for g in gens:
+            g.step_resident()                        # asynchronous: the pathways' launches overlap on the GPU
+
+    def step_e2e():
+        for g in gens:
+            g.upload(); g.sim.run(simulator.MODE_SUM)
+        for g in gens:
+            g.sim.fetch(simulator.MODE_SUM, out=g.h_out)
+
+    def timed(step, steps, warmup):
+        import time as _t
+        for _ in range(warmup):
+            step()
+        barrier()
+        # wall clock around device-synchronised steps: the pathways run on their own streams, one CUDA event pair cannot
+        # bracket them all
+        t0 = _t.perf_counter()
+        for _ in range(steps):
+            step()
+            for g in gens:
+                g.sim.sync()
+        dt = (_t.perf_counter() - t0) * 1e3
+        barrier()
+        if world > 1:
+            import torch
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = timed(step_e2e, args.steps, max(args.warmup, 3))
+    local = {i: int(g.h_out.sum()) for i, g in zip(mine, gens)}
+    sums = [local]
+    if world > 1:
+        sums = [None] * world
+        dist.all_gather_object(sums, local)          # the only communication of C4: the results, at the end
+    if rank == 0:
+        merged = {}
+        for part in sums:
+            merged.update(part)
+        ms = total_ms / args.steps
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                cores = min(len(os.sched_getaffinity(0)), 64)
+                prc = synth.make_problem(100, 12_500, cores)
+                dt, u, kind = reference_sample(prc, 12_500, cores, cores)
+                cpu = {"value": u / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                       "sample": "%d individuals x 12500 cells x 100 nodes (one of the six pathway sizes), %d concurrent scSyncBool calls, %.1f s" % (cores, cores, dt)}
+            except Exception as exc:
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % exc}
+        h2d = sum(g.h2d for g in gens); d2h = sum(g.d2h for g in gens)
+        line = {"metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": "C4: %d pathways (%s nodes) x %d cells x population %d, pathways spread over %d GPU(s) longest first, "
+                                       "no collective until the final gather of the results" % (C4_PATHWAYS, "/".join(map(str, C4_SIZES)), C4_CELLS, C4_POP, world),
+                           "pathways_on_rank0": len(mine), "timing": "wall clock around device-synchronised steps, max over ranks",
+                           "options": args.opt},
+                "e2e": {"value": units / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": "bytes of rank 0's pathways"},
+                "gpu_launches": 3 * len(mine) * args.steps,
+                "roofline": {"bound": "hbm", "achieved": None, "peak": load_peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
+                             "note": "per-kernel roofline: see the C3 line (same kernels); C4 measures the pathway-level sharding"},
+                "clocks": clocks, "cpu_baseline": cpu, "fitness_checksum": int(sum(merged.values())), "pathways_scored": len(merged)}
+        print(json.dumps(line), flush=True)
+    for g in gens:
+        g.sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# C5: attractor analysis, 100k cells x 300-node network
+# ---------------------------------------------------------------------------------------------
+def run_c5(args, rank, world, local_rank):
+    """BASELINE config 5 (singleCell.assignAttractors, singleCell.py:1162-1244): per-cell trajectories + attractor
+    windows in the reference's Python semantics (K4), the unique attractor states, then the cells x attractors Hamming
+    distance with first-minimum decider (K5).  One GPU (the path is one pathway's post-processing); replicas at N > 1."""
+    from scbonita_b200 import _lib, simulator
+    import time as _t
+    lib = _lib.load()
+    if lib.scb_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback exists)")
+    N, C = 300, 100_000
+    pr = synth.make_problem(N, C, 1, knock=False)
+    bm = np.zeros((N, C), np.uint8); bm[pr.node_positions] = pr.bin_rows
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_and_nodes[0], pr.pop_and_inv[0], pr.node_positions, pr.net.ind_len)
+    sim = simulator.Simulator(bm, model, device=local_rank)
+    ind = pr.individuals[0]
+    attrs = sim.attractor_set(ind)
+    A = int(attrs.shape[0])
+
+    def step():
+        a = sim.attractor_set(ind)
+        sim.hamming_argmin(a, want_dist=False)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_traj = t_set = t_ham = 0.0
+    for _ in range(args.steps):
+        t0 = _t.perf_counter(); sim._attractors_packed(ind, None, None, "python", 10)
+        t1 = _t.perf_counter(); a = sim.attractor_set(ind)
+        t2 = _t.perf_counter(); sim.hamming_argmin(a, want_dist=False)
+        t3 = _t.perf_counter()
+        t_traj += t1 - t0; t_set += t2 - t1; t_ham += t3 - t2
+    clocks = sampler.stop()
+    K = args.steps
+    cre = float(C) * N * 9                           # Python semantics: 10 states = 9 synchronous steps per cell
+    ham = float(C) * A * N
+    try:
+        mb = {k: sim.microbench(k) for k in ("popc",)}
+    except Exception:
+        mb = {}
+    popc_peak = mb.get("popc")
+    ms = (t_set + t_ham) / K * 1e3
+    line = {"metric": METRIC, "value": cre / (t_set / K), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "C5: attractor analysis, 100k cells x 300-node network (trajectories + windows + unique attractor states + Hamming decider)",
+                       "attractors": A, "timing": "wall clock through the host API (host buffers in, results out): every stage is an e2e number"},
+            "stages_ms": {"trajectories_windows_states_to_host": t_traj / K * 1e3, "attractor_set (the same + host dedupe)": t_set / K * 1e3,
+                          "hamming_decider": t_ham / K * 1e3},
+            "e2e": {"value": cre / (t_set / K), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(A * N * 4),
+                    "d2h_bytes_per_step": int(C * 10 * ((N + 31) // 32) * 4 + C * 12 + C * 8)},
+            "hamming": {"bit_compares_per_sec": ham / (t_ham / K), "popc_peak_ops_per_sec": popc_peak,
+                        "frac_of_popc_roof": (ham / 32.0 / (t_ham / K)) / popc_peak if popc_peak else None,
+                        "note": "one POPC per 32 node bits; includes the H2D of the attractors and the D2H of decider + distance"},
+            "gpu_launches": 4 * K, "roofline": {"bound": "hbm", "achieved": None, "peak": load_peaks()[0], "unit": "GB/s", "frac": None, "traffic": None},
+            "clocks": clocks, "cpu_baseline": None}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    sim.close()
+
+
 def main():
     # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner,
     # ...) is sent to stderr by pointing fd 1 at fd 2 until the line is written
@@ -620,7 +812,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS) + ["C4", "C5"])
     ap.add_argument("--opt", action="append", default=[], help="library option, e.g. early_exit=0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
@@ -634,7 +826,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = WORKLOADS[args.workload]
+    if args.workload == "C4" and args.impl == "ours":
+        return run_c4(args, rank, world, local_rank)
+    if args.workload == "C5" and args.impl == "ours":
+        return run_c5(args, rank, world, local_rank)
+    wl = WORKLOADS["C3" if args.workload in ("C4", "C5") else args.workload]
     if args.impl == "reference":
         run_reference(args, wl, rank)
     else:

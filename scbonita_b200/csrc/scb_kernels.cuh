@@ -450,10 +450,11 @@ SCB_DEV void scb_layout_program(uint4 *img, int *scr, const uint4 *g, int4 cnt, 
 /* scratch of the table sort at the end of K0's shared memory: bins[SCB_SORT_BINS] counts -> starts,
  * cost[SCB_SORT_BINS] rows before each bin, run[SCB_SORT_BINS] non-empty bins before each bin, rank[N] (uint16) */
 #define SCB_SORT_BINS 258          /* 256 tables, then the two constants */
-SCB_HD inline size_t scb_sort_smem_bytes(int N) { return (size_t)3 * SCB_SORT_BINS * 4 + (size_t)((N + 7) / 8) * 16 + 32 + 96 * 4; }
+/* (every part a multiple of 16 bytes: the sorted copy of the program at the end is read as uint4) */
+SCB_HD inline size_t scb_sort_smem_bytes(int N) { return (((size_t)3 * SCB_SORT_BINS * 4 + 15) & ~(size_t)15) + (size_t)((N + 7) / 8) * 16 + 32 + 96 * 4 + (size_t)N * 16; }
 SCB_HD inline size_t scb_compile_smem_bytes(int N)
 {
-    return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4 + scb_sort_smem_bytes(N);
+    return (size_t)N * 16 + (size_t)((N + 15) / 16) * 16 + 64 + (((size_t)2 * N * SCB_MAX_TERMS * SCB_MAX_IN * 4 + 15) & ~(size_t)15) + scb_sort_smem_bytes(N);
 }
 
 /* number of inputs a table in lop3 convention depends on */
@@ -472,7 +473,7 @@ SCB_HD inline int scb_lut_arity(unsigned lut)
  * Stable counting sort: within a warp __match_any_sync ranks equal keys, the warps add their counts to the bins one
  * after the other.  All threads of the CTA call it (blockDim.x a multiple of 32). */
 SCB_DEV void scb_scatter_by_table(const uint4 *sdv, const unsigned char *sarv, int N, uint4 *out, unsigned int *scr,
-                                  int tid, int nthr)
+                                  int tid, int nthr, uint4 *outShared = nullptr)
 {
     unsigned int *bins = scr, *cost = scr + SCB_SORT_BINS, *run = scr + 2 * SCB_SORT_BINS;
     unsigned short *rank = reinterpret_cast<unsigned short *>(scr + 3 * SCB_SORT_BINS);
@@ -526,6 +527,7 @@ SCB_DEV void scb_scatter_by_table(const uint4 *sdv, const unsigned char *sarv, i
             d.z |= run[key] << 16;
         }
         out[bins[key] + r] = d;
+        if (outShared) outShared[bins[key] + r] = d;      /* the layout that follows reads the sorted program from here, not from L2 */
     }
     __syncthreads();
 }
@@ -569,11 +571,12 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     __syncthreads();
     const int c3 = (int)cn[0], c2 = (int)cn[1], c1 = (int)cn[2], c0 = (int)cn[3];
     unsigned int *wc = reinterpret_cast<unsigned int *>(smraw + scb_compile_smem_bytes(N) - scb_sort_smem_bytes(N));
-    scb_scatter_by_table(sd, sar, N, A.descs + (long long)p * A.Npad, wc, tid, nthr);
     /* the images the simulator copies into its shared memory: image 0 = the full program, 1 + k = reduced program k */
-    int *lscr = reinterpret_cast<int *>(smraw + scb_compile_smem_bytes(N) - 96 * 4);
+    int *lscr = reinterpret_cast<int *>(smraw + scb_compile_smem_bytes(N) - 96 * 4 - (size_t)N * 16);
+    uint4 *ssort = reinterpret_cast<uint4 *>(smraw + scb_compile_smem_bytes(N) - (size_t)N * 16);
     uint4 *imgs = A.imgs ? A.imgs + (long long)p * (SCB_NPROG + 1) * A.imgStride : nullptr;
-    if (imgs) scb_layout_program(imgs, lscr, A.descs + (long long)p * A.Npad, make_int4(c3, c2, c1, c0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
+    scb_scatter_by_table(sd, sar, N, A.descs + (long long)p * A.Npad, wc, tid, nthr, ssort);
+    if (imgs) scb_layout_program(imgs, lscr, ssort, make_int4(c3, c2, c1, c0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
     /* ---- reduced programs by constant propagation.  c(t) = nodes whose value in S_t is the same constant for every
      * cell: c(1) = the constant rules (knock-outs, knock-ins, constant-TRUE literals), c(t+1) = rules that are
      * constant once the inputs in c(t) are fixed.  Knowledge only grows, so c(D) stays valid for every t >= D.  A
@@ -636,8 +639,8 @@ __global__ void scb_k_compile(ScbCompileArgs A)
             const int s3 = chg[1], s2 = chg[2], s1 = chg[3], s0 = chg[4];
             const int slot = last ? SCB_NPROG - 1 : stage;
             uint4 *out2 = progs + (long long)slot * (N + 1);
-            scb_scatter_by_table(sd2, sar2, N, out2, wc, tid, nthr);
-            if (imgs) scb_layout_program(imgs + (long long)(1 + slot) * A.imgStride, lscr, out2, make_int4(s3, s2, s1, s0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
+            scb_scatter_by_table(sd2, sar2, N, out2, wc, tid, nthr, ssort);
+            if (imgs) scb_layout_program(imgs + (long long)(1 + slot) * A.imgStride, lscr, ssort, make_int4(s3, s2, s1, s0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
             if (tid == 0) {
                 out2[N] = make_uint4((unsigned)s3, (unsigned)s2, (unsigned)s1, (unsigned)s0);   /* the counts travel with the program */
                 progFrom[slot] = (unsigned char)(D + 2);
@@ -1010,15 +1013,47 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
 
     if (tid == 0) sh[12] = (int)atomicAdd(A.workCounter, 1u);
     __syncthreads();
-    for (unsigned iter = 0;; ++iter) {
+    for (unsigned iter = 0;;) {
         const unsigned item = (unsigned)sh[12 + (iter & 1u)];
         if (item >= total) break;
+        if (A.fuseResolve) {
+            /* A published resolver item goes before the next tile: it is the longest piece of work there is (98 compare
+             * steps) and the launch ends when the last one does.  Claimed with a compare-and-swap on the cursor, so a
+             * CTA never holds a ticket for an item that does not exist yet. */
+            if (tid == 0) {
+                int got = -1;
+                const unsigned cur = scb_ld_volatile(A.resolveCursor);
+                unsigned cnt = scb_ld_volatile(A.resolveCount);
+                if (cnt > A.resolveCap) cnt = A.resolveCap;
+                if (cur < cnt && atomicCAS(A.resolveCursor, cur, cur + 1u) == cur) {
+                    while (scb_ld_volatile(&A.readyFlags[cur]) == 0u) scb_backoff();      /* its producer is about to publish it */
+                    __threadfence();
+                    got = (int)cur;
+                }
+                sh[15] = got;
+            }
+            __syncthreads();
+            const int it = sh[15];
+            if (it >= 0) {
+                if (TM && A.resolveGroup == K) scb_resolve_item<K, true>(A, smraw, (unsigned)it, tm, true);
+                else if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
+                else scb_resolve_item<1>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
+                __syncthreads();
+                if (tid == 0) sh[12 + (iter & 1u)] = (int)item;     /* the resolver's scratch overlaps these words */
+                __syncthreads();
+                continue;                                   /* the tile item already fetched stays pending */
+            }
+        }
         /* the next item is requested now and read after this tile's last barrier: the atomic's latency is hidden */
         if (tid == 0) sh[12 + ((iter + 1u) & 1u)] = (int)atomicAdd(A.workCounter, 1u);
-        /* tile-major order: the long tiles of a hard individual are spread over the whole launch and the last
-         * items to be handed out are the cheap, partly filled tail tiles, which keeps the end of the launch level */
-        const int pslot = (int)(item % (unsigned)A.P), tile = (int)(item / (unsigned)A.P);
-        const int p = A.order ? A.order[pslot] : pslot;      /* within a round of tiles: costliest individuals first */
+        ++iter;
+        /* With a cost order (scb_pop_set_order) the list is individual-major, costliest individual first: classic
+         * longest-processing-time scheduling, the launch ends on the cheapest individuals' short tiles.  Without one it
+         * is tile-major: the long tiles of a hard individual are spread over the whole launch and the last items handed
+         * out are the cheap, partly filled tail tiles. */
+        int p, tile;
+        if (A.order) { p = A.order[item / (unsigned)A.tiles]; tile = (int)(item % (unsigned)A.tiles); }
+        else { p = (int)(item % (unsigned)A.P); tile = (int)(item / (unsigned)A.P); }
         const long long c0 = scb_clock();
         const int w0 = A.wordBase + tile * WT;
         int4 cnt = A.counts[p];
