@@ -229,3 +229,91 @@ if __name__ == "__main__":
     save_cluster("cluster_ring.npz", ring_problem([7, 4], 3, 50), [([], []), ([12], []), ([1, 9], [3])], [0, 7, 21, 49])
     save_py_cluster("pycluster_n24.npz", 24, 70, 501)
     save_py_cluster("pycluster_n40.npz", 40, 50, 777)
+    save_ga_trace()
+
+
+# ---------------------------------------------------------------------------------------------
+# C1 on the GPU box: a trace of what the UNMODIFIED reference GA hands to scSyncBool
+# ---------------------------------------------------------------------------------------------
+def save_ga_trace(name="ga_trace_hsa00010.npz", seed=20260, pop=12, lambd=12, mu=6, gens=3):
+    """Runs ruleMaker.__eaMuPlusLambdaAdaptive (unmodified, packaged 47-gene x 100-cell example, deap stand-in) with
+    ./simulator.so = the unmodified reference C, and records every scSyncBool call at the C boundary: the bit-string,
+    the int32 [N][7][3] tables exactly as the C code reads them (the shipped wrapper passes andNodeInvertList from a
+    dtype=object array, SURVEY Q3: the C side sees pointer halves, kept here byte for byte), and the errors it wrote.
+    The GPU box replays the trace through the CUDA library: same numbers, same logbook."""
+    import copy
+    import ctypes
+    import random
+    import tempfile
+    import warnings
+    import networkx as nx
+    import scipy.sparse as sp
+    import_reference_single_cell()
+    ref_dir = "/root/reference/src/scBONITA"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sc = pickle.load(open(os.path.join(ref_dir, "data", "trainingData.csvscTest.pickle"), "rb"))
+        net = nx.read_graphml(os.path.join(ref_dir, "data", "hsa00010.graphml_processed.graphml"))
+        sc._singleCell__inherit(net, removeSelfEdges=False, restrictIncomingEdges=True, maxIncomingEdges=3, groundTruth=False)
+    sc._ruleMaker__updateCpointers()
+    sc._singleCell__setupEmptyKOKI()
+    rows = max(sc.nodePositions) + 1
+    n_cells = len(sc.sampleList)
+    dense = sc.binMat[:rows, :n_cells].toarray()
+    bm = np.zeros((rows, 15000))
+    bm[:, :dense.shape[1]] = dense
+    sc.binMat = sp.csr_matrix(bm)
+    real = ctypes.cdll.LoadLibrary(os.path.join(ROOT, "oracle", "_ref", "simulator.so"))
+    N = len(sc.nodeList)
+    calls = []
+
+    def grab(ptr, count):
+        return np.frombuffer(ctypes.string_at(ptr.value, count * 4), dtype=np.int32).copy()
+
+    def recording_scSyncBool(*a):
+        ind_len, node_num, n_samp, local = (a[2].value or 0), (a[3].value or 0), (a[11].value or 0), (a[15].value or 0)
+        rec = dict(individual=grab(a[1], ind_len), and_len=grab(a[4], node_num), parse=grab(a[5], node_num),
+                   and_nodes=grab(a[6], node_num * 21), and_inv=grab(a[7], node_num * 21), knockouts=grab(a[9], node_num),
+                   knockins=grab(a[10], node_num), node_positions=grab(a[13], node_num), local=local, n_cells=n_samp)
+        real.scSyncBool(*a)
+        rec["errors"] = grab(a[14], node_num if local else n_samp)
+        calls.append(rec)
+
+    class Proxy:
+        scSyncBool = staticmethod(recording_scSyncBool)
+        importanceScore = real.importanceScore
+
+    model = copy.deepcopy(sc)
+    model._ruleMaker__makeToolBox(None)
+    model.params.popSize, model.params.lambd, model.params.mu, model.params.generations = pop, lambd, mu, gens
+    random.seed(seed)
+    np.random.seed(seed)
+    orig = ctypes.cdll.LoadLibrary
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        ctypes.cdll.LoadLibrary = lambda path: Proxy if "simulator.so" in str(path) else orig(path)
+        try:
+            population, logbook = model._ruleMaker__eaMuPlusLambdaAdaptive(None, "graph", verbose=False)
+        finally:
+            ctypes.cdll.LoadLibrary = orig
+            os.chdir(cwd)
+    assert all(c["local"] == 0 and c["n_cells"] == n_cells for c in calls)
+    for key in ("and_len", "parse", "knockouts", "knockins", "node_positions"):
+        assert all(np.array_equal(c[key], calls[0][key]) for c in calls), key
+    nevals = [int(r["nevals"]) for r in logbook]
+    assert sum(nevals) == len(calls)
+    pos = calls[0]["node_positions"]
+    np.savez_compressed(
+        os.path.join(HERE, name), n_cells=n_cells, ind_len=len(calls[0]["individual"]), and_len=calls[0]["and_len"],
+        parse=calls[0]["parse"], knockouts=calls[0]["knockouts"], knockins=calls[0]["knockins"], node_positions=pos,
+        bin_rows=np.packbits(dense[pos].astype(np.uint8), axis=1),
+        individuals=np.array([c["individual"] for c in calls], np.int32),
+        and_nodes=np.array([c["and_nodes"].reshape(N, 7, 3) for c in calls], np.int32),
+        and_inv=np.array([c["and_inv"].reshape(N, 7, 3) for c in calls], np.int32),
+        fitness=np.array([int(c["errors"].astype(np.int64).sum()) for c in calls], np.int64),
+        cellwise=np.array([c["errors"] for c in calls], np.int32),
+        nevals=np.array(nevals, np.int32),
+        logbook=np.array([(int(r["gen"]), int(r["nevals"]), float(r["avg"]), float(r["std"]), float(r["min"]), float(r["max"])) for r in logbook], np.float64),
+        final_fitness=np.array([float(ind.fitness.values[0]) for ind in population], np.float64))
+    print(name, "%d scSyncBool calls" % len(calls), "nevals", nevals, "min per generation", [float(r["min"]) for r in logbook])
