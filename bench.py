@@ -418,7 +418,7 @@ def run_ours(args, wl, rank, world, local_rank):
     # cost-ordered work list from the warm-up generation
     gen.step_resident(); sim.sync()
     if not args.no_order:
-        sim.set_order(np.argsort(-sim.costs().astype(np.int64), kind="stable"))
+        sim.set_order(sim.cost_order())
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -478,9 +478,13 @@ def run_ours(args, wl, rank, world, local_rank):
         sim.set_option(_lib.OPT_FUSE, 0)
     gsave, gather_after = gather_after, None
     _, stats, k2_list = timed_steps(gen, gen.step_resident, min(args.steps, 5), 2, sim.sync, stats_each=True)
-    _, stats_fused, _ = (None, stats, None)
+    stages = None
     if fused_default:
         sim.set_option(_lib.OPT_FUSE, 1)
+        # the same generation as plain launches with the resolver inside K2: where the time of the graph goes
+        _, sf, _ = timed_steps(gen, gen.step_resident, 3, 1, sim.sync, stats_each=True)
+        stages = {k: round(float(sf[k]), 4) for k in ("kernel_ms", "clear_ms", "compile_ms", "sim_ms", "resolve_ms", "fill_ms", "gather_ms")}
+        stages["note"] = "plain launches (SCB_OPT_GRAPH = 0), resolver inside K2, events between the launches; last of 3 steps"
     sim.set_option(_lib.OPT_GRAPH, 1)
     gather_after = gsave
 
@@ -584,7 +588,7 @@ def run_ours(args, wl, rank, world, local_rank):
                              "note": "algorithmic = CRE/s x 7/32 (SURVEY 8d mux-tree figure); executed = one LOP3 per "
                                      "node-word-step actually simulated (upper bound: counts all N nodes, the reduced "
                                      "programs compute fewer); POPC is used once per (node, word, tile)"},
-            "stats": stats, "clocks": clocks, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1,
+            "stats": stats, "stages_ms": stages, "clocks": clocks, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1,
             "fitness_checksum": int(fit.sum()),
         }
         if e2e_compact_ms is not None:

@@ -92,6 +92,13 @@ typedef struct scb_stats {
     int64_t cyc_steps;            /*   ... the synchronous steps                                      */
     int64_t cyc_epilogue;         /*   ... chunk flags, error reduction, outputs                      */
     int64_t state_rows_moved;     /* state rows (128 x wordsPerLane bytes each) the simulator's steps loaded + stored */
+    /* the other parts of kernel_ms (SCB_OPT_GRAPH = 0 only; all 0 when the generation runs as one graph):            */
+    float   clear_ms;             /*   result / counter clears                                        */
+    float   compile_ms;           /*   K0, the rule compiler                                          */
+    float   resolve_ms;           /*   the resolver kernel (0 when it runs inside K2)                 */
+    float   fill_ms;              /*   the fill-forward kernel                                        */
+    float   gather_ms;            /*   the peer-memory fitness exchange                               */
+    float   reserved_;
 } scb_stats;
 
 const char *scb_last_error(void);
@@ -151,11 +158,13 @@ int scb_pop_upload_compact(scb_ctx *ctx, int P, const int32_t *individuals, int 
                            const int32_t *upstream, const int32_t *upstreamInvert,
                            int perIndividual, const int32_t *knockouts, const int32_t *knockins);
 int scb_pop_run(scb_ctx *ctx, int mode);
-/* Work-list order.  scb_pop_costs returns, per individual of the last finished run, a cost in state-row units
- * (rows its tiles moved plus a fixed share per step); scb_pop_set_order hands the next runs a permutation of the
- * individuals, costliest first, so that the last tiles of a launch are short ones (most individuals of a (mu + lambda)
- * generation were scored before: their last cost predicts the next).  order = NULL: back to index order. */
-int scb_pop_costs(scb_ctx *ctx, uint32_t *costs);
+/* Work-list order.  scb_pop_costs returns, per individual of the last finished run, its cost in state-row units
+ * (rows its tiles moved plus a fixed share per step; `costs` = the sum over its tiles -- what a shard of individuals
+ * will take, `tileMax`, optional = its costliest tile -- what decides how late it may start); scb_pop_set_order
+ * hands the next runs a permutation of the individuals.  With the individuals holding the costliest tiles first the
+ * last tiles of a launch are short ones (most individuals of a (mu + lambda) generation were scored before, and
+ * offspring behave much like their parents: the last cost predicts the next).  order = NULL: back to index order. */
+int scb_pop_costs(scb_ctx *ctx, uint32_t *costs, uint32_t *tileMax);
 int scb_pop_set_order(scb_ctx *ctx, const int32_t *order, int P);
 
 /* ---- the generation's fitness all-gather over peer memory (one process per GPU of a box) -----------------------

@@ -39,7 +39,9 @@ class Stats(ctypes.Structure):
                 ("resolver_chunks", ctypes.c_int64), ("steps_executed", ctypes.c_int64),
                 ("tiles", ctypes.c_int64), ("kernel_ms", ctypes.c_float), ("sim_ms", ctypes.c_float),
                 ("cyc_prologue", ctypes.c_int64), ("cyc_steps", ctypes.c_int64), ("cyc_epilogue", ctypes.c_int64),
-                ("state_rows_moved", ctypes.c_int64)]
+                ("state_rows_moved", ctypes.c_int64), ("clear_ms", ctypes.c_float), ("compile_ms", ctypes.c_float),
+                ("resolve_ms", ctypes.c_float), ("fill_ms", ctypes.c_float), ("gather_ms", ctypes.c_float),
+                ("reserved_", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -85,7 +87,7 @@ def load(path=None):
     lib.scb_pop_run.argtypes = [vp, ctypes.c_int]
     lib.scb_pop_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Stats)]
     lib.scb_pop_result_dev.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
-    lib.scb_pop_costs.argtypes = [vp, vp]
+    lib.scb_pop_costs.argtypes = [vp, vp, vp]
     lib.scb_pop_set_order.argtypes = [vp, vp, ctypes.c_int]
     lib.scb_gather_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.scb_gather_connect.argtypes = [vp, vp]

@@ -72,7 +72,7 @@ struct scb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t evRun0 = nullptr, evRun1 = nullptr, evSim0 = nullptr, evSim1 = nullptr;
+    cudaEvent_t evRun0 = nullptr, evRun1 = nullptr, evSim0 = nullptr, evSim1 = nullptr, evK0 = nullptr, evFill0 = nullptr, evFill1 = nullptr;
     int numSM = 0;
     size_t smemLimit = 0;
     int N = 0, C = 0, W = 0, Wpad = 0;
@@ -99,7 +99,8 @@ struct scb_ctx {
     DevBuf<unsigned int> dCounters;      /* [0] K2 work head, [1] resolve count, [2] K3 work head */
     DevBuf<uint2> dItems;
     DevBuf<uint4> dFillItems;
-    DevBuf<int32_t> dChunkLast;
+    DevBuf<int32_t> dChunkLast, dChunkLastErr;
+    DevBuf<uint32_t> dChunkLastBits;
     DevBuf<uint32_t> dResolveT;
     DevBuf<unsigned int> dReady;
     unsigned resolveTCap = 0;
@@ -108,7 +109,7 @@ struct scb_ctx {
     DevBuf<uint32_t> dAttr;
     DevBuf<int32_t> dDist, dDecider, dDeciderDist;
     DevBuf<unsigned char> dFlush;
-    DevBuf<unsigned int> dCost;          /* [P] rows moved per individual in the last run */
+    DevBuf<unsigned int> dCost;          /* [2][P] cost per individual in the last run: sum over its tiles, costliest tile */
     DevBuf<int32_t> dOrder;              /* [P] individuals, costliest first (scb_pop_set_order) */
     bool haveOrder = false;
     /* the generation as a CUDA graph: clears + K0 + K2 + fill (+ peer gather), replayed while nothing it refers to moves */
@@ -251,9 +252,9 @@ int pick_geometry(scb_ctx *c)
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
     /* fill-forward: one warp per item, two N-word state vectors per warp */
-    c->fillWarps = 4;
-    c->smemFill = (size_t)c->fillWarps * scb_fill_smem_per_warp(N);
-    c->fillCtas = c->numSM * 4;
+    c->fillWarps = 8;
+    c->smemFill = 0;
+    c->fillCtas = 8;
     if (c->optMaxCtas > 0) c->fillCtas = std::min(c->fillCtas, c->optMaxCtas);
     size_t zwords = (size_t)c->main.ctas * N * 32 * K;
     if ((rc = c->dZ.ensure(zwords))) return rc;
@@ -352,12 +353,13 @@ int scb_ctx_create(scb_ctx **out, int device, int nodeNum, int lenSamples, const
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaEventCreate(&c->evRun0) != cudaSuccess || cudaEventCreate(&c->evRun1) != cudaSuccess ||
-        cudaEventCreate(&c->evSim0) != cudaSuccess || cudaEventCreate(&c->evSim1) != cudaSuccess)
+        cudaEventCreate(&c->evSim0) != cudaSuccess || cudaEventCreate(&c->evSim1) != cudaSuccess ||
+        cudaEventCreate(&c->evK0) != cudaSuccess || cudaEventCreate(&c->evFill0) != cudaSuccess || cudaEventCreate(&c->evFill1) != cudaSuccess)
         return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
     int rc;
     if ((rc = c->dX.ensure((size_t)c->N * c->Wpad))) return bail(rc);
     if ((rc = c->dDiag.ensure(1))) return bail(rc);
-    if ((rc = c->dCounters.ensure(8))) return bail(rc);
+    if ((rc = c->dCounters.ensure(16))) return bail(rc);
 
     /* stage the N gene rows the network uses (row i = gene nodePositions[i]) and pack them */
     const size_t rowBytes = (size_t)lenSamples * elemBytes;
@@ -436,12 +438,13 @@ int scb_ctx_create_csr(scb_ctx **out, int device, int nodeNum, int lenSamples, c
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaEventCreate(&c->evRun0) != cudaSuccess || cudaEventCreate(&c->evRun1) != cudaSuccess ||
-        cudaEventCreate(&c->evSim0) != cudaSuccess || cudaEventCreate(&c->evSim1) != cudaSuccess)
+        cudaEventCreate(&c->evSim0) != cudaSuccess || cudaEventCreate(&c->evSim1) != cudaSuccess ||
+        cudaEventCreate(&c->evK0) != cudaSuccess || cudaEventCreate(&c->evFill0) != cudaSuccess || cudaEventCreate(&c->evFill1) != cudaSuccess)
         return bail(fail(SCB_ERR_CUDA, "cudaEventCreate failed"));
     int rc;
     if ((rc = c->dX.ensure((size_t)c->N * c->Wpad))) return bail(rc);
     if ((rc = c->dDiag.ensure(1))) return bail(rc);
-    if ((rc = c->dCounters.ensure(8))) return bail(rc);
+    if ((rc = c->dCounters.ensure(16))) return bail(rc);
     /* gather the selected rows' slices on the host (pointer arithmetic only), one H2D each */
     std::vector<int32_t> rowOf((size_t)std::max<long long>(nnz, 1)), col((size_t)std::max<long long>(nnz, 1));
     std::vector<double> val(data ? (size_t)std::max<long long>(nnz, 1) : 0);
@@ -499,10 +502,13 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dImgs.release(); c->dProgFrom.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
-    c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
+    c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dChunkLastErr.release(); c->dChunkLastBits.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
     c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dRecBits.release(); c->dRecOn.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
+    if (c->evK0) cudaEventDestroy(c->evK0);
+    if (c->evFill0) cudaEventDestroy(c->evFill0);
+    if (c->evFill1) cudaEventDestroy(c->evFill1);
     if (c->evSim1) cudaEventDestroy(c->evSim1);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->evRun0) cudaEventDestroy(c->evRun0);
@@ -594,9 +600,9 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
     if ((rc = c->dProgs.ensure((size_t)P * SCB_NPROG * (N + 1))) || (rc = c->dProgFrom.ensure((size_t)P * 8))) return rc;
     if ((rc = c->dFitness.ensure(P))) return rc;
     const size_t chunks = (size_t)c->Wpad / 32;
-    if ((rc = c->dReady.ensure((size_t)P * chunks))) return rc;
+    if ((rc = c->dReady.ensure((size_t)2 * P * chunks))) return rc;      /* ready flags of the resolver items, then the handed-back tiles */
     if ((rc = c->dItems.ensure((size_t)P * chunks)) || (rc = c->dFillItems.ensure((size_t)P * chunks)) ||
-        (rc = c->dChunkLast.ensure((size_t)P * chunks))) return rc;
+        (rc = c->dChunkLast.ensure((size_t)P * chunks)) || (rc = c->dChunkLastErr.ensure((size_t)P * chunks))) return rc;
     {   /* S_99 hand-over slots for the resolver: at most 64 MiB */
         if (!c->geomValid && (rc = pick_geometry(c))) return rc;
         const size_t per = (size_t)N * 32 * c->resGroup;
@@ -662,9 +668,10 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     const bool wantNodewise = mode == SCB_MODE_NODEWISE || mode == SCB_MODE_IMPORTANCE;
     /* every allocation happens here, before anything is enqueued (or captured) */
     if (wantNodewise && (rc = c->dNodewise.ensure((size_t)P * N))) return rc;
+    if (mode == SCB_MODE_NODEWISE && (rc = c->dChunkLastBits.ensure((size_t)P * ((c->C + 1023) / 1024) * ((N + 31) / 32)))) return rc;
     if (mode == SCB_MODE_CELLWISE && (rc = c->dCellwise.ensure((size_t)P * c->C))) return rc;
     if ((rc = c->dImgs.ensure((size_t)P * (SCB_NPROG + 1) * scb_img_entries(N, c->main.warps)))) return rc;
-    if ((rc = c->dCost.ensure(P))) return rc;
+    if ((rc = c->dCost.ensure((size_t)2 * P))) return rc;
 #ifndef SCB_EMU
     if (c->optGraph) {
         /* One launch per generation: the clears, K0, K2 (+ resolver), the fill-forward kernel and the peer exchange are
@@ -693,6 +700,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
         CK(cudaEventRecord(c->evRun1, st));
         CK(cudaEventRecord(c->evSim0, st));          /* the per-kernel split needs SCB_OPT_GRAPH = 0 */
         CK(cudaEventRecord(c->evSim1, st));
+        CK(cudaEventRecord(c->evK0, st)); CK(cudaEventRecord(c->evFill0, st)); CK(cudaEventRecord(c->evFill1, st));
         c->lastMode = mode; c->ran = true;
         return SCB_OK;
     }
@@ -713,11 +721,12 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
     cudaStream_t st = c->stream;
     const bool wantNodewise = mode == SCB_MODE_NODEWISE || mode == SCB_MODE_IMPORTANCE;
     CK(cudaMemsetAsync(c->dFitness.p, 0, (size_t)P * 8, st));
-    CK(cudaMemsetAsync(c->dCost.p, 0, (size_t)P * 4, st));
+    CK(cudaMemsetAsync(c->dCost.p, 0, (size_t)2 * P * 4, st));
     if (wantNodewise) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
-    CK(cudaMemsetAsync(c->dCounters.p, 0, 8 * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(c->dCounters.p, 0, 16 * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
 
+    if (!capturing) CK(cudaEventRecord(c->evK0, st));
     if ((rc = launch_compile(c, sem, c->dKo.p, true))) return rc;
 
     ScbSimArgs sa;
@@ -734,10 +743,11 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
         if (t < 64 ? ((c->snapLo >> t) & 1ull) : ((c->snapHi >> (t - 64)) & 1ull)) sa.firstSnap = t;
     sa.fitness = c->dFitness.p; sa.nodewise = c->dNodewise.p; sa.cellwise = c->dCellwise.p;
     sa.resolveCount = c->dCounters.p + 1;
-    sa.resolveItems = c->dItems.p; sa.resolveCap = (unsigned)std::min<size_t>(c->dItems.cap, 0xffffffffu);
+    sa.resolveItems = c->dItems.p; sa.resolveCap = (unsigned)std::min<size_t>(std::min(c->dItems.cap, c->dReady.cap / 2), 0x7fffffffu);
     sa.resolveT = c->dResolveT.p; sa.resolveGroup = c->resGroup;
     sa.resolveTCap = (unsigned)(c->dResolveT.cap / ((size_t)N * 32 * c->resGroup));
     sa.chunkLast = c->dChunkLast.p; sa.chunksPerInd = (c->C + 1023) / 1024;
+    sa.chunkLastErr = c->dChunkLastErr.p; sa.chunkLastBits = c->dChunkLastBits.p;
     sa.fillCount = c->dCounters.p + 3; sa.fillItems = c->dFillItems.p;
     sa.zscratch = c->dZ.p;
     sa.flags = (c->optEarly ? SCB_KF_EARLY : 0u) | (c->optSnap ? SCB_KF_SNAP : 0u);
@@ -763,7 +773,8 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
     sa.fuseResolve = fuse ? 1 : 0;
     sa.useTma = c->optTma;
     sa.tilesDone = c->dCounters.p + 6; sa.readyFlags = c->dReady.p; sa.resolveCursor = c->dCounters.p + 2;
-    if (fuse) CK(cudaMemsetAsync(c->dReady.p, 0, (size_t)sa.resolveCap * sizeof(unsigned int), st));
+    sa.retCount = c->dCounters.p + 8; sa.retCursor = c->dCounters.p + 9; sa.retItems = c->dReady.p + sa.resolveCap;
+    if (fuse) CK(cudaMemsetAsync(c->dReady.p, 0, (size_t)2 * sa.resolveCap * sizeof(unsigned int), st));
     if (!capturing) CK(cudaEventRecord(c->evSim0, st));
     for (int part = 0; part < 2; ++part) {
         const SimGeom &g = part == 0 ? c->main : c->tail;
@@ -802,8 +813,10 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
     }
     CK(cudaGetLastError());
     ra.itemCursor = c->dCounters.p + 4;
+    if (!capturing) CK(cudaEventRecord(c->evFill0, st));
     SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->fillCtas), dim3((unsigned)c->fillWarps * 32), c->smemFill, st, ra);
     CK(cudaGetLastError());
+    if (!capturing) CK(cudaEventRecord(c->evFill1, st));
     if (c->gConnected && mode == SCB_MODE_SUM) {
         /* the generation's all-gather: this rank's shard into every rank's buffer over peer memory */
         ScbGatherArgs ga;
@@ -820,13 +833,14 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
 }
 
 /* ---- cost-ordered work list ------------------------------------------------------------------------------------ */
-int scb_pop_costs(scb_ctx *c, uint32_t *costs)
+int scb_pop_costs(scb_ctx *c, uint32_t *costs, uint32_t *tileMax)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!c->ran || !costs) return fail(SCB_ERR_INVALID, "no finished run / null output");
     CK(cudaMemcpyAsync(costs, c->dCost.p, (size_t)c->P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (tileMax) CK(cudaMemcpyAsync(tileMax, c->dCost.p + c->P, (size_t)c->P * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SCB_OK;
 }
@@ -992,6 +1006,11 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->evRun0, c->evRun1) == cudaSuccess) stats->kernel_ms = ms;
         if (cudaEventElapsedTime(&ms, c->evSim0, c->evSim1) == cudaSuccess) stats->sim_ms = ms;
+        if (cudaEventElapsedTime(&ms, c->evRun0, c->evK0) == cudaSuccess) stats->clear_ms = ms;
+        if (cudaEventElapsedTime(&ms, c->evK0, c->evSim0) == cudaSuccess) stats->compile_ms = ms;
+        if (cudaEventElapsedTime(&ms, c->evSim1, c->evFill0) == cudaSuccess) stats->resolve_ms = ms;
+        if (cudaEventElapsedTime(&ms, c->evFill0, c->evFill1) == cudaSuccess) stats->fill_ms = ms;
+        if (cudaEventElapsedTime(&ms, c->evFill1, c->evRun1) == cudaSuccess) stats->gather_ms = ms;
     }
     if (d.bad_index_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules reference an input outside [0,%d)", d.bad_index_nodes, c->N);
     if (d.term_overflow_nodes) return fail(SCB_ERR_INVALID, "%llu (individual,node) rules span more than 7 AND-terms, leave the bit-string, or (compact upload) disagree with andLenList", d.term_overflow_nodes);
@@ -1030,6 +1049,13 @@ extern "C" int scb_debug_trace(scb_ctx *c, unsigned int *trace, unsigned int *fl
     memcpy(flags, c->hDiag.traceFlags, sizeof(c->hDiag.traceFlags));
     memcpy(flags + 100, c->hDiag.exitHist, sizeof(c->hDiag.exitHist));
     return SCB_OK;
+}
+/* timeline of the last launch: up to 16384 x {kind | CTA << 8, start ns, end ns, extra}; returns the number of events */
+extern "C" int scb_debug_events(scb_ctx *c, unsigned int *events)
+{
+    if (!c || !events) return -1;
+    memcpy(events, c->hDiag.evLog, sizeof(c->hDiag.evLog));
+    return (int)std::min(c->hDiag.evCount, 16384u);
 }
 #endif
 

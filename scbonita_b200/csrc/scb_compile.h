@@ -139,67 +139,66 @@ SCB_HD inline ScbNodeFn scb_compile_node(int i, int N, int indLen, const int32_t
     if (nt > SCB_MAX_TERMS) { flags |= SCB_NF_TERMS; nt = SCB_MAX_TERMS; }
     if (nt < 0 || start < 0 || end > indLen) { flags |= SCB_NF_TERMS; nt = 0; }
 
-    /* distinct state bits referenced by the selected terms */
-    int vars[3] = {0, 0, 0};
-    int nv = 0;
-    bool any = false, overflow = false;
+    /* One pass over the selected terms: a literal over variable k (the k-th distinct state bit met, k < 3) is the
+     * 8-minterm mask VAR[k] or its complement, a term the AND of its literals, the rule the OR of its terms. */
+    unsigned sel = 0u;
+    for (int a = 0; a < nt; ++a) sel |= ind[start + a] ? 1u << a : 0u;
+    if (!sel) return scb_const_fn(0, flags | SCB_NF_EMPTY);   /* Q9: reference reads orset[0] uninitialised */
+    int v0 = 0, v1 = 0, v2 = 0, nv = 0;                  /* scalars, not an indexed array: no local memory on the device */
+    bool overflow = false;
+    unsigned lut = 0;
     for (int a = 0; a < nt; ++a) {
-        if (!ind[start + a]) continue;
-        any = true;
+        if (!((sel >> a) & 1u)) continue;
+        unsigned t = 0xFFu;
         for (int b = 0; b < SCB_MAX_IN; ++b) {
             const int src = an_i[a * 3 + b];
             if (b > 0 && src <= -1) continue;
             if (src < 0 || src >= N) { flags |= SCB_NF_BADIDX; continue; }
             const int fl = ai_i[a * 3 + b];
             if (fl != 0 && fl != 1) continue;            /* constant TRUE literal */
-            bool seen = false;
-            for (int k = 0; k < nv; ++k) seen = seen || (vars[k] == src);
-            if (!seen) {
-                if (nv < 3) vars[nv++] = src; else overflow = true;
+            int k = (nv > 0 && v0 == src) ? 0 : ((nv > 1 && v1 == src) ? 1 : ((nv > 2 && v2 == src) ? 2 : 3));
+            if (k == 3) {
+                if (nv == 3) { overflow = true; continue; }
+                k = nv++;
+                if (k == 0) v0 = src; else if (k == 1) v1 = src; else v2 = src;
             }
+            const unsigned var = k == 0 ? 0xF0u : (k == 1 ? 0xCCu : 0xAAu);
+            t &= fl ? ~var : var;
         }
+        lut |= t & 0xFFu;
     }
+    const int vars[3] = {v0, v1, v2};
     if (overflow) return scb_const_fn(0, flags | SCB_NF_UNSUPPORTED);
-    if (!any) return scb_const_fn(0, flags | SCB_NF_EMPTY);   /* Q9: reference reads orset[0] uninitialised */
-
-    unsigned lut = 0;
-    for (int m = 0; m < 8; ++m) {
-        int v = 0;
-        for (int a = 0; a < nt; ++a) {
-            if (!ind[start + a]) continue;
-            int t = 1;
-            for (int b = 0; b < SCB_MAX_IN; ++b) {
-                const int src = an_i[a * 3 + b];
-                if (b > 0 && src <= -1) continue;
-                if (src < 0 || src >= N) continue;
-                const int fl = ai_i[a * 3 + b];
-                if (fl != 0 && fl != 1) continue;
-                int x = 0;
-                for (int k = 0; k < nv; ++k) if (vars[k] == src) x = (m >> (2 - k)) & 1;
-                t &= (x != fl);
-            }
-            v |= t;
-        }
-        lut |= (unsigned)v << m;
-    }
     return scb_finish_fn(vars, nv, lut, flags);
 }
 
 /* Constant propagation (the steady program of K2): `f` with every input whose value is known (cst[node] = 0 or 1,
  * anything else = unknown) fixed to that value, dead inputs dropped again.  Exact wherever the inputs really hold
  * those values. */
-SCB_HD inline ScbNodeFn scb_restrict_fn(const ScbNodeFn &f, const unsigned char *cst)
+/* table `lut` with input j (0 = the 4-weight bit of the index) fixed to v */
+SCB_HD inline unsigned scb_lut_fix(unsigned lut, int j, unsigned v)
+{
+    const unsigned var = j == 0 ? 0xF0u : (j == 1 ? 0xCCu : 0xAAu);
+    const int sh = 4 >> j;
+    if (v) { const unsigned hi = lut & var; return hi | (hi >> sh); }
+    const unsigned lo = lut & ~var & 0xFFu;
+    return lo | (lo << sh);
+}
+
+/* the table of `f` with every known input (cst[node] = 0 or 1) fixed */
+SCB_HD inline unsigned scb_restrict_lut(const ScbNodeFn &f, const unsigned char *cst)
 {
     unsigned lut = f.lut;
     for (int j = 0; j < f.arity; ++j) {
         const unsigned v = cst[f.in[j]];
-        if (v > 1u) continue;
-        const unsigned bit = 1u << (2 - j);
-        unsigned nl = 0;
-        for (unsigned idx = 0; idx < 8; ++idx) nl |= ((lut >> ((idx & ~bit) | (v ? bit : 0u))) & 1u) << idx;
-        lut = nl;
+        if (v <= 1u) lut = scb_lut_fix(lut, j, v);
     }
-    return scb_finish_fn(f.in, f.arity, lut, 0);
+    return lut;
+}
+
+SCB_HD inline ScbNodeFn scb_restrict_fn(const ScbNodeFn &f, const unsigned char *cst)
+{
+    return scb_finish_fn(f.in, f.arity, scb_restrict_lut(f, cst), 0);
 }
 
 /* generic table lookup on 32 cells at once (host tests and the emulator; the device path uses

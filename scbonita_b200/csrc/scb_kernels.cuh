@@ -498,21 +498,28 @@ SCB_DEV void scb_scatter_by_table(const uint4 *sdv, const unsigned char *sarv, i
         }
     }
     if (warp == 0) {
-        /* exclusive prefixes over the bins: node position, rows moved, runs */
-        unsigned cN = 0, cC = 0, cR = 0;
-        for (int k0 = 0; k0 < SCB_SORT_BINS; k0 += 32) {
-            const int k = k0 + lane;
-            const unsigned n = k < SCB_SORT_BINS ? bins[k] : 0u;
+        /* exclusive prefixes over the bins (node position, rows moved, runs): every lane sums its 9 consecutive bins,
+         * one warp scan over the 32 partial sums, then the lane walks its bins again */
+        const int PER = (SCB_SORT_BINS + 31) / 32;
+        const int k0 = lane * PER;
+        unsigned sn = 0, sc = 0, sr = 0;
+        for (int k = k0; k < k0 + PER && k < SCB_SORT_BINS; ++k) {
+            const unsigned n = bins[k];
+            sn += n;
+            if (k < 256) { sc += n * (unsigned)(scb_lut_arity((unsigned)k) + 1); sr += n != 0u ? 1u : 0u; }
+        }
+        unsigned pn = sn, pc = sc, pr = sr;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned tn = __shfl_sync(0xffffffffu, pn, (lane - o) & 31), tc = __shfl_sync(0xffffffffu, pc, (lane - o) & 31), tr = __shfl_sync(0xffffffffu, pr, (lane - o) & 31);
+            if (lane >= o) { pn += tn; pc += tc; pr += tr; }
+        }
+        unsigned cN = pn - sn, cC = pc - sc, cR = pr - sr;
+        for (int k = k0; k < k0 + PER && k < SCB_SORT_BINS; ++k) {
+            const unsigned n = bins[k];
             const unsigned rows = k < 256 ? n * (unsigned)(scb_lut_arity((unsigned)k) + 1) : 0u;
             const unsigned isrun = (n != 0u && k < 256) ? 1u : 0u;
-            unsigned pn = n, pc = rows, pr = isrun;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned tn = __shfl_sync(0xffffffffu, pn, (lane - o) & 31), tc = __shfl_sync(0xffffffffu, pc, (lane - o) & 31);
-                const unsigned tr = __shfl_sync(0xffffffffu, pr, (lane - o) & 31);
-                if (lane >= o) { pn += tn; pc += tc; pr += tr; }
-            }
-            if (k < SCB_SORT_BINS) { bins[k] = cN + pn - n; cost[k] = cC + pc - rows; run[k] = cR + pr - isrun; }
-            cN += __shfl_sync(0xffffffffu, pn, 31); cC += __shfl_sync(0xffffffffu, pc, 31); cR += __shfl_sync(0xffffffffu, pr, 31);
+            bins[k] = cN; cost[k] = cC; run[k] = cR;
+            cN += n; cC += rows; cR += isrun;
         }
     }
     __syncthreads();
@@ -532,10 +539,16 @@ SCB_DEV void scb_scatter_by_table(const uint4 *sdv, const unsigned char *sarv, i
     __syncthreads();
 }
 
+#if defined(SCB_TRACE) && defined(__CUDA_ARCH__)
+#define SCB_K0_MARK(m) do { if (blockIdx.x == 0 && threadIdx.x == 0) A.diag->trace[(m)] = (unsigned)clock64(); } while (0)
+#else
+#define SCB_K0_MARK(m) do { } while (0)
+#endif
 __global__ void scb_k_compile(ScbCompileArgs A)
 {
     SCB_DYN_SMEM(smraw);
     const int N = A.N, p = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    SCB_K0_MARK(0);
     uint4 *sd = reinterpret_cast<uint4 *>(smraw);
     unsigned int *cn = reinterpret_cast<unsigned int *>(sd + N);          /* [0..3] class counts, [4..7] flag counts */
     unsigned char *sar = reinterpret_cast<unsigned char *>(cn + 8);
@@ -556,8 +569,14 @@ __global__ void scb_k_compile(ScbCompileArgs A)
             if (nt != A.andLen[i]) atomicAdd(&cn[7], 1u);        /* triple and andLenList disagree */
         }
     } else
+    if ((TBL & 3) == 0) {                                     /* 16-byte copies when an individual's tables are 16-byte multiples */
+        const int4 *gan = reinterpret_cast<const int4 *>(A.an + toff), *gai = reinterpret_cast<const int4 *>(A.ai + toff);
+        int4 *san = reinterpret_cast<int4 *>(an), *sai = reinterpret_cast<int4 *>(ai);
+        for (int i = tid; i < TBL / 4; i += nthr) { san[i] = gan[i]; sai[i] = gai[i]; }
+    } else
     for (int i = tid; i < TBL; i += nthr) { an[i] = A.an[toff + i]; ai[i] = A.ai[toff + i]; }
     __syncthreads();
+    SCB_K0_MARK(1);
     for (int i = tid; i < N; i += nthr) {
         const ScbNodeFn f = scb_compile_node(i, N, A.indLen, ind, A.andLen, A.parse, an, ai, A.ko + (long long)p * A.koStride, A.ki, A.sem);
         sd[i] = make_uint4((unsigned)f.in[0], (unsigned)f.in[1], (unsigned)f.in[2], (unsigned)i | (f.lut << 24));
@@ -569,6 +588,7 @@ __global__ void scb_k_compile(ScbCompileArgs A)
         if (f.flags & SCB_NF_TERMS) atomicAdd(&cn[7], 1u);
     }
     __syncthreads();
+    SCB_K0_MARK(2);
     const int c3 = (int)cn[0], c2 = (int)cn[1], c1 = (int)cn[2], c0 = (int)cn[3];
     unsigned int *wc = reinterpret_cast<unsigned int *>(smraw + scb_compile_smem_bytes(N) - scb_sort_smem_bytes(N));
     /* the images the simulator copies into its shared memory: image 0 = the full program, 1 + k = reduced program k */
@@ -576,7 +596,9 @@ __global__ void scb_k_compile(ScbCompileArgs A)
     uint4 *ssort = reinterpret_cast<uint4 *>(smraw + scb_compile_smem_bytes(N) - (size_t)N * 16);
     uint4 *imgs = A.imgs ? A.imgs + (long long)p * (SCB_NPROG + 1) * A.imgStride : nullptr;
     scb_scatter_by_table(sd, sar, N, A.descs + (long long)p * A.Npad, wc, tid, nthr, ssort);
+    SCB_K0_MARK(3);
     if (imgs) scb_layout_program(imgs, lscr, ssort, make_int4(c3, c2, c1, c0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
+    SCB_K0_MARK(4);
     /* ---- reduced programs by constant propagation.  c(t) = nodes whose value in S_t is the same constant for every
      * cell: c(1) = the constant rules (knock-outs, knock-ins, constant-TRUE literals), c(t+1) = rules that are
      * constant once the inputs in c(t) are fixed.  Knowledge only grows, so c(D) stays valid for every t >= D.  A
@@ -601,31 +623,35 @@ __global__ void scb_k_compile(ScbCompileArgs A)
         /* knowledge here is c(D) */
         bool last = D >= SCB_STEADY_MAX_DEPTH;
         if (!last) {                                                       /* c(D + 1) from c(D) */
+            int grew = 0;
             for (int i = tid; i < N; i += nthr) {
                 unsigned char v = 2;
                 if (cst[i] == 2) {
+                    const uint4 d = sd[i];
                     ScbNodeFn f;
-                    f.arity = sar[i]; f.in[0] = (int)sd[i].x; f.in[1] = (int)sd[i].y; f.in[2] = (int)sd[i].z;
-                    f.lut = sd[i].w >> 24; f.flags = 0;
-                    const ScbNodeFn r = scb_restrict_fn(f, cst);
-                    if (r.arity == 0) v = r.lut ? 1 : 0;
+                    f.arity = sar[i]; f.in[0] = (int)d.x; f.in[1] = (int)d.y; f.in[2] = (int)d.z;
+                    f.lut = d.w >> 24; f.flags = 0;
+                    const unsigned rl = scb_restrict_lut(f, cst);
+                    if (rl == 0u || rl == 0xFFu) v = rl ? 1 : 0;
                 }
-                pend[i] = v;
-                if (v != 2) atomicOr(reinterpret_cast<unsigned int *>(&chg[0]), 1u);
+                pend[i] = v;                                               /* read back by this thread only */
+                grew |= v != 2;
             }
-            __syncthreads();
-            last = chg[0] == 0;                                            /* fixed point: c(D + 1) == c(D) */
+            last = __syncthreads_or(grew) == 0;                            /* fixed point: c(D + 1) == c(D) */
         }
         const bool emitStage = !last && stage < SCB_NPROG - 1 && D == stageDepth[stage];
         if (last || emitStage) {
             /* the program restricted by c(D) */
+            if (tid < 4) chg[1 + tid] = 0;
+            __syncthreads();
             for (int i = tid; i < N; i += nthr) {
+                const uint4 d = sd[i];
                 ScbNodeFn r;
                 if (cst[i] != 2) r = scb_const_fn(cst[i], 0);
                 else {
                     ScbNodeFn f;
-                    f.arity = sar[i]; f.in[0] = (int)sd[i].x; f.in[1] = (int)sd[i].y; f.in[2] = (int)sd[i].z;
-                    f.lut = sd[i].w >> 24; f.flags = 0;
+                    f.arity = sar[i]; f.in[0] = (int)d.x; f.in[1] = (int)d.y; f.in[2] = (int)d.z;
+                    f.lut = d.w >> 24; f.flags = 0;
                     r = scb_restrict_fn(f, cst);
                     /* constant under c(D) but not in c(D): constant only from S_(D+1) on -- such a node keeps its
                      * full rule in this program (there are none at the fixed point) */
@@ -639,23 +665,27 @@ __global__ void scb_k_compile(ScbCompileArgs A)
             const int s3 = chg[1], s2 = chg[2], s1 = chg[3], s0 = chg[4];
             const int slot = last ? SCB_NPROG - 1 : stage;
             uint4 *out2 = progs + (long long)slot * (N + 1);
+            SCB_K0_MARK(8 + 4 * slot);
             scb_scatter_by_table(sd2, sar2, N, out2, wc, tid, nthr, ssort);
+            SCB_K0_MARK(9 + 4 * slot);
             if (imgs) scb_layout_program(imgs + (long long)(1 + slot) * A.imgStride, lscr, ssort, make_int4(s3, s2, s1, s0), N, A.imgWarps, A.imgRowBytes, tid, nthr);
+            SCB_K0_MARK(10 + 4 * slot);
             if (tid == 0) {
                 out2[N] = make_uint4((unsigned)s3, (unsigned)s2, (unsigned)s1, (unsigned)s0);   /* the counts travel with the program */
                 progFrom[slot] = (unsigned char)(D + 2);
             }
-            __syncthreads();
-            if (tid < 8) chg[tid] = tid == 0 ? chg[0] : 0;
             if (emitStage) ++stage;
         }
         if (last) break;
+        /* every thread is past a barrier that follows the reads of cst above */
         for (int i = tid; i < N; i += nthr) if (pend[i] != 2) cst[i] = pend[i];
-        __syncthreads();
-        if (tid == 0) chg[0] = 0;
         ++D;
         __syncthreads();
     }
+    SCB_K0_MARK(5);
+#if defined(SCB_TRACE) && defined(__CUDA_ARCH__)
+    if (blockIdx.x == 0 && tid == 0) { A.diag->trace[6] = (unsigned)D; A.diag->trace[7] = (unsigned)nthr; }
+#endif
     if (tid == 0) {
         A.counts[p] = make_int4(c3, c2, c1, c0);
         if (cn[4]) atomicAdd(&A.diag->unsupported_nodes, (unsigned long long)cn[4]);
@@ -953,6 +983,24 @@ template <int KR, bool TTM = false> SCB_DEV void scb_resolve_item(const ScbSimAr
 #else
 #define SCB_TRACE_MARK(step, which, fl) do { } while (0)
 #endif
+#if defined(SCB_TRACE) && defined(__CUDA_ARCH__)
+SCB_DEV unsigned scb_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (unsigned)t; }
+#define SCB_EV_LOG(kind, t0, extra)                                                                              \
+    do {                                                                                                         \
+        if (threadIdx.x == 0) {                                                                                  \
+            const unsigned e_ = atomicAdd(&A.diag->evCount, 1u);                                                 \
+            if (e_ < 16384u) {                                                                                   \
+                A.diag->evLog[e_ * 4 + 0] = (unsigned)(kind) | (blockIdx.x << 8);                                \
+                A.diag->evLog[e_ * 4 + 1] = (t0); A.diag->evLog[e_ * 4 + 2] = scb_gtime();                       \
+                A.diag->evLog[e_ * 4 + 3] = (extra);                                                             \
+            }                                                                                                    \
+        }                                                                                                        \
+    } while (0)
+#define SCB_EV_T0(name) const unsigned name = scb_gtime()
+#else
+#define SCB_EV_LOG(kind, t0, extra) do { } while (0)
+#define SCB_EV_T0(name) do { } while (0)
+#endif
 template <int K, bool TM>
 __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArgs A)
 {
@@ -1011,42 +1059,75 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
     unsigned stepsDone = 0, tilesDone = 0, rowsMoved = 0;     /* per CTA: a few thousand steps, a few million rows */
     long long cycPro = 0, cycStep = 0, cycEpi = 0;
 
-    if (tid == 0) sh[12] = (int)atomicAdd(A.workCounter, 1u);
-    __syncthreads();
-    for (unsigned iter = 0;;) {
-        const unsigned item = (unsigned)sh[12 + (iter & 1u)];
-        if (item >= total) break;
-        if (A.fuseResolve) {
-            /* A published resolver item goes before the next tile: it is the longest piece of work there is (98 compare
-             * steps) and the launch ends when the last one does.  Claimed with a compare-and-swap on the cursor, so a
-             * CTA never holds a ticket for an item that does not exist yet. */
-            if (tid == 0) {
-                int got = -1;
-                const unsigned cur = scb_ld_volatile(A.resolveCursor);
-                unsigned cnt = scb_ld_volatile(A.resolveCount);
-                if (cnt > A.resolveCap) cnt = A.resolveCap;
-                if (cur < cnt && atomicCAS(A.resolveCursor, cur, cur + 1u) == cur) {
-                    while (scb_ld_volatile(&A.readyFlags[cur]) == 0u) scb_backoff();      /* its producer is about to publish it */
-                    __threadfence();
-                    got = (int)cur;
+    /* ---- the work loop.  Thread 0 picks the next piece of work, in this order:
+     *   1. a published resolver item: the longest piece of work there is (98 compare steps) and the launch ends when
+     *      the last one does.  Claimed with a compare-and-swap on the cursor, so a CTA never holds a ticket for an item
+     *      that does not exist yet.  The tile ticket the CTA holds at that moment is HANDED BACK (retItems): it is early
+     *      in the cost order, i.e. expensive, and would otherwise wait for the whole item (measured: those tiles were
+     *      the last to end, 250 us after the median CTA had left).
+     *   2. a handed-back tile;
+     *   3. the ticket it holds (requested while the previous tile ran: the atomic's latency is hidden), else a new one;
+     *   4. nothing left: it waits for resolver items / handed-back tiles until every tile is done and both queues are
+     *      empty (all producers are running CTAs of this launch, so waiting cannot deadlock). */
+    int pending = -1;                                   /* thread 0: the ticket held */
+    if (tid == 0) pending = (int)atomicAdd(A.workCounter, 1u);
+    for (;;) {
+        if (tid == 0) {
+            int tileItem = -1, resItem = -1, done = 0;
+            for (;;) {
+                if (A.fuseResolve) {
+                    const unsigned cur = scb_ld_volatile(A.resolveCursor);
+                    unsigned cnt = scb_ld_volatile(A.resolveCount);
+                    if (cnt > A.resolveCap) cnt = A.resolveCap;
+                    if (cur < cnt && atomicCAS(A.resolveCursor, cur, cur + 1u) == cur) {
+                        while (scb_ld_volatile(&A.readyFlags[cur]) == 0u) scb_backoff();      /* its producer is about to publish it */
+                        __threadfence();
+                        resItem = (int)cur;
+                        if (pending >= 0 && (unsigned)pending < total) {
+                            const unsigned r = atomicAdd(A.retCount, 1u);
+                            atomicExch(&A.retItems[r], (unsigned)pending + 1u);
+                            pending = -1;
+                        }
+                        break;
+                    }
+                    const unsigned rc = scb_ld_volatile(A.retCursor), rn = scb_ld_volatile(A.retCount);
+                    if (rc < rn && atomicCAS(A.retCursor, rc, rc + 1u) == rc) {
+                        unsigned v;
+                        while ((v = scb_ld_volatile(&A.retItems[rc])) == 0u) scb_backoff();
+                        tileItem = (int)(v - 1u);
+                        break;
+                    }
                 }
-                sh[15] = got;
+                if (pending < 0) pending = (int)atomicAdd(A.workCounter, 1u);
+                if ((unsigned)pending < total) { tileItem = pending; pending = -1; break; }
+                if (!A.fuseResolve) { done = 1; break; }
+                if (scb_ld_volatile(A.tilesDone) >= total) {
+                    __threadfence();
+                    unsigned cnt = scb_ld_volatile(A.resolveCount);
+                    if (cnt > A.resolveCap) cnt = A.resolveCap;
+                    if (scb_ld_volatile(A.resolveCursor) >= cnt && scb_ld_volatile(A.retCursor) >= scb_ld_volatile(A.retCount)) { done = 1; break; }
+                }
+                scb_backoff();
             }
-            __syncthreads();
+            sh[12] = tileItem; sh[15] = resItem; sh[13] = done;
+            /* the next ticket is requested now and looked at when this piece of work is over */
+            if (tileItem >= 0 && pending < 0) pending = (int)atomicAdd(A.workCounter, 1u);
+        }
+        __syncthreads();
+        if (sh[13]) break;
+        {
             const int it = sh[15];
             if (it >= 0) {
+                SCB_EV_T0(evt0);
                 if (TM && A.resolveGroup == K) scb_resolve_item<K, true>(A, smraw, (unsigned)it, tm, true);
                 else if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
                 else scb_resolve_item<1>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
-                __syncthreads();
-                if (tid == 0) sh[12 + (iter & 1u)] = (int)item;     /* the resolver's scratch overlaps these words */
-                __syncthreads();
-                continue;                                   /* the tile item already fetched stays pending */
+                SCB_EV_LOG(1, evt0, (unsigned)it);
+                __syncthreads();                            /* the resolver's scratch overlaps sh[] */
+                continue;
             }
         }
-        /* the next item is requested now and read after this tile's last barrier: the atomic's latency is hidden */
-        if (tid == 0) sh[12 + ((iter + 1u) & 1u)] = (int)atomicAdd(A.workCounter, 1u);
-        ++iter;
+        const unsigned item = (unsigned)sh[12];
         /* With a cost order (scb_pop_set_order) the list is individual-major, costliest individual first: classic
          * longest-processing-time scheduling, the launch ends on the cheapest individuals' short tiles.  Without one it
          * is tile-major: the long tiles of a hard individual are spread over the whole launch and the last items handed
@@ -1055,6 +1136,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         if (A.order) { p = A.order[item / (unsigned)A.tiles]; tile = (int)(item % (unsigned)A.tiles); }
         else { p = (int)(item % (unsigned)A.P); tile = (int)(item / (unsigned)A.P); }
         const long long c0 = scb_clock();
+        SCB_EV_T0(evTile0);
         const int w0 = A.wordBase + tile * WT;
         int4 cnt = A.counts[p];
         const uint4 *gfull = A.descs + (long long)p * A.Npad;
@@ -1289,7 +1371,14 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         stepsDone += (unsigned)t; ++tilesDone;
         rowsMoved += (unsigned)(t - segStart) * rowsPerStep;   /* state rows moved through shared memory (loads + stores) */
         /* cost of the tile in row units: its rows plus ~128 rows' worth of fixed time per step (barrier, dispatch) */
-        if (A.cost && tid == 0) atomicAdd(&A.cost[p], rowsMoved - rowsAtTileStart + 128u * (unsigned)t);
+        if (A.cost && tid == 0) {
+            /* cost of the tile in state-row units; a tile left to the resolver is followed by 98 compare steps of the
+             * same width, which cost rather more than the tile's own */
+            unsigned tc = rowsMoved - rowsAtTileStart + 128u * (unsigned)t;
+            if (!allfound) tc += tc + (tc >> 2);
+            atomicAdd(&A.cost[p], tc);
+            atomicMax(&A.cost[A.P + p], tc);
+        }
 #undef SCB_NEXT_PROGRAM
         const long long c2 = scb_clock();
 
@@ -1404,6 +1493,22 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         ScbVec<K> ok;
 #pragma unroll
         for (int k = 0; k < K; ++k) ok.v[k] = sh[4 + (lane * K + k) / 32] ? 0u : vm[lane * K + k];
+        /* The error column of every proven chunk's last valid cell is kept (count, and node bits in the per-node mode):
+         * a later chunk that starts with not-found cells repeats it (the reference's fill-forward), so the
+         * fill-forward kernel has nothing to simulate.  A lane's K words lie in one chunk; lm marks the cell. */
+        ScbVec<K> lm;
+        const int myChunk = (lane * K) / 32;
+        uint32_t *lastAcc = cm + 2 * WT;                    /* [K] counts, then [K][NB] node bits; zero since the tile began */
+        const int NB = (N + 31) >> 5;
+        {
+            const int q = w0 / 32 + myChunk;
+            const long long rem = (long long)A.C - (long long)q * 1024;
+            const int lc = rem >= 1024 ? 1023 : (int)rem - 1;
+            const bool have = q < A.chunksPerInd && !sh[4 + myChunk];
+#pragma unroll
+            for (int k = 0; k < K; ++k) lm.v[k] = (have && (lane * K + k) == myChunk * 32 + (lc >> 5)) ? 1u << (lc & 31) : 0u;
+        }
+        unsigned lastCnt = 0;
         const unsigned char *fin = sm + finOff + laneOff;
         unsigned char *oth = sm + (finOff ? 0u : BUFB) + laneOff;
         unsigned total32 = 0;
@@ -1425,6 +1530,17 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
             }
             if (!two) c1 = 0;
             total32 += c0 + c1;
+            {
+                uint32_t l0 = 0u, l1 = 0u;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { l0 |= e0.v[k] & lm.v[k]; l1 |= e1.v[k] & lm.v[k]; }
+                if (!two) l1 = 0u;
+                lastCnt += (l0 ? 1u : 0u) + (l1 ? 1u : 0u);
+                if (A.mode == 1) {
+                    if (l0) atomicOr(&lastAcc[K + myChunk * NB + (node0 >> 5)], 1u << (node0 & 31));
+                    if (l1) atomicOr(&lastAcc[K + myChunk * NB + (node1 >> 5)], 1u << (node1 & 31));
+                }
+            }
             if (A.mode == 1) {
                 c0 = scb_warp_sum(c0);
                 c1 = scb_warp_sum(c1);
@@ -1437,8 +1553,20 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         }
         total32 = scb_warp_sum(total32);
         if (lane == 0 && total32) atomicAdd(&A.fitness[p], (unsigned long long)total32);
+        if (lastCnt) atomicAdd(&lastAcc[myChunk], lastCnt);
+        __syncthreads();
+        if (tid < K && !sh[4 + tid] && w0 / 32 + tid < A.chunksPerInd) {
+            A.chunkLastErr[(long long)p * A.chunksPerInd + w0 / 32 + tid] = (int)lastAcc[tid];
+            lastAcc[tid] = 0u;
+        }
+        if (A.mode == 1)
+            for (int i = tid; i < K * NB; i += nthr) {
+                const int c = i / NB;
+                if (!sh[4 + c] && w0 / 32 + c < A.chunksPerInd)
+                    A.chunkLastBits[((long long)p * A.chunksPerInd + w0 / 32 + c) * NB + (i - c * NB)] = lastAcc[K + i];
+                lastAcc[K + i] = 0u;
+            }
         if (A.mode == 2) {
-            __syncthreads();
             const unsigned char *eb = sm + (finOff ? 0u : BUFB);
             for (int idx = tid; idx < WT * 32; idx += nthr) {
                 const int w = idx >> 5, b = idx & 31;
@@ -1452,36 +1580,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         }
         __syncthreads();
         cycPro += c1 - c0; cycStep += c2 - c1; cycEpi += scb_clock() - c2;
-    }
-    /* ---- in-kernel resolver: a CTA that found the tile queue empty takes tickets for resolver items.  An item
-     * is processed as soon as its producer has published it; a ticket beyond the final count ends the CTA.  All
-     * producers are running CTAs of this launch (the queue is empty), so waiting for them cannot deadlock. ---- */
-    if (A.fuseResolve) {
-        int *slot = reinterpret_cast<int *>(smraw + A.smemBytes - 64);
-        for (;;) {
-            __syncthreads();
-            if (tid == 0) {
-                const unsigned my = atomicAdd(A.resolveCursor, 1u);
-                int got = -1;
-                for (;;) {
-                    if (my < A.resolveCap && scb_ld_volatile(&A.readyFlags[my]) != 0u) { got = (int)my; break; }
-                    if (scb_ld_volatile(A.tilesDone) >= total) {
-                        __threadfence();
-                        if (my >= scb_ld_volatile(A.resolveCount) || my >= A.resolveCap) break;
-                    }
-                    scb_backoff();
-                }
-                __threadfence();
-                slot[0] = got;
-            }
-            __syncthreads();
-            const int it = slot[0];
-            if (it < 0) break;
-            /* K0's images are cut for this launch (K words per lane, this CTA's warps): usable where KR == K */
-            if (TM && A.resolveGroup == K) scb_resolve_item<K, true>(A, smraw, (unsigned)it, tm, true);
-            else if (A.resolveGroup == 2) scb_resolve_item<2>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
-            else scb_resolve_item<1>(A, smraw, (unsigned)it, SCB_TMEM_OFF, false);
-        }
+        SCB_EV_LOG(0, evTile0, (unsigned)t | ((unsigned)p << 8) | (allfound ? 0u : 0x80000000u));
     }
 #if defined(__CUDA_ARCH__)
     if (TM) {
@@ -1598,7 +1697,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
                 scb_st<KR>(bufT + (uint32_t)row * ROWB + laneOff,
                            scb_ld<KR>(reinterpret_cast<const unsigned char *>(Tglob + (long long)row * GW + lane * KR)));
         }
-        if (tid < GW) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; Fm[tid] = 0u; }
+        if (tid < GW) { vm[tid] = scb_valid_mask((long long)w0 + tid, A.C); dmz[tid] = 0u; dmz[GW + tid] = 0u; Fm[tid] = 0u; }
         if (TTM && pass == 1 && how == 1) {
             /* T from the simulator's hand-over buffer into this warp's tensor-memory slots */
             uint32_t tmc = tm;
@@ -1684,12 +1783,15 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
             if (tn <= 2) scb_const_rows<KR>(sa + dstOff + laneOff, gfull + e1full, n0full, warp, S, nullptr);
             if (TTM && cmp) {
                 /* compare with T in tensor memory, fold through dmz */
+                /* One barrier per step: the accumulator of step tn is folded (and cleared) by the first GW threads after
+                 * the step's barrier while the other warps already add step tn + 1 to the other accumulator; it is used
+                 * again at step tn + 2, which every warp enters through the barrier of tn + 1, after the fold. */
                 scb_step_runs<KR, SCB_SF_ZCMP>(sa + srcOff + laneOff, sa + dstOff + laneOff, wl, scb_list_head(wlp), true, d2, dz, tm);
+                uint32_t *acc = dmz + (tn & 1) * GW;
 #pragma unroll
-                for (int k = 0; k < KR; ++k) if (dz.v[k]) atomicOr(&dmz[lane * KR + k], dz.v[k]);
+                for (int k = 0; k < KR; ++k) if (dz.v[k]) atomicOr(&acc[k * 32 + lane], dz.v[k]);
                 __syncthreads();
-                if (tid < GW) { Fm[tid] |= ~dmz[tid]; dmz[tid] = 0u; }
-                __syncthreads();
+                if (tid < GW) { uint32_t *a = &acc[(tid % KR) * 32 + tid / KR]; Fm[tid] |= ~*a; *a = 0u; }   /* word tid = lane tid / KR, k = tid % KR */
                 const uint32_t x = srcOff; srcOff = dstOff; dstOff = x;
                 continue;
             }
@@ -1746,7 +1848,7 @@ SCB_HD inline size_t scb_resolve_smem_bytes(int N, int KR, bool ttm = false, int
 {
     /* state buffers (three, or two when T lives in tensor memory) + program + dmz/Fm/vm + scalars +
      * srcc[1024*KR] int16 + (shared-memory T only) D[2][<=24 warps][32*KR] + slack */
-    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + scb_img_entries(N, S) * 16 + (size_t)3 * 32 * KR * 4 + 64 + 384 + (size_t)1024 * KR * 2
+    return (size_t)(ttm ? 2 : 3) * N * 128 * KR + scb_img_entries(N, S) * 16 + (size_t)4 * 32 * KR * 4 + 64 + 384 + (size_t)1024 * KR * 2
            + (ttm ? 0 : (size_t)2 * 24 * 32 * KR * 4) + 256;
 }
 
@@ -1761,7 +1863,7 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
     unsigned char *sm = smraw;
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + (TTM ? 2u : 3u) * BUFB);
     uint32_t *dmz = reinterpret_cast<uint32_t *>(desc + scb_img_entries(N, TTM ? (int)(blockDim.x >> 5) : SCB_PROG_MAX_WARPS));
-    uint32_t *Fm = dmz + GW;
+    uint32_t *Fm = dmz + 2 * GW;                           /* dmz: two accumulators, used in turn by the compare steps */
     uint32_t *vm = Fm + GW;
     int *sh = reinterpret_cast<int *>(vm + GW);            /* [2] pending cells, [3] not-found cells */
     int *winfo = sh + 16;                                  /* [96] scratch of scb_layout_program */
@@ -1855,13 +1957,31 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
                 A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = n1;
             }
         }
-        if (tid == 0) {
-            for (int j = 0; j < KR; ++j) {
-                if (!((flagged >> j) & 1u)) continue;
-                int lastFound = -1;
-                for (int w = j * 32 + 31; w >= j * 32; --w) if (Fm[w]) { lastFound = (w - j * 32) * 32 + (31 - __clz((int)Fm[w])); break; }
-                A.chunkLast[(long long)p * A.chunksPerInd + q + j] = lastFound;
+        /* the last found cell of every flagged chunk and its error column (read by the fill-forward of later chunks) */
+        if (warp < KR && ((flagged >> warp) & 1u)) {
+            const int j = warp;
+            const unsigned any = __ballot_sync(0xffffffffu, Fm[j * 32 + lane] != 0u);
+            int lastFound = -1;
+            if (any) {
+                const int w = 31 - __clz((int)any);
+                const uint32_t fw = Fm[j * 32 + w];
+                lastFound = w * 32 + (31 - __clz((int)fw));
+                const uint32_t wofs = (uint32_t)(j * 32 + w) * 4u;
+                const int b = lastFound & 31;
+                const int NB = (N + 31) >> 5;
+                unsigned cntl = 0;
+                for (int itn = 0; itn < NB; ++itn) {
+                    const int row = itn * 32 + lane;
+                    const unsigned bit = row < N ? (*reinterpret_cast<const uint32_t *>(bufB + (uint32_t)row * ROWB + wofs) >> b) & 1u : 0u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, bit != 0u);
+                    cntl += (unsigned)__popc(bal);
+                    if (A.mode == 1 && lane == 0) A.chunkLastBits[((long long)p * A.chunksPerInd + q + j) * NB + itn] = bal;
+                }
+                if (lane == 0) A.chunkLastErr[(long long)p * A.chunksPerInd + q + j] = (int)cntl;
             }
+            if (lane == 0) A.chunkLast[(long long)p * A.chunksPerInd + q + j] = lastFound;
+        }
+        if (tid == 0) {
             if (sh[2] > 0) {
                 const unsigned idx = atomicAdd(A.fillCount, 1u);
                 A.fillItems[idx] = make_uint4((unsigned)p, (unsigned)q, (unsigned)sh[2], 0u);
@@ -1894,29 +2014,17 @@ __global__ void __launch_bounds__(768, 1) scb_k_resolve(ScbResolveArgs R)
 }
 
 /* K3 phase 2: chunks that start with not-found cells copy the last found cell of the nearest earlier chunk that
- * has one (chunkLast, complete after phase 1).  Only that ONE cell's error column is needed, so each item is
- * handled by a single warp that simulates the 32-cell word holding the cell with the NODES spread over its lanes
- * (98 synchronous steps on a [N]-word state in shared memory, generic truth-table lookup): tens of microseconds
- * instead of a full chunk re-simulation.  No earlier found cell at all: the reference's value is uninitialised
- * memory -> defined as 0 and counted.
- * dynamic shared memory: warps * (16 + 2 * 4) * N bytes (the item's program, then two state vectors). */
-SCB_HD inline size_t scb_fill_smem_per_warp(int N) { return (((size_t)24 * N) + 15) & ~(size_t)15; }
-
+ * has one (chunkLast, complete after phase 1).  Only that ONE cell's error column is needed, and the simulator / the
+ * resolver left it behind for every chunk (chunkLastErr, chunkLastBits): one warp per item, a lookup and a few
+ * atomics.  No earlier found cell at all: the reference's value is uninitialised memory -> defined as 0 and counted. */
 __global__ void scb_k_fill(ScbResolveArgs R)
 {
-    SCB_DYN_SMEM(smraw);
     const ScbSimArgs &A = R.s;
-    const int N = A.N;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint4 *sdesc = reinterpret_cast<uint4 *>(smraw + (size_t)warp * scb_fill_smem_per_warp(N));   /* this warp's copy of the program */
-    uint32_t *st = reinterpret_cast<uint32_t *>(sdesc + N);                          /* and its two state vectors */
+    const int N = A.N, NB = (N + 31) >> 5;
+    const int lane = threadIdx.x & 31;
     const unsigned nItems = *A.fillCount;
-
-    for (;;) {
-        unsigned it = 0;
-        if (lane == 0) it = atomicAdd(R.itemCursor, 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= nItems) break;
+    const unsigned nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < nItems; it += nWarps) {
         const int p = (int)A.fillItems[it].x, q = (int)A.fillItems[it].y, pend = (int)A.fillItems[it].z;
         int qq = q - 1, cell = -1;
         for (; qq >= 0; --qq) {
@@ -1929,49 +2037,14 @@ __global__ void scb_k_fill(ScbResolveArgs R)
                 for (int i = lane; i < pend; i += 32) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = 0;
             continue;
         }
-        const int word = qq * 32 + (cell >> 5), sb = cell & 31;
-        const int4 cnt = A.counts[p];
-        const uint4 *gdesc = A.descs + (long long)p * A.Npad;
-        int e1 = cnt.x + cnt.y + cnt.z, e0 = e1 + cnt.w;
-        uint32_t *cur = st, *nxt = st + N;
-        for (int i = lane; i < N; i += 32) { cur[i] = A.X[(long long)i * A.Wpad + word]; sdesc[i] = gdesc[i]; }
-        const uint4 *desc = sdesc;
-        /* from this step on the fixed-point program of K0 (constants propagated) does the same with fewer nodes:
-         * both state vectors hold its constants by then */
-        const uint4 *gfinal = A.progs + ((long long)p * SCB_NPROG + (SCB_NPROG - 1)) * (N + 1);
-        const int from = A.useSteady ? (int)A.progFrom[(long long)p * 8 + (SCB_NPROG - 1)] : 0;
-        __syncwarp();
-        for (int t = 1; t <= SCB_LAST - 1; ++t) {
-            if (t == from) {
-                for (int i = lane; i < N; i += 32) sdesc[i] = gfinal[i];
-                const uint4 c4 = gfinal[N];
-                e1 = (int)(c4.x + c4.y + c4.z); e0 = e1 + (int)c4.w;
-                __syncwarp();
-            }
-            for (int j = lane; j < e1; j += 32) {
-                const uint4 d = desc[j];
-                nxt[d.w & 0xFFFFu] = scb_lut_apply_mux(d.w >> 24, cur[d.x & 0xFFFFu], cur[d.y & 0xFFFFu], cur[d.z & 0xFFFFu]);
-            }
-            if (t <= 2)
-                for (int j = e1 + lane; j < e0; j += 32) {
-                    const uint4 d = desc[j];
-                    nxt[d.w & 0xFFFFFFu] = (d.w >> 24) ? 0xffffffffu : 0u;
-                }
-            __syncwarp();
-            uint32_t *x = cur; cur = nxt; nxt = x;
-        }
-        /* cur = S_98 of the word; error bits of the source cell, node by node */
-        unsigned bits = 0;
-        for (int i = lane; i < N; i += 32) {
-            const unsigned bit = ((cur[i] ^ A.X[(long long)i * A.Wpad + word]) >> sb) & 1u;
-            bits += bit;
-            if (bit && A.mode == 1) atomicAdd(&A.nodewise[(long long)p * N + i], pend);
-        }
-        bits = scb_warp_sum(bits);
-        if (lane == 0 && bits) atomicAdd(&A.fitness[p], (unsigned long long)bits * (unsigned long long)pend);
+        const int err = A.chunkLastErr[(long long)p * A.chunksPerInd + qq];
+        if (lane == 0 && err) atomicAdd(&A.fitness[p], (unsigned long long)err * (unsigned long long)pend);
+        if (A.mode == 1)
+            for (int i = lane; i < N; i += 32)
+                if ((A.chunkLastBits[((long long)p * A.chunksPerInd + qq) * NB + (i >> 5)] >> (i & 31)) & 1u)
+                    atomicAdd(&A.nodewise[(long long)p * N + i], pend);
         if (A.mode == 2)
-            for (int i = lane; i < pend; i += 32) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = (int)bits;
-        __syncwarp();
+            for (int i = lane; i < pend; i += 32) A.cellwise[(long long)p * A.C + (long long)q * 1024 + i] = err;
     }
 }
 

@@ -77,6 +77,8 @@ struct ScbDiag {                      /* device-side counters, zeroed per evalua
      * of its first tile, [step][warp][2]; step 0 holds the step's flags in [0][0][0] .. */
     unsigned int trace[100 * 24 * 4];
     unsigned int traceFlags[100];
+    unsigned int evCount;
+    unsigned int evLog[16384 * 4];   /* {kind (0 tile, 1 resolver item) | CTA << 8, globaltimer ns at start, at end, steps | individual << 8} */
     unsigned int exitHist[104];   /* tiles by the step their loop ended at; [100] E2 exits, [101] E3, [102] all proven, [103] queued for K3 */
 #endif
 };
@@ -143,6 +145,8 @@ struct ScbSimArgs {
     uint32_t *resolveT;           /* S_99 of queued groups: [resolveTCap][N][32*resolveGroup] words (saves K3 a pass) */
     unsigned int resolveTCap;
     int32_t *chunkLast;           /* [P][chunksPerInd]: last found valid cell of each chunk, -1 none */
+    int32_t *chunkLastErr;        /* [P][chunksPerInd]: number of nodes that cell gets wrong (its column of e = S_98 xor S_0) */
+    uint32_t *chunkLastBits;      /* [P][chunksPerInd][ceil(N/32)]: that column, bit = node; written in the per-node mode only */
     int chunksPerInd;
     unsigned int *fillCount;      /* chunks whose leading not-found cells copy an earlier chunk's cell */
     uint4 *fillItems;             /* (individual, chunk, pending cells, first pending-free cell) */
@@ -156,6 +160,9 @@ struct ScbSimArgs {
     unsigned int *tilesDone;      /* tiles completed (all their resolver items are published) */
     unsigned int *readyFlags;     /* [resolveCap] item i is complete in memory */
     unsigned int *resolveCursor;  /* ticket counter of the in-kernel resolver */
+    unsigned int *retCount;       /* tiles handed back: a CTA that takes a resolver item gives up the tile ticket it holds */
+    unsigned int *retCursor;      /*   ... taken again */
+    unsigned int *retItems;       /* [resolveCap] handed-back tile item + 1, 0 = not written yet */
     unsigned int smemBytes;       /* dynamic shared memory of the launch (the item slot sits in its last 64 bytes) */
     unsigned int *cost;           /* [P] or null: state rows each individual's tiles moved (the cost predictor of the next generation) */
     const int32_t *order;         /* [P] or null: individuals in the order their tiles are handed out (costliest first) */

@@ -193,11 +193,21 @@ class Simulator:
         return out
 
     # -- cost-ordered work list, peer-memory fitness exchange --------------------------------
-    def costs(self):
-        """uint32[P]: cost of every individual of the last run in state-row units (scb_pop_costs)."""
+    def costs(self, tile_max=False):
+        """uint32[P]: cost of every individual of the last run in state-row units (scb_pop_costs); with ``tile_max``
+        also the cost of its costliest tile."""
         out = np.zeros(self._P, dtype=np.uint32)
-        _lib.check(self.lib, self.lib.scb_pop_costs(self._ctx, _ptr(out)))
-        return out
+        if not tile_max:
+            _lib.check(self.lib, self.lib.scb_pop_costs(self._ctx, _ptr(out), None))
+            return out
+        mx = np.zeros(self._P, dtype=np.uint32)
+        _lib.check(self.lib, self.lib.scb_pop_costs(self._ctx, _ptr(out), _ptr(mx)))
+        return out, mx
+
+    def cost_order(self):
+        """The order to hand to :meth:`set_order` after a run: individuals with the costliest tiles first."""
+        total, mx = self.costs(tile_max=True)
+        return np.lexsort((-total.astype(np.int64), -mx.astype(np.int64))).astype(np.int32)
 
     def set_order(self, order):
         """Hand the next runs their individuals costliest first (``np.argsort(-costs)``); None: index order."""

@@ -6,6 +6,7 @@
  * exchange array.  Launches are synchronous.
  */
 #include "emu_cuda.h"
+#include <atomic>
 #include <barrier>
 #include <chrono>
 #include <cstdlib>
@@ -27,7 +28,8 @@ struct BlockCtx {
     std::vector<std::unique_ptr<WarpCtx>> warps;
     unsigned char *smem;
     std::vector<uint32_t> tmem;
-    explicit BlockCtx(int n) : bar(n), smem(nullptr), tmem(128 * 512, 0xDEADBEEFu) {}
+    std::atomic<int> orAcc[2];
+    explicit BlockCtx(int n) : bar(n), smem(nullptr), tmem(128 * 512, 0xDEADBEEFu) { orAcc[0] = 0; orAcc[1] = 0; }
 };
 thread_local BlockCtx *tl_block = nullptr;
 thread_local WarpCtx *tl_warp = nullptr;
@@ -43,6 +45,17 @@ uint32_t *emu_tmem_cell(uint32_t taddr, int k)
 }
 void __syncthreads() { tl_block->bar.arrive_and_wait(); }
 void __syncwarp(unsigned) { tl_warp->bar.arrive_and_wait(); }
+int __syncthreads_or(int pred)
+{
+    BlockCtx *b = tl_block;
+    if (pred) b->orAcc[0].store(1);
+    b->bar.arrive_and_wait();
+    const int r = b->orAcc[0].load();
+    b->bar.arrive_and_wait();
+    if (threadIdx.x == 0) b->orAcc[0].store(0);
+    b->bar.arrive_and_wait();
+    return r;
+}
 
 unsigned __ballot_sync(unsigned, int pred)
 {

@@ -39,6 +39,7 @@ uint32_t *emu_tmem_cell(uint32_t taddr, int k);
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 void __syncthreads();
+int __syncthreads_or(int pred);
 void __syncwarp(unsigned mask = 0xffffffffu);
 unsigned __ballot_sync(unsigned mask, int pred);
 unsigned __match_any_sync(unsigned mask, unsigned value);   /* all 32 lanes must call it */
@@ -55,6 +56,7 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetc
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+static inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) { } return o; }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 
 /* ---- runtime API subset ---------------------------------------------------------------- */
