@@ -157,6 +157,17 @@ int scb_pop_upload_compact(scb_ctx *ctx, int P, const int32_t *individuals, int 
                            const int32_t *andLenList, const int32_t *individualParse,
                            const int32_t *upstream, const int32_t *upstreamInvert,
                            int perIndividual, const int32_t *knockouts, const int32_t *knockins);
+/* Resident population.  The GA replaces part of its population every generation
+ * (ruleMaker.py:982-1006: only offspring whose fitness is invalid are re-scored) while this library keeps the
+ * population in device memory: scb_pop_update overwrites `n` individuals in place -- slots[i] (distinct, < P) gets
+ * bit-string individuals[i] and, when the population was uploaded with per-individual tables, andNodes[i] /
+ * andNodeInvertList[i] in the format of that upload ([N][7][3], or [N][3] upstream triples after
+ * scb_pop_upload_compact; ignored for shared tables) -- and the next scb_pop_run(SCB_MODE_SUM) compiles and simulates
+ * exactly those n.  scb_pop_fetch still returns all P sums: the other slots keep the value of the run that last
+ * scored them.  Before the first run of an upload the whole population is scored whatever was replaced.  The arrays
+ * may be reused when the call returns. */
+int scb_pop_update(scb_ctx *ctx, int n, const int32_t *slots, const int32_t *individuals,
+                   const int32_t *andNodes, const int32_t *andNodeInvertList);
 int scb_pop_run(scb_ctx *ctx, int mode);
 /* Work-list order.  scb_pop_costs returns, per individual of the last finished run, its cost in state-row units
  * (rows its tiles moved plus a fixed share per step; `costs` = the sum over its tiles -- what a shard of individuals

@@ -23,7 +23,7 @@ SYMBOLS = (
     "scb_last_error", "scb_version", "scb_device_count",
     "scb_ctx_create", "scb_ctx_create_csr", "scb_ctx_destroy", "scb_ctx_set_option", "scb_ctx_info",
     "scb_eval_population", "scb_pop_upload", "scb_pop_upload_compact", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev",
-    "scb_pop_costs", "scb_pop_set_order", "scb_gather_init", "scb_gather_connect", "scb_gather_result", "scb_gather_close",
+    "scb_pop_costs", "scb_pop_set_order", "scb_pop_update", "scb_gather_init", "scb_gather_connect", "scb_gather_result", "scb_gather_close",
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
     "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
     "scb_eval_local_search", "scb_eval_local_search_all", "scb_hamming_argmin", "scb_attractors", "scb_importance_score",
@@ -88,12 +88,13 @@ def load(path=None):
     lib.scb_pop_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Stats)]
     lib.scb_pop_result_dev.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
     lib.scb_pop_costs.argtypes = [vp, vp, vp]
+    lib.scb_pop_update.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     lib.scb_pop_set_order.argtypes = [vp, vp, ctypes.c_int]
     lib.scb_gather_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.scb_gather_connect.argtypes = [vp, vp]
     lib.scb_gather_result.argtypes = [vp, vp]
     lib.scb_gather_close.argtypes = [vp]
-    for name in ("scb_pop_costs", "scb_pop_set_order", "scb_gather_init", "scb_gather_connect", "scb_gather_result", "scb_gather_close"):
+    for name in ("scb_pop_costs", "scb_pop_set_order", "scb_pop_update", "scb_gather_init", "scb_gather_connect", "scb_gather_result", "scb_gather_close"):
         getattr(lib, name).restype = ctypes.c_int
     lib.scb_ctx_stream.argtypes = [vp, ctypes.POINTER(vp)]
     lib.scb_ctx_sync.argtypes = [vp]

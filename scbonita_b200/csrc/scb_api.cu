@@ -112,6 +112,10 @@ struct scb_ctx {
     DevBuf<unsigned int> dCost;          /* [2][P] cost per individual in the last run: sum over its tiles, costliest tile */
     DevBuf<int32_t> dOrder;              /* [P] individuals, costliest first (scb_pop_set_order) */
     bool haveOrder = false;
+    /* resident population (scb_pop_update): the next run scores only the replaced slots */
+    bool delta = false;
+    int nEval = 0;
+    DevBuf<int32_t> dSlots, dStage;
     /* the generation as a CUDA graph: clears + K0 + K2 + fill (+ peer gather), replayed while nothing it refers to moves */
 #ifndef SCB_EMU
     cudaGraphExec_t graphExec = nullptr;
@@ -264,7 +268,7 @@ int pick_geometry(scb_ctx *c)
 
 /* K0 on the uploaded population; `knock` is the array the rules read as knock-outs (the importance score
  * passes its knock-in list through the same slot, simulator.c:674) */
-int launch_compile(scb_ctx *c, int sem, const int32_t *knock, bool wantImages = false)
+int launch_compile(scb_ctx *c, int sem, const int32_t *knock, bool wantImages = false, bool population = false)
 {
     const int N = c->N, P = c->P;
     ScbCompileArgs ca;
@@ -274,6 +278,14 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock, bool wantImages = 
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
     ca.progs = c->dProgs.p; ca.progFrom = c->dProgFrom.p;
     ca.imgs = nullptr; ca.imgStride = 0; ca.imgWarps = 0; ca.imgRowBytes = 0;
+    ca.slots = nullptr; ca.fitness = nullptr; ca.cost = nullptr;
+    int grid = P;
+    if (population) {
+        /* the population runs clear their own result sums and cost counters; a resident population compiles only the
+         * replaced slots */
+        ca.fitness = c->dFitness.p; ca.cost = c->dCost.p;
+        if (c->delta) { ca.slots = c->dSlots.p; grid = c->nEval; }
+    }
     if (wantImages) {
         /* the program images are cut for the simulator launch that follows: its warps, its row width */
         ca.imgStride = (int)scb_img_entries(N, c->main.warps);
@@ -283,7 +295,7 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock, bool wantImages = 
         ca.imgs = c->dImgs.p;
     }
     const int cthr = std::min(256, ((N + 31) / 32) * 32);
-    SCB_LAUNCH(scb_k_compile, dim3((unsigned)P), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
+    SCB_LAUNCH(scb_k_compile, dim3((unsigned)grid), dim3((unsigned)cthr), scb_compile_smem_bytes(N), c->stream, ca);
     CK(cudaGetLastError());
     return SCB_OK;
 }
@@ -498,7 +510,7 @@ int scb_ctx_destroy(scb_ctx *c)
     gather_release(c);
     if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
 #endif
-    c->dCost.release(); c->dOrder.release();
+    c->dCost.release(); c->dOrder.release(); c->dSlots.release(); c->dStage.release();
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dImgs.release(); c->dProgFrom.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
@@ -618,10 +630,11 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
     CK(cudaMemcpyAsync(c->dKi.p, knockins, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dAn.p, andNodes, ntab * tbl * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->dAi.p, andNodeInvertList, ntab * tbl * 4, cudaMemcpyHostToDevice, st));
-    c->P = P; c->indLen = indLen; c->tpi = tablesPerIndividual ? 1 : 0;
     c->koStride = koRows > 1 ? N : 0;
+    if (P != c->P) c->haveOrder = false;            /* an order is a permutation of the population it was measured on */
+    c->P = P; c->indLen = indLen; c->tpi = tablesPerIndividual ? 1 : 0;
     c->compact = compact ? 1 : 0;
-    c->ran = false;
+    c->ran = false; c->delta = false; c->nEval = 0;
     return SCB_OK;
 }
 
@@ -642,6 +655,60 @@ int scb_pop_upload_compact(scb_ctx *c, int P, const int32_t *individuals, int in
 {
     return pop_upload_impl(c, P, P, individuals, indLen, andLenList, individualParse, upstream, upstreamInvert,
                            perIndividual, 1, knockouts, knockins, 1);
+}
+
+/* SURVEY 8f N4, resident population: `n` individuals of the uploaded population are replaced in place and the next
+ * scb_pop_run(SCB_MODE_SUM) compiles and simulates exactly those; every other slot keeps the fitness of the run that
+ * last scored it.  The rows go through a staging buffer (one copy per array) and a scatter kernel on the context's
+ * stream. */
+int scb_pop_update(scb_ctx *c, int n, const int32_t *slots, const int32_t *individuals, const int32_t *andNodes,
+                   const int32_t *andNodeInvertList)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (c->P <= 0) return fail(SCB_ERR_INVALID, "no population uploaded");
+    if (c->koStride) return fail(SCB_ERR_UNSUPPORTED, "batched importance programs cannot be updated in place");
+    if (n < 0 || n > c->P) return fail(SCB_ERR_INVALID, "%d replaced individuals for a population of %d", n, c->P);
+    if (n > 0 && (!slots || (!individuals && c->indLen > 0))) return fail(SCB_ERR_INVALID, "null argument");
+    if (n > 0 && c->tpi && (!andNodes || !andNodeInvertList)) return fail(SCB_ERR_INVALID, "the population has per-individual tables: the replaced individuals need theirs");
+    if (c->delta && !c->ran && c->nEval > 0) return fail(SCB_ERR_INVALID, "the previous update has not been run yet");
+    std::vector<char> seen((size_t)c->P, 0);
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= c->P || seen[slots[i]]) return fail(SCB_ERR_INVALID, "slot list is not a set of distinct indices below %d", c->P);
+        seen[slots[i]] = 1;
+    }
+    const int N = c->N;
+    const size_t tbl = c->compact ? (size_t)N * SCB_MAX_IN : (size_t)N * SCB_MAX_TERMS * SCB_MAX_IN;
+    const size_t rowInd = (size_t)std::max(c->indLen, 0);
+    cudaStream_t st = c->stream;
+    if (n > 0) {
+        const size_t need = (size_t)n * (rowInd + (c->tpi ? 2 * tbl : 0));
+        if ((rc = c->dSlots.ensure((size_t)c->P)) || (rc = c->dStage.ensure(std::max<size_t>(need, 1)))) return rc;
+        /* the previous update's scatter kernels have read the staging buffer: same stream, in order */
+        CK(cudaMemcpyAsync(c->dSlots.p, slots, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        int32_t *sInd = c->dStage.p, *sAn = sInd + (size_t)n * rowInd, *sAi = sAn + (size_t)n * tbl;
+        const unsigned grid = (unsigned)std::min(n, 1024);
+        if (rowInd) {
+            CK(cudaMemcpyAsync(sInd, individuals, (size_t)n * rowInd * 4, cudaMemcpyHostToDevice, st));
+            SCB_LAUNCH(scb_k_scatter_rows, dim3(grid), dim3(128), 0, st, c->dInd.p, (const int32_t *)sInd, (const int32_t *)c->dSlots.p, (int)rowInd, n);
+        }
+        if (c->tpi) {
+            CK(cudaMemcpyAsync(sAn, andNodes, (size_t)n * tbl * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(sAi, andNodeInvertList, (size_t)n * tbl * 4, cudaMemcpyHostToDevice, st));
+            SCB_LAUNCH(scb_k_scatter_rows, dim3(grid), dim3(256), 0, st, c->dAn.p, (const int32_t *)sAn, (const int32_t *)c->dSlots.p, (int)tbl, n);
+            SCB_LAUNCH(scb_k_scatter_rows, dim3(grid), dim3(256), 0, st, c->dAi.p, (const int32_t *)sAi, (const int32_t *)c->dSlots.p, (int)tbl, n);
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));                /* the caller's arrays (pageable or not) may be reused on return */
+    }
+    if (c->ran || c->delta) {
+        /* every other slot holds a valid fitness: only the replaced ones are scored.  (Before the first run of an
+         * upload the whole population is still to be scored, replaced rows included.) */
+        c->delta = true; c->nEval = n;
+        c->ran = false;
+    }
+    return SCB_OK;
 }
 
 static int pop_run_impl(scb_ctx *c, int mode, int sem);
@@ -665,6 +732,14 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     if (!c->geomValid && (rc = pick_geometry(c))) return rc;
     const int N = c->N, P = c->P;
     cudaStream_t st = c->stream;
+    if (c->delta && mode != SCB_MODE_SUM) return fail(SCB_ERR_UNSUPPORTED, "after scb_pop_update only the fitness sums (SCB_MODE_SUM) are kept up to date");
+    if (c->delta && c->nEval == 0) {                       /* nothing was replaced: every fitness is current */
+        CK(cudaEventRecord(c->evRun0, st)); CK(cudaEventRecord(c->evRun1, st));
+        CK(cudaEventRecord(c->evSim0, st)); CK(cudaEventRecord(c->evSim1, st));
+        CK(cudaEventRecord(c->evK0, st)); CK(cudaEventRecord(c->evFill0, st)); CK(cudaEventRecord(c->evFill1, st));
+        c->lastMode = mode; c->ran = true; c->delta = false;
+        return SCB_OK;
+    }
     const bool wantNodewise = mode == SCB_MODE_NODEWISE || mode == SCB_MODE_IMPORTANCE;
     /* every allocation happens here, before anything is enqueued (or captured) */
     if (wantNodewise && (rc = c->dNodewise.ensure((size_t)P * N))) return rc;
@@ -681,7 +756,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
         auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
         mix(g_allocEpoch); mix(c->optVersion); mix((unsigned long long)P); mix((unsigned long long)mode); mix((unsigned long long)sem);
         mix((unsigned long long)c->indLen); mix((unsigned long long)c->tpi); mix((unsigned long long)c->compact); mix((unsigned long long)c->koStride);
-        mix(c->haveOrder ? 1ull : 0ull); mix(c->gConnected ? (unsigned long long)(1 + c->gRank + 64 * c->gWorld + 4096ull * c->gWidth) : 0ull);
+        mix(c->haveOrder ? 1ull : 0ull); mix(c->delta ? 1ull + (unsigned long long)c->nEval : 0ull); mix(c->gConnected ? (unsigned long long)(1 + c->gRank + 64 * c->gWorld + 4096ull * c->gWidth) : 0ull);
         if (!c->graphExec || key != c->graphKey) {
             if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }
             cudaGraph_t graph = nullptr;
@@ -701,14 +776,14 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
         CK(cudaEventRecord(c->evSim0, st));          /* the per-kernel split needs SCB_OPT_GRAPH = 0 */
         CK(cudaEventRecord(c->evSim1, st));
         CK(cudaEventRecord(c->evK0, st)); CK(cudaEventRecord(c->evFill0, st)); CK(cudaEventRecord(c->evFill1, st));
-        c->lastMode = mode; c->ran = true;
+        c->lastMode = mode; c->ran = true; c->delta = false;
         return SCB_OK;
     }
 #endif
     CK(cudaEventRecord(c->evRun0, st));
     if ((rc = pop_enqueue(c, mode, sem, false))) return rc;
     CK(cudaEventRecord(c->evRun1, st));
-    c->lastMode = mode; c->ran = true;
+    c->lastMode = mode; c->ran = true; c->delta = false;
     return SCB_OK;
 }
 
@@ -720,14 +795,13 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
     const int N = c->N, P = c->P;
     cudaStream_t st = c->stream;
     const bool wantNodewise = mode == SCB_MODE_NODEWISE || mode == SCB_MODE_IMPORTANCE;
-    CK(cudaMemsetAsync(c->dFitness.p, 0, (size_t)P * 8, st));
-    CK(cudaMemsetAsync(c->dCost.p, 0, (size_t)2 * P * 4, st));
+    /* (K0 clears the fitness sums and cost counters of the individuals it compiles) */
     if (wantNodewise) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
     CK(cudaMemsetAsync(c->dCounters.p, 0, 16 * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
 
     if (!capturing) CK(cudaEventRecord(c->evK0, st));
-    if ((rc = launch_compile(c, sem, c->dKo.p, true))) return rc;
+    if ((rc = launch_compile(c, sem, c->dKo.p, true, true))) return rc;
 
     ScbSimArgs sa;
     memset(&sa, 0, sizeof(sa));
@@ -736,7 +810,8 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
     sa.progs = c->dProgs.p; sa.progFrom = c->dProgFrom.p; sa.useSteady = c->optSteady;
     sa.imgs = c->dImgs.p; sa.imgStride = (int)scb_img_entries(N, c->main.warps);
-    sa.cost = c->dCost.p; sa.order = c->haveOrder ? c->dOrder.p : nullptr;
+    sa.cost = c->dCost.p; sa.order = c->delta ? c->dSlots.p : (c->haveOrder ? c->dOrder.p : nullptr);
+    sa.nEval = c->delta ? c->nEval : P;
     sa.chkFromProg = c->optChkFrom;
     sa.firstSnap = 1000;
     for (int t = SCB_LAST - 1; t >= 1; --t)
@@ -785,7 +860,7 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
         sa.workCounter = c->dCounters.p + (part == 0 ? 0 : 5);
         sa.zstride = (unsigned long long)N * 32 * g.K;
         sa.tmemCols = g.tmemCols; sa.tmemSlotsPerWarp = g.tmemSlotsPerWarp;
-        const long long items = (long long)P * tiles;
+        const long long items = (long long)sa.nEval * tiles;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(items, g.ctas));
         const dim3 block((unsigned)g.warps * 32);
         const size_t smemLaunch = fuse ? std::max(g.smem, c->smemRes) : g.smem;

@@ -547,8 +547,9 @@ SCB_DEV void scb_scatter_by_table(const uint4 *sdv, const unsigned char *sarv, i
 __global__ void scb_k_compile(ScbCompileArgs A)
 {
     SCB_DYN_SMEM(smraw);
-    const int N = A.N, p = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int N = A.N, p = A.slots ? A.slots[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     SCB_K0_MARK(0);
+    if (tid == 0 && A.fitness) { A.fitness[p] = 0ull; A.cost[p] = 0u; A.cost[A.P + p] = 0u; }
     uint4 *sd = reinterpret_cast<uint4 *>(smraw);
     unsigned int *cn = reinterpret_cast<unsigned int *>(sd + N);          /* [0..3] class counts, [4..7] flag counts */
     unsigned char *sar = reinterpret_cast<unsigned char *>(cn + 8);
@@ -692,6 +693,16 @@ __global__ void scb_k_compile(ScbCompileArgs A)
         if (cn[5]) atomicAdd(&A.diag->empty_rule_nodes, (unsigned long long)cn[5]);
         if (cn[6]) atomicAdd(&A.diag->bad_index_nodes, (unsigned long long)cn[6]);
         if (cn[7]) atomicAdd(&A.diag->term_overflow_nodes, (unsigned long long)cn[7]);
+    }
+}
+
+/* rows of a resident population replaced in place: row j of `src` ([n][rowInts]) becomes row slots[j] of `dst` */
+__global__ void scb_k_scatter_rows(int32_t *dst, const int32_t *src, const int32_t *slots, int rowInts, int n)
+{
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+        int32_t *d = dst + (long long)slots[j] * rowInts;
+        const int32_t *s = src + (long long)j * rowInts;
+        for (int i = threadIdx.x; i < rowInts; i += blockDim.x) d[i] = s[i];
     }
 }
 
@@ -1055,7 +1066,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         __syncthreads();
     }
 #endif
-    const unsigned total = (unsigned)A.P * (unsigned)A.tiles;
+    const unsigned total = (unsigned)A.nEval * (unsigned)A.tiles;
     unsigned stepsDone = 0, tilesDone = 0, rowsMoved = 0;     /* per CTA: a few thousand steps, a few million rows */
     long long cycPro = 0, cycStep = 0, cycEpi = 0;
 
@@ -1134,7 +1145,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
          * out are the cheap, partly filled tail tiles. */
         int p, tile;
         if (A.order) { p = A.order[item / (unsigned)A.tiles]; tile = (int)(item % (unsigned)A.tiles); }
-        else { p = (int)(item % (unsigned)A.P); tile = (int)(item / (unsigned)A.P); }
+        else { p = (int)(item % (unsigned)A.nEval); tile = (int)(item / (unsigned)A.nEval); }
         const long long c0 = scb_clock();
         SCB_EV_T0(evTile0);
         const int w0 = A.wordBase + tile * WT;

@@ -108,6 +108,10 @@ struct ScbCompileArgs {
     int imgWarps;                 /* warps of the simulator CTA the images are cut for */
     unsigned int imgRowBytes;     /* bytes of a state row in the simulator's shared memory (128 * K) */
     ScbDiag *diag;
+    const int32_t *slots;         /* null: CTA b compiles individual b; else individual slots[b] (resident population,
+                                     only the replaced individuals are compiled) */
+    unsigned long long *fitness;  /* [P] result sums, cleared here for the compiled individuals (null: not wanted) */
+    unsigned int *cost;           /* [2][P] cost counters of the simulator, cleared likewise */
 };
 
 struct ScbPackArgs {
@@ -122,6 +126,7 @@ struct ScbPackArgs {
 struct ScbSimArgs {
     const uint32_t *X;            /* packed S_0: [N][Wpad] node-major, 32 cells per word */
     int N, C, Wpad, tiles, P, Npad, mode;
+    int nEval;                    /* individuals this launch simulates: P, or the replaced ones of a resident population (order[] lists them) */
     int wordBase;                 /* first word of this launch's tile range (tail tiles use a narrower K) */
     const uint4 *descs;
     const int4 *counts;

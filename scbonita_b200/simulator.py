@@ -174,6 +174,18 @@ class Simulator:
                                              _ptr(m.individual_parse), _ptr(up), _ptr(ui), per_ind, _ptr(ko), _ptr(ki))
         _lib.check(self.lib, rc)
 
+    def update(self, slots, individuals, and_nodes=None, and_inv=None):
+        """Resident population (scb_pop_update): individuals ``slots`` of the uploaded population are replaced in place
+        and the next ``run()`` scores only them; ``fetch()`` keeps returning all P sums."""
+        sl = _i32(slots).reshape(-1)
+        n = int(sl.shape[0])
+        inds = _i32(individuals).reshape(n, -1) if n else np.zeros((0, 1), np.int32)
+        an = _i32(and_nodes) if and_nodes is not None else None
+        ai = _i32(and_inv) if and_inv is not None else None
+        rc = self.lib.scb_pop_update(self._ctx, n, _ptr(sl), _ptr(inds), _ptr(an) if an is not None else None,
+                                     _ptr(ai) if ai is not None else None)
+        _lib.check(self.lib, rc)
+
     def run(self, mode=MODE_SUM):
         _lib.check(self.lib, self.lib.scb_pop_run(self._ctx, int(mode)))
 

@@ -109,3 +109,43 @@ def test_legacy_symbol_replays_every_call(backend, trace):
             assert (errors[t["n_cells"]:] == -5).all()
     finally:
         lib.scb_set_legacy_geometry(20000, 15000)
+
+
+def test_resident_population_scores_only_the_offspring(backend, trace):
+    """the population stays on the device, every generation only the offspring rows are replaced
+    (scb_pop_update) and only they are simulated; the parents keep the sums of the run that scored them."""
+    t = trace
+    n0 = int(t["nevals"][0])
+    with _simulator(t, backend[1]) as sim:
+        # slots [0, n0): the first generation; slots [n0, n0 + lambda): room for one generation of offspring
+        lam = int(t["nevals"][1:].max())
+        first = slice(0, n0)
+        filler = np.arange(lam) % n0
+        sim.upload(np.concatenate([t["individuals"][first], t["individuals"][filler]]), t["knockouts"], t["knockins"],
+                   np.concatenate([t["and_nodes"][first], t["and_nodes"][filler]]),
+                   np.concatenate([t["and_inv"][first], t["and_inv"][filler]]))
+        sim.run()
+        fit = sim.fetch()
+        assert np.array_equal(fit[:n0], t["fitness"][first])
+        assert np.array_equal(fit[n0:], t["fitness"][filler])
+        lo = n0
+        for g in range(1, len(t["nevals"])):
+            n = int(t["nevals"][g])
+            sl = slice(lo, lo + n)
+            slots = n0 + np.arange(n)
+            before = sim.fetch().copy()
+            sim.update(slots, t["individuals"][sl], t["and_nodes"][sl], t["and_inv"][sl])
+            sim.run()
+            fit = sim.fetch()
+            assert np.array_equal(fit[slots], t["fitness"][sl]), g
+            keep = np.setdiff1d(np.arange(n0 + lam), slots)
+            assert np.array_equal(fit[keep], before[keep]), g                  # untouched slots keep their sums
+            lo += n
+        # an empty update: nothing to score, everything stays
+        sim.update(np.zeros(0, np.int32), np.zeros((0, t["ind_len"]), np.int32), np.zeros((0,) + t["and_nodes"].shape[1:], np.int32),
+                   np.zeros((0,) + t["and_inv"].shape[1:], np.int32))
+        sim.run()
+        assert np.array_equal(sim.fetch(), fit)
+        # a plain run afterwards scores everything again
+        sim.run()
+        assert np.array_equal(sim.fetch(), fit)

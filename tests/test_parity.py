@@ -644,3 +644,46 @@ def test_legacy_symbol_failure_cannot_look_like_a_result(backend, how):
         assert len(sums) == 2
         for _, total, smallest in sums:
             assert int(total) > 10 ** 9 and int(smallest) > 12 * 40         # far beyond any reachable error
+
+
+# ---- resident population -------------------------------------------------------------------------
+@pytest.mark.parametrize("compact", [False, True])
+def test_update_replaces_and_scores_only_the_given_slots(backend, compact):
+    pr = Problem.synthetic(60, big(backend, 700, 9000), 8)
+    o = pr.oracle()
+    with pr.simulator(backend[1]) as sim:
+        if compact:
+            up, upinv = zip(*(simulator.upstream_from_tables(pr.net.and_len, pr.pop_an[i], pr.pop_ai[i]) for i in range(8)))
+            up, upinv = np.array(up, np.int32), np.array(upinv, np.int32)
+            sim.upload_compact(pr.individuals, up, upinv, pr.ko, pr.ki)
+        else:
+            sim.upload(pr.individuals, pr.ko, pr.ki, pr.pop_an, pr.pop_ai)
+        sim.run()
+        assert np.array_equal(sim.fetch(), o["fitness"])
+        tiles_full = sim.last_stats["tiles"]
+        slots = np.array([6, 1, 3], np.int32)
+        src = np.array([0, 2, 7])
+        new_inds = pr.individuals.copy()
+        new_an, new_ai = pr.pop_an.copy(), pr.pop_ai.copy()
+        new_inds[slots], new_an[slots], new_ai[slots] = pr.individuals[src], pr.pop_an[src], pr.pop_ai[src]
+        new_inds[6] = 1 - new_inds[6]                                             # and one rule set nobody has seen
+        m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+        want = oracle.packed_population(m, new_inds, pr.bm, pr.n_cells, and_nodes=new_an, and_inv=new_ai)["fitness"]
+        if compact:
+            sim.update(slots, new_inds[slots], up[src], upinv[src])
+        else:
+            sim.update(slots, new_inds[slots], new_an[slots], new_ai[slots])
+        sim.run()
+        got = sim.fetch()
+        assert np.array_equal(got, want)
+        assert sim.last_stats["tiles"] * 8 == 3 * tiles_full                      # 3 of 8 individuals were simulated
+        with pytest.raises(simulator.ScbError):
+            sim.update([1, 1], new_inds[:2], new_an[:2], new_ai[:2])              # a slot twice
+        with pytest.raises(simulator.ScbError):
+            sim.update([8], new_inds[:1], new_an[:1], new_ai[:1])                 # outside the population
+        sim.update([0], new_inds[:1], (up if compact else new_an)[:1], (upinv if compact else new_ai)[:1])
+        with pytest.raises(simulator.ScbError):
+            sim.run(simulator.MODE_CELLWISE)                                      # only the sums are kept current
+        sim.run()
+        assert np.array_equal(sim.fetch(), want)
+
