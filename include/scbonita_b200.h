@@ -70,6 +70,7 @@ extern "C" {
 #define SCB_OPT_STEADY       14 /* 1 (default): steps after the constants have spread run the constant-propagated program */
 #define SCB_OPT_CHECK_FROM   15 /* k (default 3): no period-<=2 check before reduced program k may run; -1: check from step 3 */
 #define SCB_OPT_GRAPH        16 /* 1 (default): a generation is one CUDA graph launch; 0: plain launches (per-kernel timing in scb_stats) */
+#define SCB_OPT_GENERIC      17 /* 1: score populations with the general simulator (any rule width, any node count; slow) even where the compiled path applies; default 0 */
 #define SCB_OPT_FUSE         12 /* 1 (default): CTAs that run out of tiles resolve queued groups in the same launch */
 
 typedef struct scb_ctx scb_ctx;

@@ -99,7 +99,7 @@ struct scb_ctx {
     DevBuf<unsigned int> dCounters;      /* [0] K2 work head, [1] resolve count, [2] K3 work head */
     DevBuf<uint2> dItems;
     DevBuf<uint4> dFillItems;
-    DevBuf<int32_t> dChunkLast, dChunkLastErr;
+    DevBuf<int32_t> dChunkLast, dChunkLastErr, dAttrRaw;
     DevBuf<uint32_t> dChunkLastBits;
     DevBuf<uint32_t> dResolveT;
     DevBuf<unsigned int> dReady;
@@ -113,6 +113,11 @@ struct scb_ctx {
     DevBuf<int32_t> dOrder;              /* [P] individuals, costliest first (scb_pop_set_order) */
     bool haveOrder = false;
     /* resident population (scb_pop_update): the next run scores only the replaced slots */
+    /* the general simulator (scb_k_generic): the only path when the state does not fit shared memory, the second pass of
+     * a population that holds rules over more than three distinct inputs, or on request (SCB_OPT_GENERIC) */
+    bool genericOnly = false, optGeneric = false, lastGeneric = false;
+    int lastSem = 0;
+    DevBuf<uint32_t> dGScratch;
     bool delta = false;
     int nEval = 0;
     DevBuf<int32_t> dSlots, dStage;
@@ -186,8 +191,13 @@ int pick_geometry(scb_ctx *c)
 {
     const int N = c->N;
     if (c->optWords != 0 && c->optWords != 1 && c->optWords != 2 && c->optWords != 4) return fail(SCB_ERR_INVALID, "SCB_OPT_WORDS must be 0, 1, 2 or 4");
-    if (scb_resolve_smem_bytes(N, 1) > c->smemLimit)
-        return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the resolver's three state buffers", N);
+    if (scb_resolve_smem_bytes(N, 1) > c->smemLimit || scb_compile_smem_bytes(N) > c->smemLimit) {
+        /* the state (or K0's staging) does not fit shared memory: populations are scored by the general simulator,
+         * everything else (attractor analysis, importance scores) is refused by its own entry point */
+        c->genericOnly = true; c->geomValid = false;
+        c->fillWarps = 8; c->smemFill = 0; c->fillCtas = 8;
+        return SCB_OK;
+    }
 #ifndef SCB_EMU
     CK((cudaError_t)scb_sim_set_smem_k1_tm0((int)c->smemLimit));
     CK((cudaError_t)scb_sim_set_smem_k2_tm0((int)c->smemLimit));
@@ -199,8 +209,9 @@ int pick_geometry(scb_ctx *c)
     CK(cudaFuncSetAttribute(scb_k_resolve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_compile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
+    /* several rule-compiler CTAs per SM: without the hint the driver sizes the shared-memory carve-out for two */
+    CK(cudaFuncSetAttribute(scb_k_compile, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(scb_k_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute(scb_k_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, SCB_HAM_SMEM_WORDS * 4));
 #endif
     /* Candidates: tile width K (words per lane) x warps per CTA.  The widest tile that fits wins: a narrower tile
      * doubles the instructions and the per-warp chain of shared-memory round trips per cell (measured on C3: two CTAs
@@ -228,8 +239,14 @@ int pick_geometry(scb_ctx *c)
             if (c->optWarps) break;
         }
     }
-    if (bestScore < 0)
-        return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the %zu-byte shared-memory state buffers", N, c->smemLimit);
+    if (bestScore < 0) {
+        /* the state does not fit shared memory: populations are scored by the general simulator, everything else
+         * (attractor analysis, importance scores) is refused by its own entry point */
+        c->genericOnly = true; c->geomValid = false;
+        c->fillWarps = 8; c->smemFill = 0; c->fillCtas = 8;
+        return SCB_OK;
+    }
+    c->genericOnly = false;
     c->main = best; c->occ = bestOcc;
     const int K = best.K;
     /* One launch covers all tiles; the last, partly filled tile is made cheap inside the kernel by
@@ -510,11 +527,11 @@ int scb_ctx_destroy(scb_ctx *c)
     gather_release(c);
     if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
 #endif
-    c->dCost.release(); c->dOrder.release(); c->dSlots.release(); c->dStage.release();
+    c->dCost.release(); c->dOrder.release(); c->dSlots.release(); c->dStage.release(); c->dGScratch.release();
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dImgs.release(); c->dProgFrom.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
-    c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dChunkLastErr.release(); c->dChunkLastBits.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dDist.release();
+    c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dChunkLastErr.release(); c->dChunkLastBits.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dAttrRaw.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
     c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dRecBits.release(); c->dRecOn.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
@@ -538,6 +555,7 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
     ++c->optVersion;
     switch (key) {
         case SCB_OPT_GRAPH: c->optGraph = value != 0; return SCB_OK;
+        case SCB_OPT_GENERIC: c->optGeneric = value != 0; return SCB_OK;
         case SCB_OPT_EARLY_EXIT: c->optEarly = value != 0; return SCB_OK;
         case SCB_OPT_SNAPSHOTS: c->optSnap = value != 0; break;
         case SCB_OPT_CHECK_EVERY:
@@ -608,15 +626,17 @@ static int pop_upload_impl(scb_ctx *c, int P, int indRows, const int32_t *indivi
     if ((rc = c->dInd.ensure((size_t)P * std::max(indLen, 1)))) return rc;
     if ((rc = c->dAndLen.ensure(N)) || (rc = c->dParse.ensure(N)) || (rc = c->dKo.ensure((size_t)koRows * N)) || (rc = c->dKi.ensure(N))) return rc;
     if ((rc = c->dAn.ensure(ntab * tbl)) || (rc = c->dAi.ensure(ntab * tbl))) return rc;
-    if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
-    if ((rc = c->dProgs.ensure((size_t)P * SCB_NPROG * (N + 1))) || (rc = c->dProgFrom.ensure((size_t)P * 8))) return rc;
+    if (!c->genericOnly) {
+        if ((rc = c->dDescs.ensure((size_t)P * N)) || (rc = c->dCounts.ensure(P))) return rc;
+        if ((rc = c->dProgs.ensure((size_t)P * SCB_NPROG * (N + 1))) || (rc = c->dProgFrom.ensure((size_t)P * 8))) return rc;
+    }
     if ((rc = c->dFitness.ensure(P))) return rc;
     const size_t chunks = (size_t)c->Wpad / 32;
     if ((rc = c->dReady.ensure((size_t)2 * P * chunks))) return rc;      /* ready flags of the resolver items, then the handed-back tiles */
     if ((rc = c->dItems.ensure((size_t)P * chunks)) || (rc = c->dFillItems.ensure((size_t)P * chunks)) ||
         (rc = c->dChunkLast.ensure((size_t)P * chunks)) || (rc = c->dChunkLastErr.ensure((size_t)P * chunks))) return rc;
-    {   /* S_99 hand-over slots for the resolver: at most 64 MiB */
-        if (!c->geomValid && (rc = pick_geometry(c))) return rc;
+    if (!c->geomValid && !c->genericOnly && (rc = pick_geometry(c))) return rc;
+    if (!c->genericOnly) {   /* S_99 hand-over slots for the resolver: at most 64 MiB */
         const size_t per = (size_t)N * 32 * c->resGroup;
         const size_t want = std::min<size_t>((size_t)P * chunks, std::max<size_t>(64, ((size_t)64 << 20) / (per * 4)));
         if ((rc = c->dResolveT.ensure(want * per))) return rc;
@@ -723,12 +743,73 @@ int scb_pop_run(scb_ctx *c, int mode)
  * sem = SCB_SEM_IMPORTANCE), whose per-node counts land in the nodewise buffer */
 static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing);
 
+/* the uploaded population through the general simulator (scb_k_generic) + the fill-forward kernel */
+static int generic_run(scb_ctx *c, int mode)
+{
+    int rc;
+    const int N = c->N, P = c->P;
+    const int cpi = (c->C + 1023) / 1024;
+    cudaStream_t st = c->stream;
+    if (c->koStride) return fail(SCB_ERR_UNSUPPORTED, "batched importance programs have no general path");
+    if (mode == SCB_MODE_NODEWISE && ((rc = c->dNodewise.ensure((size_t)P * N)) || (rc = c->dChunkLastBits.ensure((size_t)P * cpi * ((N + 31) / 32))))) return rc;
+    if (mode == SCB_MODE_CELLWISE && (rc = c->dCellwise.ensure((size_t)P * c->C))) return rc;
+    const long long items = (long long)P * cpi;
+    const size_t perCta = (size_t)3 * N * 32;                              /* words */
+    long long ctas = std::min<long long>(items, (long long)c->numSM * 4);
+    ctas = std::min<long long>(ctas, std::max<long long>(1, (long long)(((size_t)1 << 28) / perCta)));   /* at most 1 GiB of state */
+    if (c->optMaxCtas > 0) ctas = std::min<long long>(ctas, c->optMaxCtas);
+    if ((rc = c->dGScratch.ensure((size_t)ctas * perCta))) return rc;
+    CK(cudaEventRecord(c->evRun0, st));
+    CK(cudaMemsetAsync(c->dFitness.p, 0, (size_t)P * 8, st));
+    if (mode == SCB_MODE_NODEWISE) CK(cudaMemsetAsync(c->dNodewise.p, 0, (size_t)P * N * 4, st));
+    CK(cudaMemsetAsync(c->dCounters.p, 0, 16 * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(c->dDiag.p, 0, sizeof(ScbDiag), st));
+    CK(cudaEventRecord(c->evK0, st));
+    CK(cudaEventRecord(c->evSim0, st));
+    ScbGenericArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.X = c->dX.p; ga.N = N; ga.C = c->C; ga.Wpad = c->Wpad; ga.P = P; ga.indLen = c->indLen;
+    ga.tablesPerIndividual = c->tpi; ga.compact = c->compact; ga.mode = mode;
+    ga.individuals = c->dInd.p; ga.andLen = c->dAndLen.p; ga.parse = c->dParse.p; ga.an = c->dAn.p; ga.ai = c->dAi.p;
+    ga.ko = c->dKo.p; ga.ki = c->dKi.p;
+    ga.scratch = c->dGScratch.p;
+    ga.fitness = c->dFitness.p; ga.nodewise = c->dNodewise.p; ga.cellwise = c->dCellwise.p;
+    ga.chunkLast = c->dChunkLast.p; ga.chunkLastErr = c->dChunkLastErr.p; ga.chunkLastBits = c->dChunkLastBits.p;
+    ga.chunksPerInd = cpi;
+    ga.fillCount = c->dCounters.p + 3; ga.fillItems = c->dFillItems.p;
+    ga.cursor = c->dCounters.p + 0;
+    ga.diag = c->dDiag.p;
+    SCB_LAUNCH(scb_k_generic, dim3((unsigned)ctas), dim3(256), SCB_GENERIC_SMEM, st, ga);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->evSim1, st));
+    ScbResolveArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.s.N = N; ra.s.C = c->C; ra.s.Wpad = c->Wpad; ra.s.P = P; ra.s.mode = mode;
+    ra.s.fitness = c->dFitness.p; ra.s.nodewise = c->dNodewise.p; ra.s.cellwise = c->dCellwise.p;
+    ra.s.chunkLast = c->dChunkLast.p; ra.s.chunkLastErr = c->dChunkLastErr.p; ra.s.chunkLastBits = c->dChunkLastBits.p;
+    ra.s.chunksPerInd = cpi; ra.s.fillCount = c->dCounters.p + 3; ra.s.fillItems = c->dFillItems.p; ra.s.diag = c->dDiag.p;
+    ra.itemCursor = c->dCounters.p + 4;
+    CK(cudaEventRecord(c->evFill0, st));
+    SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->fillCtas), dim3((unsigned)c->fillWarps * 32), 0, st, ra);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->evFill1, st));
+    CK(cudaEventRecord(c->evRun1, st));
+    c->lastMode = mode; c->ran = true; c->delta = false; c->lastGeneric = true;
+    return SCB_OK;
+}
+
 static int pop_run_impl(scb_ctx *c, int mode, int sem)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (c->P <= 0) return fail(SCB_ERR_INVALID, "no population uploaded");
+    c->lastSem = sem;
+    if (c->genericOnly || (c->optGeneric && sem == SCB_SEM_C && mode <= 2)) {
+        if (sem != SCB_SEM_C || mode > 2) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d does not fit the %zu-byte shared-memory state buffers: only population scoring is available", c->N, c->smemLimit);
+        return generic_run(c, mode);
+    }
+    c->lastGeneric = false;
     if (!c->geomValid && (rc = pick_geometry(c))) return rc;
     const int N = c->N, P = c->P;
     cudaStream_t st = c->stream;
@@ -914,6 +995,7 @@ int scb_pop_costs(scb_ctx *c, uint32_t *costs, uint32_t *tileMax)
     if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!c->ran || !costs) return fail(SCB_ERR_INVALID, "no finished run / null output");
+    if (c->lastGeneric) return fail(SCB_ERR_UNSUPPORTED, "the general simulator keeps no per-individual costs");
     CK(cudaMemcpyAsync(costs, c->dCost.p, (size_t)c->P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (tileMax) CK(cudaMemcpyAsync(tileMax, c->dCost.p + c->P, (size_t)c->P * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1055,13 +1137,22 @@ int scb_pop_fetch(scb_ctx *c, int mode, void *out, scb_stats *stats)
     if (!c->ran) return fail(SCB_ERR_INVALID, "scb_pop_run has not been called for this population");
     if (mode != c->lastMode && mode != SCB_MODE_SUM) return fail(SCB_ERR_INVALID, "mode %d was not computed by the last run (mode %d)", mode, c->lastMode);
     cudaStream_t st = c->stream;
-    if (out) {
-        const void *src = mode == SCB_MODE_SUM ? (const void *)c->dFitness.p
-                          : mode == SCB_MODE_NODEWISE ? (const void *)c->dNodewise.p : (const void *)c->dCellwise.p;
-        CK(cudaMemcpyAsync(out, src, result_bytes(c, mode), cudaMemcpyDeviceToHost, st));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (out) {
+            const void *src = mode == SCB_MODE_SUM ? (const void *)c->dFitness.p
+                              : mode == SCB_MODE_NODEWISE ? (const void *)c->dNodewise.p : (const void *)c->dCellwise.p;
+            CK(cudaMemcpyAsync(out, src, result_bytes(c, mode), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaMemcpyAsync(&c->hDiag, c->dDiag.p, sizeof(ScbDiag), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        /* K0 met rules over more than three distinct inputs: legal input of the reference, which the compiled path
+         * cannot express -- the population is scored again by the general simulator (exact, slow) */
+        if (attempt == 0 && c->hDiag.unsupported_nodes && !c->lastGeneric && c->lastSem == SCB_SEM_C && c->lastMode <= 2 && !c->koStride) {
+            if ((rc = generic_run(c, c->lastMode))) return rc;
+            continue;
+        }
+        break;
     }
-    CK(cudaMemcpyAsync(&c->hDiag, c->dDiag.p, sizeof(ScbDiag), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     const ScbDiag &d = c->hDiag;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -1102,6 +1193,7 @@ int scb_debug_programs(scb_ctx *c, int p, int k, uint32_t *descs, int32_t *count
     if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!c->ran || p < 0 || p >= c->P || k < 0 || k >= SCB_NPROG) return fail(SCB_ERR_INVALID, "no such program in the last run");
+    if (c->genericOnly || c->lastGeneric) return fail(SCB_ERR_UNSUPPORTED, "the general simulator compiles no programs");
     const size_t n = (size_t)c->N;
     CK(cudaStreamSynchronize(c->stream));
     const uint4 *pk = c->dProgs.p + ((size_t)p * SCB_NPROG + k) * (n + 1);
@@ -1303,27 +1395,43 @@ int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t
     const int N = c->N, C = c->C, NW = (N + 31) / 32;
     if (NW > SCB_HAM_MAXW) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > %d for the Hamming kernel", N, SCB_HAM_MAXW * 32);
     std::lock_guard<std::recursive_mutex> lk(c->mu);
-    std::vector<uint32_t> packed((size_t)nAttr * NW, 0u);
-    for (int a = 0; a < nAttr; ++a)
-        for (int i = 0; i < N; ++i) {
-            const int32_t v = attractors[(size_t)a * N + i];
-            if (v != 0 && v != 1) return fail(SCB_ERR_INVALID, "attractor %d node %d is %d, not 0/1", a, i, v);
-            if (v) packed[(size_t)a * NW + (i >> 5)] |= 1u << (i & 31);
-        }
-    if ((rc = c->dAttr.ensure(packed.size())) || (rc = c->dDecider.ensure(C)) || (rc = c->dDeciderDist.ensure(C))) return rc;
+    /* the attractors go up as the caller holds them and are packed on the device (a host loop over 32 x the packed
+     * size was most of this call's time) */
+    int NW4 = (NW + 3) / 4;
+    NW4 = NW4 <= 4 ? NW4 : (NW4 <= 6 ? 6 : 8);          /* the kernel's instantiations; rows are zero padded to that width */
+    const int NWP = NW4 * 4;
+    if ((rc = c->dAttrRaw.ensure((size_t)nAttr * N)) || (rc = c->dAttr.ensure((size_t)nAttr * NWP)) || (rc = c->dDecider.ensure(C)) || (rc = c->dDeciderDist.ensure(C))) return rc;
     if (dist && (rc = c->dDist.ensure((size_t)C * nAttr))) return rc;
     cudaStream_t st = c->stream;
-    CK(cudaMemcpyAsync(c->dAttr.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dAttrRaw.p, attractors, (size_t)nAttr * N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->dCounters.p + 10, 0, sizeof(unsigned int), st));
+    {
+        const long long warps = (long long)nAttr * NWP;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((warps + 7) / 8, (long long)c->numSM * 16));
+        SCB_LAUNCH(scb_k_pack_attr, dim3(grid), dim3(256), 0, st, (const int32_t *)c->dAttrRaw.p, c->dAttr.p, nAttr, N, NWP, c->dCounters.p + 10);
+        CK(cudaGetLastError());
+    }
     ScbHammingArgs ha;
     ha.X = c->dX.p; ha.N = N; ha.C = C; ha.Wpad = c->Wpad; ha.A = nAttr; ha.attr = c->dAttr.p;
     ha.dist = dist ? c->dDist.p : nullptr; ha.decider = c->dDecider.p; ha.deciderDistance = c->dDeciderDist.p;
     const int nthr = 128;
-    SCB_LAUNCH(scb_k_hamming, dim3((unsigned)((C + nthr - 1) / nthr)), dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha);
+    const dim3 hgrid((unsigned)((C + nthr - 1) / nthr));
+    switch (NW4) {
+        case 1: SCB_LAUNCH(scb_k_hamming<1>, hgrid, dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha); break;
+        case 2: SCB_LAUNCH(scb_k_hamming<2>, hgrid, dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha); break;
+        case 3: SCB_LAUNCH(scb_k_hamming<3>, hgrid, dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha); break;
+        case 4: SCB_LAUNCH(scb_k_hamming<4>, hgrid, dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha); break;
+        case 6: SCB_LAUNCH(scb_k_hamming<6>, hgrid, dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha); break;
+        default: SCB_LAUNCH(scb_k_hamming<8>, hgrid, dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha); break;
+    }
     CK(cudaGetLastError());
+    unsigned int badValues = 0;
+    CK(cudaMemcpyAsync(&badValues, c->dCounters.p + 10, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     if (dist) CK(cudaMemcpyAsync(dist, c->dDist.p, (size_t)C * nAttr * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(decider, c->dDecider.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(deciderDistance, c->dDeciderDist.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (badValues) return fail(SCB_ERR_INVALID, "%u attractor entries are not 0/1", badValues);
     return SCB_OK;
 }
 

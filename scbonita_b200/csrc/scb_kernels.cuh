@@ -544,7 +544,7 @@ SCB_DEV void scb_scatter_by_table(const uint4 *sdv, const unsigned char *sarv, i
 #else
 #define SCB_K0_MARK(m) do { } while (0)
 #endif
-__global__ void scb_k_compile(ScbCompileArgs A)
+__global__ void __launch_bounds__(256, 3) scb_k_compile(ScbCompileArgs A)
 {
     SCB_DYN_SMEM(smraw);
     const int N = A.N, p = A.slots ? A.slots[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
@@ -2060,6 +2060,217 @@ __global__ void scb_k_fill(ScbResolveArgs R)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * KG: the general simulator.  scSyncBool accepts what K2 cannot hold: any [7][3] term table -- a rule over up to 21
+ * distinct state bits, where K0 compiles at most three into one LOP3 -- and networks up to the reference's compile-time
+ * NODE (simulator.c:4-5), whose state does not fit shared memory.  Such input takes this path (and only such input,
+ * or SCB_OPT_GENERIC): the reference's update rule evaluated term by term on packed words (32 cells per operation,
+ * simulator.c:10-50, :377-416 as restated in scb_compile.h), the state of a 1024-cell chunk in global memory
+ * (L2-resident), the attractor test literally as getAttractCycle2 (simulator.c:306-331): pass a = 99 steps -> T = S_99,
+ * pass b = the same 98 steps again, every S_t compared with T.  One CTA per (individual, chunk); the epilogue is the
+ * exact resolver's (fill-forward of not-found cells).  Exact, general and slow.
+ * ---------------------------------------------------------------------------------------- */
+SCB_DEV uint32_t scb_generic_node(const ScbGenericArgs &G, int p, int i, const uint32_t *cur, int lane, unsigned &flags)
+{
+    const int N = G.N;
+    if (G.ko[i] == 1) return 0u;
+    if (G.ki[i] == 1) return 0xffffffffu;
+    const int al = G.andLen[i];
+    int32_t tan[SCB_MAX_TERMS * SCB_MAX_IN], tai[SCB_MAX_TERMS * SCB_MAX_IN];
+    const int32_t *an_i, *ai_i;
+    if (G.compact) {
+        const long long uoff = (G.tablesPerIndividual ? (long long)p * N * SCB_MAX_IN : 0) + (long long)i * SCB_MAX_IN;
+        if (scb_expand_terms(G.an + uoff, G.ai + uoff, tan, tai) != al) flags |= SCB_NF_TERMS;
+        an_i = tan; ai_i = tai;
+    } else {
+        const long long toff = (G.tablesPerIndividual ? (long long)p * N : 0) + i;
+        an_i = G.an + toff * (SCB_MAX_TERMS * SCB_MAX_IN); ai_i = G.ai + toff * (SCB_MAX_TERMS * SCB_MAX_IN);
+    }
+    if (al == 1 || al == 0) {
+        const int src = an_i[0];
+        if (src < 0 || src >= N) { flags |= SCB_NF_BADIDX; return 0u; }
+        const int fl = al == 1 ? ai_i[0] : 0;
+        if (fl != 0 && fl != 1) return 0xffffffffu;
+        const uint32_t x = cur[(long long)src * 32 + lane];
+        return fl ? ~x : x;
+    }
+    const int32_t *ind = G.individuals + (long long)p * G.indLen;
+    const int start = G.parse[i];
+    const int end = i == N - 1 ? G.indLen : G.parse[i + 1];
+    int nt = end - start;
+    if (nt > SCB_MAX_TERMS) { flags |= SCB_NF_TERMS; nt = SCB_MAX_TERMS; }
+    if (nt < 0 || start < 0 || end > G.indLen) { flags |= SCB_NF_TERMS; nt = 0; }
+    uint32_t v = 0u;
+    bool any = false;
+    for (int a = 0; a < nt; ++a) {
+        if (!ind[start + a]) continue;
+        any = true;
+        uint32_t t = 0xffffffffu;
+        for (int b = 0; b < SCB_MAX_IN; ++b) {
+            const int src = an_i[a * 3 + b];
+            if (b > 0 && src <= -1) continue;
+            if (src < 0 || src >= N) { flags |= SCB_NF_BADIDX; continue; }
+            const int fl = ai_i[a * 3 + b];
+            if (fl != 0 && fl != 1) continue;                          /* constant TRUE literal */
+            const uint32_t x = cur[(long long)src * 32 + lane];
+            t &= fl ? ~x : x;
+        }
+        v |= t;
+    }
+    if (!any) { flags |= SCB_NF_EMPTY; return 0u; }                    /* Q9 */
+    return v;
+}
+
+#define SCB_GENERIC_SMEM (32 * 4 * 4 + 8 * 4 + 1024 * 2)
+__global__ void __launch_bounds__(256) scb_k_generic(ScbGenericArgs G)
+{
+    SCB_DYN_SMEM(smraw);                                 /* SCB_GENERIC_SMEM bytes */
+    uint32_t *Fm = reinterpret_cast<uint32_t *>(smraw), *vm = Fm + 32;
+    uint32_t (*acc)[32] = reinterpret_cast<uint32_t (*)[32]>(vm + 32);
+    int *sh = reinterpret_cast<int *>(vm + 96);
+    short *srcc = reinterpret_cast<short *>(sh + 8);
+    const int N = G.N;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
+    uint32_t *bA = G.scratch + (size_t)blockIdx.x * 3 * (size_t)N * 32, *bT = bA + (size_t)N * 32, *bC = bT + (size_t)N * 32;
+    const unsigned total = (unsigned)G.P * (unsigned)G.chunksPerInd;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh[0] = (int)atomicAdd(G.cursor, 1u);
+        __syncthreads();
+        const unsigned item = (unsigned)sh[0];
+        if (item >= total) break;
+        const int p = (int)(item / (unsigned)G.chunksPerInd), q = (int)(item % (unsigned)G.chunksPerInd);
+        const int w0 = q * 32;
+        const bool inX = w0 + lane < G.Wpad;
+        unsigned flags = 0u;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int row = warp; row < N; row += S) bA[(size_t)row * 32 + lane] = inX ? G.X[(long long)row * G.Wpad + w0 + lane] : 0u;
+            if (tid < 32) { vm[tid] = scb_valid_mask((long long)w0 + tid, G.C); acc[0][tid] = 0u; acc[1][tid] = 0u; if (pass == 0) Fm[tid] = 0u; }
+            if (tid == 0) { sh[2] = 0; sh[3] = 0; }
+            __syncthreads();
+            if (q == 0 && pass == 0) {
+                /* input diagnostics, once per individual (same counters as K0) */
+                unsigned nEmpty = 0, nBad = 0, nTerms = 0;
+                for (int i = tid; i < N; i += nthr) {
+                    unsigned f = 0u;
+                    (void)scb_generic_node(G, p, i, bA, 0, f);
+                    nEmpty += (f & SCB_NF_EMPTY) ? 1u : 0u; nBad += (f & SCB_NF_BADIDX) ? 1u : 0u; nTerms += (f & SCB_NF_TERMS) ? 1u : 0u;
+                }
+                if (nEmpty) atomicAdd(&G.diag->empty_rule_nodes, (unsigned long long)nEmpty);
+                if (nBad) atomicAdd(&G.diag->bad_index_nodes, (unsigned long long)nBad);
+                if (nTerms) atomicAdd(&G.diag->term_overflow_nodes, (unsigned long long)nTerms);
+            }
+            uint32_t *cur = bA, *nxt = pass == 0 ? bT : bC;
+            if (pass == 1) {
+                uint32_t d = 0u;
+                for (int row = warp; row < N; row += S) d |= cur[(size_t)row * 32 + lane] ^ bT[(size_t)row * 32 + lane];
+                if (d) atomicOr(&acc[0][lane], d);
+                __syncthreads();
+                if (tid < 32) { Fm[tid] |= ~acc[0][tid]; acc[0][tid] = 0u; }
+                __syncthreads();
+            }
+            const int last = pass == 0 ? SCB_LAST : SCB_LAST - 1;
+            for (int t = 1; t <= last; ++t) {
+                uint32_t d = 0u;
+                for (int row = warp; row < N; row += S) {
+                    const uint32_t v = scb_generic_node(G, p, row, cur, lane, flags);
+                    nxt[(size_t)row * 32 + lane] = v;
+                    if (pass == 1) d |= v ^ bT[(size_t)row * 32 + lane];
+                }
+                if (pass == 1 && d) atomicOr(&acc[t & 1][lane], d);
+                __syncthreads();
+                /* the accumulator of step t is folded while the other warps run step t + 1 into the other one */
+                if (pass == 1 && tid < 32) { Fm[tid] |= ~acc[t & 1][tid]; acc[t & 1][tid] = 0u; }
+                uint32_t *x = cur; cur = nxt; nxt = x;
+            }
+            /* pass 0 ends with S_99 in bT (99 is odd): the target.  Pass 1 ends with S_98 in bA (98 is even). */
+        }
+        /* e = S_98 xor S_0 on valid cells -> bC */
+        for (int row = warp; row < N; row += S)
+            bC[(size_t)row * 32 + lane] = (bA[(size_t)row * 32 + lane] ^ (inX ? G.X[(long long)row * G.Wpad + w0 + lane] : 0u)) & vm[lane];
+        if (tid < 32) Fm[tid] &= vm[tid];
+        __syncthreads();
+        /* source cell of every cell: itself when found, else the nearest earlier found cell of the chunk (the
+         * reference's fill-forward), -1 when that lies in an earlier chunk, -2 padding */
+        for (int i = tid; i < 1024; i += nthr) {
+            const int w = i >> 5, b = i & 31;
+            int s = -2;
+            if ((vm[w] >> b) & 1u) {
+                if ((Fm[w] >> b) & 1u) s = i;
+                else {
+                    s = -1;
+                    const uint32_t m = Fm[w] & ((1u << b) - 1u);
+                    if (m) s = w * 32 + (31 - __clz((int)m));
+                    else for (int ww = w - 1; ww >= 0; --ww)
+                        if (Fm[ww]) { s = ww * 32 + (31 - __clz((int)Fm[ww])); break; }
+                    atomicAdd(reinterpret_cast<unsigned int *>(&sh[3]), 1u);
+                    if (s == -1) atomicAdd(reinterpret_cast<unsigned int *>(&sh[2]), 1u);
+                }
+            }
+            srcc[i] = (short)s;
+        }
+        __syncthreads();
+        unsigned tot = 0;
+        for (int node = warp; node < N; node += S) {
+            const uint32_t e = bC[(size_t)node * 32 + lane];
+            unsigned c = (unsigned)__popc(e & Fm[lane]);
+            uint32_t nfb = ~Fm[lane] & vm[lane];
+            while (nfb) {
+                const int b = __ffs((int)nfb) - 1;
+                nfb &= nfb - 1u;
+                const int sc = srcc[lane * 32 + b];
+                if (sc >= 0) c += (bC[(size_t)node * 32 + (sc >> 5)] >> (sc & 31)) & 1u;
+            }
+            tot += c;
+            if (G.mode == 1) {
+                c = scb_warp_sum(c);
+                if (lane == 0 && c) atomicAdd(&G.nodewise[(long long)p * N + node], (int)c);
+            }
+        }
+        tot = scb_warp_sum(tot);
+        if (lane == 0 && tot) atomicAdd(&G.fitness[p], (unsigned long long)tot);
+        if (G.mode == 2) {
+            for (int i = tid; i < 1024; i += nthr) {
+                const int sc = srcc[i];
+                if (sc < 0) continue;
+                int n1 = 0;
+                for (int row = 0; row < N; ++row) n1 += (int)((bC[(size_t)row * 32 + (sc >> 5)] >> (sc & 31)) & 1u);
+                G.cellwise[(long long)p * G.C + (long long)q * 1024 + i] = n1;
+            }
+        }
+        if (warp == 0) {
+            /* the chunk's last found cell and its error column, for the fill-forward of later chunks */
+            const unsigned any = __ballot_sync(0xffffffffu, Fm[lane] != 0u);
+            int lastFound = -1;
+            if (any) {
+                const int w = 31 - __clz((int)any);
+                lastFound = w * 32 + (31 - __clz((int)Fm[w]));
+                const int b = lastFound & 31, NB = (N + 31) >> 5;
+                unsigned cntl = 0;
+                for (int itn = 0; itn < NB; ++itn) {
+                    const int row = itn * 32 + lane;
+                    const unsigned bit = row < N ? (bC[(size_t)row * 32 + w] >> b) & 1u : 0u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, bit != 0u);
+                    cntl += (unsigned)__popc(bal);
+                    if (G.mode == 1 && lane == 0) G.chunkLastBits[((long long)p * G.chunksPerInd + q) * NB + itn] = bal;
+                }
+                if (lane == 0) G.chunkLastErr[(long long)p * G.chunksPerInd + q] = (int)cntl;
+            }
+            if (lane == 0) {
+                G.chunkLast[(long long)p * G.chunksPerInd + q] = lastFound;
+                if (sh[2] > 0) {
+                    const unsigned idx = atomicAdd(G.fillCount, 1u);
+                    G.fillItems[idx] = make_uint4((unsigned)p, (unsigned)q, (unsigned)sh[2], 0u);
+                }
+                if (sh[3] > 0) atomicAdd(&G.diag->not_found_cells, (unsigned long long)sh[3]);
+                atomicAdd(&G.diag->resolver_chunks, 1ull);
+                atomicAdd(&G.diag->tiles, 1ull);
+                atomicAdd(&G.diag->steps_executed, (unsigned long long)(2 * SCB_LAST - 1));
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Fitness exchange over peer memory: the all-gather of a GA generation as the last kernel of the
  * generation's graph.  One CTA: the shard (a few hundred 8-byte values) is stored straight into every rank's gather
  * buffer over NVLink, a system-scope fence orders the stores, then this rank's flag is raised in every rank's flag
@@ -2234,36 +2445,62 @@ __global__ void scb_k_window(ScbWindowArgs A)
  * ---------------------------------------------------------------------------------------- */
 #define SCB_HAM_MAXW 32            /* N <= 1024 */
 #define SCB_HAM_SMEM_WORDS 8192    /* 32 KB of attractor words per pass */
-__global__ void scb_k_hamming(ScbHammingArgs A)
+/* attractors as the caller holds them (int32 0/1 per node) -> bit rows of NW4 * 4 words, padded with zeros: one warp
+ * per output word, a ballot per 32 values; anything but 0/1 is counted in *bad */
+__global__ void scb_k_pack_attr(const int32_t *raw, uint32_t *packed, int nAttr, int N, int NWP, unsigned int *bad)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long o = warp; o < (long long)nAttr * NWP; o += nWarps) {
+        const long long a = o / NWP;
+        const int w = (int)(o - a * NWP), i = w * 32 + lane;
+        const int32_t v = i < N ? raw[a * N + i] : 0;
+        const unsigned word = __ballot_sync(0xffffffffu, v == 1);
+        if (v != 0 && v != 1) atomicAdd(bad, 1u);
+        if (lane == 0) packed[o] = word;
+    }
+}
+
+/* NW4 = 16-byte groups per state (N <= 128 * NW4): the cell's state lives in registers, the attractors of a pass are
+ * read from shared memory as broadcast 16-byte loads; per 32 node bits one XOR and one POPC (the bound: POPC issues
+ * at a quarter of the LOP3 rate) */
+template <int NW4>
+__global__ void __launch_bounds__(128) scb_k_hamming(ScbHammingArgs A)
 {
     SCB_DYN_SMEM(smraw);
-    const int NW = (A.N + 31) / 32;
-    uint32_t *sAttr = reinterpret_cast<uint32_t *>(smraw);
+    constexpr int NWP = NW4 * 4;
+    const uint4 *sAttr = reinterpret_cast<const uint4 *>(smraw);
+    uint4 *sAttrW = reinterpret_cast<uint4 *>(smraw);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long c = (long long)blockIdx.x * nthr + tid;
-    uint32_t cs[SCB_HAM_MAXW];
+    uint32_t cs[NWP];
 #pragma unroll
-    for (int w = 0; w < SCB_HAM_MAXW; ++w) cs[w] = 0u;
-    if (c < A.C) {
-        for (int w = 0; w < NW; ++w) {
-            uint32_t acc = 0u;
+    for (int w = 0; w < NWP; ++w) {
+        uint32_t acc = 0u;
+        if (c < A.C && w * 32 < A.N) {
             const int lim = (A.N - w * 32) < 32 ? (A.N - w * 32) : 32;
             for (int b = 0; b < lim; ++b)
                 acc |= ((A.X[(long long)(w * 32 + b) * A.Wpad + (c >> 5)] >> (c & 31)) & 1u) << b;
-            cs[w] = acc;
         }
+        cs[w] = acc;
     }
     int best = -1, bestD = 0;
-    const int ACH = SCB_HAM_SMEM_WORDS / NW;               /* attractors per shared-memory pass */
+    const int ACH = (SCB_HAM_SMEM_WORDS / 4) / NW4;           /* attractors per shared-memory pass */
+    const uint4 *gAttr = reinterpret_cast<const uint4 *>(A.attr);
     for (int a0 = 0; a0 < A.A; a0 += ACH) {
         const int na = (A.A - a0) < ACH ? (A.A - a0) : ACH;
         __syncthreads();
-        for (int i = tid; i < na * NW; i += nthr) sAttr[i] = A.attr[(long long)a0 * NW + i];
+        for (int i = tid; i < na * NW4; i += nthr) sAttrW[i] = gAttr[(long long)a0 * NW4 + i];
         __syncthreads();
         if (c < A.C) {
             for (int a = 0; a < na; ++a) {
                 int d = 0;
-                for (int w = 0; w < NW; ++w) d += __popc(cs[w] ^ sAttr[a * NW + w]);
+#pragma unroll
+                for (int g = 0; g < NW4; ++g) {
+                    const uint4 t = sAttr[a * NW4 + g];
+                    d += __popc(cs[4 * g] ^ t.x) + __popc(cs[4 * g + 1] ^ t.y) + __popc(cs[4 * g + 2] ^ t.z) + __popc(cs[4 * g + 3] ^ t.w);
+                }
                 if (A.dist) A.dist[c * A.A + a0 + a] = d;
                 if (best < 0 || d < bestD) { best = a0 + a; bestD = d; }     /* first minimum */
             }

@@ -87,6 +87,23 @@ struct ScbDiag {                      /* device-side counters, zeroed per evalua
  * Sorted per individual by arity: [arity 3 | arity 2 | arity 1 | constants], counts in an int4
  * (x = n3, y = n2, z = n1, w = n0).  lut8 follows lop3's convention: bit ((a<<2)|(b<<1)|c). */
 
+/* KG, the general simulator (scb_k_generic): arguments */
+struct ScbGenericArgs {
+    const uint32_t *X;            /* packed S_0, [N][Wpad] */
+    int N, C, Wpad, P, indLen, tablesPerIndividual, compact, mode;
+    const int32_t *individuals, *andLen, *parse, *an, *ai, *ko, *ki;    /* as uploaded (ScbCompileArgs) */
+    uint32_t *scratch;            /* [CTAs][3][N][32] state buffers in global memory */
+    unsigned long long *fitness;
+    int32_t *nodewise, *cellwise;
+    int32_t *chunkLast, *chunkLastErr;
+    uint32_t *chunkLastBits;
+    int chunksPerInd;
+    unsigned int *fillCount;
+    uint4 *fillItems;
+    unsigned int *cursor;         /* work counter over the P x chunksPerInd items */
+    ScbDiag *diag;
+};
+
 struct ScbCompileArgs {
     int P, N, indLen, tablesPerIndividual, Npad;
     int sem;                      /* SCB_SEM_* (scb_compile.h) */
@@ -211,7 +228,7 @@ struct ScbGatherArgs {
 struct ScbHammingArgs {
     const uint32_t *X;            /* [N][Wpad] */
     int N, C, Wpad, A;
-    const uint32_t *attr;         /* [A][ceil(N/32)]: bit i%32 of word i/32 = node i of the attractor */
+    const uint32_t *attr;         /* [A][NWP]: bit i%32 of word i/32 = node i of the attractor; NWP = ceil(N/128) * 4 words, zero padded */
     int32_t *dist;                /* [C][A] or null */
     int32_t *decider;             /* [C] */
     int32_t *deciderDistance;     /* [C] */

@@ -208,16 +208,43 @@ def test_empty_rule_is_defined_as_zero_and_counted(backend):
 
 
 # ---- error behaviour ------------------------------------------------------------------------------------
-def test_more_than_three_distinct_inputs_is_refused(backend):
+def test_more_than_three_distinct_inputs_go_through_the_general_simulator(backend):
+    """Any [7][3] table is legal input of scSyncBool.  A rule over more than three distinct state bits cannot be one
+    LOP3: the population is scored again, exactly, by the general simulator (scb_k_generic)."""
     rng = np.random.default_rng(9)
     net = _random_tables(rng, 12, max_distinct=5, weird_flags=False)
-    rows = (rng.random((12, 64)) < 0.5).astype(np.uint8)
-    inds = np.ones((1, net.ind_len), np.int32)
+    rows = (rng.random((12, 1500)) < 0.5).astype(np.uint8)
+    inds = (rng.random((3, net.ind_len)) < 0.6).astype(np.int32)
+    inds[0] = 1
     pr = Problem(net, rows, np.arange(12, dtype=np.int32), inds)
     with pr.simulator(backend[1]) as sim:
-        with pytest.raises(simulator.ScbError) as ei:
-            sim.evaluate_population(pr.individuals)
-        assert ei.value.code == _lib.ERR_UNSUPPORTED
+        pr.check(sim)
+        assert sim.last_stats["unsupported_nodes"] == 0 and sim.last_stats["tiles"] == 3 * 2     # 3 individuals x 2 chunks, generic
+
+
+@pytest.mark.parametrize("n,cells,pop", [(20, 200, 3), (60, 2100, 4), (230, 1100, 2)])
+def test_general_simulator_matches_oracle(backend, n, cells, pop):
+    """SCB_OPT_GENERIC: ordinary populations through the general simulator, all three output shapes."""
+    pr = Problem.synthetic(n, cells, pop)
+    with pr.simulator(backend[1], generic=1) as sim:
+        pr.check(sim)
+        assert sim.last_stats["tiles"] == pop * -(-cells // 1024)
+
+
+@pytest.mark.parametrize("rings,chain,cells", [([60], 0, 300), ([45], 12, 2500), ([3, 5], 4, 1500)])
+def test_general_simulator_cycles_not_found_and_fill_forward(backend, rings, chain, cells):
+    pr = ring_problem(rings, chain, cells)
+    with pr.simulator(backend[1], generic=1) as sim:
+        pr.check(sim)
+
+
+def test_general_simulator_compact_population(backend):
+    pr = Problem.synthetic(40, 1300, 3)
+    up, upinv = zip(*(simulator.upstream_from_tables(pr.net.and_len, pr.pop_an[i], pr.pop_ai[i]) for i in range(3)))
+    with pr.simulator(backend[1], generic=1) as sim:
+        sim.upload_compact(pr.individuals, np.array(up, np.int32), np.array(upinv, np.int32), pr.ko, pr.ki)
+        sim.run()
+        assert np.array_equal(sim.fetch(), pr.oracle()["fitness"])
 
 
 def test_bad_input_index_is_refused(backend):
@@ -397,16 +424,20 @@ def test_legacy_symbol_is_reentrant(backend):
         assert np.array_equal(e, o["nodewise"][p]), p
 
 
-def test_network_too_large_for_on_chip_state_is_refused(backend):
-    """N beyond the shared-memory state buffers is refused loudly, never computed elsewhere."""
+def test_network_too_large_for_on_chip_state_uses_the_general_simulator(backend):
+    """N beyond the shared-memory state buffers (the reference allows NODE = 20000): populations are scored by the
+    general simulator, state in global memory; the other entry points refuse."""
     rng = np.random.default_rng(2)
-    n = 900
+    n = 900 if backend[0] == "emu" else 1500
     net = _random_tables(rng, n, weird_flags=False)
-    rows = (rng.random((n, 64)) < 0.5).astype(np.uint8)
-    pr = Problem(net, rows, np.arange(n, dtype=np.int32), np.ones((1, net.ind_len), np.int32))
-    with pytest.raises(simulator.ScbError) as ei:
-        pr.simulator(backend[1])
-    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    rows = (rng.random((n, 200)) < 0.5).astype(np.uint8)
+    inds = (rng.random((2, net.ind_len)) < 0.7).astype(np.int32)
+    pr = Problem(net, rows, np.arange(n, dtype=np.int32), inds)
+    with pr.simulator(backend[1]) as sim:
+        pr.check(sim, modes=(0, 2) if backend[0] == "emu" else (0, 1, 2))
+        with pytest.raises(simulator.ScbError) as ei:
+            sim.importance_scores(pr.individuals[0], [[0]])
+        assert ei.value.code == _lib.ERR_UNSUPPORTED
 
 
 # ---- compact population (SURVEY 8f N4) ------------------------------------------------------------
@@ -687,3 +718,34 @@ def test_update_replaces_and_scores_only_the_given_slots(backend, compact):
         sim.run()
         assert np.array_equal(sim.fetch(), want)
 
+
+
+def test_legacy_symbol_with_a_network_beyond_shared_memory(backend):
+    """scSyncBool on a 900-node network with rules over up to five distinct inputs: both reasons for the general path."""
+    rng = np.random.default_rng(11)
+    n, cells = 900, 150
+    net = _random_tables(rng, n, max_distinct=5, weird_flags=False)
+    rows = (rng.random((n, cells)) < 0.5).astype(np.uint8)
+    ind = (rng.random((1, net.ind_len)) < 0.7).astype(np.int32)
+    pr = Problem(net, rows, np.arange(n, dtype=np.int32), ind)
+    o = pr.oracle()
+    lib = _lib.load(backend[1])
+    stride = 256
+    lib.scb_set_legacy_geometry(20000, stride)
+    try:
+        bm = np.zeros((n, stride), np.int32)
+        bm[:, :cells] = pr.bm
+        V = ctypes.c_void_p
+        vals = np.zeros((100, n), np.int32)
+        arr = [np.ascontiguousarray(a, np.int32) for a in (pr.individuals[0], pr.net.and_len, pr.net.parse, pr.net.and_nodes,
+                                                           pr.net.and_inv, pr.ko, pr.ki, pr.node_positions)]
+        ind0, al, parse, an, ai, ko, ki, pos = arr
+        fn = lib.scSyncBool
+        fn.restype, fn.argtypes = None, None
+        errors = np.full(cells + 1, -1, np.int32)
+        fn(V(vals.ctypes.data), V(ind0.ctypes.data), V(len(ind0)), V(n), V(al.ctypes.data), V(parse.ctypes.data),
+           V(an.ctypes.data), V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data), V(cells),
+           V(bm.ctypes.data), V(pos.ctypes.data), V(errors.ctypes.data), V(0), V(0))
+        assert np.array_equal(errors[:cells], o["cellwise"][0]) and errors[cells] == -1
+    finally:
+        lib.scb_set_legacy_geometry(20000, 15000)
