@@ -765,6 +765,85 @@ def run_c4(args, rank, world, local_rank):
 
 
 # ---------------------------------------------------------------------------------------------
+# L0: the level-0 drop-in: per-call cost of the exported scSyncBool symbol
+# ---------------------------------------------------------------------------------------------
+def run_l0(args, rank, world, local_rank):
+    """What a user gets who only swaps ./simulator.so: one scSyncBool call per individual, 17 x c_void_p, dense int32
+    matrix with the reference's row stride handed over on every call (ruleMaker.py:1109-1219).  Times the exported
+    symbol of this library (context cache, upload, K0 + K2 + K3, result copy) and, on the same arguments, the unmodified
+    reference C (oracle/_ref) on one host core -- the reference's own per-call cost without its Python marshalling."""
+    import ctypes
+    import time as _t
+    from scbonita_b200 import _lib
+    lib = _lib.load()
+    if lib.scb_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback exists)")
+    if rank != 0:
+        return
+    V = ctypes.c_void_p
+    out = []
+    for name, n, cells, stride in (("C1 shape: 47 nodes x 100 cells", 47, 100, 15000), ("200 nodes x 10000 cells", 200, 10000, 15000)):
+        pr = synth.make_problem(n, cells, 4)
+        bm = np.zeros((int(pr.node_positions.max()) + 1, stride), np.int32)
+        bm[pr.node_positions, :cells] = pr.bin_rows
+        vals = np.zeros((100, 20000), np.int32)                  # simData[100][NODE] of the reference build
+        lib.scb_set_legacy_geometry(20000, stride)
+        fn = lib.scSyncBool
+        fn.restype, fn.argtypes = None, None
+        al, parse, ko, ki, pos = (np.ascontiguousarray(a, np.int32) for a in (pr.net.and_len, pr.net.parse, pr.knockouts, pr.knockins, pr.node_positions))
+
+        def call(f, i, errors):
+            ind = np.ascontiguousarray(pr.individuals[i], np.int32)
+            an = np.ascontiguousarray(pr.pop_and_nodes[i], np.int32)
+            ai = np.ascontiguousarray(pr.pop_and_inv[i], np.int32)
+            f(V(vals.ctypes.data), V(ind.ctypes.data), V(len(ind)), V(n), V(al.ctypes.data), V(parse.ctypes.data), V(an.ctypes.data),
+              V(ai.ctypes.data), V(100), V(ko.ctypes.data), V(ki.ctypes.data), V(cells), V(bm.ctypes.data), V(pos.ctypes.data),
+              V(errors.ctypes.data), V(0), V(0))
+
+        e_ours, e_ref = np.zeros(cells, np.int32), np.zeros(cells, np.int32)
+        for i in range(4):
+            call(fn, i, e_ours)                                  # warm-up: context built and cached on the first call
+        reps = max(args.steps, 5) * 4
+        t0 = _t.perf_counter()
+        for r in range(reps):
+            call(fn, r % 4, e_ours)
+        ours_ms = (_t.perf_counter() - t0) / reps * 1e3
+        ref_ms = None
+        try:
+            import oracle                                        # the checker / CPU baseline, not the product
+            path = os.path.join(oracle.REF_DIR, oracle.REF_CELL_VARIANTS[stride])
+            ref = ctypes.cdll.LoadLibrary(path) if os.path.exists(path) else None
+            if ref is not None:
+                rf = ref.scSyncBool
+                rf.restype, rf.argtypes = None, None
+                call(rf, 3, e_ref)
+                same = bool(np.array_equal(e_ref, e_ours))
+                t0 = _t.perf_counter()
+                nref = 2 if cells > 1000 else 8
+                for r in range(nref):
+                    call(rf, r % 4, e_ref)
+                ref_ms = (_t.perf_counter() - t0) / nref * 1e3
+            else:
+                same = None
+        except Exception as exc:                                 # oracle/_ref not built for this stride
+            same, ref_ms = None, None
+            sys.stderr.write("reference build unavailable for the level-0 comparison: %s\n" % exc)
+        out.append({"shape": name, "row_stride": stride, "ours_ms_per_call": ours_ms, "reference_c_ms_per_call_one_core": ref_ms,
+                    "identical_errors": same, "cre_per_call": float(cells) * n * STEPS_PER_CELL})
+    lib.scb_set_legacy_geometry(20000, 15000)
+    big = out[-1]
+    line = {"metric": METRIC, "value": big["cre_per_call"] / (big["ours_ms_per_call"] * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": big["ours_ms_per_call"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "L0: level-0 drop-in, one exported scSyncBool call per individual (wall clock per call, host buffers in and out)"},
+            "calls": out, "e2e": {"value": big["cre_per_call"] / (big["ours_ms_per_call"] * 1e-3), "unit": UNIT, "ms_per_step": big["ours_ms_per_call"],
+                                  "h2d_bytes_per_step": 200 * 21 * 4 * 2, "d2h_bytes_per_step": 10000 * 4},
+            "gpu_launches": 3, "roofline": {"bound": "hbm", "achieved": None, "peak": load_peaks()[0], "unit": "GB/s", "frac": None, "traffic": None},
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
 # C5: attractor analysis, 100k cells x 300-node network
 # ---------------------------------------------------------------------------------------------
 def run_c5(args, rank, world, local_rank):
@@ -839,7 +918,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS) + ["C4", "C5"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS) + ["C4", "C5", "L0"])
     ap.add_argument("--opt", action="append", default=[], help="library option, e.g. early_exit=0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
@@ -857,7 +936,9 @@ def main():
         return run_c4(args, rank, world, local_rank)
     if args.workload == "C5" and args.impl == "ours":
         return run_c5(args, rank, world, local_rank)
-    wl = WORKLOADS["C3" if args.workload in ("C4", "C5") else args.workload]
+    if args.workload == "L0" and args.impl == "ours":
+        return run_l0(args, rank, world, local_rank)
+    wl = WORKLOADS["C3" if args.workload in ("C4", "C5", "L0") else args.workload]
     if args.impl == "reference":
         run_reference(args, wl, rank)
     else:

@@ -60,7 +60,7 @@ extern "C" {
 #define SCB_OPT_WARPS        3  /* warps per CTA of the simulator kernel (0 = auto)                   */
 #define SCB_OPT_MAX_CTAS     4  /* cap on persistent CTAs (0 = SM count x occupancy)                  */
 #define SCB_OPT_WORDS        5  /* 32-bit words per lane (0 = auto: 4, 2 or 1 by node count)          */
-#define SCB_OPT_CHECK_EVERY  6  /* period-<=2 check cadence in steps (default 8)                      */
+#define SCB_OPT_CHECK_EVERY  6  /* period-<=2 check cadence in steps (default 12)                     */
 #define SCB_OPT_PERIOD_SEARCH 7 /* extra snapshot-compare steps spent looking for a tile-wide period  */
 #define SCB_OPT_SNAP_LO      8  /* bit t (t < 64): take a snapshot when computing S_t                 */
 #define SCB_OPT_SNAP_HI      9  /* bit t-64 for steps 64..98 (default: snapshots at 36 and 66)        */

@@ -4,7 +4,7 @@ T=$1; shift
 i=0
 for V in "$@"; do
   i=$((i+1))
-  timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline $V > gpurun_out/${T}_s$i.json 2> gpurun_out/${T}_s$i.err; rc=$?
+  timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-cases $V > gpurun_out/${T}_s$i.json 2> gpurun_out/${T}_s$i.err; rc=$?
   python - "$T" "$i" "$V" "$rc" <<'PY'
 import json,sys
 T,i,V,rc=sys.argv[1:5]

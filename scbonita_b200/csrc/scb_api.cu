@@ -77,7 +77,7 @@ struct scb_ctx {
     size_t smemLimit = 0;
     int N = 0, C = 0, W = 0, Wpad = 0;
     /* options */
-    int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 8, optSearch = 0, optMinGap = 8;
+    int optEarly = 1, optSnap = 1, optWarps = 0, optMaxCtas = 0, optWords = 0, optChk = 12, optSearch = 0, optMinGap = 8;
     int optTmem = 1, optFuse = 1, optTma = 1, optSteady = 1, optChkFrom = SCB_NPROG - 2, optGraph = 1;
     unsigned long long optVersion = 0;   /* bumped by every scb_ctx_set_option */
     unsigned long long snapLo = (1ull << 36), snapHi = (1ull << 2);   /* snapshots when computing S_36 and S_66 */
