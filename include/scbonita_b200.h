@@ -243,6 +243,18 @@ int scb_attractors(scb_ctx *ctx, const int32_t *individual, int indLen,
                    const int32_t *knockouts, const int32_t *knockins, int semantics,
                    int maxStates, int32_t *res, int32_t *nStates, uint32_t *states);
 
+/* The distinct attractor states of all cells, in first-seen order (cell-major, then state order), deduplicated on
+ * the device: what assignAttractors collects in a Python set (singleCell.py:1189-1207).  unique[min(*nUnique, cap)]
+ * [ceil(N/32)] packed like `states` above; *nUnique is the true count (call again with a larger cap if it exceeds cap). */
+int scb_attractor_states(scb_ctx *ctx, const int32_t *individual, int indLen,
+                         const int32_t *andLenList, const int32_t *individualParse,
+                         const int32_t *andNodes, const int32_t *andNodeInvertList,
+                         const int32_t *knockouts, const int32_t *knockins, int semantics,
+                         int maxStates, uint32_t *unique, int cap, int *nUnique);
+/* scb_hamming_argmin on attractors already packed that way ([nAttr][ceil(N/32)], bits beyond N zero) */
+int scb_hamming_argmin_packed(scb_ctx *ctx, const uint32_t *attractors, int nAttr, int32_t *dist,
+                              int32_t *decider, int32_t *deciderDistance);
+
 /* ---- importance score of one knock-out / knock-in pair (ruleMaker.__calcImportance calls the C function
  * importanceScore 3 x N times per network, ruleMaker.py:1268-1412): same arithmetic as simulator.c:555-755
  * on the context's packed matrix.  Fails with SCB_ERR_INVALID (score = NaN) when a cell has no attractor

@@ -27,7 +27,7 @@ SYMBOLS = (
     "scb_pop_costs", "scb_pop_set_order", "scb_pop_update", "scb_gather_init", "scb_gather_connect", "scb_gather_result", "scb_gather_close",
     "scb_ctx_stream", "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms",
     "scb_ctx_flush_l2", "scb_host_alloc", "scb_host_free",
-    "scb_eval_local_search", "scb_eval_local_search_all", "scb_hamming_argmin", "scb_attractors", "scb_importance_score",
+    "scb_eval_local_search", "scb_eval_local_search_all", "scb_hamming_argmin", "scb_attractors", "scb_attractor_states", "scb_hamming_argmin_packed", "scb_importance_score",
     "scb_importance_scores", "scb_microbench", "scb_debug_programs",
     "scb_set_legacy_geometry", "scSyncBool", "importanceScore", "cluster",
 )
@@ -110,6 +110,8 @@ def load(path=None):
                                               ctypes.c_int, i32p]
     lib.scb_eval_local_search_all.restype = ctypes.c_int
     lib.scb_hamming_argmin.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p]
+    lib.scb_hamming_argmin_packed.argtypes = [vp, vp, ctypes.c_int, i32p, i32p, i32p]
+    lib.scb_attractor_states.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     lib.scb_attractors.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, ctypes.c_int,
                                    ctypes.c_int, i32p, i32p, vp]
     lib.scb_importance_score.argtypes = [vp, i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p, vp]
@@ -126,7 +128,7 @@ def load(path=None):
                  "scb_pop_upload", "scb_pop_run", "scb_pop_fetch", "scb_pop_result_dev", "scb_ctx_stream",
                  "scb_ctx_sync", "scb_ctx_event_record", "scb_ctx_event_elapsed_ms", "scb_ctx_flush_l2", "scb_host_alloc",
                  "scb_host_free", "scb_eval_local_search",
-                 "scb_hamming_argmin", "scb_attractors"):
+                 "scb_hamming_argmin", "scb_attractors", "scb_attractor_states", "scb_hamming_argmin_packed"):
         getattr(lib, name).restype = ctypes.c_int
     _libs[path] = lib
     return lib

@@ -133,7 +133,8 @@ struct scb_ctx {
     unsigned int *gFlags = nullptr;      /* own flag array [world], then generation counter, then timeout flag */
     unsigned long long *gPeerBuf[SCB_MAX_PEERS] = {};
     unsigned int *gPeerFlag[SCB_MAX_PEERS] = {};
-    DevBuf<uint32_t> dTraj, dStates, dRecBits;
+    DevBuf<uint32_t> dTraj, dStates, dRecBits, dDedupeTable, dDedupeOut;
+    DevBuf<unsigned char> dDedupeFlags;
     DevBuf<unsigned char> dRecOn;
     DevBuf<int32_t> dRes, dNStates;
     /* current population */
@@ -533,7 +534,7 @@ int scb_ctx_destroy(scb_ctx *c)
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
     c->dItems.release(); c->dReady.release(); c->dFillItems.release(); c->dChunkLast.release(); c->dChunkLastErr.release(); c->dChunkLastBits.release(); c->dResolveT.release(); c->dZ.release(); c->dDiag.release(); c->dAttr.release(); c->dAttrRaw.release(); c->dDist.release();
     c->dDecider.release(); c->dDeciderDist.release(); c->dFlush.release();
-    c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dRecBits.release(); c->dRecOn.release();
+    c->dDedupeTable.release(); c->dDedupeOut.release(); c->dDedupeFlags.release(); c->dTraj.release(); c->dStates.release(); c->dRes.release(); c->dNStates.release(); c->dRecBits.release(); c->dRecOn.release();
     if (c->evSim0) cudaEventDestroy(c->evSim0);
     if (c->evK0) cudaEventDestroy(c->evK0);
     if (c->evFill0) cudaEventDestroy(c->evFill0);
@@ -1386,31 +1387,14 @@ int scb_eval_local_search_all(scb_ctx *c, const int32_t *individual, int indLen,
     return SCB_OK;
 }
 
-int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t *dist, int32_t *decider,
-                       int32_t *deciderDistance)
+/* distance + decider for nAttr attractors packed in c->dAttr ([nAttr][NW4 * 4]) */
+static int hamming_run(scb_ctx *c, int nAttr, int NW4, int32_t *dist, int32_t *decider, int32_t *deciderDistance, unsigned int *badValues)
 {
-    int rc = check_ctx(c);
-    if (rc) return rc;
-    if (!attractors || nAttr <= 0 || !decider || !deciderDistance) return fail(SCB_ERR_INVALID, "bad argument");
-    const int N = c->N, C = c->C, NW = (N + 31) / 32;
-    if (NW > SCB_HAM_MAXW) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > %d for the Hamming kernel", N, SCB_HAM_MAXW * 32);
-    std::lock_guard<std::recursive_mutex> lk(c->mu);
-    /* the attractors go up as the caller holds them and are packed on the device (a host loop over 32 x the packed
-     * size was most of this call's time) */
-    int NW4 = (NW + 3) / 4;
-    NW4 = NW4 <= 4 ? NW4 : (NW4 <= 6 ? 6 : 8);          /* the kernel's instantiations; rows are zero padded to that width */
-    const int NWP = NW4 * 4;
-    if ((rc = c->dAttrRaw.ensure((size_t)nAttr * N)) || (rc = c->dAttr.ensure((size_t)nAttr * NWP)) || (rc = c->dDecider.ensure(C)) || (rc = c->dDeciderDist.ensure(C))) return rc;
+    int rc;
+    const int N = c->N, C = c->C;
+    if ((rc = c->dDecider.ensure(C)) || (rc = c->dDeciderDist.ensure(C))) return rc;
     if (dist && (rc = c->dDist.ensure((size_t)C * nAttr))) return rc;
     cudaStream_t st = c->stream;
-    CK(cudaMemcpyAsync(c->dAttrRaw.p, attractors, (size_t)nAttr * N * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(c->dCounters.p + 10, 0, sizeof(unsigned int), st));
-    {
-        const long long warps = (long long)nAttr * NWP;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((warps + 7) / 8, (long long)c->numSM * 16));
-        SCB_LAUNCH(scb_k_pack_attr, dim3(grid), dim3(256), 0, st, (const int32_t *)c->dAttrRaw.p, c->dAttr.p, nAttr, N, NWP, c->dCounters.p + 10);
-        CK(cudaGetLastError());
-    }
     ScbHammingArgs ha;
     ha.X = c->dX.p; ha.N = N; ha.C = C; ha.Wpad = c->Wpad; ha.A = nAttr; ha.attr = c->dAttr.p;
     ha.dist = dist ? c->dDist.p : nullptr; ha.decider = c->dDecider.p; ha.deciderDistance = c->dDeciderDist.p;
@@ -1425,14 +1409,66 @@ int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t
         default: SCB_LAUNCH(scb_k_hamming<8>, hgrid, dim3(nthr), SCB_HAM_SMEM_WORDS * 4, st, ha); break;
     }
     CK(cudaGetLastError());
-    unsigned int badValues = 0;
-    CK(cudaMemcpyAsync(&badValues, c->dCounters.p + 10, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    if (badValues) CK(cudaMemcpyAsync(badValues, c->dCounters.p + 10, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     if (dist) CK(cudaMemcpyAsync(dist, c->dDist.p, (size_t)C * nAttr * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(decider, c->dDecider.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(deciderDistance, c->dDeciderDist.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return SCB_OK;
+}
+
+static int hamming_width(int NW)
+{
+    const int NW4 = (NW + 3) / 4;
+    return NW4 <= 4 ? NW4 : (NW4 <= 6 ? 6 : 8);           /* the kernel's instantiations; rows are zero padded to that width */
+}
+
+int scb_hamming_argmin(scb_ctx *c, const int32_t *attractors, int nAttr, int32_t *dist, int32_t *decider,
+                       int32_t *deciderDistance)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!attractors || nAttr <= 0 || !decider || !deciderDistance) return fail(SCB_ERR_INVALID, "bad argument");
+    const int N = c->N, NW = (N + 31) / 32;
+    if (NW > SCB_HAM_MAXW) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > %d for the Hamming kernel", N, SCB_HAM_MAXW * 32);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    /* the attractors go up as the caller holds them and are packed on the device (a host loop over 32 x the packed
+     * size was most of this call's time) */
+    const int NW4 = hamming_width(NW), NWP = NW4 * 4;
+    if ((rc = c->dAttrRaw.ensure((size_t)nAttr * N)) || (rc = c->dAttr.ensure((size_t)nAttr * NWP))) return rc;
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(c->dAttrRaw.p, attractors, (size_t)nAttr * N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->dCounters.p + 10, 0, sizeof(unsigned int), st));
+    {
+        const long long warps = (long long)nAttr * NWP;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((warps + 7) / 8, (long long)c->numSM * 16));
+        SCB_LAUNCH(scb_k_pack_attr, dim3(grid), dim3(256), 0, st, (const int32_t *)c->dAttrRaw.p, c->dAttr.p, nAttr, N, NWP, c->dCounters.p + 10);
+        CK(cudaGetLastError());
+    }
+    unsigned int badValues = 0;
+    if ((rc = hamming_run(c, nAttr, NW4, dist, decider, deciderDistance, &badValues))) return rc;
     if (badValues) return fail(SCB_ERR_INVALID, "%u attractor entries are not 0/1", badValues);
     return SCB_OK;
+}
+
+int scb_hamming_argmin_packed(scb_ctx *c, const uint32_t *attractors, int nAttr, int32_t *dist, int32_t *decider,
+                              int32_t *deciderDistance)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!attractors || nAttr <= 0 || !decider || !deciderDistance) return fail(SCB_ERR_INVALID, "bad argument");
+    const int N = c->N, NW = (N + 31) / 32;
+    if (NW > SCB_HAM_MAXW) return fail(SCB_ERR_UNSUPPORTED, "nodeNum %d > %d for the Hamming kernel", N, SCB_HAM_MAXW * 32);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    const int NW4 = hamming_width(NW), NWP = NW4 * 4;
+    if ((rc = c->dAttr.ensure((size_t)nAttr * NWP))) return rc;
+    cudaStream_t st = c->stream;
+    if (NWP == NW) CK(cudaMemcpyAsync(c->dAttr.p, attractors, (size_t)nAttr * NW * 4, cudaMemcpyHostToDevice, st));
+    else {
+        CK(cudaMemsetAsync(c->dAttr.p, 0, (size_t)nAttr * NWP * 4, st));
+        CK(cudaMemcpy2DAsync(c->dAttr.p, (size_t)NWP * 4, attractors, (size_t)NW * 4, (size_t)NW * 4, (size_t)nAttr, cudaMemcpyHostToDevice, st));
+    }
+    return hamming_run(c, nAttr, NW4, dist, decider, deciderDistance, nullptr);
 }
 
 }  /* extern "C" */

@@ -2445,6 +2445,81 @@ __global__ void scb_k_window(ScbWindowArgs A)
  * ---------------------------------------------------------------------------------------- */
 #define SCB_HAM_MAXW 32            /* N <= 1024 */
 #define SCB_HAM_SMEM_WORDS 8192    /* 32 KB of attractor words per pass */
+/* ---- unique attractor states (singleCell.py:1189-1207 collects them in a Python set) ------------------------------
+ * A hash table of row indices: every valid row finds the slot of its state (linear probing; a slot is claimed once and
+ * then only lowered to the smallest row index with that state), a second pass flags the rows that are their state's
+ * first occurrence, a one-CTA pass writes those states out in row order (= first-seen order). */
+SCB_DEV unsigned scb_row_hash(const uint32_t *k, int NW)
+{
+    unsigned h = 2166136261u;
+    for (int w = 0; w < NW; ++w) { h ^= k[w]; h *= 16777619u; h ^= h >> 15; }
+    return h;
+}
+SCB_DEV bool scb_row_valid(const ScbDedupeArgs &A, long long r)
+{
+    const int c = (int)(r / A.maxStates), s = (int)(r % A.maxStates);
+    const int n = A.nStates[c] < A.maxStates ? A.nStates[c] : A.maxStates;
+    return s < n;
+}
+SCB_DEV bool scb_row_equal(const uint32_t *a, const uint32_t *b, int NW)
+{
+    for (int w = 0; w < NW; ++w) if (a[w] != b[w]) return false;
+    return true;
+}
+__global__ void scb_k_dedupe_insert(ScbDedupeArgs A)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (long long)A.C * A.maxStates || !scb_row_valid(A, r)) return;
+    const uint32_t *key = A.states + r * A.NW;
+    unsigned slot = scb_row_hash(key, A.NW) & A.mask;
+    for (;;) {
+        unsigned cur = scb_ld_volatile(&A.table[slot]);
+        if (cur == 0xffffffffu) {
+            const unsigned prev = atomicCAS(&A.table[slot], 0xffffffffu, (unsigned)r);
+            if (prev == 0xffffffffu) return;
+            cur = prev;
+        }
+        if (scb_row_equal(A.states + (long long)cur * A.NW, key, A.NW)) { atomicMin(&A.table[slot], (unsigned)r); return; }
+        slot = (slot + 1u) & A.mask;
+    }
+}
+__global__ void scb_k_dedupe_flag(ScbDedupeArgs A)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (long long)A.C * A.maxStates || !scb_row_valid(A, r)) return;
+    const uint32_t *key = A.states + r * A.NW;
+    unsigned slot = scb_row_hash(key, A.NW) & A.mask;
+    for (;;) {
+        const unsigned cur = A.table[slot];
+        if (scb_row_equal(A.states + (long long)cur * A.NW, key, A.NW)) { A.flags[r] = cur == (unsigned)r ? 1 : 0; return; }
+        slot = (slot + 1u) & A.mask;
+    }
+}
+__global__ void scb_k_dedupe_compact(ScbDedupeArgs A)
+{
+    SCB_DYN_SMEM(smraw);                                  /* blockDim.x + 1 unsigned */
+    unsigned *pre = reinterpret_cast<unsigned *>(smraw);
+    const long long rows = (long long)A.C * A.maxStates;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const long long seg = (rows + nthr - 1) / nthr, lo = seg * tid, hi = lo + seg < rows ? lo + seg : rows;
+    unsigned n = 0;
+    for (long long r = lo; r < hi; ++r) n += A.flags[r];
+    pre[tid + 1] = n;
+    __syncthreads();
+    if (tid == 0) {
+        pre[0] = 0u;
+        for (int t = 0; t < nthr; ++t) pre[t + 1] += pre[t];
+        *A.count = pre[nthr];
+    }
+    __syncthreads();
+    unsigned o = pre[tid];
+    for (long long r = lo; r < hi; ++r) {
+        if (!A.flags[r]) continue;
+        if (o < (unsigned)A.cap) for (int w = 0; w < A.NW; ++w) A.out[(long long)o * A.NW + w] = A.states[r * A.NW + w];
+        ++o;
+    }
+}
+
 /* attractors as the caller holds them (int32 0/1 per node) -> bit rows of NW4 * 4 words, padded with zeros: one warp
  * per output word, a ballot per 32 values; anything but 0/1 is counted in *bad */
 __global__ void scb_k_pack_attr(const int32_t *raw, uint32_t *packed, int nAttr, int N, int NWP, unsigned int *bad)

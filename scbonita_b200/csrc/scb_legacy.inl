@@ -260,6 +260,57 @@ int scb_attractors(scb_ctx *c, const int32_t *individual, int indLen, const int3
     return check_compile_diag(c);
 }
 
+int scb_attractor_states(scb_ctx *c, const int32_t *individual, int indLen, const int32_t *andLenList,
+                         const int32_t *individualParse, const int32_t *andNodes, const int32_t *andNodeInvertList,
+                         const int32_t *knockouts, const int32_t *knockins, int semantics, int maxStates,
+                         uint32_t *unique, int cap, int *nUnique)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (semantics != 0 && semantics != 1) return fail(SCB_ERR_INVALID, "semantics must be 0 (C cluster) or 1 (Python __cluster)");
+    if (maxStates <= 0 || cap < 0 || !nUnique || (cap > 0 && !unique)) return fail(SCB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    rc = scb_pop_upload(c, 1, individual, indLen, andLenList, individualParse, andNodes, andNodeInvertList, 0, knockouts, knockins);
+    if (rc) return rc;
+    const int N = c->N, NW = (N + 31) / 32;
+    std::vector<unsigned char> recOn;
+    std::vector<uint32_t> recBits;
+    if (semantics == 1) {
+        const int al = andLenList[N - 1];                   /* singleCell.py:1037-1038, as in scb_attractors */
+        if (knockouts[N - 1] != 1 && knockins[N - 1] != 1 && al != 1 && al != 0) {
+            recOn.assign((size_t)N, 0); recBits.assign((size_t)N * 4, 0u);
+            recOn[N - 1] = 1;
+        }
+    }
+    rc = run_trajectories(c, semantics == 1 ? SCB_SEM_PY : SCB_SEM_C, semantics == 1 ? 10 : SCB_STEPS, maxStates,
+                          recOn.empty() ? nullptr : recOn.data(), recOn.empty() ? nullptr : recBits.data());
+    if (rc) return rc;
+    const long long rows = (long long)c->C * maxStates;
+    size_t tsize = 1024;
+    while (tsize < (size_t)rows * 2) tsize <<= 1;
+    if ((rc = c->dDedupeTable.ensure(tsize)) || (rc = c->dDedupeFlags.ensure((size_t)rows)) || (rc = c->dDedupeOut.ensure((size_t)std::max(cap, 1) * NW))) return rc;
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(c->dDedupeTable.p, 0xff, tsize * 4, st));
+    CK(cudaMemsetAsync(c->dDedupeFlags.p, 0, (size_t)rows, st));
+    ScbDedupeArgs da;
+    da.states = c->dStates.p; da.nStates = c->dNStates.p; da.C = c->C; da.maxStates = maxStates; da.NW = NW;
+    da.table = c->dDedupeTable.p; da.mask = (unsigned)(tsize - 1); da.flags = c->dDedupeFlags.p;
+    da.count = c->dCounters.p + 11; da.out = c->dDedupeOut.p; da.cap = cap;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    SCB_LAUNCH(scb_k_dedupe_insert, dim3(grid), dim3(256), 0, st, da);
+    SCB_LAUNCH(scb_k_dedupe_flag, dim3(grid), dim3(256), 0, st, da);
+    const int cthr = c->optMaxCtas > 0 ? 64 : 1024;         /* (the emulator runs a thread per CUDA thread) */
+    SCB_LAUNCH(scb_k_dedupe_compact, dim3(1), dim3((unsigned)cthr), (size_t)(cthr + 1) * 4, st, da);
+    CK(cudaGetLastError());
+    unsigned int n = 0;
+    CK(cudaMemcpyAsync(&n, c->dCounters.p + 11, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *nUnique = (int)n;
+    const size_t take = std::min<size_t>(n, (size_t)cap);
+    if (take) CK(cudaMemcpyAsync(unique, c->dDedupeOut.p, take * NW * 4, cudaMemcpyDeviceToHost, st));
+    return check_compile_diag(c);
+}
+
 /* simulator.c:487-552.  One cell (`sampleIndex`); resSubmit = attractor window; the scratch `simData[step][column]`
  * (row stride = legacy NODE) is left exactly as the reference leaves it.  That includes the slip of its knock-out
  * branch, which records a knocked node i in column i instead of column nodePositions[i] (simulator.c:518): the

@@ -225,6 +225,20 @@ struct ScbGatherArgs {
     unsigned int *timeout;               /* set when a peer did not show up */
 };
 
+/* unique attractor states on the device (scb_k_dedupe_*): rows = [C][maxStates][NW] packed states, valid where
+ * s < min(nStates[c], maxStates) */
+struct ScbDedupeArgs {
+    const uint32_t *states;
+    const int32_t *nStates;
+    int C, maxStates, NW;
+    unsigned int *table;          /* open addressing, 0xffffffff = empty, else the lowest row index seen with that state */
+    unsigned int mask;            /* table size - 1 (a power of two, >= 2 x rows) */
+    unsigned char *flags;         /* [rows] 1 = first occurrence of its state */
+    unsigned int *count;          /* number of distinct states */
+    uint32_t *out;                /* [cap][NW] distinct states in first-seen order */
+    int cap;
+};
+
 struct ScbHammingArgs {
     const uint32_t *X;            /* [N][Wpad] */
     int N, C, Wpad, A;

@@ -441,34 +441,54 @@ class Simulator:
         bits = np.unpackbits(packed.view(np.uint8), axis=-1, bitorder="little")[..., :self.model.n]
         return res, nst, bits
 
-    def attractor_set(self, individual, knockouts=None, knockins=None, remove_zero=True):
+    def attractor_set(self, individual, knockouts=None, knockins=None, remove_zero=True, packed=False):
         """The unique attractor states of all cells, as assignAttractors collects them
-        (singleCell.py:1189-1207), in first-seen order (the reference's order is Python set order).  The states
-        are deduplicated as packed words (one sort of the [cells x states] rows), only the unique ones are unpacked."""
-        n = self.model.n
-        _, nst, packed = self._attractors_packed(individual, knockouts, knockins, "python", 10)
-        nw = packed.shape[2]
-        rows = packed[np.arange(packed.shape[1])[None, :] < np.minimum(nst, 10)[:, None]]       # cell-major, then state order
-        if rows.shape[0] == 0:
-            return np.zeros((0, n), dtype=np.int32)
-        keys = np.ascontiguousarray(rows).view(np.dtype((np.void, nw * 4))).ravel()
-        _, first = np.unique(keys, return_index=True)
-        uniq = rows[np.sort(first)]
-        out = np.unpackbits(uniq.view(np.uint8), axis=-1, bitorder="little")[:, :n].astype(np.int32)
+        (singleCell.py:1189-1207), in first-seen order (the reference's order is Python set order).  Deduplicated on
+        the device (scb_attractor_states); ``packed=True`` returns the bit rows uint32[A][ceil(N/32)] as
+        :meth:`hamming_argmin` also accepts them, else 0/1 int32[A][N]."""
+        m = self.model
+        n = m.n
+        ind = _i32(individual)
+        ko = _i32(knockouts if knockouts is not None else np.zeros(n))
+        ki = _i32(knockins if knockins is not None else np.zeros(n))
+        nw = (n + 31) // 32
+        cap = 1 << 14
+        while True:
+            uniq = np.zeros((cap, nw), dtype=np.uint32)
+            cnt = ctypes.c_int(0)
+            rc = self.lib.scb_attractor_states(self._ctx, _ptr(ind), m.ind_len, _ptr(m.and_len_list), _ptr(m.individual_parse),
+                                               _ptr(m.and_nodes), _ptr(m.and_node_invert_list), _ptr(ko), _ptr(ki), 1, 10,
+                                               _ptr(uniq), cap, ctypes.byref(cnt))
+            _lib.check(self.lib, rc)
+            if cnt.value <= cap:
+                break
+            cap = cnt.value
+        uniq = uniq[:cnt.value]
         if remove_zero:
-            out = out[out.sum(axis=1) > 0]
+            uniq = uniq[uniq.any(axis=1)]
+        if packed:
+            return np.ascontiguousarray(uniq)
+        if uniq.shape[0] == 0:
+            return np.zeros((0, n), dtype=np.int32)
+        out = np.unpackbits(np.ascontiguousarray(uniq).view(np.uint8), axis=-1, bitorder="little")[:, :n].astype(np.int32)
         return np.ascontiguousarray(out).reshape(-1, n)
 
     def hamming_argmin(self, attractors, want_dist=True):
-        """singleCell.py:1211-1238: returns (dist[C][A] or None, decider[C], deciderDistance[C])."""
-        at = _i32(attractors)
-        if at.ndim != 2 or at.shape[1] != self.model.n:
+        """singleCell.py:1211-1238: returns (dist[C][A] or None, decider[C], deciderDistance[C]).  ``attractors``:
+        0/1 values [A][nodeNum], or (dtype uint32) bit rows [A][ceil(nodeNum/32)] as ``attractor_set(packed=True)``
+        returns them."""
+        raw = np.asarray(attractors)
+        nw = (self.model.n + 31) // 32
+        is_packed = raw.dtype == np.uint32 and raw.ndim == 2 and raw.shape[1] == nw and nw != self.model.n
+        at = np.ascontiguousarray(raw) if is_packed else _i32(raw)
+        if at.ndim != 2 or at.shape[1] != (nw if is_packed else self.model.n):
             raise ValueError("attractors must be [A][nodeNum]")
         A = at.shape[0]
         dist = np.zeros((self.n_cells, A), dtype=np.int32) if want_dist else None
         dec = np.zeros(self.n_cells, dtype=np.int32)
         dd = np.zeros(self.n_cells, dtype=np.int32)
-        rc = self.lib.scb_hamming_argmin(self._ctx, _ptr(at), A, _ptr(dist), _ptr(dec), _ptr(dd))
+        fn = self.lib.scb_hamming_argmin_packed if is_packed else self.lib.scb_hamming_argmin
+        rc = fn(self._ctx, _ptr(at), A, _ptr(dist), _ptr(dec), _ptr(dd))
         _lib.check(self.lib, rc)
         return dist, dec, dd
 
