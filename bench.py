@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- GA-generation throughput of the rule-inference fitness hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C3|C2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C3|C2|C4|C5|L0]
+                    [--scaling strong|weak] [--gather peer|nccl] [--no-order] [--no-cases] [--opt key=value ...]
 
-A "step" is one GA generation: every individual of the population scored against every cell
-(rule compilation K0 + simulator K2 + resolver K3, plus the fitness all-gather when N > 1).
-Workload C3 = BASELINE.json configs[2], the configuration the north-star target is quoted on:
-synthetic 50 000 cells x 200-node KEGG-shaped network, population 500 (per GPU: the population is
-sharded across ranks, every rank holds the packed matrix; weak scaling).  Unit: cell-rule
-evaluations (CRE) = cells x nodes x 99 synchronous steps per individual.
+A "step" is one GA generation: every individual of the population scored against every cell (one CUDA graph per rank:
+rule compilation K0 + simulator K2 with the resolver inside + fill-forward, plus the fitness exchange when N > 1).
+Workload C3 = BASELINE.json configs[2], the configuration the north-star target is quoted on: synthetic 50 000 cells x
+200-node KEGG-shaped network, population 500.  With N > 1 the population stays 500 (strong scaling, the default: the
+individuals are dealt to the ranks by measured cost, every rank holds the packed matrix, the gathered fitness vector is
+checked against a single-GPU evaluation); `--scaling weak` gives every rank its own 500.  Unit: cell-rule evaluations
+(CRE) = cells x nodes x 99 synchronous steps per individual.
 
-One JSON line on stdout (rank 0).  `value` times device-resident inputs with CUDA events on the
-library's stream, L2 flushed between steps; `e2e` times the public host-buffer API (pinned host
-tables -> H2D -> kernels -> D2H fitness).  `--impl reference` times the UNMODIFIED reference C
-(oracle/_ref, built from /root/reference in the build container) on all host cores.
+One JSON line on stdout (rank 0).  `value` times device-resident inputs with CUDA events on the library's stream, L2
+flushed between steps, max over ranks per step; `e2e` times the public host-buffer API (pinned host tables -> H2D ->
+kernels -> D2H fitness); `e2e_compact` / `e2e_resident` the same generation handed over as upstream triples / as an
+in-place replacement of half the population.  `robustness` repeats the generation on other network seeds, without
+knock-outs, with a fresh population every step and on an adversarial network.  `--impl reference` times the UNMODIFIED
+reference C (oracle/_ref, built from /root/reference in the build container) on all host cores.
+Other workloads: C2 (small configuration), C4 (independent pathways over the GPUs), C5 (attractor analysis),
+L0 (per-call cost of the exported legacy symbol).
 """
 import argparse
 import json
@@ -562,7 +568,7 @@ def run_ours(args, wl, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": args.scaling if world > 1 else "weak",
+            "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl["name"], "population_global": Pglobal if (strong or world == 1) else world * P,
                        "population_per_gpu": P, "cells": C, "nodes": N,

@@ -116,6 +116,7 @@ struct scb_ctx {
     /* the general simulator (scb_k_generic): the only path when the state does not fit shared memory, the second pass of
      * a population that holds rules over more than three distinct inputs, or on request (SCB_OPT_GENERIC) */
     bool genericOnly = false, optGeneric = false, lastGeneric = false;
+    int optResGroup = 0;
     int lastSem = 0;
     DevBuf<uint32_t> dGScratch;
     bool delta = false;
@@ -261,9 +262,12 @@ int pick_geometry(scb_ctx *c)
      * adjacent chunks (one for K = 1 or when three 64-word buffers do not fit) with three shared-memory buffers */
     c->resGroup = (K >= 2 && scb_resolve_smem_bytes(N, 2) <= c->smemLimit) ? 2 : 1;
     c->smemRes = scb_resolve_smem_bytes(N, c->resGroup);
-    if (c->optFuse && c->main.tmemCols > 0) {
+    if (c->optFuse && c->main.tmemCols > 0 && c->optResGroup == 0) {
         c->resGroup = K;
         c->smemRes = scb_resolve_smem_bytes(N, K, true, c->main.warps);
+    } else if (c->optResGroup && c->optResGroup <= K && scb_resolve_smem_bytes(N, c->optResGroup) <= c->smemLimit) {
+        c->resGroup = c->optResGroup;
+        c->smemRes = scb_resolve_smem_bytes(N, c->resGroup);
     }
     int occR = 1;
     c->resWarps = std::min(c->resGroup == 2 ? 24 : 16, std::max(c->resGroup, (N + 3) / 4));
@@ -557,6 +561,9 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
     switch (key) {
         case SCB_OPT_GRAPH: c->optGraph = value != 0; return SCB_OK;
         case SCB_OPT_GENERIC: c->optGeneric = value != 0; return SCB_OK;
+        case SCB_OPT_RESOLVE_GROUP:
+            if (value != 0 && value != 1 && value != 2) return fail(SCB_ERR_INVALID, "resolver group must be 0, 1 or 2");
+            c->optResGroup = (int)value; break;
         case SCB_OPT_EARLY_EXIT: c->optEarly = value != 0; return SCB_OK;
         case SCB_OPT_SNAPSHOTS: c->optSnap = value != 0; break;
         case SCB_OPT_CHECK_EVERY:
