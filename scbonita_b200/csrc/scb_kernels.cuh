@@ -364,12 +364,16 @@ SCB_HD inline size_t scb_smem_bytes(int N, int K, int nbuf, int S)
     return (size_t)nbuf * N * 128 * K + scb_img_entries(N, S) * 16 + (size_t)8 * 32 * K * 4 + 512;
 }
 
-/* {offset, entries} of `warp` in an image */
-SCB_DEV void scb_img_warp(const uint4 *img, int warp, int &off, int &nw)
+/* {offset, entries} of the piece `warp` of S executes.  Pieces are consecutive stretches of the table-sorted list, so
+ * neighbouring pieces run the same specialised loops; the four warps of a scheduler (warp % 4) take four NEIGHBOURING
+ * pieces, so that a scheduler's small instruction cache sees few different loops (measured on the trace build: with
+ * piece = warp, warps with identical static work differed by 60 % in time). */
+SCB_DEV void scb_img_warp(const uint4 *img, int warp, int S, int &off, int &nw)
 {
-    const uint4 h = img[1 + (warp >> 1)];
-    off = (int)((warp & 1) ? h.z : h.x);
-    nw = (int)((warp & 1) ? h.w : h.y);
+    const int piece = (S & 3) ? warp : (warp & 3) * (S >> 2) + (warp >> 2);
+    const uint4 h = img[1 + (piece >> 1)];
+    off = (int)((piece & 1) ? h.z : h.x);
+    nw = (int)((piece & 1) ? h.w : h.y);
 }
 
 /* table-sorted program g (fields of scb_scatter_by_table) -> image for S warps and rows of ROWB bytes, in global or
@@ -1121,8 +1125,10 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 scb_backoff();
             }
             sh[12] = tileItem; sh[15] = resItem; sh[13] = done;
-            /* the next ticket is requested now and looked at when this piece of work is over */
-            if (tileItem >= 0 && pending < 0) pending = (int)atomicAdd(A.workCounter, 1u);
+            /* The next ticket is requested now and looked at when this piece of work is over -- except among the last
+             * gridDim tickets: a ticket held by a CTA that is busy with a long tile cannot be taken by one that has run
+             * dry (measured at 300 tiles on 296 CTAs: the launch ended on second tiles queued behind 98-step ones). */
+            if (tileItem >= 0 && pending < 0 && (unsigned)tileItem + gridDim.x < total) pending = (int)atomicAdd(A.workCounter, 1u);
         }
         __syncthreads();
         if (sh[13]) break;
@@ -1163,7 +1169,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         scb_cp_async_wait();
         __syncthreads();
         int nw, woff;
-        scb_img_warp(desc, warp, woff, nw);
+        scb_img_warp(desc, warp, S, woff, nw);
         scb_saddr wl = sdesc + 16u * (uint32_t)woff;
         ScbListHead hd = scb_list_head(desc + woff);
         unsigned long long fromBytes = A.useSteady ? *reinterpret_cast<const unsigned long long *>(A.progFrom + (long long)p * 8) : 0ull;
@@ -1268,7 +1274,7 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
                 const uint4 c4 = desc[0];
                 cnt = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
                 rowsPerStep = (unsigned)(4 * cnt.x + 3 * cnt.y + 2 * cnt.z);
-                scb_img_warp(desc, warp, woff, nw);
+                scb_img_warp(desc, warp, S, woff, nw);
                 wl = sdesc + 16u * (uint32_t)woff;
                 hd = scb_list_head(desc + woff);
                 SCB_NEXT_PROGRAM(tn);
@@ -1684,7 +1690,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
     const uint4 *gfull = A.descs + (long long)p * A.Npad;
     const int e1full = cntFull.x + cntFull.y + cntFull.z, n0full = cntFull.w;
     int woff, nw;                                                 /* this warp's list: offset, entries (run headers included) */
-    scb_img_warp(desc, warp, woff, nw);
+    scb_img_warp(desc, warp, S, woff, nw);
     const uint4 *wlp = desc + woff;
     scb_saddr wl = sdesc + 16u * (uint32_t)woff;
 
@@ -1692,7 +1698,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
         const bool cmp = pass == 1 && how != 2;
         if (replaced) {                       /* the previous pass ended on a reduced program: start again with the full one */
             cnt = scb_fetch_program<KR>(A, desc, winfo, p, 0, useImg, S, tid, nthr);
-            scb_img_warp(desc, warp, woff, nw);
+            scb_img_warp(desc, warp, S, woff, nw);
             wlp = desc + woff; wl = sdesc + 16u * (uint32_t)woff;
             replaced = false;
         }
@@ -1763,7 +1769,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
             if (tn == switchAt) {
                 /* every warp is past the barrier that ended step tn - 1: the program can be replaced in place */
                 cnt = scb_fetch_program<KR>(A, desc, winfo, p, 1 + nextProg, useImg, S, tid, nthr);
-                scb_img_warp(desc, warp, woff, nw);
+                scb_img_warp(desc, warp, S, woff, nw);
                 wlp = desc + woff; wl = sdesc + 16u * (uint32_t)woff;
                 replaced = true;
                 if (TTM && cmp) {
@@ -2340,7 +2346,7 @@ __global__ void scb_k_traj(ScbTrajArgs A)
     scb_layout_program(desc, winfo, A.descs, cnt, N, S, 128u, tid, nthr);
     const int e1 = cnt.x + cnt.y + cnt.z;
     int woff, nw;
-    scb_img_warp(desc, warp, woff, nw);
+    scb_img_warp(desc, warp, S, woff, nw);
     const scb_saddr wl = sdesc + 16u * (uint32_t)woff;
     for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
         const int w0 = tile * 32;
