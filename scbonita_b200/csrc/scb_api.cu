@@ -1472,8 +1472,12 @@ int scb_hamming_argmin_packed(scb_ctx *c, const uint32_t *attractors, int nAttr,
     cudaStream_t st = c->stream;
     if (NWP == NW) CK(cudaMemcpyAsync(c->dAttr.p, attractors, (size_t)nAttr * NW * 4, cudaMemcpyHostToDevice, st));
     else {
-        CK(cudaMemsetAsync(c->dAttr.p, 0, (size_t)nAttr * NWP * 4, st));
-        CK(cudaMemcpy2DAsync(c->dAttr.p, (size_t)NWP * 4, attractors, (size_t)NW * 4, (size_t)NW * 4, (size_t)nAttr, cudaMemcpyHostToDevice, st));
+        /* one contiguous copy, then re-strided on the device (a pitched copy from pageable memory goes row by row) */
+        if ((rc = c->dAttrRaw.ensure((size_t)nAttr * NW))) return rc;
+        CK(cudaMemcpyAsync(c->dAttrRaw.p, attractors, (size_t)nAttr * NW * 4, cudaMemcpyHostToDevice, st));
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(((long long)nAttr * NWP + 255) / 256, (long long)c->numSM * 8));
+        SCB_LAUNCH(scb_k_restride, dim3(grid), dim3(256), 0, st, (const uint32_t *)c->dAttrRaw.p, c->dAttr.p, (long long)nAttr, NW, NWP);
+        CK(cudaGetLastError());
     }
     return hamming_run(c, nAttr, NW4, dist, decider, deciderDistance, nullptr);
 }

@@ -2543,6 +2543,16 @@ __global__ void scb_k_pack_attr(const int32_t *raw, uint32_t *packed, int nAttr,
     }
 }
 
+/* packed attractor rows of NW words -> rows of NWP >= NW words, zero padded */
+__global__ void scb_k_restride(const uint32_t *src, uint32_t *dst, long long rows, int NW, int NWP)
+{
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < rows * NWP; o += (long long)gridDim.x * blockDim.x) {
+        const long long r = o / NWP;
+        const int w = (int)(o - r * NWP);
+        dst[o] = w < NW ? src[r * NW + w] : 0u;
+    }
+}
+
 /* NW4 = 16-byte groups per state (N <= 128 * NW4): the cell's state lives in registers, the attractors of a pass are
  * read from shared memory as broadcast 16-byte loads; per 32 node bits one XOR and one POPC (the bound: POPC issues
  * at a quarter of the LOP3 rate) */
@@ -2576,12 +2586,23 @@ __global__ void __launch_bounds__(128) scb_k_hamming(ScbHammingArgs A)
         __syncthreads();
         if (c < A.C) {
             for (int a = 0; a < na; ++a) {
+                /* Hamming weight of NWP words with carry-save adders (Harley-Seal): three words -> a sum word and a
+                 * carry word with two LOP3 (0x96 = a^b^c, 0xE8 = majority), so that 4 words cost 2 POPC + 2 weighted adds
+                 * less the carries deferred to the next group, instead of 4 POPC: POPC issues at a quarter of the LOP3 rate */
                 int d = 0;
+                uint32_t ones = 0u, twos = 0u;
 #pragma unroll
                 for (int g = 0; g < NW4; ++g) {
                     const uint4 t = sAttr[a * NW4 + g];
-                    d += __popc(cs[4 * g] ^ t.x) + __popc(cs[4 * g + 1] ^ t.y) + __popc(cs[4 * g + 2] ^ t.z) + __popc(cs[4 * g + 3] ^ t.w);
+                    const uint32_t x0 = cs[4 * g] ^ t.x, x1 = cs[4 * g + 1] ^ t.y, x2 = cs[4 * g + 2] ^ t.z, x3 = cs[4 * g + 3] ^ t.w;
+                    /* ones + x0 + x1 -> (ones', c0);  ones' + x2 + x3 -> (ones'', c1);  twos + c0 + c1 -> (twos', fours) */
+                    const uint32_t s0 = ones ^ x0 ^ x1, c0 = (ones & x0) | (ones & x1) | (x0 & x1);
+                    const uint32_t s1 = s0 ^ x2 ^ x3, c1 = (s0 & x2) | (s0 & x3) | (x2 & x3);
+                    const uint32_t t2 = twos ^ c0 ^ c1, fours = (twos & c0) | (twos & c1) | (c0 & c1);
+                    ones = s1; twos = t2;
+                    d += 4 * __popc(fours);
                 }
+                d += __popc(ones) + 2 * __popc(twos);
                 if (A.dist) A.dist[c * A.A + a0 + a] = d;
                 if (best < 0 || d < bestD) { best = a0 + a; bestD = d; }     /* first minimum */
             }

@@ -130,8 +130,37 @@ def test_attractor_set_then_decider(backend):
         attrs = sim.attractor_set(pr.individuals[0])
         assert {tuple(int(x) for x in a) for a in attrs} == want
         dist, dec, dd = sim.hamming_argmin(attrs)
+        # the same states in first-seen order (cell-major, then window order), deduplicated on the device
+        seen, order = set(), []
+        for c in range(400):
+            r0, r1 = wres[c]
+            for r in (range(r0, r1 + 1) if r0 >= 0 else [9]):
+                a = tuple(int(x) for x in vals[c, r])
+                if a not in seen and sum(a) > 0:
+                    seen.add(a); order.append(a)
+        assert [tuple(int(x) for x in a) for a in attrs] == order
+        # and as bit rows, which the decider takes without unpacking
+        packed = sim.attractor_set(pr.individuals[0], packed=True)
+        assert packed.dtype == np.uint32 and packed.shape == (len(order), 1)
+        _, dec_p, dd_p = sim.hamming_argmin(packed, want_dist=False)
+        assert np.array_equal(dec_p, dec) and np.array_equal(dd_p, dd)
     wd, wdec, wdd = oracle.hamming_argmin(attrs, pr.bm, pr.node_positions, 400)
     assert np.array_equal(dist, wd) and np.array_equal(dec, wdec) and np.array_equal(dd, wdd)
+
+
+def test_packed_attractors_wider_than_one_group(backend):
+    """150 nodes = 5 words per state, padded to 8 on the device (the instantiated widths are 4, 8, 12, 16, 24, 32)."""
+    pr = Problem.synthetic(150, 300, 1, knock=False)
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_an[0], pr.pop_ai[0], pr.node_positions, pr.net.ind_len)
+    with simulator.Simulator(pr.bm, model, lib_path=backend[1]) as sim:
+        attrs = sim.attractor_set(pr.individuals[0])
+        packed = sim.attractor_set(pr.individuals[0], packed=True)
+        assert packed.shape == (attrs.shape[0], 5)
+        _, dec, dd = sim.hamming_argmin(attrs, want_dist=False)
+        _, dec_p, dd_p = sim.hamming_argmin(packed, want_dist=False)
+        assert np.array_equal(dec_p, dec) and np.array_equal(dd_p, dd)
+    _, wdec, wdd = oracle.hamming_argmin(attrs, pr.bm, pr.node_positions, 300, want_dist=False)
+    assert np.array_equal(dec, wdec) and np.array_equal(dd, wdd)
 
 
 @pytest.mark.parametrize("n,cells,seed", [(12, 30, None), (20, 200, 4242), (9, 64, 99)])
@@ -236,6 +265,8 @@ def test_importance_scores_distinct_knockin_arrays(backend):
 
 @pytest.mark.parametrize("rings,cells", [([40, 5], 1300), ([60, 7], 700)])
 def test_importance_scores_long_cycles(backend, rings, cells):
+    if backend[0] == "emu":
+        cells = 200 if cells > 1000 else 90            # one chunk under the host-thread emulator: same code paths, a tenth of the time
     """Rings of period 80 (found only by the exact resolver: window length 80 adds (int)(state / 80) = 0) and of
     period 120 (no attractor window in 100 rows: the reference divides by zero -> NaN for the items that leave
     the ring alive, exact scores for the items that knock it)."""

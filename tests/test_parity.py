@@ -280,7 +280,7 @@ def test_evaluate_by_node_mirrors_reference_returns(backend):
 
 
 def test_check_node_possibilities(backend):
-    pr = Problem.synthetic(big(backend, 10, 25), big(backend, 200, 4000), 1)
+    pr = Problem.synthetic(big(backend, 8, 25), big(backend, 100, 4000), 1)
     pr.pop_an = pr.pop_ai = None
     m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
     with pr.simulator(backend[1]) as sim:
@@ -303,7 +303,7 @@ def test_check_node_possibilities(backend):
 
 
 def test_local_search_all_nodes_in_one_launch(backend):
-    pr = Problem.synthetic(big(backend, 10, 25), big(backend, 200, 4000), 1)
+    pr = Problem.synthetic(big(backend, 8, 25), big(backend, 100, 4000), 1)
     pr.pop_an = pr.pop_ai = None
     with pr.simulator(backend[1]) as sim:
         every = sim.local_search(pr.individuals[0].tolist(), [0] * pr.n, [0] * pr.n)
@@ -428,9 +428,9 @@ def test_network_too_large_for_on_chip_state_uses_the_general_simulator(backend)
     """N beyond the shared-memory state buffers (the reference allows NODE = 20000): populations are scored by the
     general simulator, state in global memory; the other entry points refuse."""
     rng = np.random.default_rng(2)
-    n = 900 if backend[0] == "emu" else 1500
+    n = 800 if backend[0] == "emu" else 1500
     net = _random_tables(rng, n, weird_flags=False)
-    rows = (rng.random((n, 200)) < 0.5).astype(np.uint8)
+    rows = (rng.random((n, 70 if backend[0] == "emu" else 200)) < 0.5).astype(np.uint8)
     inds = (rng.random((2, net.ind_len)) < 0.7).astype(np.int32)
     pr = Problem(net, rows, np.arange(n, dtype=np.int32), inds)
     with pr.simulator(backend[1]) as sim:
