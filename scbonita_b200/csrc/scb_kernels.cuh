@@ -2126,7 +2126,7 @@ SCB_DEV uint32_t scb_generic_node(const ScbGenericArgs &G, int p, int i, const u
     return v;
 }
 
-#define SCB_GENERIC_SMEM (32 * 4 * 4 + 8 * 4 + 1024 * 2)
+#define SCB_GENERIC_SMEM (32 * 4 * 4 + 8 * 4 + 1024 * 2 + 1024 * 2)
 __global__ void __launch_bounds__(256) scb_k_generic(ScbGenericArgs G)
 {
     SCB_DYN_SMEM(smraw);                                 /* SCB_GENERIC_SMEM bytes */
@@ -2134,6 +2134,7 @@ __global__ void __launch_bounds__(256) scb_k_generic(ScbGenericArgs G)
     uint32_t (*acc)[32] = reinterpret_cast<uint32_t (*)[32]>(vm + 32);
     int *sh = reinterpret_cast<int *>(vm + 96);
     short *srcc = reinterpret_cast<short *>(sh + 8);
+    short *jst = srcc + 1024;                            /* per cell: the largest t < 99 with S_t == S_99 = start of its attractor window */
     const int N = G.N;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, S = nthr >> 5;
     uint32_t *bA = G.scratch + (size_t)blockIdx.x * 3 * (size_t)N * 32, *bT = bA + (size_t)N * 32, *bC = bT + (size_t)N * 32;
@@ -2171,7 +2172,11 @@ __global__ void __launch_bounds__(256) scb_k_generic(ScbGenericArgs G)
                 for (int row = warp; row < N; row += S) d |= cur[(size_t)row * 32 + lane] ^ bT[(size_t)row * 32 + lane];
                 if (d) atomicOr(&acc[0][lane], d);
                 __syncthreads();
-                if (tid < 32) { Fm[tid] |= ~acc[0][tid]; acc[0][tid] = 0u; }
+                if (tid < 32) {
+                    const uint32_t eq = ~acc[0][tid] & vm[tid];
+                    Fm[tid] |= eq; acc[0][tid] = 0u;
+                    for (uint32_t e = eq; e; e &= e - 1u) jst[tid * 32 + __ffs((int)e) - 1] = 0;
+                }
                 __syncthreads();
             }
             const int last = pass == 0 ? SCB_LAST : SCB_LAST - 1;
@@ -2185,7 +2190,11 @@ __global__ void __launch_bounds__(256) scb_k_generic(ScbGenericArgs G)
                 if (pass == 1 && d) atomicOr(&acc[t & 1][lane], d);
                 __syncthreads();
                 /* the accumulator of step t is folded while the other warps run step t + 1 into the other one */
-                if (pass == 1 && tid < 32) { Fm[tid] |= ~acc[t & 1][tid]; acc[t & 1][tid] = 0u; }
+                if (pass == 1 && tid < 32) {
+                    const uint32_t eq = ~acc[t & 1][tid] & vm[tid];
+                    Fm[tid] |= eq; acc[t & 1][tid] = 0u;
+                    for (uint32_t e = eq; e; e &= e - 1u) jst[tid * 32 + __ffs((int)e) - 1] = (short)t;     /* ascending t: the last one stays */
+                }
                 uint32_t *x = cur; cur = nxt; nxt = x;
             }
             /* pass 0 ends with S_99 in bT (99 is odd): the target.  Pass 1 ends with S_98 in bA (98 is even). */
@@ -2271,6 +2280,48 @@ __global__ void __launch_bounds__(256) scb_k_generic(ScbGenericArgs G)
                 atomicAdd(&G.diag->resolver_chunks, 1ull);
                 atomicAdd(&G.diag->tiles, 1ull);
                 atomicAdd(&G.diag->steps_executed, (unsigned long long)(2 * SCB_LAST - 1));
+            }
+        }
+        if (G.mode == 1 && N >= 1000) {
+            /* SURVEY Q8 (simulator.c:457-468): walking a found cell's window [j, 99) in order, the first state whose
+             * error count is a new minimum AND <= 0.001 * nodeNum adds its error vector to the per-node sums one extra
+             * time (and ends the search: minError = 0).  Below 1000 nodes the threshold is < 1, the vector is all zero
+             * and nothing happens; from 1000 nodes on it changes the sums, so a third pass replays the trajectory and
+             * does exactly that, one thread per cell. */
+            __syncthreads();
+            for (int row = warp; row < N; row += S) bA[(size_t)row * 32 + lane] = inX ? G.X[(long long)row * G.Wpad + w0 + lane] : 0u;
+            __syncthreads();
+            int mn[4];
+            bool live[4];
+            for (int k = 0; k < 4; ++k) {
+                const int cell = tid + k * nthr;
+                mn[k] = 100000;
+                live[k] = cell < 1024 && ((Fm[cell >> 5] >> (cell & 31)) & 1u);
+            }
+            uint32_t *cur = bA, *nxt = bT;
+            for (int t = 0; t <= SCB_LAST - 1; ++t) {
+                if (t > 0) {
+                    for (int row = warp; row < N; row += S) nxt[(size_t)row * 32 + lane] = scb_generic_node(G, p, row, cur, lane, flags);
+                    __syncthreads();
+                    uint32_t *x = cur; cur = nxt; nxt = x;
+                }
+                for (int k = 0; k < 4; ++k) {
+                    const int cell = tid + k * nthr;
+                    if (!live[k] || t < (int)jst[cell]) continue;
+                    const int w = cell >> 5, b = cell & 31;
+                    int tot = 0;
+                    for (int row = 0; row < N; ++row)
+                        tot += (int)(((cur[(size_t)row * 32 + w] ^ G.X[(long long)row * G.Wpad + w0 + w]) >> b) & 1u);
+                    if (tot < mn[k]) {
+                        mn[k] = tot;
+                        if ((double)tot <= 0.001 * (double)N) {
+                            mn[k] = 0; live[k] = false;
+                            for (int row = 0; row < N && tot > 0; ++row)
+                                if (((cur[(size_t)row * 32 + w] ^ G.X[(long long)row * G.Wpad + w0 + w]) >> b) & 1u) atomicAdd(&G.nodewise[(long long)p * N + row], 1);
+                        }
+                    }
+                }
+                __syncthreads();
             }
         }
     }

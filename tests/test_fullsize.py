@@ -63,6 +63,41 @@ def test_c5_decider_stage(cuda_lib):
     assert np.array_equal(dist[np.arange(len(dec)), dec], dist.min(axis=1))
 
 
+def test_c5_trajectories_windows_and_unique_states(cuda_lib):
+    """K4 at C5 size (100 000 cells x 300 nodes, Python semantics): every window and every window state against the
+    restated singleCell.__cluster, and the device-side dedupe against the first-seen order of those states."""
+    from common import oracle_model
+    C = 100_000
+    pr = Problem.synthetic(300, C, 1, knock=False)
+    model = simulator.ModelTables(pr.net.and_len, pr.net.parse, pr.pop_an[0], pr.pop_ai[0], pr.node_positions, pr.net.ind_len)
+    m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+    m.and_nodes, m.and_inv = pr.pop_an[0], pr.pop_ai[0]
+    with simulator.Simulator(pr.bm, model, lib_path=cuda_lib) as sim:
+        res, nst, bits = sim.attractors(pr.individuals[0], semantics="python", max_states=10)
+        uniq = sim.attractor_set(pr.individuals[0], remove_zero=False)
+    seen, order = set(), []
+    step = 20_000                                               # the restatement's int32 trajectory: 240 MB per slice
+    for lo in range(0, C, step):
+        vals, wres, _ = oracle.py_cluster(m, pr.individuals[0], np.ascontiguousarray(pr.bm[:, lo:lo + step]), step)
+        assert np.array_equal(res[lo:lo + step], wres)
+        first = np.where(wres[:, 0] >= 0, wres[:, 0], 9)
+        last = np.where(wres[:, 0] >= 0, wres[:, 1], 9)
+        assert np.array_equal(nst[lo:lo + step], last - first + 1)
+        for s in range(10):                                     # state s of every window that has one
+            has = first + s <= last
+            idx = np.nonzero(has)[0]
+            assert np.array_equal(bits[lo + idx, s], vals[idx, first[idx] + s].astype(np.uint8))
+        packed = np.packbits(vals.astype(np.uint8), axis=2)
+        for c in range(step):
+            for r in range(first[c], last[c] + 1):
+                k = packed[c, r].tobytes()
+                if k not in seen:
+                    seen.add(k); order.append((lo + c, r - first[c]))
+    assert uniq.shape[0] == len(order)
+    want = np.stack([bits[c, s] for c, s in order]).astype(np.int32)
+    assert np.array_equal(uniq, want)
+
+
 def test_two_gpu_sharding_nccl(cuda_lib):
     """individuals sharded over 2 ranks + NCCL all-gather (skipped on a one-GPU box; the gloo test covers the logic)."""
     import torch

@@ -749,3 +749,40 @@ def test_legacy_symbol_with_a_network_beyond_shared_memory(backend):
         assert np.array_equal(errors[:cells], o["cellwise"][0]) and errors[cells] == -1
     finally:
         lib.scb_set_legacy_geometry(20000, 15000)
+
+
+def test_q8_extra_accumulation_from_1000_nodes(backend):
+    """SURVEY Q8 (simulator.c:457-468): with nodeNum >= 1000 the threshold 0.001 * nodeNum reaches 1 and the first
+    window state with a new-minimum error count at or below it adds its error vector to the per-node sums once more.
+    A 1200-node network of self-copies with two negated copies and one self-negating node (period 2): cells with one
+    wrong node are counted twice, cells with two are not, and the order of the two window states matters."""
+    class Net:
+        pass
+    n, cells = 1200, 96
+    net = Net()
+    net.n = n
+    net.and_len = np.zeros(n, np.int32)
+    net.parse = np.zeros(n + 1, np.int32)
+    net.and_nodes = np.zeros((n, 7, 3), np.int32)
+    net.and_inv = np.zeros((n, 7, 3), np.int32)
+    net.and_nodes[:, 0, 0] = np.arange(n)                      # andLen 0: a copy of andNodes[i][0][0] = itself (Q2)
+    for node, src in ((1, 2), (3, 4), (5, 5)):                 # node <- NOT src; node 5 negates itself: period 2
+        net.and_len[node] = 1
+        net.and_nodes[node, 0] = [src, -1, -1]
+        net.and_inv[node, 0] = [1, -1, -1]
+    net.parse[:] = np.concatenate([[0], np.cumsum(net.and_len)])
+    net.ind_len = int(net.parse[n])
+    rng = np.random.default_rng(5)
+    rows = (rng.random((n, cells)) < 0.5).astype(np.uint8)
+    ind = np.ones((1, max(net.ind_len, 1)), np.int32)[:, :net.ind_len] if net.ind_len else np.zeros((1, 0), np.int32)
+    pr = Problem(net, rows, np.arange(n, dtype=np.int32), ind, ko=np.zeros(n, np.int32), ki=np.zeros(n, np.int32))
+    m = oracle_model(pr.net, pr.node_positions, pr.ko, pr.ki)
+    want, _ = oracle.sync_bool(m, pr.individuals[0], pr.bm, cells, 1)          # the scalar restatement implements Q8
+    plain = rows[1] == rows[2]
+    assert want[1] > int(plain.sum())                                           # the case really exercises the quirk
+    with pr.simulator(backend[1]) as sim:
+        got = sim.evaluate_population(pr.individuals, pr.ko, pr.ki, None, None, mode=simulator.MODE_NODEWISE)
+        assert np.array_equal(got[0], want)
+        cw = sim.evaluate_population(pr.individuals, pr.ko, pr.ki, None, None, mode=simulator.MODE_CELLWISE)
+        wc, _ = oracle.sync_bool(m, pr.individuals[0], pr.bm, cells, 0)
+        assert np.array_equal(cw[0][:cells], wc[:cells])
