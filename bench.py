@@ -73,6 +73,11 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            # nvidia-smi's own start-up (NVML initialisation takes driver locks) must not fall into the timed region:
+            # wait for its first sample
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 3.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -492,6 +497,24 @@ def run_ours(args, wl, rank, world, local_rank):
         if rank == 0 and not (all(flags) and ok_single):
             raise RuntimeError("multi-GPU fitness vector differs from the single-GPU evaluation: %s" % verify)
 
+    # ---- N > 1, strong scaling: the weak figure beside it (every rank scores its own copy of the whole population,
+    # no exchange: the reference's "one job per network" at full size on every GPU)
+    weak = None
+    if world > 1 and strong:
+        try:
+            prw, bmw = build_problem(wl)
+            gw = Generation(prw, bmw, local_rank, args.opt)
+            gw.upload(); gw.step_resident(); gw.sim.sync()
+            gw.sim.set_order(gw.sim.cost_order())
+            w_ms, _, _ = timed_steps(gw, gw.step_resident, args.steps, args.warmup, barrier)
+            w_max, _ = reduce_max(w_ms)
+            gw.sim.close()
+            weak = {"ms_per_step": float(w_max[-1]) / args.steps, "population_per_gpu": Pglobal,
+                    "value": float(world) * Pglobal * C * N * STEPS_PER_CELL / (float(w_max[-1]) / args.steps * 1e-3), "unit": UNIT,
+                    "note": "weak scaling: the full population on every GPU, no exchange; max over ranks"}
+        except Exception as exc:                      # an extra, never a reason to lose the main line
+            weak = {"error": str(exc)}
+
     # ---- roofline pass: K2 on its own (plain launches, resolver not fused, so that the duration is K2's own)
     gen.upload()
     sim.set_option(_lib.OPT_GRAPH, 0)
@@ -544,7 +567,7 @@ def run_ours(args, wl, rank, world, local_rank):
         lop_alg = per_gpu_units * 0.21875 / (k2_ms * 1e-3)
         lop_exec = stats["steps_executed"] * N * 32.0 * info["words_per_lane"] / (k2_ms * 1e-3)
         cpu, cpu1 = None, None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the reported CPU baseline is an N = 1 item (the other ranks would wait ~4 s in the final barrier)
             try:
                 prc, _ = build_problem(wl)
                 cores = min(len(os.sched_getaffinity(0)), 64)
@@ -626,6 +649,8 @@ def run_ours(args, wl, rank, world, local_rank):
                                     "h2d_bytes_per_step": int(gen.h2d_compact * half // P), "d2h_bytes_per_step": int(gen.d2h),
                                     "note": "(mu + lambda) generation on a resident population (scb_pop_update): only the "
                                             "offspring half is uploaded, compiled and simulated; value counts only those"}
+        if weak is not None:
+            line["weak_scaling"] = weak
         if costs_note:
             line["shard_balance"] = costs_note
         if verify:
