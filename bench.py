@@ -383,6 +383,13 @@ def run_ours(args, wl, rank, world, local_rank):
             import torch
             torch.cuda.synchronize()
             dist.barrier()
+            # The ranks leave an NCCL barrier up to a few hundred microseconds apart (host wake-ups), which the first
+            # timed generation's exchange would then wait out.  All ranks of a box share CLOCK_MONOTONIC: leave together.
+            t = torch.tensor([time.monotonic() + 0.003], dtype=torch.float64, device="cuda")
+            dist.broadcast(t, 0)
+            deadline = float(t.item())
+            while time.monotonic() < deadline:
+                pass
 
     # ---- the generation's exchange: fitness shards over peer memory (one kernel at the end of the graph), or NCCL
     gather_after, gather_kind, allfit = None, "none", None
@@ -607,6 +614,7 @@ def run_ours(args, wl, rank, world, local_rank):
                        "options": args.opt},
             "ga_generations_per_sec": 1e3 / ms_per_step,
             "per_step_ms": {"max_over_ranks": spread(res_max[:-1]), "min_over_ranks": spread(res_min[:-1]),
+                            "every_step_max_over_ranks": [round(float(x), 4) for x in res_max[:-1]],
                             "note": "device time of every timed generation incl. the exchange; max - min over ranks at a step = wait for the slowest rank"},
             "e2e": {"value": units_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(gen.h2d), "d2h_bytes_per_step": int(gen.d2h)},

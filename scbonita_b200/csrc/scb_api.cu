@@ -13,6 +13,7 @@
 #include "scb_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -44,15 +45,15 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 /* bumped by every (re)allocation of a device buffer: a captured generation graph holds raw pointers */
-unsigned long long g_allocEpoch = 0;
+std::atomic<unsigned long long> g_allocEpoch{0};
 
 template <class T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;            /* elements */
-    int ensure(size_t n)
+    int ensure(size_t n, bool inGraphs = true)
     {
         if (n <= cap && p) return SCB_OK;
-        ++g_allocEpoch;
+        if (inGraphs) ++g_allocEpoch;                /* (a buffer no captured graph refers to leaves the graphs valid) */
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         const size_t want = std::max<size_t>(n, 1);
@@ -843,7 +844,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
          * options, peers).  The generation's inputs change in place (uploads into the same buffers). */
         unsigned long long key = 1469598103934665603ull;
         auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
-        mix(g_allocEpoch); mix(c->optVersion); mix((unsigned long long)P); mix((unsigned long long)mode); mix((unsigned long long)sem);
+        mix(g_allocEpoch.load()); mix(c->optVersion); mix((unsigned long long)P); mix((unsigned long long)mode); mix((unsigned long long)sem);
         mix((unsigned long long)c->indLen); mix((unsigned long long)c->tpi); mix((unsigned long long)c->compact); mix((unsigned long long)c->koStride);
         mix(c->haveOrder ? 1ull : 0ull); mix(c->delta ? 1ull + (unsigned long long)c->nEval : 0ull); mix(c->gConnected ? (unsigned long long)(1 + c->gRank + 64 * c->gWorld + 4096ull * c->gWidth) : 0ull);
         if (!c->graphExec || key != c->graphKey) {
@@ -1301,7 +1302,7 @@ int scb_ctx_flush_l2(scb_ctx *c)
     int rc = check_ctx(c);
     if (rc) return rc;
     const size_t bytes = (size_t)256 << 20;              /* > 126 MB of L2 */
-    if ((rc = c->dFlush.ensure(bytes))) return rc;
+    if ((rc = c->dFlush.ensure(bytes, false))) return rc;
     CK(cudaMemsetAsync(c->dFlush.p, 0x5a, bytes, c->stream));
     return SCB_OK;
 }
