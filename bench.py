@@ -385,7 +385,7 @@ def run_ours(args, wl, rank, world, local_rank):
             dist.barrier()
             # The ranks leave an NCCL barrier up to a few hundred microseconds apart (host wake-ups), which the first
             # timed generation's exchange would then wait out.  All ranks of a box share CLOCK_MONOTONIC: leave together.
-            t = torch.tensor([time.monotonic() + 0.003], dtype=torch.float64, device="cuda")
+            t = torch.tensor([time.monotonic() + 0.02], dtype=torch.float64, device="cuda")        # generous: the first broadcast sets up channels
             dist.broadcast(t, 0)
             deadline = float(t.item())
             while time.monotonic() < deadline:

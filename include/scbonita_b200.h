@@ -187,7 +187,9 @@ int scb_pop_set_order(scb_ctx *ctx, const int32_t *order, int P);
  * (128 bytes); the caller exchanges them between the ranks (any transport; bench.py uses torch.distributed) and
  * passes all of them, in rank order, to scb_gather_connect.  From then on every scb_pop_run(ctx, SCB_MODE_SUM) ends
  * with the exchange; scb_gather_result waits and copies the gathered vector int64[world * width] (rank r's shard at
- * r * width).  All ranks must run the same number of generations. */
+ * r * width).  All ranks must run the same number of generations.  The exchange carries what the compiled path
+ * computed: scb_gather_result fails on a rank whose population needs the general simulator (rules over more than three
+ * inputs) or holds malformed rules; such populations go through scb_pop_fetch + any host-side collective. */
 int scb_gather_init(scb_ctx *ctx, int world, int rank, int width, unsigned char *handles128);
 int scb_gather_connect(scb_ctx *ctx, const unsigned char *allHandles);
 int scb_gather_result(scb_ctx *ctx, int64_t *gathered);

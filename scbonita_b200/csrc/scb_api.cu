@@ -1117,8 +1117,15 @@ int scb_gather_result(scb_ctx *c, int64_t *out)
     unsigned int tail[2] = {0u, 0u};
     CK(cudaMemcpyAsync(both.data(), c->gBuf, 2 * n * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(tail, c->gFlags + SCB_MAX_PEERS, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->hDiag, c->dDiag.p, sizeof(ScbDiag), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (tail[1]) return fail(SCB_ERR_CUDA, "a peer did not take part in the fitness exchange (timeout)");
+    /* this rank's own shard went out as K0 + K2 computed it: garbage must not pass for fitness (the other ranks' input
+     * problems are reported by their own scb_gather_result) */
+    if (c->hDiag.bad_index_nodes || c->hDiag.term_overflow_nodes)
+        return fail(SCB_ERR_INVALID, "the population of this rank holds malformed rules (input index outside [0,%d), more than 7 terms): use scb_pop_fetch for the details", c->N);
+    if (c->hDiag.unsupported_nodes)
+        return fail(SCB_ERR_UNSUPPORTED, "%llu rules of this rank's population use more than 3 distinct inputs: such populations are scored by the general simulator at scb_pop_fetch and cannot take part in the in-graph exchange", c->hDiag.unsupported_nodes);
     memcpy(out, both.data() + (size_t)(tail[0] & 1u) * n, n * 8);
     return SCB_OK;
 #endif
