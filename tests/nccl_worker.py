@@ -27,5 +27,24 @@ with simulator.Simulator(pr.bm, model, device=r) as sim:
 want = pr.oracle()["fitness"]
 assert np.array_equal(full, want), (full, want)
 assert np.array_equal(odd, want[:15]), (odd, want[:15])
+
+# the same exchange over peer memory, as the last kernel of each generation's graph (scb_gather_*): three generations,
+# so that both halves of the double-buffered gather buffers are used, with a different shard every time
+world = dist.get_world_size()
+width = 8
+with simulator.Simulator(pr.bm, model, device=r) as sim:
+    mine = torch.from_numpy(sim.gather_init(world, r, width)).cuda()
+    handles = torch.empty(world * 128, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(handles, mine)
+    sim.gather_connect(handles.cpu().numpy())
+    for g in range(3):
+        order = np.roll(np.arange(16), 5 * g)
+        sl = order[r * width:(r + 1) * width]
+        sim.upload(pr.individuals[sl], pr.ko, pr.ki, pr.pop_an[sl], pr.pop_ai[sl])
+        sim.run()
+        got = sim.gather_result()
+        assert np.array_equal(got, want[order]), (g, got, want[order])
+    dist.barrier()
+    sim.gather_close()
 dist.destroy_process_group()
 print("rank", r, "ok")
