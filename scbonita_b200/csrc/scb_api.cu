@@ -86,7 +86,7 @@ struct scb_ctx {
     int K = 0, warps = 0, ctas = 0, occ = 1;
     SimGeom main, tail;
     int mainTiles = 0, tailTiles = 0;
-    size_t smemSim = 0, smemRes = 0, smemFill = 0;
+    size_t smemSim = 0, smemRes = 0;
     int resWarps = 8, resCtas = 0, resGroup = 1, fillWarps = 8, fillCtas = 0;
     bool geomValid = false;
     /* device data */
@@ -198,7 +198,7 @@ int pick_geometry(scb_ctx *c)
         /* the state (or K0's staging) does not fit shared memory: populations are scored by the general simulator,
          * everything else (attractor analysis, importance scores) is refused by its own entry point */
         c->genericOnly = true; c->geomValid = false;
-        c->fillWarps = 8; c->smemFill = 0; c->fillCtas = 8;
+        c->fillWarps = 8; c->fillCtas = 8;
         return SCB_OK;
     }
 #ifndef SCB_EMU
@@ -210,7 +210,6 @@ int pick_geometry(scb_ctx *c)
     CK((cudaError_t)scb_sim_set_smem_k4_tm1((int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_resolve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
-    CK(cudaFuncSetAttribute(scb_k_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     CK(cudaFuncSetAttribute(scb_k_compile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemLimit));
     /* several rule-compiler CTAs per SM: without the hint the driver sizes the shared-memory carve-out for two */
     CK(cudaFuncSetAttribute(scb_k_compile, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -246,7 +245,7 @@ int pick_geometry(scb_ctx *c)
         /* the state does not fit shared memory: populations are scored by the general simulator, everything else
          * (attractor analysis, importance scores) is refused by its own entry point */
         c->genericOnly = true; c->geomValid = false;
-        c->fillWarps = 8; c->smemFill = 0; c->fillCtas = 8;
+        c->fillWarps = 8; c->fillCtas = 8;
         return SCB_OK;
     }
     c->genericOnly = false;
@@ -278,9 +277,8 @@ int pick_geometry(scb_ctx *c)
     }
     c->resCtas = c->numSM * std::max(1, occR);
     if (c->optMaxCtas > 0) c->resCtas = std::min(c->resCtas, c->optMaxCtas);
-    /* fill-forward: one warp per item, two N-word state vectors per warp */
+    /* fill-forward: one warp per item, a lookup each */
     c->fillWarps = 8;
-    c->smemFill = 0;
     c->fillCtas = 8;
     if (c->optMaxCtas > 0) c->fillCtas = std::min(c->fillCtas, c->optMaxCtas);
     size_t zwords = (size_t)c->main.ctas * N * 32 * K;
@@ -979,7 +977,7 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
     CK(cudaGetLastError());
     ra.itemCursor = c->dCounters.p + 4;
     if (!capturing) CK(cudaEventRecord(c->evFill0, st));
-    SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->fillCtas), dim3((unsigned)c->fillWarps * 32), c->smemFill, st, ra);
+    SCB_LAUNCH(scb_k_fill, dim3((unsigned)c->fillCtas), dim3((unsigned)c->fillWarps * 32), 0, st, ra);
     CK(cudaGetLastError());
     if (!capturing) CK(cudaEventRecord(c->evFill1, st));
     if (c->gConnected && mode == SCB_MODE_SUM) {

@@ -212,16 +212,4 @@ SCB_HD inline uint32_t scb_lut_apply(unsigned lut, uint32_t a, uint32_t b, uint3
     return r;
 }
 
-/* the same, branch-free (a three-level multiplexer on broadcast table bits): for code where every lane of a warp
- * applies a different table */
-SCB_HD inline uint32_t scb_lut_apply_mux(unsigned lut, uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t m[8];
-    for (int k = 0; k < 8; ++k) m[k] = 0u - ((lut >> k) & 1u);
-    uint32_t v[4];
-    for (int k = 0; k < 4; ++k) v[k] = m[2 * k] ^ (c & (m[2 * k] ^ m[2 * k + 1]));
-    const uint32_t w0 = v[0] ^ (b & (v[0] ^ v[1])), w1 = v[2] ^ (b & (v[2] ^ v[3]));
-    return w0 ^ (a & (w0 ^ w1));
-}
-
 #endif

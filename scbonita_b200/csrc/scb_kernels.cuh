@@ -1661,7 +1661,7 @@ SCB_DEV int4 scb_fetch_program(const ScbSimArgs &A, uint4 *desc, int *scr, int p
 template <int KR, bool TTM = false>
 SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *desc, int *winfo, bool useImg, int4 cnt, int p,
                                uint32_t *dmz, uint32_t *Fm, uint32_t *vm, int q, int how,
-                               const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr, int onlyLane = -1,
+                               const uint32_t *Tglob, int tid, int nthr, uint32_t *D = nullptr,
                                uint32_t tm = SCB_TMEM_OFF)
 {
     /* Like the simulator, the passes switch to K0's reduced programs as soon as each one is exact (program k from step
@@ -1677,7 +1677,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
      * so that a whole 4-chunk tile fits; the per-step fold then goes through dmz with one extra barrier. */
     /* D: [2][warps][32*KR] per-step difference words of every warp (double buffered by step parity), so that the
      * per-step "equal to T" reduction needs no atomics and no barrier of its own.
-     * onlyLane >= 0: only that lane's words are simulated (the fill-forward needs a single cell). */
+     */
     const int N = A.N;
     const uint32_t ROWB = 128u * KR, BUFB = (uint32_t)N * ROWB;
     const int GW = 32 * KR;
@@ -1794,7 +1794,7 @@ SCB_DEV void scb_resolve_chunk(const ScbSimArgs &A, unsigned char *sm, uint4 *de
             if (cmp) f |= TTM ? SCB_SF_ZCMP : SCB_SF_TCMP;
 #pragma unroll
             for (int k = 0; k < KR; ++k) { d2.v[k] = 0u; dz.v[k] = 0u; }
-            const bool act = onlyLane < 0 || lane == onlyLane;
+            const bool act = true;
             /* the constant rows of the full program (it is the one in use at steps 1, 2): they equal T's, so the
              * compare leaves them out */
             if (tn <= 2) scb_const_rows<KR>(sa + dstOff + laneOff, gfull + e1full, n0full, warp, S, nullptr);
@@ -1898,7 +1898,7 @@ SCB_DEV void scb_resolve_item(const ScbSimArgs &A, unsigned char *smraw, unsigne
         __syncthreads();
         const bool haveT = it < A.resolveTCap;
         scb_resolve_chunk<KR, TTM>(A, sm, desc, winfo, useImg, cnt, p, dmz, Fm, vm, q, haveT ? 1 : 0,
-                                   A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf, -1, tm);
+                                   A.resolveT + (unsigned long long)it * N * GW, tid, nthr, Dbuf, tm);
 
         /* source cell of every cell: itself when found, else the nearest earlier found cell of the group
          * (the reference's fill-forward), -1 when that lies in an earlier chunk, -2 padding */
