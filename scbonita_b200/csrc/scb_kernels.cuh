@@ -2,22 +2,30 @@
  * scb_kernels.cuh -- sm_100a kernels of the rule-inference fitness hot path.
  *
  *   K0  scb_k_compile    reference-format rule tables (or upstream triples) -> per-individual programs of 3-input
- *                        truth tables (scb_compile.h), sorted by arity; one CTA per individual.  Also the REDUCED
- *                        programs: constants (knocked nodes, their copies, the AND-terms they erase) propagated to
- *                        depths 2, 5, 8, 12 and to the fixed point, each exact from step depth + 2 on
+ *                        truth tables (scb_compile.h), sorted by table; one CTA per (replaced) individual.  Also the
+ *                        REDUCED programs: constants (knocked nodes, their copies, the AND-terms they erase) propagated
+ *                        to depths 2, 5, 8, 12 and to the fixed point, each exact from step depth + 2 on; and every
+ *                        program as the IMAGE the simulator's warps consume (runs of nodes with the same table, cut into
+ *                        cost-balanced pieces, one per warp)
  *   K1  scb_k_pack       int32 / uint8 binarized matrix -> node-major 32-cells-per-word S_0
  *   K1b scb_k_pack_csr   the same straight from a CSR matrix
  *   K2  scb_k_sim<K,TM>  the simulator: persistent CTAs, one (individual, cell tile) per work item, state
- *                        ping-pong in shared memory, one LOP3 per node per 32 cells reached through a brx.idx
- *                        jump table, snapshot in tensor memory (TM); the next reduced program is staged with
- *                        cp.async and replaces the current one at its first legal step; CTAs that run out of tiles
- *                        resolve queued groups in the same launch
- *   K3  scb_resolve_item / scb_k_resolve   exact second pass for the 1024-cell chunks K2 could not prove
- *                        "attractor found" for (literally getAttractCycle2 on packed words);
- *       scb_k_fill       the reference's fill-forward across chunks, one warp per item
+ *                        ping-pong in shared memory, one LOP3 per node per 32 cells inside loops specialised per truth
+ *                        table (generated PTX, one brx.idx per run), snapshot in tensor memory (TM), static schedule of
+ *                        compares / snapshots / program switches, resolver items and handed-back tiles taken from the
+ *                        same work loop
+ *   K3  scb_resolve_item / scb_k_resolve   exact second pass for the tiles K2 could not prove "attractor found" for
+ *                        (literally getAttractCycle2 on packed words), target state in tensor memory inside K2;
+ *       scb_k_fill       the reference's fill-forward across chunks: a lookup of the recorded error column
+ *                        of the nearest earlier found cell, one warp per item
+ *   KG  scb_k_generic    the general simulator: any [7][3] table, any node count, state in global memory; the path
+ *                        for input K0 / K2 cannot hold (exact, slow), incl. SURVEY Q8 from 1000 nodes on
  *   K4  scb_k_traj + scb_k_window   trajectories, attractor windows and their states (C `cluster` and Python
- *                        `__cluster` semantics)
- *   K5  scb_k_hamming    cell x attractor Hamming distance + first-minimum argmin
+ *                        `__cluster` semantics); scb_k_dedupe_*: the distinct states in first-seen order
+ *   K5  scb_k_hamming<NW4>  cell x attractor Hamming distance + first-minimum argmin (carry-save popcount);
+ *       scb_k_pack_attr / scb_k_restride  attractors into the kernel's bit rows
+ *       scb_k_gather     the generation's fitness all-gather over peer memory (last kernel of the generation's graph)
+ *       scb_k_scatter_rows  replaced individuals of a resident population into their slots
  *   importanceScore (simulator.c:555-755) has no kernel of its own: K0 compiles its single-literal rules, K2/K3 run
  *   in the SCB_MODE_IMPORTANCE output shape (per-node counts over fixed-point cells), one program per knock array
  *
@@ -27,8 +35,8 @@
  * S_t == S_j (j < t <= 99), which implies transient + period <= 99; cells without such a proof go to K3.
  *
  * Data layout in shared memory (per CTA): two state buffers [N][32*K] uint32 (row = node, lane l owns words
- * l*K .. l*K+K-1, so every access is a conflict-free LDS/STS.(32*K)), followed by the CTA's program (uint4 per
- * node) and a few 32*K-word masks.
+ * l*K .. l*K+K-1, so every access is a conflict-free LDS/STS.(32*K)), followed by one program image and a few
+ * 32*K-word masks.
  *
  * The file also compiles with g++ -DSCB_EMU against tests/emu (host-thread emulator, test infrastructure).
  */
