@@ -1035,9 +1035,8 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
     uint4 *desc = reinterpret_cast<uint4 *>(smraw + 2u * BUFB);
     /* one program image; the next program waits in registers (fetched right after a switch, stored at the next one) */
     const uint32_t IMGB = (uint32_t)scb_img_entries(N, (int)(blockDim.x >> 5)) * 16u;
-    /* compare accumulators: three buffers of {d2[WT], dz[WT]} used in turn, so that a compare step needs no barrier of
-     * its own (the buffer of compare n is cleared after the barrier of compare n + 1 and reused by compare n + 3);
-     * word lane * K + k of the tile sits at [k * 32 + lane]: a warp's atomics hit 32 different banks */
+    /* compare accumulators {d2[WT], dz[WT]} (word lane * K + k of the tile sits at [k * 32 + lane]: a warp's atomics hit
+     * 32 different banks), then scratch of the epilogue: [2 * WT ...) the error column of each chunk's last valid cell */
     uint32_t *cm = reinterpret_cast<uint32_t *>(smraw + 2u * BUFB + IMGB);
     uint32_t *vm = cm + 6 * WT;
     uint32_t *Rm = vm + WT;                              /* cells a repeat has been seen for (found) */
@@ -1166,10 +1165,11 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         int4 cnt = A.counts[p];
         const uint4 *gfull = A.descs + (long long)p * A.Npad;
         const int e1full = cnt.x + cnt.y + cnt.z, n0full = cnt.w;      /* the constants of the FULL program are written at steps 1, 2 */
-        /* K0 laid every program out as the image this CTA's warps consume: the full program is copied into one
-         * image buffer now, the next reduced program (program k may compute steps >= from[k]) is staged into the other
-         * one by asynchronous copies while the current one runs, and a switch just swaps the two.  All switches happen
-         * before the first snapshot, whose tensor-memory slots follow the program's node order. */
+        /* K0 laid every program out as the image this CTA's warps consume: the full program is copied into the image
+         * buffer now; the next reduced program (program k may compute steps >= from[k]) is fetched into registers
+         * (`stage`, three uint4 per thread) right after a switch and stored over the buffer at the next one, between two
+         * barriers.  All switches happen before the first snapshot, whose tensor-memory slots follow the program's
+         * node order. */
         const uint4 *imgBase = A.imgs + (long long)p * (SCB_NPROG + 1) * A.imgStride;
         uint4 stage[SCB_STAGE_REGS];                        /* this thread's entries of the next program image */
         for (int j = tid; j < A.imgStride; j += nthr) scb_cp_async16(&desc[j], &imgBase[j]);
