@@ -446,6 +446,8 @@ def run_ours(args, wl, rank, world, local_rank):
     gen.step_resident(); sim.sync()
     if not args.no_order:
         sim.set_order(sim.cost_order())
+    else:
+        sim.set_option(_lib.OPT_AUTO_ORDER, 0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -608,7 +610,7 @@ def run_ours(args, wl, rank, world, local_rank):
                                     "packed matrix replicated, fitness exchange: " + gather_kind),
                        "launch": "one CUDA graph per generation and rank (clears, K0, K2 + in-kernel resolver, fill-forward%s)" % (
                            ", peer exchange" if (world > 1 and args.gather == "peer") else ""),
-                       "work_order": "tiles handed out costliest individual first (costs of the previous generation)" if not args.no_order else "index order",
+                       "work_order": "tiles handed out costliest individual first (costs of the previous generation; the robustness cases: the cost K0 predicts)" if not args.no_order else "index order",
                        "l2": "flushed (256 MiB memset) between timed steps", "geometry": info,
                        "clock_sampling": "nvidia-smi every 100 ms on rank 0 during the resident timed region",
                        "options": args.opt},

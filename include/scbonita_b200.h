@@ -72,6 +72,7 @@ extern "C" {
 #define SCB_OPT_GRAPH        16 /* 1 (default): a generation is one CUDA graph launch; 0: plain launches (per-kernel timing in scb_stats) */
 #define SCB_OPT_GENERIC      17 /* 1: score populations with the general simulator (any rule width, any node count; slow) even where the compiled path applies; default 0 */
 #define SCB_OPT_RESOLVE_GROUP 18 /* chunks per resolver item inside the simulator launch: 0 (default) = a whole tile with the target state in tensor memory; 1 or 2 = narrower items with three shared-memory buffers (shorter critical path, more SM time) */
+#define SCB_OPT_AUTO_ORDER   19 /* 1 (default): without an scb_pop_set_order, tiles are handed out by the cost K0 predicts for each individual (rows of its fixed-point program); 0: index order, tile-major */
 #define SCB_OPT_FUSE         12 /* 1 (default): CTAs that run out of tiles resolve queued groups in the same launch */
 
 typedef struct scb_ctx scb_ctx;

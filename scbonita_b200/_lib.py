@@ -19,6 +19,7 @@ OPT_EARLY_EXIT, OPT_SNAPSHOTS, OPT_WARPS, OPT_MAX_CTAS, OPT_WORDS, OPT_CHECK_EVE
 OPT_SNAP_LO, OPT_SNAP_HI, OPT_SNAP_MIN_GAP, OPT_TMEM, OPT_FUSE, OPT_TMA, OPT_STEADY, OPT_CHECK_FROM, OPT_GRAPH = 8, 9, 10, 11, 12, 13, 14, 15, 16
 OPT_GENERIC = 17
 OPT_RESOLVE_GROUP = 18
+OPT_AUTO_ORDER = 19
 
 # every symbol include/scbonita_b200.h declares (tests check that the library exports them all)
 SYMBOLS = (

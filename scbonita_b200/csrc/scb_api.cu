@@ -118,6 +118,9 @@ struct scb_ctx {
      * a population that holds rules over more than three distinct inputs, or on request (SCB_OPT_GENERIC) */
     bool genericOnly = false, optGeneric = false, lastGeneric = false;
     int optResGroup = 0;
+    bool optAutoOrder = true;
+    DevBuf<unsigned int> dPred;
+    DevBuf<int32_t> dOrderAuto;
     int lastSem = 0;
     DevBuf<uint32_t> dGScratch;
     bool delta = false;
@@ -299,12 +302,12 @@ int launch_compile(scb_ctx *c, int sem, const int32_t *knock, bool wantImages = 
     ca.descs = c->dDescs.p; ca.counts = c->dCounts.p; ca.diag = c->dDiag.p;
     ca.progs = c->dProgs.p; ca.progFrom = c->dProgFrom.p;
     ca.imgs = nullptr; ca.imgStride = 0; ca.imgWarps = 0; ca.imgRowBytes = 0;
-    ca.slots = nullptr; ca.fitness = nullptr; ca.cost = nullptr;
+    ca.slots = nullptr; ca.fitness = nullptr; ca.cost = nullptr; ca.pred = nullptr;
     int grid = P;
     if (population) {
         /* the population runs clear their own result sums and cost counters; a resident population compiles only the
          * replaced slots */
-        ca.fitness = c->dFitness.p; ca.cost = c->dCost.p;
+        ca.fitness = c->dFitness.p; ca.cost = c->dCost.p; ca.pred = c->dPred.p;
         if (c->delta) { ca.slots = c->dSlots.p; grid = c->nEval; }
     }
     if (wantImages) {
@@ -531,7 +534,7 @@ int scb_ctx_destroy(scb_ctx *c)
     gather_release(c);
     if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
 #endif
-    c->dCost.release(); c->dOrder.release(); c->dSlots.release(); c->dStage.release(); c->dGScratch.release();
+    c->dCost.release(); c->dOrder.release(); c->dSlots.release(); c->dStage.release(); c->dGScratch.release(); c->dPred.release(); c->dOrderAuto.release();
     c->dX.release(); c->dInd.release(); c->dAndLen.release(); c->dParse.release(); c->dAn.release();
     c->dAi.release(); c->dKo.release(); c->dKi.release(); c->dDescs.release(); c->dCounts.release(); c->dProgs.release(); c->dImgs.release(); c->dProgFrom.release();
     c->dFitness.release(); c->dNodewise.release(); c->dCellwise.release(); c->dCounters.release();
@@ -560,6 +563,7 @@ int scb_ctx_set_option(scb_ctx *c, int key, int64_t value)
     switch (key) {
         case SCB_OPT_GRAPH: c->optGraph = value != 0; return SCB_OK;
         case SCB_OPT_GENERIC: c->optGeneric = value != 0; return SCB_OK;
+        case SCB_OPT_AUTO_ORDER: c->optAutoOrder = value != 0; return SCB_OK;
         case SCB_OPT_RESOLVE_GROUP:
             if (value != 0 && value != 1 && value != 2) return fail(SCB_ERR_INVALID, "resolver group must be 0, 1 or 2");
             c->optResGroup = (int)value; break;
@@ -834,7 +838,7 @@ static int pop_run_impl(scb_ctx *c, int mode, int sem)
     if (mode == SCB_MODE_NODEWISE && (rc = c->dChunkLastBits.ensure((size_t)P * ((c->C + 1023) / 1024) * ((N + 31) / 32)))) return rc;
     if (mode == SCB_MODE_CELLWISE && (rc = c->dCellwise.ensure((size_t)P * c->C))) return rc;
     if ((rc = c->dImgs.ensure((size_t)P * (SCB_NPROG + 1) * scb_img_entries(N, c->main.warps)))) return rc;
-    if ((rc = c->dCost.ensure((size_t)2 * P))) return rc;
+    if ((rc = c->dCost.ensure((size_t)2 * P)) || (rc = c->dPred.ensure(P)) || (rc = c->dOrderAuto.ensure(P))) return rc;
 #ifndef SCB_EMU
     if (c->optGraph) {
         /* One launch per generation: the clears, K0, K2 (+ resolver), the fill-forward kernel and the peer exchange are
@@ -890,6 +894,12 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
 
     if (!capturing) CK(cudaEventRecord(c->evK0, st));
     if ((rc = launch_compile(c, sem, c->dKo.p, true, true))) return rc;
+    /* a population nobody gave an order for is handed out by the cost K0 predicts (individual-major, costliest first) */
+    const bool autoOrder = c->optAutoOrder && !c->haveOrder && !c->delta && c->optSteady && P <= SCB_ORDER_MAX_P && P > 1;
+    if (autoOrder) {
+        SCB_LAUNCH(scb_k_order, dim3(1), dim3((unsigned)std::min(1024, ((P + 31) / 32) * 32)), (size_t)P * 4, st, (const unsigned int *)c->dPred.p, c->dOrderAuto.p, P);
+        CK(cudaGetLastError());
+    }
 
     ScbSimArgs sa;
     memset(&sa, 0, sizeof(sa));
@@ -898,7 +908,7 @@ static int pop_enqueue(scb_ctx *c, int mode, int sem, bool capturing)
     sa.descs = c->dDescs.p; sa.counts = c->dCounts.p;
     sa.progs = c->dProgs.p; sa.progFrom = c->dProgFrom.p; sa.useSteady = c->optSteady;
     sa.imgs = c->dImgs.p; sa.imgStride = (int)scb_img_entries(N, c->main.warps);
-    sa.cost = c->dCost.p; sa.order = c->delta ? c->dSlots.p : (c->haveOrder ? c->dOrder.p : nullptr);
+    sa.cost = c->dCost.p; sa.order = c->delta ? c->dSlots.p : (c->haveOrder ? c->dOrder.p : (autoOrder ? c->dOrderAuto.p : nullptr));
     sa.nEval = c->delta ? c->nEval : P;
     sa.chkFromProg = c->optChkFrom;
     sa.firstSnap = 1000;

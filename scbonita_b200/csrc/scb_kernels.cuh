@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(256, 3) scb_k_compile(ScbCompileArgs A)
             if (tid == 0) {
                 out2[N] = make_uint4((unsigned)s3, (unsigned)s2, (unsigned)s1, (unsigned)s0);   /* the counts travel with the program */
                 progFrom[slot] = (unsigned char)(D + 2);
+                if (last && A.pred) A.pred[p] = (unsigned)(4 * s3 + 3 * s2 + 2 * s1);
             }
             if (emitStage) ++stage;
         }
@@ -705,6 +706,23 @@ __global__ void __launch_bounds__(256, 3) scb_k_compile(ScbCompileArgs A)
         if (cn[5]) atomicAdd(&A.diag->empty_rule_nodes, (unsigned long long)cn[5]);
         if (cn[6]) atomicAdd(&A.diag->bad_index_nodes, (unsigned long long)cn[6]);
         if (cn[7]) atomicAdd(&A.diag->term_overflow_nodes, (unsigned long long)cn[7]);
+    }
+}
+
+/* order[rank] = individual, by predicted cost, costliest first (ties by index): one CTA, every thread ranks its
+ * individuals against all others (P <= SCB_ORDER_MAX_P values in shared memory) */
+#define SCB_ORDER_MAX_P 4096
+__global__ void scb_k_order(const unsigned int *pred, int32_t *order, int P)
+{
+    SCB_DYN_SMEM(smraw);
+    unsigned int *sp = reinterpret_cast<unsigned int *>(smraw);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) sp[i] = pred[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const unsigned int v = sp[i];
+        int rank = 0;
+        for (int j = 0; j < P; ++j) rank += (sp[j] > v || (sp[j] == v && j < i)) ? 1 : 0;
+        order[rank] = i;
     }
 }
 

@@ -129,6 +129,8 @@ struct ScbCompileArgs {
                                      only the replaced individuals are compiled) */
     unsigned long long *fitness;  /* [P] result sums, cleared here for the compiled individuals (null: not wanted) */
     unsigned int *cost;           /* [2][P] cost counters of the simulator, cleared likewise */
+    unsigned int *pred;           /* [P] predicted cost of the individual = state rows per step of its fixed-point program
+                                     (Spearman 0.7-0.8 with the measured cost on C3); orders a population never scored before */
 };
 
 struct ScbPackArgs {
