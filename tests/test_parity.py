@@ -786,3 +786,21 @@ def test_q8_extra_accumulation_from_1000_nodes(backend):
         cw = sim.evaluate_population(pr.individuals, pr.ko, pr.ki, None, None, mode=simulator.MODE_CELLWISE)
         wc, _ = oracle.sync_bool(m, pr.individuals[0], pr.bm, cells, 0)
         assert np.array_equal(cw[0][:cells], wc[:cells])
+
+
+@pytest.mark.gpu
+def test_population_beyond_the_device_side_ordering(cuda_lib):
+    """More individuals than the one-CTA rank sort orders (SCB_ORDER_MAX_P = 4096): index order, same integers; and the
+    same population with the predicted-cost order switched off and with an explicit order."""
+    pr = Problem.synthetic(16, 700, 4200)
+    want = pr.oracle()["fitness"]
+    with pr.simulator(cuda_lib) as sim:
+        assert np.array_equal(sim.evaluate_population(pr.individuals, pr.ko, pr.ki, pr.pop_an, pr.pop_ai), want)
+    sl = slice(0, 3000)
+    with pr.simulator(cuda_lib) as sim:
+        a = sim.evaluate_population(pr.individuals[sl], pr.ko, pr.ki, pr.pop_an[sl], pr.pop_ai[sl])          # ordered by K0's prediction
+        sim.set_option(_lib.OPT_AUTO_ORDER, 0)
+        b = sim.evaluate_population(pr.individuals[sl], pr.ko, pr.ki, pr.pop_an[sl], pr.pop_ai[sl])          # index order
+        sim.set_order(sim.cost_order())
+        c = sim.evaluate_population(pr.individuals[sl], pr.ko, pr.ki, pr.pop_an[sl], pr.pop_ai[sl])          # measured order
+    assert np.array_equal(a, want[sl]) and np.array_equal(b, want[sl]) and np.array_equal(c, want[sl])
