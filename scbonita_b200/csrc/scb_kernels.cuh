@@ -1555,43 +1555,41 @@ __global__ void __launch_bounds__(SCB_SIM_MAX_WARPS * 32, 1) scb_k_sim(ScbSimArg
         const unsigned char *fin = sm + finOff + laneOff;
         unsigned char *oth = sm + (finOff ? 0u : BUFB) + laneOff;
         unsigned total32 = 0;
-        for (int j0 = warp; j0 < N; j0 += 2 * S) {
-            /* two nodes in flight per warp: the S_0 rows come from L2 */
-            const int j1 = j0 + S;
-            const bool two = j1 < N;
-            const int node0 = j0, node1 = two ? j1 : j0;
-            const uint32_t dsto0 = (uint32_t)node0 * ROWB, dsto1 = (uint32_t)node1 * ROWB;
-            const ScbVec<K> x0 = scb_ldg<K>(A.X + (long long)node0 * A.Wpad + w0 + lane * K);
-            const ScbVec<K> x1 = scb_ldg<K>(A.X + (long long)node1 * A.Wpad + w0 + lane * K);
-            const ScbVec<K> s0 = scb_ld<K>(fin + dsto0), s1 = scb_ld<K>(fin + dsto1);
-            ScbVec<K> e0, e1;
-            unsigned c0 = 0, c1 = 0;
+        constexpr int RF = 4;                                /* rows in flight per warp: the S_0 rows come from L2 */
+        for (int j0 = warp; j0 < N; j0 += RF * S) {
+            ScbVec<K> x[RF];
+            int node[RF];
+            bool live[RF];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                e0.v[k] = (s0.v[k] ^ x0.v[k]) & ok.v[k]; c0 += (unsigned)__popc(e0.v[k]);
-                e1.v[k] = (s1.v[k] ^ x1.v[k]) & ok.v[k]; c1 += (unsigned)__popc(e1.v[k]);
+            for (int r = 0; r < RF; ++r) {
+                const int j = j0 + r * S;
+                live[r] = j < N;
+                node[r] = live[r] ? j : j0;
+                x[r] = scb_ldg<K>(A.X + (long long)node[r] * A.Wpad + w0 + lane * K);
             }
-            if (!two) c1 = 0;
-            total32 += c0 + c1;
-            {
-                uint32_t l0 = 0u, l1 = 0u;
 #pragma unroll
-                for (int k = 0; k < K; ++k) { l0 |= e0.v[k] & lm.v[k]; l1 |= e1.v[k] & lm.v[k]; }
-                if (!two) l1 = 0u;
-                lastCnt += (l0 ? 1u : 0u) + (l1 ? 1u : 0u);
-                if (A.mode == 1) {
-                    if (l0) atomicOr(&lastAcc[K + myChunk * NB + (node0 >> 5)], 1u << (node0 & 31));
-                    if (l1) atomicOr(&lastAcc[K + myChunk * NB + (node1 >> 5)], 1u << (node1 & 31));
+            for (int r = 0; r < RF; ++r) {
+                const uint32_t dsto = (uint32_t)node[r] * ROWB;
+                const ScbVec<K> sv = scb_ld<K>(fin + dsto);
+                ScbVec<K> e;
+                unsigned c = 0;
+                uint32_t l = 0u;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    e.v[k] = (sv.v[k] ^ x[r].v[k]) & ok.v[k];
+                    c += (unsigned)__popc(e.v[k]);
+                    l |= e.v[k] & lm.v[k];
                 }
-            }
-            if (A.mode == 1) {
-                c0 = scb_warp_sum(c0);
-                c1 = scb_warp_sum(c1);
-                if (lane == 0 && c0) atomicAdd(&A.nodewise[(long long)p * N + node0], (int)c0);
-                if (lane == 0 && c1) atomicAdd(&A.nodewise[(long long)p * N + node1], (int)c1);
-            } else if (A.mode == 2) {
-                scb_st<K>(oth + dsto0, e0);
-                if (two) scb_st<K>(oth + dsto1, e1);
+                if (!live[r]) { c = 0; l = 0u; }
+                total32 += c;
+                lastCnt += l ? 1u : 0u;
+                if (A.mode == 1) {
+                    if (l) atomicOr(&lastAcc[K + myChunk * NB + (node[r] >> 5)], 1u << (node[r] & 31));
+                    c = scb_warp_sum(c);
+                    if (lane == 0 && c) atomicAdd(&A.nodewise[(long long)p * N + node[r]], (int)c);
+                } else if (A.mode == 2) {
+                    if (live[r]) scb_st<K>(oth + dsto, e);
+                }
             }
         }
         total32 = scb_warp_sum(total32);
