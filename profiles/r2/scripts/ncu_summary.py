@@ -58,7 +58,35 @@ for name in sys.argv[2:]:
                      "duration_under_ncu": " ".join(d["gpu__time_duration.sum"])}
 if traffic:
     k2 = traffic.get("%s_k2" % tag)
+    tot = (k2["dram_bytes_read"] + k2["dram_bytes_write"]) if k2 else None
     json.dump({"source": "ncu --set full --clock-control none, one launch of K2 of the C3 generation (plain launch, resolver not fused)",
-               "k2_dram_bytes_per_launch": (k2["dram_bytes_read"] + k2["dram_bytes_write"]) if k2 else None, "captures": traffic},
+               "workload": "C3", "dram_bytes_per_launch": tot, "k2_dram_bytes_per_launch": tot,
+               "note": "ncu flushes the caches before the profiled launch, so the 22.6 MB of program images K0 has just written "
+                       "(6 images x 7.5 KB x 500 individuals, L2-resident in a live run) are counted as DRAM reads; the algorithmic "
+                       "figure is 2.85 MB (matrix + one 16-byte descriptor per node and individual + results)",
+               "captures": traffic},
               open(os.path.join(out_dir, "k2_dram_traffic.json"), "w"), indent=1)
+    # before / after table of K2
+    def load(name):
+        out = {}
+        path = os.path.join(out_dir, "ncu_%s.csv" % name)
+        if os.path.exists(path):
+            for r in list(csv.reader(open(path)))[1:]:
+                if len(r) >= 3:
+                    out[r[0]] = (r[2], r[1])
+        return out
+    mid, head = load("r1kernel_k2"), load("%s_k2" % tag)
+    r1 = {"gpu__time_duration.sum": ("2.758208", "ms"), "dram__bytes_read.sum": ("10.355712", "Mbyte"), "smsp__inst_executed.sum": ("1621452466", "inst"),
+          "smsp__issue_active.avg.pct_of_peak_sustained_active": ("54.130978", "%"), "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": ("459698450", ""),
+          "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": ("57.915651", "%"), "launch__registers_per_thread": ("89", "register/thread"),
+          "sm__warps_active.avg.pct_of_peak_sustained_active": ("31.245146", "%"), "sm__throughput.avg.pct_of_peak_sustained_elapsed": ("51.094344", "%")}
+    with open(os.path.join(out_dir, "k2_before_after.md"), "w") as f:
+        f.write("K2 (`scb_k_sim<4, true>`) on the C3 generation, one launch, `ncu --set full --clock-control none`, resolver not fused.\n"
+                "Columns: the kernel in the middle of round 1 (round-1 sources rebuilt and captured on a round-2 box), the kernel at the end of\n"
+                "round 1 (`profiles/r1/ncu_raw_scb_k_sim4_round1_final.txt`, the metrics kept there), HEAD of round 2.\n"
+                "Durations under ncu are cold-cache, serialised replays; the live numbers are in bench.py's line.\n\n")
+        f.write("| metric | mid round 1 | end of round 1 | round 2 (HEAD) |\n|---|---:|---:|---:|\n")
+        for w in WANT:
+            if w in mid or w in head or w in r1:
+                f.write("| %s | %s | %s | %s |\n" % (w, " ".join(mid.get(w, ("", ""))), " ".join(r1.get(w, ("", ""))), " ".join(head.get(w, ("", "")))))
     print(open(os.path.join(out_dir, "k2_dram_traffic.json")).read())
